@@ -74,13 +74,13 @@ __global__ void __launch_bounds__(T) fps_ballquery_kernel(XyzView xyz, int N, in
                                                           float* __restrict__ new_xyz, int do_bq, float radius2,
                                                           int nsample, int32_t* __restrict__ bq_idx,
                                                           int32_t* __restrict__ bq_cnt) {
-  extern __shared__ float smem[];
-  float* sx = smem;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int NW = T / 32;
+  unsigned long long* s_slot = reinterpret_cast<unsigned long long*>(smem_raw);  // 2*NW keys (8-byte aligned)
+  float* sx = reinterpret_cast<float*>(s_slot + 2 * NW);
   float* sy = sx + N;
   float* sz = sy + N;
   float* s_ctr = sz + N;  // m*3 centroids
-  unsigned long long* s_slot = reinterpret_cast<unsigned long long*>(s_ctr + ((m * 3 + 1) & ~1));  // 2*(T/32)
-  constexpr int NW = T / 32;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* base = xyz.p + (long long)b * xyz.sb;
 
@@ -163,8 +163,8 @@ __global__ void __launch_bounds__(T) fps_ballquery_kernel(XyzView xyz, int N, in
 __global__ void __launch_bounds__(512) ball_query_kernel(XyzView xyz, int N, int m, const float* __restrict__ new_xyz,
                                                          float radius2, int nsample, int32_t* __restrict__ bq_idx,
                                                          int32_t* __restrict__ bq_cnt) {
-  extern __shared__ float smem[];
-  float* sx = smem;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* sx = reinterpret_cast<float*>(smem_raw);
   float* sy = sx + N;
   float* sz = sy + N;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -298,7 +298,7 @@ int ilog2_floor(int n) {
 template <int T, int P>
 int launch_fps(XyzView v, int B, int N, int m, int bs, int32_t* fps_idx, float* new_xyz, int do_bq, float radius,
                int nsample, int32_t* bq_idx, int32_t* bq_cnt, cudaStream_t st) {
-  size_t smem = sizeof(float) * (3 * (size_t)N + ((m * 3 + 1) & ~1)) + sizeof(unsigned long long) * 2 * (T / 32);
+  size_t smem = sizeof(float) * (3 * (size_t)N + (size_t)m * 3) + sizeof(unsigned long long) * 2 * (T / 32);
   auto kern = fps_ballquery_kernel<T, P>;
   if (smem > 48 * 1024) GADDPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int log2bs = ilog2_floor(bs);
