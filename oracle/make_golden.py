@@ -1,0 +1,128 @@
+"""Pin the oracle against the UNMODIFIED reference and write tests/golden/ (build container only).
+
+    python -m oracle.make_golden            # check + (re)write fixtures
+    python -m oracle.make_golden --check    # check only
+
+For DDPG and BC at B=8, N=512 (BASELINE config 1 shape) it builds the reference agent the way
+core/train_test_offline.py:305-349 does (through oracle/refstack.py) and ``OracleAgent`` under the same
+seed, asserts bit-identical initial weights, runs STEPS update steps on the same synthetic batches with
+the same RNG state and asserts every returned scalar and every parameter/buffer is IDENTICAL.  Only then
+are the fixtures written: per-step scalars, the TD3 noise, index-op outputs on the first batch,
+per-tensor parameter digests and a select_action known answer.  tests/test_oracle_golden.py replays them
+with the oracle alone (that is what runs on the GPU box, where /root/reference does not exist).
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from gaddpg_b200 import synthetic  # noqa: E402
+from oracle import refstack  # noqa: E402
+from oracle.ddpg_cpu import LOSS_KEYS, OracleAgent  # noqa: E402
+from oracle.pointnet2_ops_cpu import pointnet2_utils as U  # noqa: E402
+
+B, N, STEPS, SEED = 8, 512, 4, 123456
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def ref_state_dicts(ref):
+    d = {"policy": ref.policy.state_dict(), "policy_target": ref.policy_target.state_dict(),
+         "state_feat": ref.state_feature_extractor.state_dict()}
+    if hasattr(ref, "critic"):
+        d["critic"] = ref.critic.state_dict()
+        d["critic_target"] = ref.critic_target.state_dict()
+    return d
+
+
+def assert_same_weights(a, b, what):
+    for k in a:
+        assert list(a[k].keys()) == list(b[k].keys()), (what, k)
+        for n in a[k]:
+            assert torch.equal(a[k][n], b[k][n]), (what, k, n)
+
+
+def digest(sd):
+    """name -> (sum, abs-sum) in float64: small, order-independent fingerprint of every tensor."""
+    out = {}
+    for k, d in sd.items():
+        for n, v in d.items():
+            v = v.double()
+            out[k + "/" + n] = np.array([float(v.sum()), float(v.abs().sum())])
+    return out
+
+
+def run(policy, write):
+    ns, ref, _ = refstack.make_reference_agent(policy, seed=SEED)
+    ora = OracleAgent(policy, seed=SEED)
+    assert_same_weights(ref_state_dicts(ref), ora.state_dicts(), policy + " init")
+    scalars = np.zeros((STEPS, len(LOSS_KEYS)))
+    noise = np.zeros((STEPS, B, 6), np.float32)
+    for step in range(STEPS):
+        batch = synthetic.make_batch(B, N, step=step)
+        torch.manual_seed(1000 + step)
+        r = ref.update_parameters(batch, ref.update_step, 0)
+        ref.step_scheduler(ref.update_step)
+        torch.manual_seed(1000 + step)
+        if policy == "DDPG":
+            torch.randn(B, 6)
+            noise[step] = torch.rand(B, 6).numpy()  # the draw get_noise_delta will make (utils.py:575)
+            torch.manual_seed(1000 + step)
+        o = ora.update_parameters(batch)
+        ora.step_scheduler()
+        for i, k in enumerate(LOSS_KEYS):
+            assert r[k] == o[k] or (np.isnan(r[k]) and np.isnan(o[k])), (policy, step, k, r[k], o[k])
+            scalars[step, i] = o[k]
+    assert_same_weights(ref_state_dicts(ref), ora.state_dicts(), policy + " after %d steps" % STEPS)
+    # explicit-noise path of the oracle must reproduce the generator path
+    ora2 = OracleAgent(policy, seed=SEED)
+    for step in range(STEPS):
+        o2 = ora2.update_parameters(synthetic.make_batch(B, N, step=step), noise_u=noise[step])
+        ora2.step_scheduler()
+        assert all(o2[k] == scalars[step, i] or np.isnan(o2[k]) for i, k in enumerate(LOSS_KEYS)), (policy, step)
+    assert_same_weights(ora.state_dicts(), ora2.state_dicts(), policy + " explicit noise")
+    # select_action known answer (eval-mode BN, batch of one) vs the reference
+    cloud = synthetic.make_batch(1, N, step=99)["point_state_batch"][0]
+    torch.manual_seed(77)
+    ra = ref.select_action([[cloud, np.zeros((1,), np.float32)]], remain_timestep=7)
+    torch.manual_seed(77)
+    oa = ora.select_action(cloud, 7)
+    for x, y in zip(ra, oa):
+        assert np.array_equal(np.asarray(x), np.asarray(y)), (policy, "select_action")
+    print("[make_golden] %s: oracle == unmodified reference over %d steps (scalars, weights, select_action)" % (policy, STEPS))
+    if write:
+        fx = dict(scalars=scalars, noise=noise, loss_keys=np.array(LOSS_KEYS), B=B, N=N, steps=STEPS, seed=SEED,
+                  sel_mean=oa[0], sel_logp=np.float32(oa[1]), sel_action=oa[2], sel_aux=oa[3])
+        for k, v in digest(ora.state_dicts()).items():
+            fx["digest:" + k] = v
+        np.savez_compressed(os.path.join(GOLDEN, "%s_b%d_n%d.npz" % (policy.lower(), B, N)), **fx)
+
+
+def index_fixture(write):
+    """FPS / ball-query outputs of the oracle's C code on the first synthetic batch and on tie-heavy clouds."""
+    cloud = torch.from_numpy(synthetic.make_batch(B, N, step=0)["point_state_batch"])
+    xyz = cloud[:, :3, 6:].transpose(1, 2).contiguous()
+    f1 = U.fps_raw(xyz, 32)
+    c1 = torch.gather(xyz, 1, f1.long().unsqueeze(-1).expand(-1, -1, 3))
+    b1, n1 = U.ball_query_raw(0.02, 64, xyz, c1, return_cnt=True)
+    f2 = U.fps_raw(c1, 32)
+    c2 = torch.gather(c1, 1, f2.long().unsqueeze(-1).expand(-1, -1, 3))
+    b2, n2 = U.ball_query_raw(0.04, 128, c1, c2, return_cnt=True)
+    if write:
+        np.savez_compressed(os.path.join(GOLDEN, "index_b%d_n%d.npz" % (B, N)), fps1=f1.numpy(), bq1=b1.numpy().astype(np.int16),
+                            cnt1=n1.numpy(), fps2=f2.numpy(), bq2=b2.numpy().astype(np.int8), cnt2=n2.numpy())
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--check", action="store_true")
+    a = ap.parse_args()
+    os.makedirs(GOLDEN, exist_ok=True)
+    run("DDPG", not a.check)
+    run("BC", not a.check)
+    index_fixture(not a.check)
+    print("[make_golden] done")
