@@ -20,3 +20,69 @@ int gaddpg_group_points_grad_impl(int B, int C, int N, int m, int s, const float
                                   float* grad_pts, void* stream);
 int gaddpg_row_table_impl(int S, int nsample, const int32_t* cnt, const int32_t* idx, int32_t* seg_off,
                           int32_t* row_seg, int32_t* row_src, float* row_w, void* stream);
+
+// gemm_rows.cu
+#include "gemm_rows.cuh"
+#include <stddef.h>
+int gaddpg_gemm_nt_impl(const NTGroup* g, int nprob, int amode, int emode, void* stream);
+size_t gaddpg_gemm_tn_workspace_bytes_impl();
+int gaddpg_gemm_tn_impl(const TNProblem* p, int pmode, int qmode, float* dW, int ldd, int Ntrue, int Ktrue, int rot,
+                        float* dbias, int accumulate, float* ws, size_t ws_bytes, void* stream);
+int gaddpg_bn_finalize_fwd_impl(const float* stats, int C, double count, const float* gamma, const float* beta, float eps,
+                                float momentum, float* running_mean, float* running_var, long long* nbt, int training,
+                                float* scale, float* shift, float* mean_out, float* rstd_out, void* stream);
+int gaddpg_bn_finalize_bwd_impl(const float* stats, int C, double count, const float* gamma, const float* rstd, float* g,
+                                float* m1, float* m2, float* dgamma, float* dbeta, int accumulate, void* stream);
+// sa_ops.cu
+int gaddpg_sa1_l1_fwd_impl(const float* cloud, long long cloud_sb, int cloud_sc, int skip, int Cp, const float* bc, int Cb,
+                           int B, const float* ctr, int npoint, const int32_t* row_seg, const int32_t* row_src,
+                           const float* row_w, int M_max, const int* M_dev, const float* W, int ldw, float* bcbias_ws,
+                           float* Y, float* stats, void* stream);
+int gaddpg_sa1_l1_bwd_impl(const float* cloud, long long cloud_sb, int cloud_sc, int skip, int Cp, const float* bc, int Cb,
+                           int B, const float* ctr, int npoint, const int32_t* seg_off, const int32_t* row_seg,
+                           const int32_t* row_src, const float* row_w, int M_max, const int* M_dev, const float* D,
+                           const float* Y, const float* g, const float* m1, const float* m2, const float* mean,
+                           const float* rstd, const float* W, int ldw, float* dW, int accumulate, float* dbc, float* dY_ws,
+                           float* ws, size_t ws_bytes, void* stream);
+int gaddpg_gather_rows_impl(const float* feats, int C, const float* xyz, int n_src, const float* ctr, int npoint,
+                            const int32_t* row_seg, const int32_t* row_src, int M_max, const int* M_dev, float* G, int ldg,
+                            void* stream);
+int gaddpg_scatter_rows_impl(const float* dG, int ldg, int C, int B, int n_src, int npoint, const int32_t* seg_off,
+                             const int32_t* row_src, float* dfeats, void* stream);
+int gaddpg_pool_fwd_impl(const float* Y, int C, const float* scale, const float* shift, const int32_t* seg_off, int fixed_len,
+                         int S, float* out, int32_t* arg, void* stream);
+int gaddpg_pool_bwd_impl(const float* dOut, int ldo, const float* out, const int32_t* arg, const float* Y, int C,
+                         const int32_t* row_seg, int fixed_len, int M_max, const int* M_dev, const float* mean,
+                         const float* rstd, float* D, float* stats, void* stream);
+int gaddpg_feat_finish_impl(const float* Y, int C, const float* scale, const float* shift, const float* time,
+                            float time_offset, int B, float* feat, int ld, void* stream);
+// head_ops.cu
+int gaddpg_heads_init_impl(const float* act_scale, const float* act_bias, const float* cp_rotz);
+int gaddpg_policy_head_fwd_impl(const float* raw, int ldr, int B, float* pi, void* stream);
+int gaddpg_td3_next_action_impl(const float* raw_t, int ldr, const float* u, float noise_scale, int B, float* next_action,
+                                void* stream);
+int gaddpg_td3_target_impl(const float* q1t, const float* q2t, const float* reward, const float* done, float gamma, int B,
+                           float* y, void* stream);
+int gaddpg_critic_loss_impl(const float* qa, int ldq, int oq2, int oaux, const float* y, const float* perturb_flag, const float* ret,
+                            const float* goal, int use_aux, int B, float grad_scale, float* dqa, float* out, void* stream);
+int gaddpg_actor_loss_impl(const float* praw, int ldr, const float* pi, const float* expert_action, const float* expert_flag,
+                           const float* ret, const float* goal, int use_aux, float bc_weight, const float* dpi_ac, int B,
+                           float grad_scale, float* dpraw, int n_head, float* out, void* stream);
+int gaddpg_actor_critic_loss_impl(const float* qa, int ldq, int oq2, const float* ret, const float* expert_flag, float mix, int B,
+                                  float grad_scale, int n_head, float* dqa, float* out, void* stream);
+int gaddpg_quat_head_impl(const float* raw, int ldr, int B, float* out7, void* stream);
+int gaddpg_policy_sample_impl(const float* raw, int ldr, int off_logstd, const float* eps, int B, float* action, float* logp,
+                              void* stream);
+// optim.cu
+int gaddpg_adam_step_impl(float* p, float* g, float* m, float* v, long long n, double lr, double beta1, double beta2, double eps,
+                          double weight_decay, long long step, const float* dyn, double grad_scale, const float* clip,
+                          int write_back_grad, float* target, double tau, void* stream);
+int gaddpg_wprep_batched_impl(const long long* jobs_dev, int njobs, void* stream);
+int gaddpg_dmask_stats_impl(const float* dX, int ldx, const float* Yprev, int C, int M, const float* psc, const float* psh,
+                            const float* pmean, const float* prstd, float* D, float* stats, void* stream);
+int gaddpg_polyak_impl(float* target, const float* source, long long n, double tau, void* stream);
+int gaddpg_polyak_vec_impl(float* target, const float* source, const float* tau_vec, long long n, void* stream);
+int gaddpg_absmax_impl(const float* x, long long n, float* out, float* ws, void* stream);
+int gaddpg_clip_coef_impl(const float* g, long long n, float max_norm, float* coef_out, float* norm_out, float* ws, void* stream);
+int gaddpg_wprep_impl(const float* W, int N, int K, int rot, float* Wp, int ldp, float* WT, int ldt, void* stream);
+int gaddpg_f64_to_f32_impl(const double* src, float* dst, long long n, void* stream);

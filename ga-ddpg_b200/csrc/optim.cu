@@ -1,0 +1,293 @@
+// optim.cu — flat-arena optimiser kernels (sm_100a): Adam with L2 weight decay, gradient-norm clipping,
+// Polyak target updates, abs-max statistics, derived weight layouts, input conversion.
+//
+// Replaces torch.optim.Adam.step (policy/critic: eps=1e-5, weight_decay=1e-5, /root/reference/core/utils.py:
+// 969-970,993-994; encoders: lr=1e-3, utils.py:221-234), torch.nn.utils.clip_grad_norm_ (ddpg.py:141),
+// soft_update / half_soft_update / half_hard_update (utils.py:750-770), module_max_param / module_max_gradient
+// (utils.py:92-108) and torch.cuda.FloatTensor(ndarray) (agent.py:221-222).  These are the HBM-streaming
+// kernels of the step: 16 B read + 12 B written per parameter for Adam (+8/4 for a fused Polyak target),
+// float4 vectorised, grid-stride over 148 x 8 CTAs.
+#include "common.cuh"
+#include "impl.h"
+
+namespace {
+
+struct AdamArgs {
+  float lr_over_bc1;    // step_size = lr / (1 - beta1^t)
+  float bc2_sqrt;       // sqrt(1 - beta2^t)
+  float beta1, beta2, one_minus_beta1, one_minus_beta2, eps, weight_decay;
+  float grad_scale;     // 1/world_size for sample-sharded replicas
+  const float* clip;    // device scalar: clip coefficient (NULL = 1)
+  const float* dyn;     // device {step_size, bc2_sqrt}: overrides the two immediates (graph replay across steps)
+  int write_back_grad;  // store the clipped/scaled gradient (clip_grad_norm_ semantics)
+  float tau;            // Polyak factor when target != NULL
+  float one_minus_tau;
+};
+
+__device__ __forceinline__ void adam_one(float& p, float& g, float& m, float& v, const AdamArgs& a, float clip) {
+  g = g * a.grad_scale * clip;
+  float gg = fmaf(a.weight_decay, p, g);             // grad.add(param, alpha=weight_decay)
+  m = fmaf(gg - m, a.one_minus_beta1, m);            // exp_avg.lerp_(grad, 1 - beta1)
+  v = fmaf(a.one_minus_beta2 * gg, gg, a.beta2 * v); // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+  float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
+  p = p - a.lr_over_bc1 * (m / denom);               // param.addcdiv_(exp_avg, denom, value=-step_size)
+}
+
+__global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            long long n, AdamArgs a, float* __restrict__ target) {
+  const float clip = a.clip ? *a.clip : 1.f;
+  if (a.dyn) {
+    a.lr_over_bc1 = a.dyn[0];
+    a.bc2_sqrt = a.dyn[1];
+  }
+  const long long n4 = n / 4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 P = reinterpret_cast<float4*>(p)[i], G = reinterpret_cast<float4*>(g)[i], Mm = reinterpret_cast<float4*>(m)[i],
+           V = reinterpret_cast<float4*>(v)[i];
+    adam_one(P.x, G.x, Mm.x, V.x, a, clip);
+    adam_one(P.y, G.y, Mm.y, V.y, a, clip);
+    adam_one(P.z, G.z, Mm.z, V.z, a, clip);
+    adam_one(P.w, G.w, Mm.w, V.w, a, clip);
+    reinterpret_cast<float4*>(p)[i] = P;
+    reinterpret_cast<float4*>(m)[i] = Mm;
+    reinterpret_cast<float4*>(v)[i] = V;
+    if (a.write_back_grad) reinterpret_cast<float4*>(g)[i] = G;
+    if (target) {
+      float4 T = reinterpret_cast<float4*>(target)[i];
+      T.x = T.x * a.one_minus_tau + P.x * a.tau;
+      T.y = T.y * a.one_minus_tau + P.y * a.tau;
+      T.z = T.z * a.one_minus_tau + P.z * a.tau;
+      T.w = T.w * a.one_minus_tau + P.w * a.tau;
+      reinterpret_cast<float4*>(target)[i] = T;
+    }
+  }
+  for (long long i = n4 * 4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float P = p[i], G = g[i], Mm = m[i], V = v[i];
+    adam_one(P, G, Mm, V, a, clip);
+    p[i] = P;
+    m[i] = Mm;
+    v[i] = V;
+    if (a.write_back_grad) g[i] = G;
+    if (target) target[i] = target[i] * a.one_minus_tau + P * a.tau;
+  }
+}
+
+// target = target*(1-tau) + source*tau   (utils.py:750-754)
+__global__ void polyak_kernel(float* __restrict__ t, const float* __restrict__ s, long long n, float tau, float one_minus_tau) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    t[i] = t[i] * one_minus_tau + s[i] * tau;
+}
+
+__global__ void polyak_vec_kernel(float* __restrict__ t, const float* __restrict__ s, const float* __restrict__ tv, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float tau = tv[i];
+    if (tau != 0.f) t[i] = t[i] * (1.0f - tau) + s[i] * tau;
+  }
+}
+
+// two-stage deterministic reductions: per-CTA partial -> fixed-order final
+__global__ void __launch_bounds__(256) reduce_partial_kernel(const float* __restrict__ x, long long n, int op,
+                                                             float* __restrict__ partial) {
+  __shared__ float red[8];
+  float a = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v = x[i];
+    a = op == 0 ? fmaxf(a, fabsf(v)) : fmaf(v, v, a);
+  }
+  a = op == 0 ? warp_max(a) : warp_sum(a);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float r = red[0];
+    for (int w = 1; w < 8; ++w) r = op == 0 ? fmaxf(r, red[w]) : r + red[w];
+    partial[blockIdx.x] = r;
+  }
+}
+// op 0: out = max(partials)   op 1: out = min(1, max_norm / (sqrt(sum partials) + 1e-6))  [clip coefficient]
+__global__ void reduce_final_kernel(const float* __restrict__ partial, int nblk, int op, float max_norm, float* __restrict__ out,
+                                    float* __restrict__ norm_out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (op == 0) {
+    float r = 0.f;
+    for (int i = 0; i < nblk; ++i) r = fmaxf(r, partial[i]);
+    *out = r;
+  } else {
+    double s = 0.0;
+    for (int i = 0; i < nblk; ++i) s += (double)partial[i];
+    float nrm = (float)sqrt(s);
+    float c = max_norm / (nrm + 1e-6f);
+    *out = c < 1.f ? c : 1.f;
+    if (norm_out) *norm_out = nrm;
+  }
+}
+
+// derived weight layouts: Wp[n][kp] = W[n][(kp+rot) % K] for kp < K else 0 (ldp >= K, multiple of 4);
+// WT[kp][n] = Wp[n][kp] with row length ldt >= N (multiple of 4), rows kp < ldp
+__global__ void wprep_kernel(const float* __restrict__ W, int N, int K, int rot, float* __restrict__ Wp, int ldp,
+                             float* __restrict__ WT, int ldt) {
+  long long total = (long long)(Wp ? N : 0) * ldp;
+  long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = i0; e < total; e += stride) {
+    int n = (int)(e / ldp), kp = (int)(e % ldp);
+    float v = 0.f;
+    if (kp < K) {
+      int k = kp + rot;
+      if (k >= K) k -= K;
+      v = W[(long long)n * K + k];
+    }
+    Wp[e] = v;
+  }
+  if (WT) {
+    long long tt = (long long)ldp * ldt;
+    for (long long e = i0; e < tt; e += stride) {
+      int kp = (int)(e / ldt), n = (int)(e % ldt);
+      float v = 0.f;
+      if (n < N && kp < K) {
+        int k = kp + rot;
+        if (k >= K) k -= K;
+        v = W[(long long)n * K + k];
+      }
+      WT[e] = v;
+    }
+  }
+}
+
+// batched form: jobs[j] = {W, N, K, rot, Wp, ldp, WT, ldt} as 8 x int64 in device memory (pointers are static)
+__global__ void wprep_batched_kernel(const long long* __restrict__ jobs) {
+  const long long* J = jobs + (long long)blockIdx.y * 8;
+  const float* W = reinterpret_cast<const float*>(J[0]);
+  const int N = (int)J[1], K = (int)J[2], rot = (int)J[3];
+  float* Wp = reinterpret_cast<float*>(J[4]);
+  const int ldp = (int)J[5];
+  float* WT = reinterpret_cast<float*>(J[6]);
+  const int ldt = (int)J[7];
+  long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+  if (Wp) {
+    for (long long e = i0; e < (long long)N * ldp; e += stride) {
+      int n = (int)(e / ldp), kp = (int)(e % ldp);
+      float v = 0.f;
+      if (kp < K) {
+        int k = kp + rot;
+        if (k >= K) k -= K;
+        v = W[(long long)n * K + k];
+      }
+      Wp[e] = v;
+    }
+  }
+  if (WT) {
+    for (long long e = i0; e < (long long)ldp * ldt; e += stride) {
+      int kp = (int)(e / ldt), n = (int)(e % ldt);
+      float v = 0.f;
+      if (n < N && kp < K) {
+        int k = kp + rot;
+        if (k >= K) k -= K;
+        v = W[(long long)n * K + k];
+      }
+      WT[e] = v;
+    }
+  }
+}
+
+__global__ void f64_to_f32_kernel(const double* __restrict__ src, float* __restrict__ dst, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = (float)src[i];
+}
+
+int stream_grid(long long n) {
+  long long g = (n + 255) / 256;
+  long long cap = (long long)gaddpg_sm_count() * 8;
+  return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
+}
+
+}  // namespace
+
+int gaddpg_adam_step_impl(float* p, float* g, float* m, float* v, long long n, double lr, double beta1, double beta2, double eps,
+                          double weight_decay, long long step, const float* dyn, double grad_scale, const float* clip,
+                          int write_back_grad, float* target, double tau, void* stream) {
+  GADDPG_CHECK_ARG(p && g && m && v && n >= 0 && (step >= 1 || dyn), "adam_step: bad argument");
+  GADDPG_CHECK_ARG(((uintptr_t)p % 16) == 0 && ((uintptr_t)g % 16) == 0 && ((uintptr_t)m % 16) == 0 && ((uintptr_t)v % 16) == 0 &&
+                       (!target || ((uintptr_t)target % 16) == 0),
+                   "adam_step: arena segments must be 16-byte aligned");
+  if (n == 0) return GADDPG_OK;
+  AdamArgs a;
+  if (step < 1) step = 1;
+  double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+  a.dyn = dyn;
+  a.lr_over_bc1 = (float)(lr / bc1);
+  a.bc2_sqrt = (float)sqrt(bc2);
+  a.beta1 = (float)beta1;
+  a.beta2 = (float)beta2;
+  a.one_minus_beta1 = (float)(1.0 - beta1);
+  a.one_minus_beta2 = (float)(1.0 - beta2);
+  a.eps = (float)eps;
+  a.weight_decay = (float)weight_decay;
+  a.grad_scale = (float)grad_scale;
+  a.clip = clip;
+  a.write_back_grad = write_back_grad;
+  a.tau = (float)tau;
+  a.one_minus_tau = (float)(1.0 - tau);
+  adam_kernel<<<stream_grid(n / 4 + 1), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, a, target);
+  GADDPG_CHECK_LAUNCH("adam_kernel");
+  return GADDPG_OK;
+}
+
+int gaddpg_polyak_impl(float* target, const float* source, long long n, double tau, void* stream) {
+  GADDPG_CHECK_ARG(target && source && n >= 0, "polyak: bad argument");
+  if (n == 0) return GADDPG_OK;
+  polyak_kernel<<<stream_grid(n), 256, 0, (cudaStream_t)stream>>>(target, source, n, (float)tau, (float)(1.0 - tau));
+  GADDPG_CHECK_LAUNCH("polyak_kernel");
+  return GADDPG_OK;
+}
+
+int gaddpg_polyak_vec_impl(float* target, const float* source, const float* tau_vec, long long n, void* stream) {
+  GADDPG_CHECK_ARG(target && source && tau_vec && n >= 0, "polyak_vec: bad argument");
+  if (n == 0) return GADDPG_OK;
+  polyak_vec_kernel<<<stream_grid(n), 256, 0, (cudaStream_t)stream>>>(target, source, tau_vec, n);
+  GADDPG_CHECK_LAUNCH("polyak_vec_kernel");
+  return GADDPG_OK;
+}
+
+// ws: >= 1184 floats
+int gaddpg_absmax_impl(const float* x, long long n, float* out, float* ws, void* stream) {
+  GADDPG_CHECK_ARG(x && out && ws && n >= 1, "absmax: bad argument");
+  int grid = stream_grid(n);
+  reduce_partial_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, n, 0, ws);
+  GADDPG_CHECK_LAUNCH("reduce_partial_kernel");
+  reduce_final_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(ws, grid, 0, 0.f, out, nullptr);
+  GADDPG_CHECK_LAUNCH("reduce_final_kernel");
+  return GADDPG_OK;
+}
+
+int gaddpg_clip_coef_impl(const float* g, long long n, float max_norm, float* coef_out, float* norm_out, float* ws, void* stream) {
+  GADDPG_CHECK_ARG(g && coef_out && ws && n >= 1, "clip_coef: bad argument");
+  int grid = stream_grid(n);
+  reduce_partial_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, n, 1, ws);
+  GADDPG_CHECK_LAUNCH("reduce_partial_kernel");
+  reduce_final_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(ws, grid, 1, max_norm, coef_out, norm_out);
+  GADDPG_CHECK_LAUNCH("reduce_final_kernel");
+  return GADDPG_OK;
+}
+
+int gaddpg_wprep_impl(const float* W, int N, int K, int rot, float* Wp, int ldp, float* WT, int ldt, void* stream) {
+  GADDPG_CHECK_ARG(W && N >= 1 && K >= 1 && rot >= 0 && rot < K, "wprep: bad argument");
+  GADDPG_CHECK_ARG(ldp >= K && (ldp % 4) == 0 && (!WT || (ldt >= N && (ldt % 4) == 0)), "wprep: bad leading dimensions");
+  long long work = (long long)(N > ldt ? N : ldt) * ldp;
+  wprep_kernel<<<stream_grid(work), 256, 0, (cudaStream_t)stream>>>(W, N, K, rot, Wp, ldp, WT, ldt);
+  GADDPG_CHECK_LAUNCH("wprep_kernel");
+  return GADDPG_OK;
+}
+
+int gaddpg_f64_to_f32_impl(const double* src, float* dst, long long n, void* stream) {
+  GADDPG_CHECK_ARG(src && dst && n >= 0, "f64_to_f32: bad argument");
+  if (n == 0) return GADDPG_OK;
+  f64_to_f32_kernel<<<stream_grid(n), 256, 0, (cudaStream_t)stream>>>(src, dst, n);
+  GADDPG_CHECK_LAUNCH("f64_to_f32_kernel");
+  return GADDPG_OK;
+}
+
+int gaddpg_wprep_batched_impl(const long long* jobs_dev, int njobs, void* stream) {
+  GADDPG_CHECK_ARG(jobs_dev && njobs >= 1 && njobs <= 65535, "wprep_batched: bad argument");
+  wprep_batched_kernel<<<dim3(64, njobs), 256, 0, (cudaStream_t)stream>>>(jobs_dev);
+  GADDPG_CHECK_LAUNCH("wprep_batched_kernel");
+  return GADDPG_OK;
+}

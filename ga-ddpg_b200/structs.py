@@ -1,0 +1,64 @@
+"""ctypes mirrors of the descriptor structs in include/gaddpg_b200.h, plus small builders.
+
+``check_sizes()`` compares ``ctypes.sizeof`` with the library's own ``sizeof`` so a header edit that is not
+mirrored here fails at import on the GPU box instead of corrupting a launch.
+"""
+import ctypes
+
+from .capi import lib
+
+OP_PLAIN, OP_BNRELU, OP_BNBWD = 0, 1, 2
+EPI_STORE, EPI_DMASK = 0, 1
+STAT_SLOTS = 296
+MAX_GROUP = 4
+
+_P = ctypes.c_void_p
+_I = ctypes.c_int
+
+
+class Operand(ctypes.Structure):
+    _fields_ = [("X", _P), ("ldx", _I), ("Y", _P), ("ldy", _I), ("rw", _P),
+                ("c0", _P), ("c1", _P), ("c2", _P), ("c3", _P), ("c4", _P)]
+
+
+class NTProblem(ctypes.Structure):
+    _fields_ = [("A", Operand), ("Bw", _P), ("ldb", _I), ("bias", _P), ("C", _P), ("ldc", _I),
+                ("M_max", _I), ("M_dev", _P), ("N", _I), ("K", _I), ("relu", _I),
+                ("stats", _P), ("srw", _P), ("Yprev", _P), ("ldyp", _I),
+                ("psc", _P), ("psh", _P), ("pmean", _P), ("prstd", _P)]
+
+
+class NTGroup(ctypes.Structure):
+    _fields_ = [("p", NTProblem * MAX_GROUP)]
+
+
+class TNProblem(ctypes.Structure):
+    _fields_ = [("P", Operand), ("Q", Operand), ("M_max", _I), ("M_dev", _P), ("N", _I), ("K", _I)]
+
+
+def check_sizes():
+    a, b, c = _I(), _I(), _I()
+    lib.gaddpg_struct_sizes(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
+    got = (ctypes.sizeof(Operand), ctypes.sizeof(NTProblem), ctypes.sizeof(TNProblem))
+    if got != (a.value, b.value, c.value):
+        raise RuntimeError("ctypes struct mirror out of sync with include/gaddpg_b200.h: %r vs %r" % (got, (a.value, b.value, c.value)))
+
+
+def dp(t):
+    """device pointer (int) of a tensor or None"""
+    return None if t is None else t.data_ptr()
+
+
+def op_plain(x, ld=None):
+    return Operand(X=dp(x), ldx=ld if ld is not None else x.shape[-1])
+
+
+def op_bnrelu(y, bn, ld=None):
+    """relu(y*scale+shift); bn has .scale/.shift"""
+    return Operand(X=dp(y), ldx=ld if ld is not None else y.shape[-1], c0=dp(bn.scale), c1=dp(bn.shift))
+
+
+def op_bnbwd(d, y, bn, bb, rw=None):
+    """BN backward of (D, Y): bn has .mean/.rstd, bb has .g/.m1/.m2"""
+    return Operand(X=dp(d), ldx=d.shape[-1], Y=dp(y), ldy=y.shape[-1], rw=dp(rw),
+                   c0=dp(bb.g), c1=dp(bb.m1), c2=dp(bb.m2), c3=dp(bn.mean), c4=dp(bn.rstd))

@@ -86,6 +86,144 @@ GADDPG_API int gaddpg_group_points_grad(const float* grad_out, const int32_t* id
 GADDPG_API int gaddpg_row_table(const int32_t* bq_cnt, const int32_t* bq_idx, int S, int nsample, int32_t* seg_off,
                      int32_t* row_seg, int32_t* row_src, float* row_w, void* stream);
 
+/* ---- row-GEMMs with fused BatchNorm prologues / epilogues -------------------------------------------
+ * Replace the cuDNN 1x1 Conv2d + BatchNorm2d + ReLU chain of upstream build_shared_mlp (SA modules built at
+ * /root/reference/core/networks.py:65-92), nn.Linear + BatchNorm1d of the FC head (networks.py:84-91) and the
+ * nn.Linear layers of QNetwork / GaussianPolicy (networks.py:265-300,315-351), forward and backward.
+ *   NT:  C[M,N]  = epi( pro(A)[M,K] . B[N,K]^T )         TN:  dW[N,K] = sum_r pro1(P)[r,:]^T pro2(Q)[r,:]
+ * pro: GADDPG_OP_PLAIN x | GADDPG_OP_BNRELU relu(x*c0[c]+c1[c]) |
+ *      GADDPG_OP_BNBWD  c0[c]*(X - rw[r]*(c1[c] + (Y-c3[c])*c4[c]*c2[c]))   (c0=gamma*rstd, c1=m1, c2=m2, c3=mean, c4=rstd)
+ * epi: GADDPG_EPI_STORE  C = [relu](acc + bias), optional weighted (sum, sum^2) column statistics;
+ *      GADDPG_EPI_DMASK  C = acc * [Yprev*psc+psh > 0], optional (sum, sum*xhat_prev) statistics.
+ * Statistics land in GADDPG_STAT_SLOTS per-CTA slots ([slots][2][N] floats) and are summed in a fixed order by
+ * the finalize calls below (deterministic; no float atomics). */
+#define GADDPG_STAT_SLOTS 296
+#define GADDPG_MAX_GROUP 4
+enum { GADDPG_OP_PLAIN = 0, GADDPG_OP_BNRELU = 1, GADDPG_OP_BNBWD = 2 };
+enum { GADDPG_EPI_STORE = 0, GADDPG_EPI_DMASK = 1 };
+
+typedef struct gaddpg_operand {
+  const float* X; int ldx;
+  const float* Y; int ldy;
+  const float* rw;
+  const float* c0; const float* c1; const float* c2; const float* c3; const float* c4;
+} gaddpg_operand;
+
+typedef struct gaddpg_nt_problem {
+  gaddpg_operand A;
+  const float* Bw; int ldb;
+  const float* bias;
+  float* C; int ldc;
+  int M_max; const int* M_dev;
+  int N, K;
+  int relu;
+  float* stats; const float* srw;
+  const float* Yprev; int ldyp;
+  const float* psc; const float* psh; const float* pmean; const float* prstd;
+} gaddpg_nt_problem;
+
+typedef struct gaddpg_nt_group { gaddpg_nt_problem p[GADDPG_MAX_GROUP]; } gaddpg_nt_group;
+
+typedef struct gaddpg_tn_problem {
+  gaddpg_operand P; gaddpg_operand Q;
+  int M_max; const int* M_dev;
+  int N, K;
+} gaddpg_tn_problem;
+
+/* sizeof() of the three structs above, for binding self-checks */
+GADDPG_API int gaddpg_struct_sizes(int* operand, int* nt_problem, int* tn_problem);
+
+/* up to GADDPG_MAX_GROUP independent NT problems in one launch (blockIdx.y = problem) */
+GADDPG_API int gaddpg_gemm_nt(const gaddpg_nt_group* group, int nprob, int amode, int emode, void* stream);
+/* dW[n][(k+rot) % Ktrue] (+)= TN product for n < Ntrue (rows >= Ntrue and columns >= Ktrue are padding);
+ * dbias[n] (+)= column sums of P */
+GADDPG_API long long gaddpg_gemm_tn_workspace_bytes(void);
+GADDPG_API int gaddpg_gemm_tn(const gaddpg_tn_problem* prob, int pmode, int qmode, float* dW, int ldd, int Ntrue, int Ktrue,
+                              int rot, float* dbias, int accumulate, float* ws, long long ws_bytes, void* stream);
+
+/* BatchNorm finalize.  fwd: slots -> batch mean / biased var -> scale, shift, mean, rstd and PyTorch's running-stat
+ * update (momentum, unbiased var, num_batches_tracked += 1); training=0 uses the running stats (eval mode).
+ * bwd: slots -> g = gamma*rstd, m1, m2 and dgamma / dbeta. */
+GADDPG_API int gaddpg_bn_finalize_fwd(const float* stats, int C, double count, const float* gamma, const float* beta, float eps,
+                                      float momentum, float* running_mean, float* running_var, long long* num_batches_tracked,
+                                      int training, float* scale, float* shift, float* mean_out, float* rstd_out, void* stream);
+GADDPG_API int gaddpg_bn_finalize_bwd(const float* stats, int C, double count, const float* gamma, const float* rstd, float* g,
+                                      float* m1, float* m2, float* dgamma, float* dbeta, int accumulate, void* stream);
+
+/* ---- set-abstraction glue (SURVEY.md §8 Spec S3; upstream QueryAndGroup / GroupAll / F.max_pool2d) ------------- */
+/* SA1 first layer straight from the channel-major cloud (B, *, skip+N): W[64][3+Cp+Cb] = [dxyz | per-point | broadcast];
+ * bc (B,Cb) are per-sample constant channels (the action, utils.py:291-297); bcbias_ws (B,64) scratch. */
+GADDPG_API int gaddpg_sa1_l1_fwd(const float* cloud, long long cloud_stride_b, int cloud_stride_c, int skip, int Cp, const float* bc,
+                                 int Cb, int B, const float* ctr, int npoint, const int32_t* row_seg, const int32_t* row_src,
+                                 const float* row_w, int M_max, const int* M_dev, const float* W, int ldw, float* bcbias_ws,
+                                 float* Y, float* stats, void* stream);
+/* backward of the same layer: dW (may be NULL), dbc (B,Cb) (may be NULL); dY_ws (M,64) scratch needed when Cb > 0 */
+GADDPG_API int gaddpg_sa1_l1_bwd(const float* cloud, long long cloud_stride_b, int cloud_stride_c, int skip, int Cp, const float* bc,
+                                 int Cb, int B, const float* ctr, int npoint, const int32_t* seg_off, const int32_t* row_seg,
+                                 const int32_t* row_src, const float* row_w, int M_max, const int* M_dev, const float* D,
+                                 const float* Y, const float* g, const float* m1, const float* m2, const float* mean,
+                                 const float* rstd, const float* W, int ldw, float* dW, int accumulate, float* dbc, float* dY_ws,
+                                 float* ws, long long ws_bytes, void* stream);
+/* G[r] = [feats[src] (C) | xyz[src]-ctr[seg] (3) | 0-pad]; row tables NULL: identity rows, absolute xyz (GroupAll) */
+GADDPG_API int gaddpg_gather_rows(const float* feats, int C, const float* xyz, int n_src, const float* ctr, int npoint,
+                                  const int32_t* row_seg, const int32_t* row_src, int M_max, const int* M_dev, float* G, int ldg,
+                                  void* stream);
+/* deterministic group_points_grad over the compact rows: dfeats (B, n_src, C) */
+GADDPG_API int gaddpg_scatter_rows(const float* dG, int ldg, int C, int B, int n_src, int npoint, const int32_t* seg_off,
+                                   const int32_t* row_src, float* dfeats, void* stream);
+/* out[seg][c] = max_r relu(Y[r][c]*scale[c]+shift[c]) over the segment, arg = first arg-max row */
+GADDPG_API int gaddpg_pool_fwd(const float* Y, int C, const float* scale, const float* shift, const int32_t* seg_off, int fixed_len,
+                               int S, float* out, int32_t* arg, void* stream);
+GADDPG_API int gaddpg_pool_bwd(const float* dOut, int ld_dout, const float* out, const int32_t* arg, const float* Y, int C,
+                               const int32_t* row_seg, int fixed_len, int M_max, const int* M_dev, const float* mean,
+                               const float* rstd, float* D, float* stats, void* stream);
+/* feat[b] = [relu(Y*scale+shift) (C) | time[b]+time_offset | 0-pad to ld]  (ddpg.py:56-57 appends the time column) */
+GADDPG_API int gaddpg_feat_finish(const float* Y, int C, const float* scale, const float* shift, const float* time,
+                                  float time_offset, int B, float* feat, int ld, void* stream);
+
+/* ---- heads, TD3 target, losses (networks.py:339-371; ddpg.py:61-88,119-130,170-177; agent.py:127-139; loss.py:17-31) -- */
+GADDPG_API int gaddpg_heads_init(const float* act_scale, const float* act_bias, const float* cp_rotz); /* HOST pointers */
+GADDPG_API int gaddpg_policy_head_fwd(const float* raw, int ldr, int B, float* pi, void* stream);
+GADDPG_API int gaddpg_td3_next_action(const float* raw_t, int ldr, const float* u, float noise_scale, int B, float* next_action,
+                                      void* stream);
+GADDPG_API int gaddpg_td3_target(const float* q1t, const float* q2t, const float* reward, const float* done, float gamma, int B,
+                                 float* y, void* stream);
+/* qa/dqa [B,ldq]: q1 at column 0, q2 at column oq2, aux_raw(7) at column oaux;
+ * out[0]=critic_loss out[1]=critic_grasp_aux_loss out[2]=#(return>0) */
+GADDPG_API int gaddpg_critic_loss(const float* qa, int ldq, int oq2, int oaux, const float* y, const float* perturb_flag, const float* ret,
+                                  const float* goal, int use_aux, int B, float grad_scale, float* dqa, float* out, void* stream);
+/* praw/dpraw [B,ldr] = [mean(6) | extra | ...]; out[0]=bc_loss*bc_weight out[1]=policy_grasp_aux_loss */
+GADDPG_API int gaddpg_actor_loss(const float* praw, int ldr, const float* pi, const float* expert_action, const float* expert_flag,
+                                 const float* ret, const float* goal, int use_aux, float bc_weight, const float* dpi_ac, int B,
+                                 float grad_scale, float* dpraw, int n_head, float* out, void* stream);
+GADDPG_API int gaddpg_actor_critic_loss(const float* qa, int ldq, int oq2, const float* ret, const float* expert_flag, float mix, int B,
+                                        float grad_scale, int n_head, float* dqa, float* out, void* stream);
+GADDPG_API int gaddpg_quat_head(const float* raw, int ldr, int B, float* out7, void* stream);
+GADDPG_API int gaddpg_policy_sample(const float* raw, int ldr, int off_logstd, const float* eps, int B, float* action, float* logp,
+                                    void* stream);
+
+/* ---- optimiser / target networks / statistics (utils.py:750-770,960-1006,92-108; ddpg.py:141; agent.py:221-222) ------ */
+/* torch.optim.Adam (L2 weight decay, not AdamW) on one arena segment; clip: device scalar multiplied into the gradient
+ * (clip_grad_norm_), grad_scale: 1/world_size; target != NULL fuses target = target*(1-tau) + p*tau. */
+GADDPG_API int gaddpg_adam_step(float* p, float* g, float* m, float* v, long long n, double lr, double beta1, double beta2,
+                                double eps, double weight_decay, long long step, const float* dyn, double grad_scale,
+                                const float* clip, int write_back_grad, float* target, double tau, void* stream);
+/* dyn (optional, device): {lr/(1-beta1^t), sqrt(1-beta2^t)} read at run time, so one captured graph serves every step */
+GADDPG_API int gaddpg_polyak(float* target, const float* source, long long n, double tau, void* stream);
+/* target = target*(1-tau_vec[i]) + source*tau_vec[i]: half_soft_update / half_hard_update as one masked launch */
+GADDPG_API int gaddpg_polyak_vec(float* target, const float* source, const float* tau_vec, long long n, void* stream);
+GADDPG_API int gaddpg_absmax(const float* x, long long n, float* out, float* ws, void* stream);        /* ws: 1184 floats */
+GADDPG_API int gaddpg_clip_coef(const float* g, long long n, float max_norm, float* coef_out, float* norm_out, float* ws,
+                                void* stream);
+/* derived layouts of a weight W[N][K]: Wp[N][ldp] (columns rotated by rot, zero padded), WT[ldp][ldt] = Wp^T */
+GADDPG_API int gaddpg_wprep(const float* W, int N, int K, int rot, float* Wp, int ldp, float* WT, int ldt, void* stream);
+/* all derived layouts of a network in one launch: jobs_dev[j] = {W, N, K, rot, Wp, ldp, WT, ldt} as 8 x int64 (device) */
+GADDPG_API int gaddpg_wprep_batched(const long long* jobs_dev, int njobs, void* stream);
+/* stand-alone EPI_DMASK: D = dX*[Yprev*psc+psh > 0] plus its BN-backward sums (for gradients arriving from autograd) */
+GADDPG_API int gaddpg_dmask_stats(const float* dX, int ldx, const float* Yprev, int C, int M, const float* psc, const float* psh,
+                                  const float* pmean, const float* prstd, float* D, float* stats, void* stream);
+GADDPG_API int gaddpg_f64_to_f32(const double* src, float* dst, long long n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

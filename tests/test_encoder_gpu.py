@@ -1,0 +1,128 @@
+"""GPU parity of the fused CUDA encoder (forward, train-mode BatchNorm statistics, eval mode, and the
+hand-written backward) against the CPU oracle's PointNet++ encoder under autograd.
+Tolerances: 1e-4 relative to the tensor's max magnitude (north_star: fp32 outputs within 1e-4)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def _build(in_features, seed, device):
+    from gaddpg_b200 import engine, nets
+    from oracle import nets_cpu
+
+    torch.manual_seed(seed)
+    ora = nets_cpu.make_encoder(in_features)
+    # non-trivial BN affine parameters so gamma/beta gradients and the sign-dependent pooling are exercised
+    with torch.no_grad():
+        for m in ora.modules():
+            if isinstance(m, (torch.nn.BatchNorm1d, torch.nn.BatchNorm2d)):
+                m.weight.uniform_(-1.0, 1.5)
+                m.bias.uniform_(-0.3, 0.3)
+    mine = nets.make_encoder_params(in_features)
+    mine.load_state_dict(ora.state_dict())
+    ef = engine.EncoderFlat(mine, device)
+    return ora, mine, ef
+
+
+def _oracle_forward(ora, cloud, action):
+    from oracle.nets_cpu import PointFeature
+
+    x = cloud[..., 6:]
+    if action is not None:
+        x = torch.cat((x, action.unsqueeze(2).expand(-1, -1, x.shape[2])), 1)
+    x = x.contiguous()
+    xyz = x.transpose(1, -1)[..., :3].contiguous()
+    return PointFeature.encode(ora, xyz, x)
+
+
+@pytest.mark.parametrize("B,N,with_action", [(4, 512, False), (4, 512, True), (6, 1024, True)])
+def test_encoder_forward_backward_matches_oracle(cuda, B, N, with_action):
+    from gaddpg_b200 import engine, synthetic
+
+    in_features = 10 if with_action else 4
+    ora, mine, ef = _build(in_features, 11, cuda)
+    batch = synthetic.make_batch(B, N, step=5)
+    cloud = torch.from_numpy(batch["point_state_batch"])
+    action = torch.from_numpy(batch["action_batch"]) if with_action else None
+    time = torch.from_numpy(batch["time_batch"])
+    R = torch.from_numpy(np.random.RandomState(3).randn(B, 512).astype(np.float32))
+
+    # ---- oracle (CPU, autograd)
+    ora.train()
+    act_o = action.clone().requires_grad_(True) if with_action else None
+    z_o = _oracle_forward(ora, cloud, act_o)
+    (z_o * R).sum().backward()
+
+    # ---- CUDA
+    ws = engine.Workspace(cuda)
+    geom = engine.Geometry(B, N, cuda).build(cloud.to(cuda), 6)
+    caps = (geom.lv[0].cap, geom.lv[1].cap)
+    ctx = engine.EncoderCtx(B, caps, engine.WIDTHS, cuda)
+    sc = engine.BwdScratch(B, caps, engine.WIDTHS, cuda)
+    cl = cloud.to(cuda)
+    bc = action.to(cuda).contiguous() if with_action else None
+    feat = engine.encoder_forward(ws, ef, geom, cl, 6, 4, bc, ctx, time=time.to(cuda), time_offset=-1.0, train=True)
+    torch.cuda.synchronize()
+    assert _rel(feat[:, :512], z_o) < 1e-4
+    assert torch.equal(feat[:, 512].cpu(), time - 1.0) and float(feat[:, 513:].abs().max()) == 0.0
+    # running statistics / counters updated exactly like torch's BatchNorm in train mode
+    sd_o, sd_m = ora.state_dict(), mine.state_dict()
+    for k in sd_o:
+        if "running" in k:
+            assert _rel(sd_m[k], sd_o[k]) < 1e-4, k
+        if "num_batches_tracked" in k:
+            assert int(sd_m[k]) == int(sd_o[k]) == 1, k
+    dfeat = torch.zeros(B, 516, device=cuda)
+    dfeat[:, :512] = R.to(cuda)
+    dbc = engine.encoder_backward(ws, ef, ctx, sc, want_dw=True, want_dbc=with_action, dfeat=dfeat)
+    torch.cuda.synchronize()
+    worst = {}
+    for (k, po), (_, pm) in zip(ora.named_parameters(), mine.named_parameters()):
+        worst[k] = _rel(pm.grad, po.grad)
+    # Linear biases in front of BatchNorm1d have an exactly-zero true gradient (pure rounding noise on both sides)
+    bad = {k: v for k, v in worst.items() if v > 2e-4 and not k.endswith(("1.0.bias", "1.3.bias"))}
+    assert not bad, bad
+    for k in ("1.0.bias", "1.3.bias"):
+        pm = dict(mine.named_parameters())[k]
+        assert float(pm.grad.abs().max()) < 1e-4 * float(R.abs().max()) * B
+    if with_action:
+        assert _rel(dbc, act_o.grad) < 2e-4
+
+    # ---- eval mode (running statistics), as select_action uses it
+    ora.eval()
+    with torch.no_grad():
+        z_e = _oracle_forward(ora, cloud, action)
+    feat_e = engine.encoder_forward(ws, ef, geom, cl, 6, 4, bc, ctx, time=None, train=False)
+    torch.cuda.synchronize()
+    assert _rel(feat_e[:, :512], z_e) < 1e-4
+    for k in sd_o:
+        if "num_batches_tracked" in k:
+            assert int(mine.state_dict()[k]) == 1, k
+
+
+def test_duplicate_folding_matches_dense_semantics(cuda):
+    """A sparse cloud (few neighbours per ball) forces heavy padding: the folded rows + multiplicities must
+    reproduce BatchNorm over the full (B, C, npoint, nsample) tensor the oracle materialises."""
+    from gaddpg_b200 import engine, synthetic
+
+    B, N = 3, 300
+    ora, mine, ef = _build(4, 5, cuda)
+    rs = np.random.RandomState(0)
+    cloud = torch.from_numpy(synthetic.make_batch(B, N, step=1)["point_state_batch"]).clone()
+    cloud[:, :3, 6:] = torch.from_numpy(rs.uniform(0.05, 0.6, (B, 3, N)).astype(np.float32))  # ~1-3 hits per ball
+    ora.train()
+    z_o = _oracle_forward(ora, cloud, None)
+    ws = engine.Workspace(cuda)
+    geom = engine.Geometry(B, N, cuda).build(cloud.to(cuda), 6)
+    M1 = int(geom.lv[0].seg_off[-1])
+    assert M1 < B * 32 * 8  # really folded
+    ctx = engine.EncoderCtx(B, (geom.lv[0].cap, geom.lv[1].cap), engine.WIDTHS, cuda)
+    feat = engine.encoder_forward(ws, ef, geom, cloud.to(cuda), 6, 4, None, ctx, train=True)
+    assert _rel(feat[:, :512], z_o) < 1e-4
