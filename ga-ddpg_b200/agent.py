@@ -1,0 +1,540 @@
+"""Fused B200 agents: ``DDPGB200`` / ``BCB200`` — drop-ins for the reference's ``DDPG`` / ``BC`` classes.
+
+Same public surface as /root/reference/core/agent.py + ddpg.py + bc.py: constructor
+``(num_inputs, action_space, CONFIG)``, ``setup_feature_extractor(net_dict)``, ``update_parameters(batch_data,
+updates, k) -> dict[str, float]`` with the 11 keys of get_loss_info_dict (utils.py:1008-1020),
+``select_action(state, remain_timestep=...)``, ``step_scheduler``, ``get_lr``, ``update_step``,
+``get_weight/load_weight`` — but ``update_parameters`` is one fixed sequence of hand-written CUDA kernels:
+no autograd graph, no allocation, no host synchronisation except the single read-back of the scalars.
+
+Step structure (ddpg.py:146-185; F = encoder forward, B = backward):
+  phase 1   geometry(state), geometry(next); F1 value(state,a); F2 policy(next) -> policy_target -> TD3 noise;
+            F3 value(next,a') -> critic_target -> y; critic(F1) -> losses; B1 through critic + value encoder
+  [all-reduce of the value-encoder + critic gradient range when sample-sharded over several GPUs]
+  phase 2   clip_grad_norm(critic), Adam(value encoder), Adam(critic); F4 policy(state) -> policy -> pi;
+            even steps: F5 value(state,pi) -> critic -> -mix*mean(minQ), B through critic + value encoder to dpi;
+            actor losses; B2 through policy + policy encoder
+  [all-reduce of the policy-encoder + policy gradient range]
+  phase 3   Adam(policy), Adam(policy encoder), Polyak targets, statistics
+Each phase is captured once per step parity into a CUDA graph and replayed.
+"""
+import math
+from types import SimpleNamespace as NS
+
+import numpy as np
+import torch
+from torch.optim.lr_scheduler import MultiStepLR
+
+from . import engine, nets
+from .capi import current_stream, lib
+from .config import DEFAULTS, LOSS_KEYS
+from .engine import FEAT_LD, QA_AUX, QA_LD, QA_Q2, dp
+from .networks import PointNetFeatureB200
+
+O_CRITIC, O_CRITIC_AUX, O_NGOAL_C, O_BC, O_POLICY_AUX, O_NGOAL_A, O_AC, O_PPARAM, O_CGRAD, O_CPARAM, O_CLIP, O_GNORM = range(12)
+
+
+class _Sched:
+    """MultiStepLR on a parameter-less optimiser: keeps torch's own schedule arithmetic for the lr."""
+
+    def __init__(self, lr, milestones, gamma):
+        self.opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=lr)
+        self.sched = MultiStepLR(self.opt, milestones=list(milestones), gamma=gamma)
+        self.opt._opt_called = True  # silence the "scheduler before optimizer" warning; our Adam is fused
+
+    def step(self):
+        self.sched.step()
+
+    @property
+    def lr(self):
+        return self.opt.param_groups[0]["lr"]
+
+
+def _cfg_get(cfg, k):
+    if cfg is not None:
+        try:
+            if k in cfg:
+                return cfg[k]
+        except TypeError:
+            pass
+        if hasattr(cfg, k):
+            return getattr(cfg, k)
+    return DEFAULTS[k]
+
+
+class AgentB200:
+    name = "Agent"
+
+    def __init__(self, num_inputs=512, action_space=None, args=None, device=None, seed=None, world=None):
+        for k in DEFAULTS:
+            setattr(self, k, _cfg_get(args, k))
+        if args is not None:
+            try:
+                for k, v in args.items():
+                    setattr(self, k, v)
+            except AttributeError:
+                pass
+        if not torch.cuda.is_available():
+            raise RuntimeError("gaddpg_b200 agents need a CUDA device: there is no CPU fallback")
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.has_critic = self.name != "BC"
+        self.update_step = 1
+        self.init_step = 1
+        self.extra_pred_dim = 7 if self.policy_aux else 1
+        self.critic_extra_pred_dim = 7 if self.critic_aux else 0
+        self.num_inputs = num_inputs + (1 if self.use_time else 0)
+        assert self.num_inputs == 513 and self.hidden_size == 256 and self.use_time, "fused kernels cover the reference widths"
+        assert self.sa_channel_concat and self.noise_type == "uniform" and self.use_action_limit
+        self.world = world  # None or a torch.distributed process group handle (see dist.py)
+        if seed is not None:
+            torch.manual_seed(seed)
+        self._own_extractor = None
+        self._built = False
+        self._pending_seeded_build = seed is not None
+        # policy / target policy are created here, like Agent.__init__ (agent.py:21-48, utils.py:960-981) — but only
+        # after the feature extractor exists when we own the seed, to keep the reference's RNG order
+        if not self._pending_seeded_build:
+            self._make_heads()
+
+    # ---- construction ----------------------------------------------------------------------------------
+    def _make_heads(self):
+        self.policy = nets.GaussianPolicyParams(self.num_inputs, 6, self.hidden_size, self.extra_pred_dim)
+        self.policy_target = nets.GaussianPolicyParams(self.num_inputs, 6, self.hidden_size, self.extra_pred_dim)
+        if self.has_critic:
+            self.critic = nets.QNetworkParams(self.num_inputs, self.hidden_size, self.critic_extra_pred_dim)
+            self.critic_target = nets.QNetworkParams(self.num_inputs, self.hidden_size, self.critic_extra_pred_dim)
+
+    def build_standalone(self):
+        """Create the feature extractor the way the reference driver does (model-spec order: goal extractor first,
+        utils.py:188-201) and then the heads, so ``seed`` reproduces the reference's initial weights."""
+        nets.burn_goal_feature_rng()
+        net = PointNetFeatureB200(input_dim=self.channel_num, extra_latent=self.extra_latent,
+                                  policy_extra_latent=self.policy_extra_latent, critic_extra_latent=self.critic_extra_latent,
+                                  action_concat=self.sa_channel_concat)
+        self._make_heads()
+        self._pending_seeded_build = False
+        self.setup_feature_extractor({"state_feature_extractor": {"net": net}, "goal_feature_extractor": {"net": None}})
+        return self
+
+    def setup_feature_extractor(self, net_dict, eval=False):
+        """agent.py:149-164.  Accepts the reference's net_dict (net possibly wrapped in nn.DataParallel); optimisers
+        in it are not used — Adam runs fused on the arenas — but their schedulers keep driving the learning rates."""
+        if self._pending_seeded_build:
+            self._make_heads()
+            self._pending_seeded_build = False
+        sfe = net_dict["state_feature_extractor"]
+        net = sfe["net"]
+        self.state_feature_extractor = net
+        self._extractor = net.module if hasattr(net, "module") else net
+        assert isinstance(self._extractor, PointNetFeatureB200), "model_spec must select class: PointNetFeatureB200"
+        self.goal_feature_extractor = net_dict.get("goal_feature_extractor", {}).get("net")
+        c = self
+        self._sch = NS(
+            policy=_Sched(c.lr, c.policy_milestones, c.lr_gamma),
+            critic=_Sched(c.value_lr, c.value_milestones, c.value_lr_gamma) if self.has_critic else None,
+            enc=_Sched(c.feat_lr, c.overwrite_feat_milestone or c.feat_milestones, c.feat_gamma),
+            venc=_Sched(c.feat_lr, c.overwrite_feat_milestone or c.feat_milestones, c.feat_gamma),  # never stepped
+        )
+        dev = self.device
+        self.ws = engine.Workspace(dev)
+        self.ef_p = engine.EncoderFlat(self._extractor.encoder, dev)
+        self.ef_v = engine.EncoderFlat(self._extractor.value_encoder, dev)
+        self._extractor._flats[("policy", str(dev))] = self.ef_p
+        self._extractor._flats[("value", str(dev))] = self.ef_v
+        self.pf = engine.PolicyFlat(self.policy, dev)
+        self.pft = engine.PolicyFlat(self.policy_target, dev, with_opt=False)
+        if self.has_critic:
+            self.cf = engine.CriticFlat(self.critic, dev)
+            self.cft = engine.CriticFlat(self.critic_target, dev, with_opt=False)
+            self.tau_soft, self.tau_hard = self.cft.tau_vectors(self.tau)
+        self.Cp_policy = min(self._extractor.policy_input_dim, 3 + self.extra_latent)
+        self.Cb_value = self._extractor.critic_input_dim - min(3 + self.extra_latent, self._extractor.critic_input_dim)
+        self.Cp_value = self._extractor.critic_input_dim - self.Cb_value
+        self.opt_steps = dict(policy=0, critic=0, enc=0, venc=0)
+        self.dyn = torch.zeros(4, 2, dtype=torch.float32, device=dev)
+        self.dyn_host = torch.zeros(4, 2, dtype=torch.float32).pin_memory()
+        self.out = torch.zeros(16, dtype=torch.float32, device=dev)
+        self.out_host = torch.zeros(16, dtype=torch.float32).pin_memory()
+        self._shape = None
+        self._graphs = {}
+        self.use_graph = True
+        self._built = True
+
+    # ---- buffers sized for one (B, C, N) ------------------------------------------------------------------
+    def _alloc(self, B, C, Np):
+        dev = self.device
+        skip = 6 if Np != 1024 else 0
+        N = Np - skip
+        self._shape = (B, C, Np)
+        self.B, self.skip, self.N = B, skip, N
+        self.cloud = torch.zeros(B, C, Np, dtype=torch.float32, device=dev)
+        self.next_cloud = torch.zeros(B, C, Np, dtype=torch.float32, device=dev)
+        seg = lambda n: (n + 3) // 4 * 4  # noqa: E731
+        names = [("action", 6), ("expert_action", 6), ("goal", 7), ("noise_u", 6), ("reward", 1), ("ret", 1), ("done", 1),
+                 ("time", 1), ("expert_flag", 1), ("perturb_flag", 1)]
+        total, self._vec_off = 0, {}
+        for n, w in names:
+            self._vec_off[n] = (total, w)
+            total += seg(B * w)
+        self.vec = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.vec_host = torch.zeros(total, dtype=torch.float32).pin_memory()
+        self.cloud_host = torch.zeros(B, C, Np, dtype=torch.float32).pin_memory()
+        self.next_cloud_host = torch.zeros(B, C, Np, dtype=torch.float32).pin_memory()
+        self.v = NS(**{n: self.vec[o: o + B * w].view(B, w) if w > 1 else self.vec[o: o + B] for n, (o, w) in self._vec_off.items()})
+        self.vh = NS(**{n: self.vec_host[o: o + B * w].view(B, w) if w > 1 else self.vec_host[o: o + B]
+                        for n, (o, w) in self._vec_off.items()})
+        self.geom_s = engine.Geometry(B, N, dev)
+        self.geom_n = engine.Geometry(B, N, dev)
+        caps = (self.geom_s.lv[0].cap, self.geom_s.lv[1].cap)
+        mk = lambda: engine.EncoderCtx(B, caps, engine.WIDTHS, dev)  # noqa: E731
+        self.ctx_p = mk()                      # F4 (policy encoder, state) — kept for B2
+        if self.has_critic:
+            self.ctx_v1, self.ctx_n, self.ctx_v5 = mk(), mk(), mk()   # F1 | F2,F3 (no grad) | F5
+            self.cc1, self.cct, self.cc5 = (engine.critic_ctx(B, self.cf, dev) for _ in range(3))
+            self.pct = engine.policy_ctx(B, self.pft, dev)
+            self.next_action = torch.zeros(B, 6, dtype=torch.float32, device=dev)
+            self.y = torch.zeros(B, dtype=torch.float32, device=dev)
+        self.sc = engine.BwdScratch(B, caps, engine.WIDTHS, dev)
+        self.pc = engine.policy_ctx(B, self.pf, dev)
+        self.dpi_ac = torch.zeros(B, 6, dtype=torch.float32, device=dev)
+        self._bc_buf = [torch.zeros(B, max(self.Cb_value, 1), dtype=torch.float32, device=dev) for _ in range(3)]
+        self._graphs = {}
+
+    def _bc(self, action, slot):
+        """The value encoder sees critic_input_dim - cloud_channels action channels (6 with the reference spec; the
+        hard-coded critic_input_dim = 10 truncates the action when the cloud has more channels, networks.py:206-207,238)."""
+        if self.Cb_value == action.shape[1]:
+            return action
+        self._bc_buf[slot].copy_(action[:, : self.Cb_value])
+        return self._bc_buf[slot]
+
+    # ---- data staging (agent.py:211-240 prepare_data) ------------------------------------------------------
+    def prepare_data(self, batch, noise_u=None):
+        """Stage one replay minibatch (the dict BaseMemory.sample returns, replay_memory.py:166-176) into pinned
+        host buffers and issue the H2D copies.  float64 clouds are converted on the host like
+        torch.cuda.FloatTensor(ndarray) does in the reference."""
+        cloud = batch["point_state_batch"]
+        B, C, Np = cloud.shape
+        if self._shape != (B, C, Np):
+            self._alloc(B, C, Np)
+        self.cloud_host.copy_(torch.as_tensor(cloud))
+        self.cloud.copy_(self.cloud_host, non_blocking=True)
+        if self.has_critic:
+            self.next_cloud_host.copy_(torch.as_tensor(batch["next_point_state_batch"]))
+            self.next_cloud.copy_(self.next_cloud_host, non_blocking=True)
+        vh = self.vh
+        put = lambda dst, key: dst.copy_(torch.as_tensor(np.asarray(batch[key], dtype=np.float32)).view(dst.shape))  # noqa: E731
+        put(vh.action, "action_batch"), put(vh.expert_action, "expert_action_batch"), put(vh.goal, "goal_batch")
+        put(vh.reward, "reward_batch"), put(vh.ret, "return_batch"), put(vh.done, "mask_batch"), put(vh.time, "time_batch")
+        put(vh.expert_flag, "expert_flag_batch"), put(vh.perturb_flag, "perturb_flag_batch")
+        if self.has_critic:
+            if noise_u is None:
+                vh.noise_u.copy_(torch.rand(B, 6))  # torch.rand_like in get_noise_delta (utils.py:575)
+            else:
+                vh.noise_u.copy_(torch.as_tensor(np.asarray(noise_u, dtype=np.float32)))
+        self.vec.copy_(self.vec_host, non_blocking=True)
+
+    def h2d_bytes(self):
+        n = self.cloud_host.numel() * (2 if self.has_critic else 1) + self.vec_host.numel()
+        return 4 * n
+
+    # ---- schedules ---------------------------------------------------------------------------------------
+    def _mix_idx(self):
+        return int((self.update_step > np.array(self.mix_milestones)).sum())
+
+    def get_mix_ratio(self, update_step=None):
+        idx = self._mix_idx()
+        pick = lambda lst: lst[min(len(lst) - 1, idx)]  # noqa: E731
+        return (min(pick(self.mix_value_ratio_list), self.ddpg_coefficients[3]),
+                min(pick(self.mix_policy_ratio_list), self.ddpg_coefficients[4]))
+
+    def _noise_scale(self):
+        idx = self._mix_idx()
+        return self.action_noise * self.noise_ratio_list[min(len(self.noise_ratio_list) - 1, idx)]
+
+    def step_scheduler(self, step=None):
+        """agent.py:179-190: critic, policy, whole-extractor and policy-encoder schedulers; the value-encoder
+        scheduler is never stepped in the reference, so its lr stays at the initial value."""
+        if self.has_critic:
+            self._sch.critic.step()
+        self._sch.policy.step()
+        if self.train_feature or self.train_value_feature:
+            self._sch.enc.step()
+
+    def get_lr(self):
+        return {"policy_lr": self._sch.policy.lr, "feature_lr": self._sch.enc.lr,
+                "value_lr": self._sch.critic.lr if self.has_critic else 0}
+
+    def _set_dyn(self, names):
+        lrs = dict(policy=self._sch.policy.lr, critic=self._sch.critic.lr if self.has_critic else 0.0, enc=self._sch.enc.lr,
+                   venc=self._sch.venc.lr)
+        for i, n in enumerate(("policy", "critic", "enc", "venc")):
+            if n in names:
+                self.opt_steps[n] += 1
+            t = max(self.opt_steps[n], 1)
+            self.dyn_host[i, 0] = lrs[n] / (1.0 - 0.9 ** t)
+            self.dyn_host[i, 1] = math.sqrt(1.0 - 0.999 ** t)
+        self.dyn.copy_(self.dyn_host, non_blocking=True)
+
+    # ---- fused optimiser helpers ---------------------------------------------------------------------------
+    def _adam(self, arena, off, n, which, eps, wd, clip=None, write_back=0):
+        i = ("policy", "critic", "enc", "venc").index(which)
+        gs = 1.0  # sharded runs average the gradients right after the all-reduce (see _allreduce)
+        lib.gaddpg_adam_step(arena.p.data_ptr() + 4 * off, arena.g.data_ptr() + 4 * off, arena.m.data_ptr() + 4 * off,
+                             arena.v.data_ptr() + 4 * off, n, 0.0, 0.9, 0.999, eps, wd, 0, self.dyn.data_ptr() + 8 * i, gs,
+                             clip, write_back, None, 0.0, current_stream())
+
+    def _allreduce(self, arenas):
+        if self.world is not None and self.world.size > 1:
+            for a in arenas:
+                self.world.all_reduce_mean(a.g)  # DDP semantics: per-rank mean losses averaged over ranks
+
+    def _run(self, key, fn):
+        """Run ``fn`` eagerly the first time for a key, then capture and replay it as a CUDA graph."""
+        if not self.use_graph:
+            return fn()
+        g = self._graphs.get(key)
+        if g is None:
+            fn()  # eager warm-up doubles as this call's execution
+            self._graphs[key] = "warm"
+            return
+        if g == "warm":
+            # capture for the NEXT calls: state-changing kernels must not run twice, so capture happens on a side
+            # stream without executing (torch.cuda.graph records, it does not run)
+            graph = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(graph):
+                fn()
+            self._graphs[key] = graph
+            g = graph
+        g.replay()
+
+    # ---- statistics / result ----------------------------------------------------------------------------
+    def _finish(self):
+        self.out_host.copy_(self.out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        o = self.out_host
+        r = {k: 0.0 for k in LOSS_KEYS}
+        r.update(bc_loss=float(o[O_BC]), policy_grasp_aux_loss=float(o[O_POLICY_AUX]), policy_param=float(o[O_PPARAM]))
+        if self.has_critic:
+            r.update(critic_grasp_aux_loss=float(o[O_CRITIC_AUX]), critic_loss=float(o[O_CRITIC]), actor_critic_loss=float(o[O_AC]),
+                     reward_mask_num=float(o[O_NGOAL_C]), critic_grad=float(o[O_CGRAD]), critic_param=float(o[O_CPARAM]))
+        else:
+            r.update(reward_mask_num=float(o[O_NGOAL_A]))
+        return r
+
+    # ---- inference (agent.py:82-125) ----------------------------------------------------------------------
+    @torch.no_grad()
+    def select_action(self, state, actions=None, goal_state=None, vis=False, remain_timestep=0, grasp_set=None,
+                      gt_goal_rollout=False, repeat=False, eps=None):
+        cloud = torch.as_tensor(np.asarray(state[0][0], dtype=np.float32))[None].to(self.device).contiguous()
+        return self._act(cloud, float(remain_timestep), eps)
+
+    def _act(self, cloud, remain, eps):
+        dev = self.device
+        B, C, Np = cloud.shape
+        skip = 6 if Np != 1024 else 0
+        key = ("act", B, C, Np)
+        st = getattr(self, "_act_state", None)
+        if st is None or st.key != key:
+            geom = engine.Geometry(B, Np - skip, dev)
+            caps = (geom.lv[0].cap, geom.lv[1].cap)
+            st = NS(key=key, geom=geom, ctx=engine.EncoderCtx(B, caps, engine.WIDTHS, dev), pc=engine.policy_ctx(B, self.pf, dev),
+                    time=torch.zeros(B, device=dev), aux=torch.zeros(B, 7, device=dev), act=torch.zeros(B, 6, device=dev),
+                    logp=torch.zeros(B, device=dev), eps=torch.zeros(B, 6, device=dev))
+            self._act_state = st
+        st.time.fill_(remain)
+        st.eps.copy_(torch.randn(B, 6) if eps is None else torch.as_tensor(eps, dtype=torch.float32).view(B, 6))
+        st.geom.build(cloud, skip)
+        feat = engine.encoder_forward(self.ws, self.ef_p, st.geom, cloud, skip, self.Cp_policy, None, st.ctx, time=st.time,
+                                      train=False)
+        raw = engine.policy_forward(self.pf, feat, st.pc, B)
+        s = current_stream()
+        lib.gaddpg_policy_head_fwd(dp(raw), self.pf.NHp, B, dp(st.pc.pi), s)
+        lib.gaddpg_policy_sample(dp(raw), self.pf.NHp, 6 + self.pf.E, dp(st.eps), B, dp(st.act), dp(st.logp), s)
+        if self.policy_aux:
+            lib.gaddpg_quat_head(raw.data_ptr() + 4 * 6, self.pf.NHp, B, dp(st.aux), s)
+            aux = st.aux.cpu().numpy()[0]
+        else:
+            aux = raw[:, 6:6 + self.pf.E].cpu().numpy()[0]
+        return st.pc.pi.cpu().numpy()[0], st.logp.cpu().numpy()[0], st.act.cpu().numpy()[0], aux
+
+    # ---- weights (ddpg.py:22-34, bc.py:15-25) -------------------------------------------------------------
+    def state_dicts(self):
+        d = {"policy": self.policy.state_dict(), "policy_target": self.policy_target.state_dict(),
+             "state_feat": {"module." + k: v for k, v in self._extractor.state_dict().items()}}
+        if self.has_critic:
+            d["critic"], d["critic_target"] = self.critic.state_dict(), self.critic_target.state_dict()
+        return d
+
+    def load_state_dicts(self, d):
+        self.policy.load_state_dict(d["policy"])
+        self.policy_target.load_state_dict(d["policy_target"])
+        self._extractor.load_state_dict({k[len("module."):] if k.startswith("module.") else k: v for k, v in d["state_feat"].items()})
+        if self.has_critic:
+            self.critic.load_state_dict(d["critic"])
+            self.critic_target.load_state_dict(d["critic_target"])
+        self.refresh_all()
+
+    def refresh_all(self):
+        for f in (self.ef_p, self.ef_v, self.pf, self.pft) + ((self.cf, self.cft) if self.has_critic else ()):
+            f.refresh_derived()
+
+
+class DDPGB200(AgentB200):
+    name = "DDPG"
+
+    def get_weight(self):
+        return [self.policy.state_dict(), self.critic.state_dict(), {}, self.state_feature_extractor.state_dict()]
+
+    def load_weight(self, weights):
+        self.policy.load_state_dict(weights[0])
+        self.critic.load_state_dict(weights[1])
+        self.state_feature_extractor.load_state_dict(weights[3])
+        self.refresh_all()
+
+    # -- phase 1: critic side ------------------------------------------------------------------------------
+    def _phase1(self):
+        B, ws, v, s = self.B, self.ws, self.v, current_stream()
+        self.out.zero_()
+        self.geom_s.build(self.cloud, self.skip)
+        self.geom_n.build(self.next_cloud, self.skip)
+        f1 = engine.encoder_forward(ws, self.ef_v, self.geom_s, self.cloud, self.skip, self.Cp_value, self._bc(v.action, 0), self.ctx_v1,
+                                    time=v.time, time_offset=0.0, train=True)                                    # F1
+        f2 = engine.encoder_forward(ws, self.ef_p, self.geom_n, self.next_cloud, self.skip, self.Cp_policy, None, self.ctx_n,
+                                    time=v.time, time_offset=-1.0, train=True)                                   # F2
+        rawt = engine.policy_forward(self.pft, f2, self.pct, B)
+        lib.gaddpg_td3_next_action(dp(rawt), self.pft.NHp, dp(v.noise_u), float(self._noise_scale()), B, dp(self.next_action), s)
+        f3 = engine.encoder_forward(ws, self.ef_v, self.geom_n, self.next_cloud, self.skip, self.Cp_value, self._bc(self.next_action, 1),
+                                    self.ctx_n, time=v.time, time_offset=-1.0, train=True)                       # F3
+        qat = engine.critic_forward(self.cft, f3, self.cct, B, nb=2)
+        lib.gaddpg_td3_target(dp(qat), QA_LD, QA_Q2, dp(v.reward), dp(v.done), float(self.gamma), B, dp(self.y), s)
+        qa = engine.critic_forward(self.cf, f1, self.cc1, B)
+        lib.gaddpg_critic_loss(dp(qa), QA_LD, QA_Q2, QA_AUX, dp(self.y), dp(v.perturb_flag), dp(v.ret), dp(v.goal),
+                               1 if self.critic_aux else 0, B, 1.0, dp(self.cc1.dqa), self.out.data_ptr() + 4 * O_CRITIC, s)
+        engine.critic_backward(ws, self.cf, f1, self.cc1, B, self.cf.nb, self.ctx_v1, self.sc, accumulate=0)         # B1
+        engine.encoder_backward(ws, self.ef_v, self.ctx_v1, self.sc, want_dw=True, want_dbc=False, accumulate=0)
+
+    # -- phase 2: critic/value-encoder step, then the actor side -----------------------------------------------
+    def _phase2(self, even):
+        B, ws, v, s = self.B, self.ws, self.v, current_stream()
+        cA = self.cf.arena
+        lib.gaddpg_clip_coef(dp(cA.g), cA.n, float(self.clip_grad), self.out.data_ptr() + 4 * O_CLIP,
+                             self.out.data_ptr() + 4 * O_GNORM, dp(ws.red), s)
+        self._adam(self.ef_v.arena, 0, self.ef_v.arena.n, "venc", 1e-8, 0.0)
+        self._adam(cA, 0, cA.n, "critic", 1e-5, 1e-5, clip=self.out.data_ptr() + 4 * O_CLIP, write_back=1)
+        self.ef_v.refresh_derived()
+        self.cf.refresh_derived()
+        f4 = engine.encoder_forward(ws, self.ef_p, self.geom_s, self.cloud, self.skip, self.Cp_policy, None, self.ctx_p,
+                                    time=v.time, time_offset=0.0, train=True)                                    # F4
+        raw = engine.policy_forward(self.pf, f4, self.pc, B)
+        lib.gaddpg_policy_head_fwd(dp(raw), self.pf.NHp, B, dp(self.pc.pi), s)
+        mix = self.get_mix_ratio()[1]
+        dpi = None
+        if even:
+            f5 = engine.encoder_forward(ws, self.ef_v, self.geom_s, self.cloud, self.skip, self.Cp_value, self._bc(self.pc.pi, 2),
+                                        self.ctx_v5, time=v.time, time_offset=0.0, train=True)                   # F5
+            qa5 = engine.critic_forward(self.cf, f5, self.cc5, B, nb=2)
+            lib.gaddpg_actor_critic_loss(dp(qa5), QA_LD, QA_Q2, dp(v.ret), dp(v.expert_flag), float(mix), B, 1.0, QA_LD,
+                                         dp(self.cc5.dqa), self.out.data_ptr() + 4 * O_AC, s)
+            engine.critic_backward(ws, self.cf, f5, self.cc5, B, 2, self.ctx_v5, self.sc, accumulate=1)
+            dpi = engine.encoder_backward(ws, self.ef_v, self.ctx_v5, self.sc, want_dw=False, want_dbc=True)
+            self.dpi_ac.zero_()
+            self.dpi_ac[:, : self.Cb_value].copy_(dpi)
+        ranges, n_grad = self.pf.adam_ranges(self.policy_aux)
+        lib.gaddpg_actor_loss(dp(raw), self.pf.NHp, dp(self.pc.pi), dp(v.expert_action), dp(v.expert_flag), dp(v.ret), dp(v.goal),
+                              1 if self.policy_aux else 0, float(1.0 - mix), dp(self.dpi_ac) if even else None, B, 1.0,
+                              dp(self.pc.draw), self.pf.NHp, self.out.data_ptr() + 4 * O_BC, s)
+        engine.policy_backward(ws, self.pf, f4, self.pc, B, n_grad, self.ctx_p, self.sc, accumulate=0)              # B2
+        engine.encoder_backward(ws, self.ef_p, self.ctx_p, self.sc, want_dw=True, want_dbc=False, accumulate=0)
+
+    # -- phase 3: actor step, targets, statistics --------------------------------------------------------------
+    def _phase3(self, hard):
+        ws, s = self.ws, current_stream()
+        ranges, _ = self.pf.adam_ranges(self.policy_aux)
+        for off, n in ranges:
+            self._adam(self.pf.arena, off, n, "policy", 1e-5, 1e-5)
+        if self.train_feature:
+            self._adam(self.ef_p.arena, 0, self.ef_p.arena.n, "enc", 1e-8, 0.0)
+        lib.gaddpg_polyak(dp(self.pft.arena.p), dp(self.pf.arena.p), self.pf.arena.n, float(self.tau), s)
+        lib.gaddpg_polyak_vec(dp(self.cft.arena.p), dp(self.cf.arena.p), dp(self.tau_soft), self.cf.arena.n, s)
+        if hard:
+            lib.gaddpg_polyak_vec(dp(self.cft.arena.p), dp(self.cf.arena.p), dp(self.tau_hard), self.cf.arena.n, s)
+        for f in (self.pf, self.ef_p, self.pft, self.cft):
+            f.refresh_derived()
+        lib.gaddpg_absmax(dp(self.pf.arena.p), self.pf.arena.n, self.out.data_ptr() + 4 * O_PPARAM, dp(ws.red), s)
+        lib.gaddpg_absmax(dp(self.cf.arena.g), self.cf.arena.n, self.out.data_ptr() + 4 * O_CGRAD, dp(ws.red), s)
+        lib.gaddpg_absmax(dp(self.cf.arena.p), self.cf.arena.n, self.out.data_ptr() + 4 * O_CPARAM, dp(ws.red), s)
+
+    def update_parameters(self, batch_data, updates=None, k=None, test=False, noise_u=None, staged=False):
+        """ddpg.py:146-185.  ``staged=True``: the batch is already in the device buffers (bench/value path)."""
+        if not staged:
+            self.prepare_data(batch_data, noise_u)
+        even = (self.update_step % self.policy_update_gap) == 0
+        hard = (self.update_step % self.target_update_interval) == 0
+        sig = (self._mix_idx(),)
+        self._set_dyn(("critic", "venc", "policy") + (("enc",) if self.train_feature else ()))
+        self._run(("p1",) + sig, self._phase1)
+        self._allreduce([self.ef_v.arena, self.cf.arena])
+        self._run(("p2", even) + sig, lambda: self._phase2(even))
+        self._allreduce([self.ef_p.arena, self.pf.arena])
+        self._run(("p3", hard) + sig, lambda: self._phase3(hard))
+        self.update_step += 1
+        return self._finish()
+
+
+class BCB200(AgentB200):
+    name = "BC"
+
+    def get_weight(self):
+        return [self.policy.state_dict(), {}, self.state_feature_extractor.state_dict()]
+
+    def load_weight(self, weights):
+        self.policy.load_state_dict(weights[0])
+        self.state_feature_extractor.load_state_dict(weights[2])
+        self.refresh_all()
+
+    def _phase(self):
+        B, ws, v, s = self.B, self.ws, self.v, current_stream()
+        self.out.zero_()
+        self.geom_s.build(self.cloud, self.skip)
+        f = engine.encoder_forward(ws, self.ef_p, self.geom_s, self.cloud, self.skip, self.Cp_policy, None, self.ctx_p,
+                                   time=v.time, time_offset=0.0, train=True)
+        raw = engine.policy_forward(self.pf, f, self.pc, B)
+        lib.gaddpg_policy_head_fwd(dp(raw), self.pf.NHp, B, dp(self.pc.pi), s)
+        ranges, n_grad = self.pf.adam_ranges(self.policy_aux)
+        lib.gaddpg_actor_loss(dp(raw), self.pf.NHp, dp(self.pc.pi), dp(v.expert_action), dp(v.expert_flag), dp(v.ret), dp(v.goal),
+                              1 if self.policy_aux else 0, 1.0, None, B, 1.0, dp(self.pc.draw), self.pf.NHp,
+                              self.out.data_ptr() + 4 * O_BC, s)
+        engine.policy_backward(ws, self.pf, f, self.pc, B, n_grad, self.ctx_p, self.sc, accumulate=0)
+        engine.encoder_backward(ws, self.ef_p, self.ctx_p, self.sc, want_dw=True, want_dbc=False, accumulate=0)
+
+    def _phase_opt(self):
+        ws, s = self.ws, current_stream()
+        ranges, _ = self.pf.adam_ranges(self.policy_aux)
+        for off, n in ranges:
+            self._adam(self.pf.arena, off, n, "policy", 1e-5, 1e-5)
+        if self.train_feature:
+            self._adam(self.ef_p.arena, 0, self.ef_p.arena.n, "enc", 1e-8, 0.0)
+        lib.gaddpg_polyak(dp(self.pft.arena.p), dp(self.pf.arena.p), self.pf.arena.n, float(self.tau), s)
+        for f in (self.pf, self.ef_p, self.pft):
+            f.refresh_derived()
+        lib.gaddpg_absmax(dp(self.pf.arena.p), self.pf.arena.n, self.out.data_ptr() + 4 * O_PPARAM, dp(ws.red), s)
+
+    def update_parameters(self, batch_data, updates=None, k=None, noise_u=None, staged=False):
+        """bc.py:40-56."""
+        if not staged:
+            self.prepare_data(batch_data)
+        self._set_dyn(("policy",) + (("enc",) if self.train_feature else ()))
+        self._run(("bc",), self._phase)
+        self._allreduce([self.ef_p.arena, self.pf.arena])
+        self._run(("bcopt",), self._phase_opt)
+        self.update_step += 1
+        return self._finish()
+
+
+def make_agent(policy="DDPG", seed=123456, device=None, world=None, **overrides):
+    """Stand-alone construction (no reference code needed): same seed -> same initial weights as the reference
+    driver (core/train_test_offline.py:305-349), checked against the oracle in tests."""
+    cls = DDPGB200 if policy == "DDPG" else BCB200
+    return cls(512, None, dict(DEFAULTS, **overrides), device=device, seed=seed, world=world).build_standalone()

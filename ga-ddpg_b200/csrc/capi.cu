@@ -141,9 +141,9 @@ int gaddpg_td3_next_action(const float* raw_t, int ldr, const float* u, float no
                            void* stream) {
   return gaddpg_td3_next_action_impl(raw_t, ldr, u, noise_scale, B, next_action, stream);
 }
-int gaddpg_td3_target(const float* q1t, const float* q2t, const float* reward, const float* done, float gamma, int B, float* y,
+int gaddpg_td3_target(const float* qa, int ldq, int oq2, const float* reward, const float* done, float gamma, int B, float* y,
                       void* stream) {
-  return gaddpg_td3_target_impl(q1t, q2t, reward, done, gamma, B, y, stream);
+  return gaddpg_td3_target_impl(qa, ldq, oq2, reward, done, gamma, B, y, stream);
 }
 int gaddpg_critic_loss(const float* qa, int ldq, int oq2, int oaux, const float* y, const float* perturb_flag, const float* ret,
                        const float* goal, int use_aux, int B, float grad_scale, float* dqa, float* out, void* stream) {

@@ -152,11 +152,11 @@ __global__ void td3_next_action_kernel(const float* __restrict__ raw_t, int ldr,
 }
 
 // y = r + (1-done)*gamma*min(q1t,q2t)   (ddpg.py:86-87)
-__global__ void td3_target_kernel(const float* __restrict__ q1t, const float* __restrict__ q2t, const float* __restrict__ reward,
+__global__ void td3_target_kernel(const float* __restrict__ qa, int ldq, int oq2, const float* __restrict__ reward,
                                   const float* __restrict__ done, float gamma, int B, float* __restrict__ y) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
-  y[b] = reward[b] + (1.f - done[b]) * gamma * fminf(q1t[b], q2t[b]);
+  y[b] = reward[b] + (1.f - done[b]) * gamma * fminf(qa[(long long)b * ldq], qa[(long long)b * ldq + oq2]);
 }
 
 // critic losses + gradients.  out[0]=critic_loss, out[1]=critic_grasp_aux_loss, out[2]=reward_mask_num.
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(256) critic_loss_kernel(const float* __restric
 }
 
 // actor losses + gradients w.r.t. the RAW policy head output praw [B, ldr] = [mean(6) | extra(E)...].
-// out[0]=bc_loss (already * (1-mix) when has_critic), out[1]=policy_grasp_aux_loss, out[2]=actor_critic_loss.
+// out[0]=bc_loss (already * bc_weight), out[1]=policy_grasp_aux_loss, out[2]=#(return>0).
 // dpi_ac [B,6] (may be NULL): gradient of the actor-critic term w.r.t. pi, produced by the value-encoder backward.
 __global__ void __launch_bounds__(256) actor_loss_kernel(const float* __restrict__ praw, int ldr, const float* __restrict__ pi,
                                                          const float* __restrict__ expert_action,
@@ -238,6 +238,7 @@ __global__ void __launch_bounds__(256) actor_loss_kernel(const float* __restrict
   if (threadIdx.x == 0) {
     out[0] = bc_weight * lbc / (6.f * nexp);
     out[1] = use_aux ? la / (6.f * ngoal) : 0.f;
+    out[2] = ngoal;
   }
 }
 
@@ -336,11 +337,11 @@ int gaddpg_td3_next_action_impl(const float* raw_t, int ldr, const float* u, flo
   GADDPG_CHECK_LAUNCH("td3_next_action_kernel");
   return GADDPG_OK;
 }
-int gaddpg_td3_target_impl(const float* q1t, const float* q2t, const float* reward, const float* done, float gamma, int B,
+int gaddpg_td3_target_impl(const float* qa, int ldq, int oq2, const float* reward, const float* done, float gamma, int B,
                            float* y, void* stream) {
-  GADDPG_CHECK_ARG(q1t && q2t && reward && done && y, "td3_target: null pointer");
+  GADDPG_CHECK_ARG(qa && reward && done && y && oq2 >= 1 && oq2 < ldq, "td3_target: bad argument");
   if (B == 0) return GADDPG_OK;
-  td3_target_kernel<<<ceil_div(B, 128), 128, 0, (cudaStream_t)stream>>>(q1t, q2t, reward, done, gamma, B, y);
+  td3_target_kernel<<<ceil_div(B, 128), 128, 0, (cudaStream_t)stream>>>(qa, ldq, oq2, reward, done, gamma, B, y);
   GADDPG_CHECK_LAUNCH("td3_target_kernel");
   return GADDPG_OK;
 }

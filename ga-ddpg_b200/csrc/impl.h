@@ -61,7 +61,7 @@ int gaddpg_heads_init_impl(const float* act_scale, const float* act_bias, const 
 int gaddpg_policy_head_fwd_impl(const float* raw, int ldr, int B, float* pi, void* stream);
 int gaddpg_td3_next_action_impl(const float* raw_t, int ldr, const float* u, float noise_scale, int B, float* next_action,
                                 void* stream);
-int gaddpg_td3_target_impl(const float* q1t, const float* q2t, const float* reward, const float* done, float gamma, int B,
+int gaddpg_td3_target_impl(const float* qa, int ldq, int oq2, const float* reward, const float* done, float gamma, int B,
                            float* y, void* stream);
 int gaddpg_critic_loss_impl(const float* qa, int ldq, int oq2, int oaux, const float* y, const float* perturb_flag, const float* ret,
                             const float* goal, int use_aux, int B, float grad_scale, float* dqa, float* out, void* stream);

@@ -433,3 +433,209 @@ def _sa_backward(ws, layers, s, sc, lvl, dOut, ld_dout, row_seg, fixed_len, M_ma
             tn(ws, dy, op_plain(s.G), OP_BNBWD, OP_PLAIN, M_max, M_dev, L0.N, L0.Kp, L0.dW, L0.K, L0.N, L0.K, rot=L0.rot,
                accumulate=accumulate)
         nt([nt_problem(dy, L0.WT, L0.N, sc.dG[lvl], L0.Kp, M_max, M_dev, L0.Kp, L0.N)], OP_BNBWD, EPI_STORE)
+
+
+# ------------------------------------------------------------------------------------------------
+# actor / critic heads
+# ------------------------------------------------------------------------------------------------
+H = 256          # hidden_size (experiments/config.py:74)
+FEAT_LD = 516    # 512 features + time column, padded to a multiple of 4
+QA_LD, QA_Q2, QA_AUX = 16, 4, 8   # critic output row: q1 @0, q2 @4, aux(7) @8 (16-byte aligned sub-blocks)
+
+
+def _jobs_tensor(jobs, device):
+    return torch.tensor(jobs, dtype=torch.int64, device=device)
+
+
+class PolicyFlat:
+    """GaussianPolicy (networks.py:303-351): 513 -> 256 -> 256 -> [mean(6) | extra_pred(E) | log_std(6)]."""
+
+    def __init__(self, mod, device, with_opt=True):
+        self.mod, self.E = mod, mod.extra_pred_dim
+        E = self.E
+        order = [("l1.W", mod.linear1.weight, False), ("l1.b", mod.linear1.bias, False),
+                 ("l2.W", mod.linear2.weight, False), ("l2.b", mod.linear2.bias, False),
+                 ("h.W", mod.mean.weight, False), ("h.W.e", mod.extra_pred.weight, True), ("h.W.s", mod.log_std_linear.weight, True),
+                 ("h.b", mod.mean.bias, False), ("h.b.e", mod.extra_pred.bias, True), ("h.b.s", mod.log_std_linear.bias, True)]
+        self.arena = A = nets.Arena(order, device, with_opt=with_opt)
+        self.NH = 6 + E + 6
+        self.NHp = _pad4(self.NH)
+        self.Kin = mod.linear1.weight.shape[1]
+        o = A.offsets
+
+        def v(base, name, n, shape):
+            return None if base is None else base[o[name]: o[name] + n].view(shape)
+
+        self.W1, self.b1 = v(A.p, "l1.W", H * self.Kin, (H, self.Kin)), v(A.p, "l1.b", H, (H,))
+        self.W2, self.b2 = v(A.p, "l2.W", H * H, (H, H)), v(A.p, "l2.b", H, (H,))
+        self.Wh, self.bh = v(A.p, "h.W", self.NH * H, (self.NH, H)), v(A.p, "h.b", self.NH, (self.NH,))
+        self.dW1, self.db1 = v(A.g, "l1.W", H * self.Kin, (H, self.Kin)), v(A.g, "l1.b", H, (H,))
+        self.dW2, self.db2 = v(A.g, "l2.W", H * H, (H, H)), v(A.g, "l2.b", H, (H,))
+        self.dWh, self.dbh = v(A.g, "h.W", self.NH * H, (self.NH, H)), v(A.g, "h.b", self.NH, (self.NH,))
+        Kp = _pad4(self.Kin)
+        self.derived = _f(device, H * Kp + Kp * H + H * H + H * self.NHp)
+        d, off = self.derived, 0
+        self.W1f = d[off: off + H * Kp].view(H, Kp); off += H * Kp
+        self.W1T = d[off: off + Kp * H].view(Kp, H); off += Kp * H
+        self.W2T = d[off: off + H * H].view(H, H); off += H * H
+        self.WhT = d[off: off + H * self.NHp].view(H, self.NHp)
+        self.jobs = _jobs_tensor([[self.W1.data_ptr(), H, self.Kin, 0, self.W1f.data_ptr(), Kp, self.W1T.data_ptr(), H],
+                                  [self.W2.data_ptr(), H, H, 0, 0, H, self.W2T.data_ptr(), H],
+                                  [self.Wh.data_ptr(), self.NH, H, 0, 0, H, self.WhT.data_ptr(), self.NHp]], device)
+        self.refresh_derived()
+
+    def refresh_derived(self):
+        lib.gaddpg_wprep_batched(dp(self.jobs), self.jobs.shape[0], current_stream())
+
+    def adam_ranges(self, use_aux):
+        """(offset, count) ranges that receive gradients in update(): everything except log_std_linear, and
+        extra_pred when policy_aux is off (their .grad stays None in the reference, so Adam skips them)."""
+        o, s = self.arena.offsets, self.arena.sizes
+        wend = (o["h.W.e"] + s["h.W.e"]) if use_aux else (o["h.W"] + s["h.W"])
+        nb = 6 + (self.E if use_aux else 0)
+        return [(0, wend), (o["h.b"], nb)], nb
+
+
+def policy_ctx(B, pf, device):
+    return NS(H1=_f(device, B, H), H2=_f(device, B, H), raw=_f(device, B, pf.NHp), pi=_f(device, B, 6),
+              draw=_f(device, B, pf.NHp), dZ2=_f(device, B, H), dZ1=_f(device, B, H))
+
+
+def policy_forward(pf, feat, pc, B):
+    nt([nt_problem(op_plain(feat, FEAT_LD), pf.W1f, FEAT_LD, pc.H1, H, B, None, H, FEAT_LD, bias=pf.b1, relu=1)], OP_PLAIN, EPI_STORE)
+    nt([nt_problem(op_plain(pc.H1), pf.W2, H, pc.H2, H, B, None, H, H, bias=pf.b2, relu=1)], OP_PLAIN, EPI_STORE)
+    nt([nt_problem(op_plain(pc.H2), pf.Wh, H, pc.raw, pf.NHp, B, None, pf.NH, H, bias=pf.bh)], OP_PLAIN, EPI_STORE)
+    return pc.raw
+
+
+def policy_backward(ws, pf, feat, pc, B, n_grad, enc_ctx, sc, accumulate=0):
+    """pc.draw (B, NHp): gradient w.r.t. the raw head output (columns >= n_grad are zero).  Ends in the encoder's
+    FC head through the fused mask epilogue: sc.Dfc[1] + BN sums in ws.stats (entry state of encoder_backward)."""
+    tn(ws, op_plain(pc.draw), op_plain(pc.H2), OP_PLAIN, OP_PLAIN, B, None, pf.NHp, H, pf.dWh, H, n_grad, H, dbias=pf.dbh,
+       accumulate=accumulate)
+    nt([nt_problem(op_plain(pc.draw), pf.WhT, pf.NHp, pc.dZ2, H, B, None, H, pf.NHp, Yprev=pc.H2, ldyp=H)], OP_PLAIN, EPI_DMASK)
+    tn(ws, op_plain(pc.dZ2), op_plain(pc.H1), OP_PLAIN, OP_PLAIN, B, None, H, H, pf.dW2, H, H, H, dbias=pf.db2, accumulate=accumulate)
+    nt([nt_problem(op_plain(pc.dZ2), pf.W2T, H, pc.dZ1, H, B, None, H, H, Yprev=pc.H1, ldyp=H)], OP_PLAIN, EPI_DMASK)
+    tn(ws, op_plain(pc.dZ1), op_plain(feat, FEAT_LD), OP_PLAIN, OP_PLAIN, B, None, H, FEAT_LD, pf.dW1, pf.Kin, H, pf.Kin,
+       dbias=pf.db1, accumulate=accumulate)
+    f = enc_ctx.fc
+    nt([nt_problem(op_plain(pc.dZ1), pf.W1T, H, sc.Dfc[1], 512, B, None, 512, H, stats=ws.stats, Yprev=f.Y[1], ldyp=512,
+                   pbn=f.bn[1])], OP_PLAIN, EPI_DMASK)
+
+
+class CriticFlat:
+    """QNetwork (networks.py:253-300, num_actions=0): twin Q (linear1-3, linear4-6) + aux branch (linear7, 8,
+    extra_pred) when extra_pred_dim > 0.  First layers are stacked into one (256*nb, 513) matrix."""
+
+    def __init__(self, mod, device, with_opt=True):
+        self.mod, self.E = mod, mod.extra_pred_dim
+        self.nb = 3 if self.E > 0 else 2
+        l1 = [mod.linear1, mod.linear4] + ([mod.linear7] if self.E else [])
+        l2 = [mod.linear2, mod.linear5] + ([mod.linear8] if self.E else [])
+        l3 = [mod.linear3, mod.linear6] + ([mod.extra_pred] if self.E else [])
+        self.nout = [1, 1] + ([self.E] if self.E else [])
+        self.cols = [0, QA_Q2, QA_AUX][: self.nb]
+        order = []
+        for i, m in enumerate(l1):
+            order.append(("l1.W.%d" % i, m.weight, i > 0))
+        for i, m in enumerate(l1):
+            order.append(("l1.b.%d" % i, m.bias, i > 0))
+        for i, m in enumerate(l2):
+            order.append(("l2.W.%d" % i, m.weight, False))
+            order.append(("l2.b.%d" % i, m.bias, False))
+        for i, m in enumerate(l3):
+            order.append(("l3.W.%d" % i, m.weight, False))
+            order.append(("l3.b.%d" % i, m.bias, False))
+        self.arena = A = nets.Arena(order, device, with_opt=with_opt)
+        self.Kin = mod.linear1.weight.shape[1]
+        o, nb = A.offsets, self.nb
+        Kp = _pad4(self.Kin)
+
+        def v(base, name, n, shape):
+            return None if base is None else base[o[name]: o[name] + n].view(shape)
+
+        self.W1, self.b1 = v(A.p, "l1.W.0", nb * H * self.Kin, (nb * H, self.Kin)), v(A.p, "l1.b.0", nb * H, (nb * H,))
+        self.dW1, self.db1 = v(A.g, "l1.W.0", nb * H * self.Kin, (nb * H, self.Kin)), v(A.g, "l1.b.0", nb * H, (nb * H,))
+        self.W2 = [v(A.p, "l2.W.%d" % i, H * H, (H, H)) for i in range(nb)]
+        self.b2 = [v(A.p, "l2.b.%d" % i, H, (H,)) for i in range(nb)]
+        self.dW2 = [v(A.g, "l2.W.%d" % i, H * H, (H, H)) for i in range(nb)]
+        self.db2 = [v(A.g, "l2.b.%d" % i, H, (H,)) for i in range(nb)]
+        self.W3 = [v(A.p, "l3.W.%d" % i, self.nout[i] * H, (self.nout[i], H)) for i in range(nb)]
+        self.b3 = [v(A.p, "l3.b.%d" % i, self.nout[i], (self.nout[i],)) for i in range(nb)]
+        self.dW3 = [v(A.g, "l3.W.%d" % i, self.nout[i] * H, (self.nout[i], H)) for i in range(nb)]
+        self.db3 = [v(A.g, "l3.b.%d" % i, self.nout[i], (self.nout[i],)) for i in range(nb)]
+        self.npad = [_pad4(n) for n in self.nout]
+        size = nb * H * Kp + Kp * nb * H + nb * H * H + sum(H * p for p in self.npad)
+        self.derived = d = _f(device, size)
+        off = 0
+        self.W1f = d[off: off + nb * H * Kp].view(nb * H, Kp); off += nb * H * Kp
+        self.W1T = d[off: off + Kp * nb * H].view(Kp, nb * H); off += Kp * nb * H
+        self.W2T, self.W3T = [], []
+        for i in range(nb):
+            self.W2T.append(d[off: off + H * H].view(H, H)); off += H * H
+        for i in range(nb):
+            self.W3T.append(d[off: off + H * self.npad[i]].view(H, self.npad[i])); off += H * self.npad[i]
+        jobs = [[self.W1.data_ptr(), nb * H, self.Kin, 0, self.W1f.data_ptr(), Kp, self.W1T.data_ptr(), nb * H]]
+        for i in range(nb):
+            jobs.append([self.W2[i].data_ptr(), H, H, 0, 0, H, self.W2T[i].data_ptr(), H])
+            jobs.append([self.W3[i].data_ptr(), self.nout[i], H, 0, 0, H, self.W3T[i].data_ptr(), self.npad[i]])
+        self.jobs = _jobs_tensor(jobs, device)
+        self.refresh_derived()
+
+    def refresh_derived(self):
+        lib.gaddpg_wprep_batched(dp(self.jobs), self.jobs.shape[0], current_stream())
+
+    def tau_vectors(self, tau):
+        """half_soft_update / half_hard_update masks (utils.py:757-770): Polyak on linear1-3 only; hard copy of
+        linear4-6 every target_update_interval; the aux branch of the target is never touched."""
+        A = self.arena
+        soft = torch.zeros(A.n, dtype=torch.float32, device=A.p.device)
+        hard = torch.zeros(A.n, dtype=torch.float32, device=A.p.device)
+        for name in ("l1.W.0", "l1.b.0", "l2.W.0", "l2.b.0", "l3.W.0", "l3.b.0"):
+            soft[A.offsets[name]: A.offsets[name] + A.sizes[name]] = tau
+        for name in ("l1.W.1", "l1.b.1", "l2.W.1", "l2.b.1", "l3.W.1", "l3.b.1"):
+            hard[A.offsets[name]: A.offsets[name] + A.sizes[name]] = 1.0
+        return soft, hard
+
+
+def critic_ctx(B, cf, device):
+    n = cf.nb * H
+    return NS(H1=_f(device, B, n), H2=_f(device, B, n), qa=_f(device, B, QA_LD), dqa=_f(device, B, QA_LD),
+              dZ2=_f(device, B, n), dZ1=_f(device, B, n))
+
+
+def _off(t, col):
+    return t.data_ptr() + 4 * col
+
+
+def critic_forward(cf, feat, cc, B, nb=None):
+    nb = cf.nb if nb is None else nb
+    n = cf.nb * H
+    nt([nt_problem(op_plain(feat, FEAT_LD), cf.W1f, FEAT_LD, cc.H1, n, B, None, nb * H, FEAT_LD, bias=cf.b1, relu=1)],
+       OP_PLAIN, EPI_STORE)
+    nt([nt_problem(Operand(X=_off(cc.H1, H * i), ldx=n), cf.W2[i], H, _off(cc.H2, H * i), n, B, None, H, H, bias=cf.b2[i], relu=1)
+        for i in range(nb)], OP_PLAIN, EPI_STORE)
+    nt([nt_problem(Operand(X=_off(cc.H2, H * i), ldx=n), cf.W3[i], H, _off(cc.qa, cf.cols[i]), QA_LD, B, None, cf.nout[i], H,
+                   bias=cf.b3[i]) for i in range(nb)], OP_PLAIN, EPI_STORE)
+    return cc.qa
+
+
+def critic_backward(ws, cf, feat, cc, B, nb, enc_ctx, sc, accumulate=0):
+    """cc.dqa (B,16): gradient w.r.t. [q1 | q2 | aux_raw]; ``nb`` = branches that carry gradient (2 in the actor
+    step, where the aux branch is not part of the loss).  Ends like policy_backward in sc.Dfc[1] + ws.stats."""
+    n = cf.nb * H
+    for i in range(nb):
+        tn(ws, Operand(X=_off(cc.dqa, cf.cols[i]), ldx=QA_LD), Operand(X=_off(cc.H2, H * i), ldx=n), OP_PLAIN, OP_PLAIN, B, None,
+           cf.npad[i], H, cf.dW3[i], H, cf.nout[i], H, dbias=cf.db3[i], accumulate=accumulate)
+    nt([nt_problem(Operand(X=_off(cc.dqa, cf.cols[i]), ldx=QA_LD), cf.W3T[i], cf.npad[i], _off(cc.dZ2, H * i), n, B, None, H,
+                   cf.npad[i], Yprev=_off(cc.H2, H * i), ldyp=n) for i in range(nb)], OP_PLAIN, EPI_DMASK)
+    for i in range(nb):
+        tn(ws, Operand(X=_off(cc.dZ2, H * i), ldx=n), Operand(X=_off(cc.H1, H * i), ldx=n), OP_PLAIN, OP_PLAIN, B, None, H, H,
+           cf.dW2[i], H, H, H, dbias=cf.db2[i], accumulate=accumulate)
+    nt([nt_problem(Operand(X=_off(cc.dZ2, H * i), ldx=n), cf.W2T[i], H, _off(cc.dZ1, H * i), n, B, None, H, H,
+                   Yprev=_off(cc.H1, H * i), ldyp=n) for i in range(nb)], OP_PLAIN, EPI_DMASK)
+    tn(ws, op_plain(cc.dZ1, n), op_plain(feat, FEAT_LD), OP_PLAIN, OP_PLAIN, B, None, nb * H, FEAT_LD, cf.dW1, cf.Kin, nb * H,
+       cf.Kin, dbias=cf.db1, accumulate=accumulate)
+    f = enc_ctx.fc
+    nt([nt_problem(op_plain(cc.dZ1, n), cf.W1T, n, sc.Dfc[1], 512, B, None, 512, nb * H, stats=ws.stats, Yprev=f.Y[1], ldyp=512,
+                   pbn=f.bn[1])], OP_PLAIN, EPI_DMASK)

@@ -186,13 +186,13 @@ GADDPG_API int gaddpg_heads_init(const float* act_scale, const float* act_bias, 
 GADDPG_API int gaddpg_policy_head_fwd(const float* raw, int ldr, int B, float* pi, void* stream);
 GADDPG_API int gaddpg_td3_next_action(const float* raw_t, int ldr, const float* u, float noise_scale, int B, float* next_action,
                                       void* stream);
-GADDPG_API int gaddpg_td3_target(const float* q1t, const float* q2t, const float* reward, const float* done, float gamma, int B,
-                                 float* y, void* stream);
+GADDPG_API int gaddpg_td3_target(const float* qa, int ldq, int oq2, const float* reward, const float* done, float gamma, int B,
+                                 float* y, void* stream); /* y = r + (1-done)*gamma*min(qa[:,0], qa[:,oq2]) */
 /* qa/dqa [B,ldq]: q1 at column 0, q2 at column oq2, aux_raw(7) at column oaux;
  * out[0]=critic_loss out[1]=critic_grasp_aux_loss out[2]=#(return>0) */
 GADDPG_API int gaddpg_critic_loss(const float* qa, int ldq, int oq2, int oaux, const float* y, const float* perturb_flag, const float* ret,
                                   const float* goal, int use_aux, int B, float grad_scale, float* dqa, float* out, void* stream);
-/* praw/dpraw [B,ldr] = [mean(6) | extra | ...]; out[0]=bc_loss*bc_weight out[1]=policy_grasp_aux_loss */
+/* praw/dpraw [B,ldr] = [mean(6) | extra | ...]; out[0]=bc_loss*bc_weight out[1]=policy_grasp_aux_loss out[2]=#(return>0) */
 GADDPG_API int gaddpg_actor_loss(const float* praw, int ldr, const float* pi, const float* expert_action, const float* expert_flag,
                                  const float* ret, const float* goal, int use_aux, float bc_weight, const float* dpi_ac, int B,
                                  float grad_scale, float* dpraw, int n_head, float* out, void* stream);

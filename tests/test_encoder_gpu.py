@@ -112,7 +112,7 @@ def test_duplicate_folding_matches_dense_semantics(cuda):
     reproduce BatchNorm over the full (B, C, npoint, nsample) tensor the oracle materialises."""
     from gaddpg_b200 import engine, synthetic
 
-    B, N = 3, 300
+    B, N = 8, 300
     ora, mine, ef = _build(4, 5, cuda)
     rs = np.random.RandomState(0)
     cloud = torch.from_numpy(synthetic.make_batch(B, N, step=1)["point_state_batch"]).clone()
