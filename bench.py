@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py — offline DDPG update steps/s on B200 (BASELINE.json metric) + roofline + CPU baseline.
+
+    python bench.py --gpus 1 --steps K --warmup W            # fused CUDA agent (one rank per GPU under torchrun for N>1)
+    python bench.py --impl reference --steps K --warmup W     # the reference algorithm's CPU path (oracle port), host cores
+
+One "step" = one ``agent.update_parameters`` (ddpg.py:146-185) + ``step_scheduler`` on one synthetic replay
+minibatch.  Workload at N=1: BASELINE config 2 — DDPG, B=256, 4096-point x 6-channel clouds (extra_latent=3),
+policy_aux = critic_aux = False; under N ranks every rank takes its own 256-sample shard (weak scaling) with the
+two per-step gradient all-reduces over NCCL.
+
+JSON keys beyond the base contract: ``roofline`` (dominant entry point of the step, timed live with CUDA events in
+an eager profiled pass after the timed region), ``cpu_baseline`` (oracle port on the host cores, bounded sample),
+``kernels`` (top entry points with their share of the step), ``clocks``.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "offline DDPG update steps/sec (B=256, 4096 pts)"
+UNIT = "update steps/s (256-sample minibatch per GPU)"
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # 148 SMs x 128 FFMA lanes x 2 flop x max SM clock = 74.5
+
+
+def workload(args):
+    return dict(workload="cfg2: offline TD3/DDPG update, B=%d per GPU, N=%d points x 6 channels (extra_latent=3), aux heads off"
+                % (args.batch, args.points), B=args.batch, N=args.points, channels=6, policy_update_gap=2,
+                l2="per-step working set (activations of 5 encoder passes, ~GBs) >> 126 MB L2 and 4 distinct batches are cycled: no flush needed")
+
+
+AGENT_KW = dict(extra_latent=3, policy_aux=False, critic_aux=False)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tensor_burst=d["bf16_tflops"], tensor_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tensor_burst=1590.0, tensor_sustained=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(threading.Thread):
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x10: "sync_boost",
+               0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        while not self.stop_flag and self.nv is not None:
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(self.nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def result(self):
+        s = sorted(self.samples)
+        return dict(sm_mhz=s[len(s) // 2] if s else None, sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons), samples=len(s))
+
+
+def make_batches(B, N, nb, pinned=True):
+    import numpy as np
+    import torch
+
+    from gaddpg_b200 import synthetic
+
+    out = []
+    for i in range(nb):
+        b = synthetic.make_batch(B, N, step=i, channels=6)
+        t = {}
+        for k, v in b.items():
+            if k in ("grasp_sample_batch", "batch_idx"):
+                continue
+            x = torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32))
+            t[k] = x.pin_memory() if pinned else x
+        t["noise_u"] = torch.rand(B, 6).pin_memory() if pinned else torch.rand(B, 6)
+        out.append(t)
+    return out
+
+
+def run_reference(args):
+    """The reference algorithm's CPU implementation of the step (oracle port of core/ddpg.py + networks + pointnet2_ops,
+    pinned to the unmodified reference by oracle/make_golden.py), all host threads, a bounded sub-batch per step."""
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from gaddpg_b200 import synthetic
+    from oracle.ddpg_cpu import OracleAgent
+
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    Bs = args.ref_batch
+    agent = OracleAgent("DDPG", seed=123456, **AGENT_KW)
+    batches = [synthetic.make_batch(Bs, args.points, step=i, channels=6) for i in range(2)]
+    for i in range(args.warmup):
+        agent.update_parameters(batches[i % 2])
+        agent.step_scheduler()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        agent.update_parameters(batches[i % 2])
+        agent.step_scheduler()
+    dt = time.perf_counter() - t0
+    value = args.steps / dt * (Bs / float(args.batch))
+    sample = "each step = one full DDPG update on a %d-sample sub-batch of the %d-sample minibatch (N=%d, 6 ch); value scaled by %d/%d" % (
+        Bs, args.batch, args.points, Bs, args.batch)
+    print(json.dumps(dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                          ms_per_step=1e3 * dt / args.steps * (args.batch / float(Bs)), higher_is_better=True, scaling="weak",
+                          vs_baseline=None, dtype="f32", data="synthetic", config=workload(args), impl="reference",
+                          cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port", sample=sample,
+                                            torch=torch.__version__),
+                          e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
+
+
+def cpu_baseline(args):
+    import torch
+
+    from gaddpg_b200 import synthetic
+    from oracle.ddpg_cpu import OracleAgent
+
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    Bs = args.ref_batch
+    agent = OracleAgent("DDPG", seed=123456, **AGENT_KW)
+    batches = [synthetic.make_batch(Bs, args.points, step=i, channels=6) for i in range(2)]
+    agent.update_parameters(batches[0])  # warm-up (odd step)
+    t0 = time.perf_counter()
+    n = 2
+    for i in range(n):  # one even + one odd step
+        agent.update_parameters(batches[(i + 1) % 2])
+    dt = time.perf_counter() - t0
+    return dict(value=n / dt * (Bs / float(args.batch)), unit=UNIT, cores=cores, kind="port", torch=torch.__version__,
+                sample="oracle port, %d timed DDPG steps (one even, one odd) on a %d-sample sub-batch (N=%d, 6 ch) after 1 warm-up; "
+                       "scaled by %d/%d to the 256-sample unit; %.1f s of CPU work" % (n, Bs, args.points, Bs, args.batch, dt))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--points", type=int, default=4096)
+    ap.add_argument("--ref-batch", type=int, default=32)
+    ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+
+    from gaddpg_b200 import agent as ag
+    from gaddpg_b200.capi import lib
+    from gaddpg_b200.dist import World
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product has no CPU fallback (use --impl reference for the CPU arm)")
+    world = World("nccl") if int(os.environ.get("WORLD_SIZE", "1")) > 1 else None
+    rank = world.rank if world else 0
+    local = world.local_rank if world else 0
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    W = max(args.warmup, 3)
+    K = args.steps
+    torch.manual_seed(1000 + rank)
+    agent = ag.make_agent("DDPG", seed=123456, device=dev, world=world, **AGENT_KW)
+    agent.use_graph = not args.no_graph
+    nb = 4
+    host = make_batches(args.batch, args.points, nb)
+    devb = [{k: v.to(dev) for k, v in b.items()} for b in host]
+
+    def sync_all():
+        if world:
+            world.barrier()
+        torch.cuda.synchronize()
+
+    def run(batches, n, timed):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            b = batches[i % nb]
+            agent.update_parameters(b, agent.update_step, 0, noise_u=b["noise_u"])
+            agent.step_scheduler(agent.update_step)
+        e1.record()
+        sync_all()
+        ms = e0.elapsed_time(e1)
+        if world and timed:
+            t = torch.tensor([ms], device=dev)
+            world.all_reduce_max(t)
+            ms = float(t)
+        return ms
+
+    # ---- launches per step (eager, one odd + one even step) — also the first warm-up
+    agent.use_graph = False
+    l0 = lib.gaddpg_launch_count()
+    run(devb, 2, False)
+    launches_per_2 = lib.gaddpg_launch_count() - l0
+    agent.use_graph = not args.no_graph
+    run(devb, max(W, 4), False)  # graph warm-up + capture for both parities
+
+    # ---- value: inputs resident in HBM
+    clk = ClockSampler(local)
+    clk.start()
+    ms_dev = run(devb, K, True)
+    # ---- e2e: pinned host buffers through the public API (H2D of the batch + D2H of the scalars inside the timed region)
+    run(host, 2, False)
+    ms_e2e = run(host, K, True)
+    clk.stop_flag = True
+    clk.join(timeout=2)
+    n_gpus = world.size if world else 1
+    value = n_gpus * K / (ms_dev / 1e3)
+    e2e = n_gpus * K / (ms_e2e / 1e3)
+
+    out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=n_gpus, steps=K, warmup=W, ms_per_step=ms_dev / K, higher_is_better=True,
+               scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", config=workload(args),
+               e2e=dict(value=e2e, unit=UNIT, ms_per_step=ms_e2e / K, h2d_bytes_per_step=agent.h2d_bytes(), d2h_bytes_per_step=64),
+               gpu_launches=int(launches_per_2 * K / 2), clocks=clk.result(), graph=bool(agent.use_graph))
+
+    if rank == 0 and not args.no_profile:
+        out.update(profile(agent, devb, args))
+    if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args)
+    if world:
+        world.barrier()
+    if rank == 0:
+        print(json.dumps(out))
+    if world:
+        world.close()
+
+
+def profile(agent, devb, args):
+    """Roofline leg: two eager steps (even + odd) with every C-ABI call bracketed by CUDA events on its stream."""
+    import torch
+
+    from gaddpg_b200.profiler import KernelProfile
+
+    pk = peaks()
+    agent.use_graph = False
+    prof = KernelProfile()
+    with prof:
+        for i in range(2):
+            b = devb[i % len(devb)]
+            agent.update_parameters(b, agent.update_step, 0, noise_u=b["noise_u"])
+    torch.cuda.synchronize()
+    mres = {}
+    for g in (agent.geom_s, agent.geom_n):
+        for l in g.lv:
+            mres[l.M_dev] = int(l.seg_off[-1])
+    tab = prof.table(mres)
+    total = sum(r["ms"] for r in tab.values())
+    rows = sorted(tab.items(), key=lambda kv: -kv[1]["ms"])
+    kernels = [dict(entry=k, ms_per_step=r["ms"] / 2, share=r["ms"] / total, calls_per_step=r["calls"] / 2,
+                    tflops=(r["flops"] / (r["ms"] * 1e-3) / 1e12) if r["ms"] > 0 else 0.0,
+                    gbs=(r["bytes"] / (r["ms"] * 1e-3) / 1e9) if r["ms"] > 0 else 0.0) for k, r in rows[:12]]
+    # group all row-GEMM launches: they are one kernel family and dominate the step
+    fam = {"nt": dict(ms=0.0, flops=0.0, bytes=0.0, calls=0), "tn": dict(ms=0.0, flops=0.0, bytes=0.0, calls=0)}
+    for k, r in tab.items():
+        f = "nt" if k.startswith("gemm_nt") else ("tn" if k.startswith("gemm_tn") else None)
+        if f:
+            for kk in ("ms", "flops", "bytes"):
+                fam[f][kk] += r[kk]
+            fam[f]["calls"] += r["calls"]
+    dom = max(fam, key=lambda f: fam[f]["ms"])
+    d = fam[dom]
+    achieved = d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0
+    roof = dict(kernel="gemm_%s_kernel (all launches of the step)" % dom, bound="tensor", achieved=achieved, peak=pk["tensor_sustained"],
+                unit="TFLOP/s", frac=achieved / pk["tensor_sustained"], traffic=None, peak_source=pk["src"] + ", sustained bf16",
+                share_of_step=d["ms"] / total, avg_launch_ms=d["ms"] / max(d["calls"], 1),
+                algorithmic_gbs=d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else 0.0, hbm_peak_gbs=pk["hbm"],
+                fp32_ffma_peak_tflops=FP32_PEAK_TFLOPS, frac_of_fp32_ffma_peak=achieved / FP32_PEAK_TFLOPS,
+                note="FP32 FFMA row-GEMM (CUDA cores; 1e-4 parity rules out single-pass TF32): the bf16 tensor peak is the contract's "
+                     "denominator, the FP32 FFMA peak is the pipe this kernel actually runs on")
+    rows_live = {("state" if g is agent.geom_s else "next") + ".sa%d" % (i + 1): int(l.seg_off[-1]) for g in (agent.geom_s, agent.geom_n)
+                 for i, l in enumerate(g.lv)}
+    return dict(roofline=roof, kernels=kernels, eager_ms_per_step=total / 2, folded_rows=rows_live,
+                dense_rows={"sa1": agent.B * 32 * 64, "sa2": agent.B * 32 * 128})
+
+
+if __name__ == "__main__":
+    main()

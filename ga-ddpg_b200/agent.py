@@ -217,22 +217,34 @@ class AgentB200:
         B, C, Np = cloud.shape
         if self._shape != (B, C, Np):
             self._alloc(B, C, Np)
-        self.cloud_host.copy_(torch.as_tensor(cloud))
-        self.cloud.copy_(self.cloud_host, non_blocking=True)
-        if self.has_critic:
-            self.next_cloud_host.copy_(torch.as_tensor(batch["next_point_state_batch"]))
-            self.next_cloud.copy_(self.next_cloud_host, non_blocking=True)
-        vh = self.vh
-        put = lambda dst, key: dst.copy_(torch.as_tensor(np.asarray(batch[key], dtype=np.float32)).view(dst.shape))  # noqa: E731
-        put(vh.action, "action_batch"), put(vh.expert_action, "expert_action_batch"), put(vh.goal, "goal_batch")
-        put(vh.reward, "reward_batch"), put(vh.ret, "return_batch"), put(vh.done, "mask_batch"), put(vh.time, "time_batch")
-        put(vh.expert_flag, "expert_flag_batch"), put(vh.perturb_flag, "perturb_flag_batch")
-        if self.has_critic:
-            if noise_u is None:
-                vh.noise_u.copy_(torch.rand(B, 6))  # torch.rand_like in get_noise_delta (utils.py:575)
+
+        def put_cloud(dst, stage, src):
+            if torch.is_tensor(src) and src.dtype == torch.float32 and (src.is_cuda or src.is_pinned()):
+                dst.copy_(src, non_blocking=True)       # already pinned fp32 (or device resident): straight DMA
             else:
-                vh.noise_u.copy_(torch.as_tensor(np.asarray(noise_u, dtype=np.float32)))
-        self.vec.copy_(self.vec_host, non_blocking=True)
+                stage.copy_(torch.as_tensor(src))        # float64 ndarray of the reference's replay buffer: convert on host
+                dst.copy_(stage, non_blocking=True)
+
+        put_cloud(self.cloud, self.cloud_host, cloud)
+        if self.has_critic:
+            put_cloud(self.next_cloud, self.next_cloud_host, batch["next_point_state_batch"])
+        on_device = torch.is_tensor(cloud) and cloud.is_cuda
+        tgt = self.v if on_device else self.vh   # device-resident batch: D2D straight into the kernel inputs
+
+        def put(dst, key_or_val):
+            src = batch[key_or_val] if isinstance(key_or_val, str) else key_or_val
+            if not torch.is_tensor(src):
+                src = torch.as_tensor(np.asarray(src, dtype=np.float32))
+            dst.copy_(src.view(dst.shape), non_blocking=True)
+
+        put(tgt.action, "action_batch"), put(tgt.expert_action, "expert_action_batch"), put(tgt.goal, "goal_batch")
+        put(tgt.reward, "reward_batch"), put(tgt.ret, "return_batch"), put(tgt.done, "mask_batch"), put(tgt.time, "time_batch")
+        put(tgt.expert_flag, "expert_flag_batch"), put(tgt.perturb_flag, "perturb_flag_batch")
+        if self.has_critic:
+            # torch.rand_like in get_noise_delta (utils.py:575) unless the caller injects the uniform draw
+            put(tgt.noise_u, torch.rand(B, 6, device=self.device if on_device else "cpu") if noise_u is None else noise_u)
+        if not on_device:
+            self.vec.copy_(self.vec_host, non_blocking=True)
 
     def h2d_bytes(self):
         n = self.cloud_host.numel() * (2 if self.has_critic else 1) + self.vec_host.numel()

@@ -68,10 +68,13 @@ class _Lib:
     def __getattr__(self, name):
         lib = self.load()
         fn = getattr(lib, name)
-        if self.protos[name][0] != "int" or name in ("gaddpg_version", "gaddpg_opt_n_threads"):
+        if self.protos[name][0] != "int" or name in ("gaddpg_version", "gaddpg_opt_n_threads", "gaddpg_launch_count"):
             return fn
 
         def checked(*a):
+            prof = PROFILE
+            if prof is not None:
+                return prof.call(name, fn, a, lib)
             rc = fn(*a)
             if rc != 0:
                 raise RuntimeError("%s failed (%d): %s" % (name, rc, lib.gaddpg_last_error().decode()))
@@ -83,6 +86,7 @@ class _Lib:
 
 
 lib = _Lib()
+PROFILE = None  # set to a profiler.KernelProfile to bracket every C-ABI call with CUDA events (bench.py roofline leg)
 
 
 def ptr(t):

@@ -9,6 +9,7 @@
 #define GADDPG_ABI_VERSION 1
 
 static thread_local char g_err[512] = "";
+long long g_gaddpg_launches = 0;
 
 void gaddpg_set_error(const char* fmt, ...) {
   va_list ap;
@@ -20,6 +21,7 @@ void gaddpg_set_error(const char* fmt, ...) {
 extern "C" {
 
 int gaddpg_version(void) { return GADDPG_ABI_VERSION; }
+long long gaddpg_launch_count(void) { return g_gaddpg_launches; }
 const char* gaddpg_last_error(void) { return g_err; }
 const char* gaddpg_build_info(void) {
   return "gaddpg_b200 sm_100a, nvcc " GADDPG_STR(__CUDACC_VER_MAJOR__) "." GADDPG_STR(__CUDACC_VER_MINOR__);

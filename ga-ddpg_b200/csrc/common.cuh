@@ -10,6 +10,7 @@
 #define GADDPG_ERR_UNSUPPORTED (-3)
 
 void gaddpg_set_error(const char* fmt, ...);
+extern long long g_gaddpg_launches;  // kernels launched by this library in this process (bench.py "gpu_launches")
 
 #define GADDPG_CHECK_ARG(cond, ...)      \
   do {                                   \
@@ -23,6 +24,7 @@ void gaddpg_set_error(const char* fmt, ...);
 // caller's next synchronisation, as with any stream-ordered API)
 #define GADDPG_CHECK_LAUNCH(name)                                                         \
   do {                                                                                    \
+    ++g_gaddpg_launches;                                                                  \
     cudaError_t e__ = cudaGetLastError();                                                 \
     if (e__ != cudaSuccess) {                                                             \
       gaddpg_set_error("%s: CUDA launch failed: %s", name, cudaGetErrorString(e__));     \

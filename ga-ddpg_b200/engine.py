@@ -77,10 +77,24 @@ class Workspace:
 # ------------------------------------------------------------------------------------------------
 # thin launch helpers
 # ------------------------------------------------------------------------------------------------
+def _tag(kind, M_max, M_dev, flops_per_row, bytes_per_row, bytes_fixed=0.0):
+    from . import capi
+
+    if capi.PROFILE is not None:
+        capi.PROFILE.tag = dict(kind=kind, M_max=M_max, M_dev=M_dev, flops_per_row=flops_per_row, bytes_per_row=bytes_per_row,
+                                bytes_fixed=bytes_fixed)
+
+
 def nt(problems, amode, emode):
     g = NTGroup()
     for i, p in enumerate(problems):
         g.p[i] = p
+    p0 = problems[0]
+    # algorithmic work of the launch: 2*N*K flops per row; bytes = A row (+Y for BN-backward, +Yprev for the mask
+    # epilogue) read once + C row written once, weights read once
+    rd = p0.K * (2 if amode == OP_BNBWD else 1) + (p0.N if emode == EPI_DMASK else 0)
+    _tag("nt[%dx%d,a%d,e%d]" % (p0.N, p0.K, amode, emode), p0.M_max, p0.M_dev,
+         sum(2.0 * q.N * q.K for q in problems), 4.0 * len(problems) * (rd + p0.N), 4.0 * sum(q.N * q.K for q in problems))
     lib.gaddpg_gemm_nt(ctypes.byref(g), len(problems), amode, emode, current_stream())
 
 
@@ -96,6 +110,8 @@ def nt_problem(A, Bw, ldb, C, ldc, M_max, M_dev, N, K, bias=None, relu=0, stats=
 
 def tn(ws, P, Q, pmode, qmode, M_max, M_dev, N, K, dW, ldd, Ntrue, Ktrue, rot=0, dbias=None, accumulate=0):
     prob = TNProblem(P=P, Q=Q, M_max=M_max, M_dev=M_dev, N=N, K=K)
+    _tag("tn[%dx%d,p%d,q%d]" % (N, K, pmode, qmode), M_max, M_dev, 2.0 * N * K, 4.0 * (N * (2 if pmode == OP_BNBWD else 1) + K),
+         4.0 * N * K)
     lib.gaddpg_gemm_tn(ctypes.byref(prob), pmode, qmode, dp(dW), ldd, Ntrue, Ktrue, rot, dp(dbias), accumulate,
                        dp(ws.tn), ws.tn_bytes, current_stream())
 

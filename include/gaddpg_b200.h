@@ -44,6 +44,7 @@ extern "C" {
 
 /* library identity */
 GADDPG_API int gaddpg_version(void);                 /* ABI version, bumped on any signature change */
+GADDPG_API long long gaddpg_launch_count(void);      /* kernels launched by this library so far (this process) */
 GADDPG_API const char* gaddpg_last_error(void);      /* message of the last failing call on this thread */
 GADDPG_API const char* gaddpg_build_info(void);      /* "sm_100a nvcc x.y ..." */
 GADDPG_API int gaddpg_device_info(int* sm_count, int* cc_major, int* cc_minor, long long* total_mem);
