@@ -15,7 +15,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
-    "-Xptxas", "-warn-spills",
+    "-Xptxas", "-warn-spills", "-DGADDPG_NT_MINB=2",
 ]
 
 
@@ -31,6 +31,15 @@ def _stamp():
         h.update(open(f, "rb").read())
     h.update(" ".join(FLAGS).encode())
     return h.hexdigest()
+
+
+def build_variant(name, defines):
+    """Experimental build with extra -D flags into lib/libgaddpg_b200_<name>.so (selected with GADDPG_LIB)."""
+    os.makedirs(LIBDIR, exist_ok=True)
+    out = os.path.join(LIBDIR, "libgaddpg_b200_%s.so" % name)
+    cmd = [NVCC] + FLAGS + ["-D%s" % d for d in defines] + ["-shared", "-o", out] + _sources() + ["-lcudart_static", "-lpthread", "-ldl", "-lrt"]
+    subprocess.run(cmd, check=True)
+    return out
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

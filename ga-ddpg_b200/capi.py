@@ -56,7 +56,10 @@ class _Lib:
         if self._lib is None:
             from . import build as _build
 
-            path = _build.LIB if os.path.exists(_build.LIB) and os.environ.get("GADDPG_NO_REBUILD") else _build.build()
+            if os.environ.get("GADDPG_LIB"):       # kernel experiments: load an explicitly named build
+                path = os.environ["GADDPG_LIB"]
+            else:
+                path = _build.LIB if os.path.exists(_build.LIB) and os.environ.get("GADDPG_NO_REBUILD") else _build.build()
             lib = ctypes.CDLL(path)
             for name, (ret, args) in self.protos.items():
                 fn = getattr(lib, name)  # AttributeError if the .so lacks a declared symbol
@@ -68,7 +71,7 @@ class _Lib:
     def __getattr__(self, name):
         lib = self.load()
         fn = getattr(lib, name)
-        if self.protos[name][0] != "int" or name in ("gaddpg_version", "gaddpg_opt_n_threads", "gaddpg_launch_count"):
+        if self.protos[name][0] != "int" or name in ("gaddpg_version", "gaddpg_opt_n_threads", "gaddpg_launch_count", "gaddpg_get_tensor_core"):
             return fn
 
         def checked(*a):

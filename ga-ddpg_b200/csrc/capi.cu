@@ -77,6 +77,11 @@ int gaddpg_struct_sizes(int* operand, int* nt_problem, int* tn_problem) {
   if (tn_problem) *tn_problem = (int)sizeof(gaddpg_tn_problem);
   return GADDPG_OK;
 }
+int gaddpg_set_tensor_core(int enable) {
+  gaddpg_set_tensor_core_impl(enable);
+  return GADDPG_OK;
+}
+int gaddpg_get_tensor_core(void) { return gaddpg_get_tensor_core_impl(); }
 int gaddpg_gemm_nt(const gaddpg_nt_group* group, int nprob, int amode, int emode, void* stream) {
   return gaddpg_gemm_nt_impl(group, nprob, amode, emode, stream);
 }

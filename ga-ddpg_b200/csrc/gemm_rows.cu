@@ -12,6 +12,8 @@
 // one slot per CTA -> a fixed-order FP64 sum in the finalize kernel.  No float atomics anywhere.
 #include "common.cuh"
 #include "gemm_rows.cuh"
+#include <stdlib.h>
+
 #include "impl.h"
 
 namespace {
@@ -50,8 +52,11 @@ __device__ __forceinline__ float4 load_operand4(const Operand& d, int row, int c
 // ------------------------------------------------------------------------------------------------
 // NT: C[M,N] = epi(pro(A)[M,K] . B[N,K]^T).  256 threads, thread (ty,tx) owns rows ty+TY*i, cols tx+TX*j.
 // ------------------------------------------------------------------------------------------------
+#ifndef GADDPG_NT_MINB
+#define GADDPG_NT_MINB 1
+#endif
 template <int BM, int BN, int TM, int TN, int AMODE, int EMODE>
-__global__ void __launch_bounds__(256) gemm_nt_kernel(const NTGroup grp) {
+__global__ void __launch_bounds__(256, GADDPG_NT_MINB) gemm_nt_kernel(const NTGroup grp) {
   constexpr int TX = BN / TN, TY = BM / TM;
   static_assert(TX * TY == 256, "tile shape must map onto 256 threads");
   constexpr int TILE_FLOATS = (BM + BN) * LDS;
@@ -412,6 +417,16 @@ int check_operand(const Operand& o, int mode, int W, const char* what) {
 
 }  // namespace
 
+static int g_tc_enabled = -1;
+void gaddpg_set_tensor_core_impl(int enable) { g_tc_enabled = enable ? 1 : 0; }
+int gaddpg_get_tensor_core_impl() {
+  if (g_tc_enabled < 0) {
+    const char* e = getenv("GADDPG_TC");
+    g_tc_enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_tc_enabled;
+}
+
 int gaddpg_gemm_nt_impl(const NTGroup* g, int nprob, int amode, int emode, void* stream) {
   GADDPG_CHECK_ARG(g && nprob >= 1 && nprob <= GADDPG_MAX_GROUP, "gemm_nt: bad group size %d", nprob);
   for (int i = 0; i < nprob; ++i) {
@@ -429,6 +444,8 @@ int gaddpg_gemm_nt_impl(const NTGroup* g, int nprob, int amode, int emode, void*
       GADDPG_CHECK_ARG(!p.psc || p.psh, "gemm_nt[%d]: psc without psh", i);
     }
   }
+  if (nprob == 1 && gaddpg_get_tensor_core_impl() && gaddpg_tc_gemm_supported(g->p[0], amode, emode))
+    return gaddpg_tc_gemm_nt_impl(&g->p[0], amode, emode, stream);  // tcgen05 3xTF32 path for the wide SA layers
   cudaStream_t st = (cudaStream_t)stream;
 #define NT_CASE(A, E) \
   if (amode == A && emode == E) return launch_nt<A, E>(*g, nprob, st)

@@ -86,3 +86,8 @@ int gaddpg_absmax_impl(const float* x, long long n, float* out, float* ws, void*
 int gaddpg_clip_coef_impl(const float* g, long long n, float max_norm, float* coef_out, float* norm_out, float* ws, void* stream);
 int gaddpg_wprep_impl(const float* W, int N, int K, int rot, float* Wp, int ldp, float* WT, int ldt, void* stream);
 int gaddpg_f64_to_f32_impl(const double* src, float* dst, long long n, void* stream);
+// tc_gemm.cu
+bool gaddpg_tc_gemm_supported(const NTProblem& p, int amode, int emode);
+int gaddpg_tc_gemm_nt_impl(const NTProblem* p, int amode, int emode, void* stream);
+void gaddpg_set_tensor_core_impl(int enable);
+int gaddpg_get_tensor_core_impl();

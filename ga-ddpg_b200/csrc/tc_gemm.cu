@@ -1,0 +1,398 @@
+// tc_gemm.cu — tcgen05 (5th-gen tensor core) row-GEMM for the wide set-abstraction layers (sm_100a only).
+//
+//   C[M,N] = epi( pro(A)[M,K] . W[N,K]^T )     same operand prologues / epilogues as gemm_rows.cu
+//
+// used for the SA1 shared-MLP layers (1x1 convs 64->64, 64->128 and their dX), which hold ~80 % of the step's rows
+// (~420 k compact rows at B=256): reached from /root/reference/core/networks.py:66-71 through upstream
+// build_shared_mlp.  FP32 parity (1e-4 through nine BN layers) is kept with a 3xTF32 split: x = hi + lo with
+// hi = tf32(x), lo = x - hi (exact), and  a.b ~= lo_a.hi_b + hi_a.lo_b + hi_a.hi_b  accumulated in FP32 in TMEM
+// (dropped term lo.lo ~ 2^-22 relative).
+//
+// Warp-specialised persistent kernel, one CTA per SM, 128-row tiles:
+//   warps 0-3  producers : coalesced float4 loads of the A tile, BN(+ReLU) / BN-backward prologue in registers,
+//                          hi/lo split, st.shared into the canonical K-major SWIZZLE_128B UMMA layout
+//                          (the weights are staged the same way once per CTA), fence.proxy.async, mbarrier arrive
+//   warp  4    MMA issuer: one thread issues 3*K/8 tcgen05.mma.kind::tf32 (M=128, N=N, K=8) per tile into a
+//                          double-buffered TMEM accumulator and tcgen05.commit's the smem stage / accumulator barriers
+//   warps 5-8  epilogue  : tcgen05.ld 32x32b -> registers -> padded smem transpose -> coalesced global stores, mask
+//                          epilogue reads and per-column BatchNorm statistics (fixed order, one slot per CTA)
+// No TMA here by design: every A element passes through a per-element prologue before it may reach the tensor
+// core, so the producer warps ARE the copy engine; W is 16-64 KB and loaded once per CTA.
+#include "common.cuh"
+#include "gemm_rows.cuh"
+#include "impl.h"
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const uint32_t addr = smem_u32(bar);
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] . B[smem desc]^T, kind::tf32, one thread issues for the CTA
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* r) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(r);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]),
+        "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]), "=r"(u[17]), "=r"(u[18]),
+        "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]),
+        "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO>>4 <<16 |
+// SBO>>4 <<32 | version 1 <<46 | layout SWIZZLE_128B(2) <<61.  SBO = 1024 B (8 rows x 128 B); LBO unused (=1).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// byte offset of the 16-byte chunk holding (row r, k..k+3) inside an operand stored as K/32 blocks of [rows x 128 B]
+__device__ __forceinline__ uint32_t sw128_off(int r, int k, int rows) {
+  const int kb = k >> 5, chunk = (k & 31) >> 2;
+  return (uint32_t)(kb * rows * 128 + (r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4));
+}
+__device__ __forceinline__ void split_store(unsigned char* hi_base, unsigned char* lo_base, uint32_t off, float4 v) {
+  float4 h, l;
+  h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+  h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+  h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+  h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+  l.x = v.x - h.x;
+  l.y = v.y - h.y;
+  l.z = v.z - h.z;
+  l.w = v.w - h.w;
+  *reinterpret_cast<float4*>(hi_base + off) = h;
+  *reinterpret_cast<float4*>(lo_base + off) = l;
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+template <int MODE>
+__device__ __forceinline__ float4 load_operand4(const Operand& d, int row, int col, int M, int W) {
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (row >= M || col >= W) return r;
+  float4 x = ldg4(d.X + (long long)row * d.ldx + col);
+  if (MODE == OP_PLAIN) {
+    r = x;
+  } else if (MODE == OP_BNRELU) {
+    float4 s = ldg4(d.c0 + col), t = ldg4(d.c1 + col);
+    r.x = fmaxf(fmaf(x.x, s.x, t.x), 0.f);
+    r.y = fmaxf(fmaf(x.y, s.y, t.y), 0.f);
+    r.z = fmaxf(fmaf(x.z, s.z, t.z), 0.f);
+    r.w = fmaxf(fmaf(x.w, s.w, t.w), 0.f);
+  } else {
+    float4 y = ldg4(d.Y + (long long)row * d.ldy + col);
+    float4 g = ldg4(d.c0 + col), m1 = ldg4(d.c1 + col), m2 = ldg4(d.c2 + col), mu = ldg4(d.c3 + col), rs = ldg4(d.c4 + col);
+    float w = d.rw ? d.rw[row] : 1.f;
+    r.x = g.x * (x.x - w * (m1.x + (y.x - mu.x) * rs.x * m2.x));
+    r.y = g.y * (x.y - w * (m1.y + (y.y - mu.y) * rs.y * m2.y));
+    r.z = g.z * (x.z - w * (m1.z + (y.z - mu.z) * rs.z * m2.z));
+    r.w = g.w * (x.w - w * (m1.w + (y.w - mu.w) * rs.w * m2.w));
+  }
+  return r;
+}
+
+constexpr int TC_BM = 128;
+constexpr int TC_THREADS = 288;  // 4 producer warps + 1 MMA warp + 4 epilogue warps
+
+struct TcSmemLayout {
+  uint32_t w_hi, w_lo, a_hi[2], a_lo[2], stage_buf, bars, total;
+};
+__host__ __device__ inline TcSmemLayout tc_layout(int N, int K, int stages) {
+  TcSmemLayout L;
+  uint32_t off = 0;
+  L.w_hi = off; off += (uint32_t)N * K * 4;
+  L.w_lo = off; off += (uint32_t)N * K * 4;
+  for (int s = 0; s < 2; ++s) {
+    L.a_hi[s] = off; if (s < stages) off += (uint32_t)TC_BM * K * 4;
+    L.a_lo[s] = off; if (s < stages) off += (uint32_t)TC_BM * K * 4;
+  }
+  L.stage_buf = off; off += 4 * 32 * 33 * 4;   // per-epilogue-warp transpose buffers
+  L.bars = off; off += 256;                     // mbarriers + tmem address + stats scratch header
+  off += 2 * 4 * 256 * 4;                       // cross-warp stats combine: [2][4 warps][N<=256]
+  L.total = off;
+  return L;
+}
+
+template <int AMODE, int EMODE>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProblem p, int stages) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // SWIZZLE_128B operands need 1024-byte aligned bases (the host adds 1024 bytes of slack)
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int N = p.N, K = p.K;
+  const TcSmemLayout L = tc_layout(N, K, stages);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
+  uint64_t* a_full = bars;           // [2]
+  uint64_t* a_empty = bars + 2;      // [2]
+  uint64_t* acc_full = bars + 4;     // [2]
+  uint64_t* acc_empty = bars + 6;    // [2]
+  uint64_t* w_full = bars + 8;       // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  float* stat_comb = reinterpret_cast<float*>(smem + L.bars + 256);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int M = p.M_dev ? *p.M_dev : p.M_max;
+  M = M < p.M_max ? M : p.M_max;
+  const int ntiles = (M + TC_BM - 1) / TC_BM;
+  const uint32_t tmem_cols = (2 * N <= 32) ? 32 : (2 * N <= 64) ? 64 : (2 * N <= 128) ? 128 : (2 * N <= 256) ? 256 : 512;
+
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&a_full[s], 128);
+      mbar_init(&a_empty[s], 1);
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 4);
+    }
+    mbar_init(w_full, 128);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ===================== producers =====================
+    const int kq4 = K >> 2;  // float4 per row
+    for (int idx = tid; idx < N * kq4; idx += 128) {
+      int n = idx / kq4, k = (idx % kq4) << 2;
+      float4 v = ldg4(p.Bw + (long long)n * p.ldb + k);
+      split_store(smem + L.w_hi, smem + L.w_lo, sw128_off(n, k, N), v);
+    }
+    fence_proxy_async();
+    mbar_arrive(w_full);
+    int it = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      const int s = it % stages;
+      const uint32_t ph = (uint32_t)(it / stages) & 1u;
+      mbar_wait(&a_empty[s], ph ^ 1u);
+      const int row0 = t * TC_BM;
+      for (int idx = tid; idx < TC_BM * kq4; idx += 128) {
+        int r = idx / kq4, k = (idx % kq4) << 2;
+        float4 v = load_operand4<AMODE>(p.A, row0 + r, k, M, K);
+        split_store(smem + L.a_hi[s], smem + L.a_lo[s], sw128_off(r, k, TC_BM), v);
+      }
+      fence_proxy_async();
+      mbar_arrive(&a_full[s]);
+    }
+  } else if (warp == 4) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 (1<<4), a=b=TF32 (2<<7, 2<<10), K-major A and B,
+      // N>>3 at bit 17, M>>4 at bit 24
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      const uint32_t sbase = smem_u32(smem);
+      mbar_wait(w_full, 0);
+      tc_fence_after();
+      int it = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const int s = it % stages, b = it & 1;
+        const uint32_t ph = (uint32_t)(it / stages) & 1u, bph = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(&acc_empty[b], bph ^ 1u);
+        mbar_wait(&a_full[s], ph);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(b * N);
+        uint32_t acc = 0;
+        for (int kb = 0; kb < (K >> 5); ++kb) {
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t aoff = (uint32_t)(kb * TC_BM * 128 + ks * 32), boff = (uint32_t)(kb * N * 128 + ks * 32);
+            const uint64_t a_hi = make_desc(sbase + L.a_hi[s] + aoff), a_lo = make_desc(sbase + L.a_lo[s] + aoff);
+            const uint64_t b_hi = make_desc(sbase + L.w_hi + boff), b_lo = make_desc(sbase + L.w_lo + boff);
+            umma_tf32(d_tmem, a_lo, b_hi, idesc, acc);
+            umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
+            umma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
+            acc = 1u;
+          }
+        }
+        umma_commit(&a_empty[s]);   // smem stage may be refilled once these MMAs have read it
+        umma_commit(&acc_full[b]);  // accumulator ready for the epilogue
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    float* stage = reinterpret_cast<float*>(smem + L.stage_buf) + (warp - 5) * 32 * 33;
+    const bool do_stats = (p.stats != nullptr);
+    float s0[8], s1[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) s0[c] = s1[c] = 0.f;
+    int it = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      const int b = it & 1;
+      const uint32_t bph = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(&acc_full[b], bph);
+      tc_fence_after();
+      const int row_base = t * TC_BM + q * 32;
+#pragma unroll
+      for (int cb = 0; cb < 8; ++cb) {
+        if (cb * 32 < N) {
+          float r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * N + cb * 32), r);
+#pragma unroll
+          for (int c = 0; c < 32; ++c) stage[lane * 33 + c] = r[c];
+          __syncwarp();
+          const int col = cb * 32 + lane;
+          if (col < N) {
+            float bias = 0.f, psc = 1.f, psh = 0.f, pmu = 0.f, prs = 0.f;
+            if (EMODE == EPI_STORE) {
+              if (p.bias) bias = p.bias[col];
+            } else {
+              if (p.psc) {
+                psc = p.psc[col];
+                psh = p.psh[col];
+              }
+              if (do_stats) {
+                pmu = p.pmean[col];
+                prs = p.prstd[col];
+              }
+            }
+            float a0 = 0.f, a1 = 0.f;
+            for (int rr = 0; rr < 32; ++rr) {
+              const int row = row_base + rr;
+              if (row < M) {
+                float v = stage[rr * 33 + lane];
+                if (EMODE == EPI_STORE) {
+                  v += bias;
+                  if (p.relu) v = fmaxf(v, 0.f);
+                  p.C[(long long)row * p.ldc + col] = v;
+                  if (do_stats) {
+                    const float w = p.srw ? p.srw[row] : 1.f;
+                    a0 = fmaf(w, v, a0);
+                    a1 = fmaf(w * v, v, a1);
+                  }
+                } else {
+                  const float yp = p.Yprev[(long long)row * p.ldyp + col];
+                  const float z = p.psc ? fmaf(yp, psc, psh) : yp;
+                  v = z > 0.f ? v : 0.f;
+                  p.C[(long long)row * p.ldc + col] = v;
+                  if (do_stats) {
+                    a0 += v;
+                    a1 = fmaf(v, (yp - pmu) * prs, a1);
+                  }
+                }
+              }
+            }
+            s0[cb] += a0;
+            s1[cb] += a1;
+          }
+          __syncwarp();
+        }
+      }
+      tc_fence_before();
+      if (lane == 0) mbar_arrive(&acc_empty[b]);
+    }
+    if (do_stats) {
+#pragma unroll
+      for (int cb = 0; cb < 8; ++cb) {
+        const int col = cb * 32 + lane;
+        if (col < N) {
+          stat_comb[(warp - 5) * 256 + col] = s0[cb];
+          stat_comb[1024 + (warp - 5) * 256 + col] = s1[cb];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (p.stats) {
+    for (int c = tid; c < N; c += TC_THREADS) {
+      float a0 = stat_comb[c] + stat_comb[256 + c] + stat_comb[512 + c] + stat_comb[768 + c];
+      float a1 = stat_comb[1024 + c] + stat_comb[1280 + c] + stat_comb[1536 + c] + stat_comb[1792 + c];
+      p.stats[(long long)blockIdx.x * 2 * N + c] = a0;
+      p.stats[(long long)blockIdx.x * 2 * N + N + c] = a1;
+    }
+    for (int slot = blockIdx.x + gridDim.x; slot < GADDPG_STAT_SLOTS; slot += gridDim.x)
+      for (int c = tid; c < 2 * N; c += TC_THREADS) p.stats[(long long)slot * 2 * N + c] = 0.f;
+  }
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+}  // namespace
+
+// Shapes the tensor-core kernel takes; everything else stays on the FP32 FFMA kernel of gemm_rows.cu.
+bool gaddpg_tc_gemm_supported(const NTProblem& p, int amode, int emode) {
+  if (p.M_max < 8192) return false;  // small problems are latency bound either way
+  if (p.K % 32 != 0 || p.K < 32 || p.K > 128) return false;
+  if (p.N % 16 != 0 || p.N < 16 || p.N > 256) return false;
+  if (p.ldb != p.K) {
+    if (p.ldb % 4 != 0) return false;
+  }
+  int stages = (p.K <= 64) ? 2 : 1;
+  if (tc_layout(p.N, p.K, stages).total + 1024 > 227 * 1024) return false;
+  (void)amode;
+  (void)emode;
+  return true;
+}
+
+int gaddpg_tc_gemm_nt_impl(const NTProblem* p, int amode, int emode, void* stream) {
+  const int stages = (p->K <= 64) ? 2 : 1;
+  const TcSmemLayout L = tc_layout(p->N, p->K, stages);
+  const size_t smem = L.total + 1024;  // slack for the 1024-byte alignment of the operand regions
+  int tiles = ceil_div(p->M_max, TC_BM);
+  int grid = tiles < gaddpg_sm_count() ? tiles : gaddpg_sm_count();
+  cudaStream_t st = (cudaStream_t)stream;
+#define TC_CASE(A, E)                                                                                          \
+  if (amode == A && emode == E) {                                                                              \
+    auto kern = tc_gemm_nt_kernel<A, E>;                                                                       \
+    GADDPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
+    kern<<<grid, TC_THREADS, smem, st>>>(*p, stages);                                                          \
+    GADDPG_CHECK_LAUNCH("tc_gemm_nt_kernel");                                                                  \
+    return GADDPG_OK;                                                                                          \
+  }
+  TC_CASE(OP_PLAIN, EPI_STORE)
+  TC_CASE(OP_BNRELU, EPI_STORE)
+  TC_CASE(OP_BNBWD, EPI_DMASK)
+  TC_CASE(OP_BNBWD, EPI_STORE)
+  TC_CASE(OP_PLAIN, EPI_DMASK)
+#undef TC_CASE
+  gaddpg_set_error("tc_gemm_nt: unsupported mode pair (%d,%d)", amode, emode);
+  return GADDPG_ERR_UNSUPPORTED;
+}

@@ -134,6 +134,10 @@ typedef struct gaddpg_tn_problem {
 /* sizeof() of the three structs above, for binding self-checks */
 GADDPG_API int gaddpg_struct_sizes(int* operand, int* nt_problem, int* tn_problem);
 
+/* Wide layers (M >= 8192 rows, K in {32,64,96,128}, N <= 256) run on tcgen05 tensor cores with a 3xTF32 split
+ * (FP32-level accuracy); 0 forces every NT product onto the FP32 FFMA kernel (also: env GADDPG_TC=0). */
+GADDPG_API int gaddpg_set_tensor_core(int enable);
+GADDPG_API int gaddpg_get_tensor_core(void);
 /* up to GADDPG_MAX_GROUP independent NT problems in one launch (blockIdx.y = problem) */
 GADDPG_API int gaddpg_gemm_nt(const gaddpg_nt_group* group, int nprob, int amode, int emode, void* stream);
 /* dW[n][(k+rot) % Ktrue] (+)= TN product for n < Ntrue (rows >= Ntrue and columns >= Ktrue are padding);
