@@ -157,12 +157,47 @@ __host__ __device__ inline TcSmemLayout tc_layout(int N, int K, int stages) {
   return L;
 }
 
-template <int AMODE, int EMODE>
+// per-column prologue constants: each producer thread always serves the same 4 columns, so they live in registers
+template <int MODE>
+struct ColConsts {
+  float4 c0, c1, c2, c3, c4;
+  __device__ __forceinline__ void load(const Operand& d, int col) {
+    if (MODE == OP_BNRELU) {
+      c0 = ldg4(d.c0 + col);
+      c1 = ldg4(d.c1 + col);
+    } else if (MODE == OP_BNBWD) {
+      c0 = ldg4(d.c0 + col);
+      c1 = ldg4(d.c1 + col);
+      c2 = ldg4(d.c2 + col);
+      c3 = ldg4(d.c3 + col);
+      c4 = ldg4(d.c4 + col);
+    }
+  }
+  __device__ __forceinline__ float4 apply(float4 x, float4 y, float w) const {
+    float4 r;
+    if (MODE == OP_PLAIN) {
+      r = x;
+    } else if (MODE == OP_BNRELU) {
+      r.x = fmaxf(fmaf(x.x, c0.x, c1.x), 0.f);
+      r.y = fmaxf(fmaf(x.y, c0.y, c1.y), 0.f);
+      r.z = fmaxf(fmaf(x.z, c0.z, c1.z), 0.f);
+      r.w = fmaxf(fmaf(x.w, c0.w, c1.w), 0.f);
+    } else {
+      r.x = c0.x * (x.x - w * (c1.x + (y.x - c3.x) * c4.x * c2.x));
+      r.y = c0.y * (x.y - w * (c1.y + (y.y - c3.y) * c4.y * c2.y));
+      r.z = c0.z * (x.z - w * (c1.z + (y.z - c3.z) * c4.z * c2.z));
+      r.w = c0.w * (x.w - w * (c1.w + (y.w - c3.w) * c4.w * c2.w));
+    }
+    return r;
+  }
+};
+
+template <int K, int AMODE, int EMODE>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProblem p, int stages) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // SWIZZLE_128B operands need 1024-byte aligned bases (the host adds 1024 bytes of slack)
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int N = p.N, K = p.K;
+  const int N = p.N;
   const TcSmemLayout L = tc_layout(N, K, stages);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint64_t* a_full = bars;           // [2]
@@ -197,24 +232,53 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
 
   if (warp < 4) {
     // ===================== producers =====================
-    const int kq4 = K >> 2;  // float4 per row
-    for (int idx = tid; idx < N * kq4; idx += 128) {
-      int n = idx / kq4, k = (idx % kq4) << 2;
+    constexpr int KQ4 = K / 4;        // float4 per row
+    constexpr int RPI = 128 / KQ4;    // rows covered by the 128 producer threads per iteration
+    constexpr int ITERS = TC_BM / RPI;
+    constexpr int U = 8;              // loads in flight per thread
+    static_assert(128 % KQ4 == 0 && ITERS % U == 0, "K must be 32, 64 or 128");
+    for (int idx = tid; idx < N * KQ4; idx += 128) {
+      int n = idx / KQ4, k = (idx % KQ4) << 2;
       float4 v = ldg4(p.Bw + (long long)n * p.ldb + k);
       split_store(smem + L.w_hi, smem + L.w_lo, sw128_off(n, k, N), v);
     }
     fence_proxy_async();
     mbar_arrive(w_full);
+    const int kcol = (tid % KQ4) << 2, rsub = tid / KQ4;
+    ColConsts<AMODE> cc;
+    cc.load(p.A, kcol);
     int it = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
       const int s = it % stages;
       const uint32_t ph = (uint32_t)(it / stages) & 1u;
       mbar_wait(&a_empty[s], ph ^ 1u);
       const int row0 = t * TC_BM;
-      for (int idx = tid; idx < TC_BM * kq4; idx += 128) {
-        int r = idx / kq4, k = (idx % kq4) << 2;
-        float4 v = load_operand4<AMODE>(p.A, row0 + r, k, M, K);
-        split_store(smem + L.a_hi[s], smem + L.a_lo[s], sw128_off(r, k, TC_BM), v);
+      unsigned char* ah = smem + L.a_hi[s];
+      unsigned char* al = smem + L.a_lo[s];
+#pragma unroll 1
+      for (int i0 = 0; i0 < ITERS; i0 += U) {
+        float4 x[U], y[U];
+        float w[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int r = rsub + (i0 + u) * RPI, row = row0 + r;
+          x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          y[u] = x[u];
+          w[u] = 1.f;
+          if (row < M) {
+            x[u] = ldg4(p.A.X + (long long)row * p.A.ldx + kcol);
+            if (AMODE == OP_BNBWD) {
+              y[u] = ldg4(p.A.Y + (long long)row * p.A.ldy + kcol);
+              if (p.A.rw) w[u] = p.A.rw[row];
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int r = rsub + (i0 + u) * RPI;
+          float4 v = (row0 + r < M) ? cc.apply(x[u], y[u], w[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+          split_store(ah, al, sw128_off(r, kcol, TC_BM), v);
+        }
       }
       fence_proxy_async();
       mbar_arrive(&a_full[s]);
@@ -237,7 +301,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(b * N);
         uint32_t acc = 0;
+#pragma unroll
         for (int kb = 0; kb < (K >> 5); ++kb) {
+#pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const uint32_t aoff = (uint32_t)(kb * TC_BM * 128 + ks * 32), boff = (uint32_t)(kb * N * 128 + ks * 32);
             const uint64_t a_hi = make_desc(sbase + L.a_hi[s] + aoff), a_lo = make_desc(sbase + L.a_lo[s] + aoff);
@@ -265,20 +331,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
       const int b = it & 1;
       const uint32_t bph = (uint32_t)(it >> 1) & 1u;
+      const int row_base = t * TC_BM + q * 32;
+      // row weight of "my" row (lane = row), broadcast by shuffle inside the row loop
+      float wrow = 1.f;
+      if (EMODE == EPI_STORE && do_stats && p.srw) wrow = (row_base + lane < M) ? p.srw[row_base + lane] : 0.f;
       mbar_wait(&acc_full[b], bph);
       tc_fence_after();
-      const int row_base = t * TC_BM + q * 32;
 #pragma unroll
       for (int cb = 0; cb < 8; ++cb) {
         if (cb * 32 < N) {
+          const int col = cb * 32 + lane;
+          const bool cval = col < N;
+          float yp[32];
+          if (EMODE == EPI_DMASK) {  // issue all mask-source loads of this 32x32 block before touching TMEM
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr)
+              yp[rr] = (cval && row_base + rr < M) ? p.Yprev[(long long)(row_base + rr) * p.ldyp + col] : 0.f;
+          }
           float r[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * N + cb * 32), r);
 #pragma unroll
           for (int c = 0; c < 32; ++c) stage[lane * 33 + c] = r[c];
           __syncwarp();
-          const int col = cb * 32 + lane;
-          if (col < N) {
-            float bias = 0.f, psc = 1.f, psh = 0.f, pmu = 0.f, prs = 0.f;
+          float bias = 0.f, psc = 1.f, psh = 0.f, pmu = 0.f, prs = 0.f;
+          if (cval) {
             if (EMODE == EPI_STORE) {
               if (p.bias) bias = p.bias[col];
             } else {
@@ -291,35 +367,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
                 prs = p.prstd[col];
               }
             }
-            float a0 = 0.f, a1 = 0.f;
-            for (int rr = 0; rr < 32; ++rr) {
-              const int row = row_base + rr;
-              if (row < M) {
-                float v = stage[rr * 33 + lane];
-                if (EMODE == EPI_STORE) {
-                  v += bias;
-                  if (p.relu) v = fmaxf(v, 0.f);
-                  p.C[(long long)row * p.ldc + col] = v;
-                  if (do_stats) {
-                    const float w = p.srw ? p.srw[row] : 1.f;
-                    a0 = fmaf(w, v, a0);
-                    a1 = fmaf(w * v, v, a1);
-                  }
-                } else {
-                  const float yp = p.Yprev[(long long)row * p.ldyp + col];
-                  const float z = p.psc ? fmaf(yp, psc, psh) : yp;
-                  v = z > 0.f ? v : 0.f;
-                  p.C[(long long)row * p.ldc + col] = v;
-                  if (do_stats) {
-                    a0 += v;
-                    a1 = fmaf(v, (yp - pmu) * prs, a1);
-                  }
-                }
+          }
+          float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) {
+            const int row = row_base + rr;
+            float v = stage[rr * 33 + lane];
+            const float w = __shfl_sync(0xffffffffu, wrow, rr);
+            if (cval && row < M) {
+              if (EMODE == EPI_STORE) {
+                v += bias;
+                if (p.relu) v = fmaxf(v, 0.f);
+                p.C[(long long)row * p.ldc + col] = v;
+                a0 = fmaf(w, v, a0);
+                a1 = fmaf(w * v, v, a1);
+              } else {
+                const float z = p.psc ? fmaf(yp[rr], psc, psh) : yp[rr];
+                v = z > 0.f ? v : 0.f;
+                p.C[(long long)row * p.ldc + col] = v;
+                a0 += v;
+                a1 = fmaf(v, (yp[rr] - pmu) * prs, a1);
               }
             }
-            s0[cb] += a0;
-            s1[cb] += a1;
           }
+          s0[cb] += a0;
+          s1[cb] += a1;
           __syncwarp();
         }
       }
@@ -360,7 +432,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
 // Shapes the tensor-core kernel takes; everything else stays on the FP32 FFMA kernel of gemm_rows.cu.
 bool gaddpg_tc_gemm_supported(const NTProblem& p, int amode, int emode) {
   if (p.M_max < 8192) return false;  // small problems are latency bound either way
-  if (p.K % 32 != 0 || p.K < 32 || p.K > 128) return false;
+  if (p.K != 32 && p.K != 64 && p.K != 128) return false;
   if (p.N % 16 != 0 || p.N < 16 || p.N > 256) return false;
   if (p.ldb != p.K) {
     if (p.ldb % 4 != 0) return false;
@@ -379,13 +451,19 @@ int gaddpg_tc_gemm_nt_impl(const NTProblem* p, int amode, int emode, void* strea
   int tiles = ceil_div(p->M_max, TC_BM);
   int grid = tiles < gaddpg_sm_count() ? tiles : gaddpg_sm_count();
   cudaStream_t st = (cudaStream_t)stream;
-#define TC_CASE(A, E)                                                                                          \
-  if (amode == A && emode == E) {                                                                              \
-    auto kern = tc_gemm_nt_kernel<A, E>;                                                                       \
+#define TC_LAUNCH(KK, A, E)                                                                                    \
+  {                                                                                                            \
+    auto kern = tc_gemm_nt_kernel<KK, A, E>;                                                                   \
     GADDPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
     kern<<<grid, TC_THREADS, smem, st>>>(*p, stages);                                                          \
     GADDPG_CHECK_LAUNCH("tc_gemm_nt_kernel");                                                                  \
     return GADDPG_OK;                                                                                          \
+  }
+#define TC_CASE(A, E)                                                                                          \
+  if (amode == A && emode == E) {                                                                              \
+    if (p->K == 32) TC_LAUNCH(32, A, E)                                                                        \
+    if (p->K == 64) TC_LAUNCH(64, A, E)                                                                        \
+    if (p->K == 128) TC_LAUNCH(128, A, E)                                                                      \
   }
   TC_CASE(OP_PLAIN, EPI_STORE)
   TC_CASE(OP_BNRELU, EPI_STORE)
@@ -393,6 +471,7 @@ int gaddpg_tc_gemm_nt_impl(const NTProblem* p, int amode, int emode, void* strea
   TC_CASE(OP_BNBWD, EPI_STORE)
   TC_CASE(OP_PLAIN, EPI_DMASK)
 #undef TC_CASE
+#undef TC_LAUNCH
   gaddpg_set_error("tc_gemm_nt: unsupported mode pair (%d,%d)", amode, emode);
   return GADDPG_ERR_UNSUPPORTED;
 }
