@@ -212,71 +212,78 @@ __global__ void __launch_bounds__(256, GADDPG_NT_MINB) gemm_nt_kernel(const NTGr
 // TN: partial[s][N][K] = sum over the rows of split s of pro1(P)[r,:]^T pro2(Q)[r,:]; optional column
 // sums of pro1(P) (bias gradients).  Output tile 128x128 (or 64x64), 256 threads, 8x8 (4x4) per thread.
 // ------------------------------------------------------------------------------------------------
-template <int BT, int TT, int PMODE, int QMODE>
+template <int BTN, int BTK, int PMODE, int QMODE>
 __global__ void __launch_bounds__(256) gemm_tn_kernel(const TNProblem p, float* __restrict__ partial,
                                                       float* __restrict__ partial_bias, int splits) {
-  constexpr int BR = 16;              // rows per staged chunk
-  constexpr int H = TT / 2;           // each thread owns two runs of H consecutive outputs per dimension
-  static_assert(16 * TT == BT, "16x16 threads");
-  __shared__ __align__(16) float Ps[BR * BT];
-  __shared__ __align__(16) float Qs[BR * BT];
+  constexpr int BR = 16;                        // rows per staged chunk
+  constexpr int TN_ = BTN / 16, TK_ = BTK / 16;  // outputs per thread in each dimension (two runs of H each)
+  constexpr int HN = TN_ / 2, HK = TK_ / 2;
+  static_assert(BTN % 32 == 0 && BTK % 32 == 0, "16x16 threads, two runs per dimension");
+  __shared__ __align__(16) float Ps[BR * BTN];
+  __shared__ __align__(16) float Qs[BR * BTK];
   const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
   int M = p.M_dev ? *p.M_dev : p.M_max;
   M = M < p.M_max ? M : p.M_max;
   const int N = p.N, K = p.K;
-  const int tiles_k = (K + BT - 1) / BT;
+  const int tiles_k = (K + BTK - 1) / BTK;
   const int tile = blockIdx.x, split = blockIdx.y;
-  const int n0 = (tile / tiles_k) * BT, k0 = (tile % tiles_k) * BT;
+  const int n0 = (tile / tiles_k) * BTN, k0 = (tile % tiles_k) * BTK;
   const bool want_bias = (partial_bias != nullptr) && (tile % tiles_k == 0);
 
-  float acc[TT][TT];
-  float bsum[TT];
+  float acc[TN_][TK_];
+  float bsum[TN_];
 #pragma unroll
-  for (int i = 0; i < TT; ++i) {
+  for (int i = 0; i < TN_; ++i) {
     bsum[i] = 0.f;
 #pragma unroll
-    for (int j = 0; j < TT; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < TK_; ++j) acc[i][j] = 0.f;
   }
   const int nchunks = (M + BR - 1) / BR;
-  constexpr int LD4 = (BR * BT / 4 + 255) / 256;
-  float4 rp[LD4], rq[LD4];
+  constexpr int LDP = (BR * BTN / 4 + 255) / 256, LDQ = (BR * BTK / 4 + 255) / 256;
+  float4 rp[LDP], rq[LDQ];
   auto fetch = [&](int ch) {
 #pragma unroll
-    for (int i = 0; i < LD4; ++i) {
+    for (int i = 0; i < LDP; ++i) {
       int f = tid + 256 * i;
-      int r = f / (BT / 4), c = (f % (BT / 4)) * 4;
-      bool ok = f < BR * BT / 4;
-      rp[i] = ok ? load_operand4<PMODE>(p.P, ch * BR + r, n0 + c, M, N) : make_float4(0.f, 0.f, 0.f, 0.f);
-      rq[i] = ok ? load_operand4<QMODE>(p.Q, ch * BR + r, k0 + c, M, K) : make_float4(0.f, 0.f, 0.f, 0.f);
+      int r = f / (BTN / 4), c = (f % (BTN / 4)) * 4;
+      rp[i] = (f < BR * BTN / 4) ? load_operand4<PMODE>(p.P, ch * BR + r, n0 + c, M, N) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < LDQ; ++i) {
+      int f = tid + 256 * i;
+      int r = f / (BTK / 4), c = (f % (BTK / 4)) * 4;
+      rq[i] = (f < BR * BTK / 4) ? load_operand4<QMODE>(p.Q, ch * BR + r, k0 + c, M, K) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
   int ch = split;
   if (ch < nchunks) fetch(ch);
   for (; ch < nchunks; ch += splits) {
 #pragma unroll
-    for (int i = 0; i < LD4; ++i) {
+    for (int i = 0; i < LDP; ++i) {
       int f = tid + 256 * i;
-      if (f < BR * BT / 4) {
-        *reinterpret_cast<float4*>(Ps + f * 4) = rp[i];
-        *reinterpret_cast<float4*>(Qs + f * 4) = rq[i];
-      }
+      if (f < BR * BTN / 4) *reinterpret_cast<float4*>(Ps + f * 4) = rp[i];
+    }
+#pragma unroll
+    for (int i = 0; i < LDQ; ++i) {
+      int f = tid + 256 * i;
+      if (f < BR * BTK / 4) *reinterpret_cast<float4*>(Qs + f * 4) = rq[i];
     }
     __syncthreads();
     if (ch + splits < nchunks) fetch(ch + splits);
 #pragma unroll
     for (int r = 0; r < BR; ++r) {
-      float a[TT], b[TT];
+      float a[TN_], b[TK_];
 #pragma unroll
-      for (int h = 0; h < 2; ++h)
+      for (int h = 0; h < 2; ++h) {
 #pragma unroll
-        for (int e = 0; e < H; ++e) {
-          a[h * H + e] = Ps[r * BT + h * (BT / 2) + ty * H + e];
-          b[h * H + e] = Qs[r * BT + h * (BT / 2) + tx * H + e];
-        }
+        for (int e = 0; e < HN; ++e) a[h * HN + e] = Ps[r * BTN + h * (BTN / 2) + ty * HN + e];
 #pragma unroll
-      for (int i = 0; i < TT; ++i) {
+        for (int e = 0; e < HK; ++e) b[h * HK + e] = Qs[r * BTK + h * (BTK / 2) + tx * HK + e];
+      }
 #pragma unroll
-        for (int j = 0; j < TT; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      for (int i = 0; i < TN_; ++i) {
+#pragma unroll
+        for (int j = 0; j < TK_; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
         bsum[i] += a[i];
       }
     }
@@ -284,12 +291,12 @@ __global__ void __launch_bounds__(256) gemm_tn_kernel(const TNProblem p, float* 
   }
   float* out = partial + (long long)split * N * K;
 #pragma unroll
-  for (int i = 0; i < TT; ++i) {
-    int n = n0 + (i / H) * (BT / 2) + ty * H + (i % H);
+  for (int i = 0; i < TN_; ++i) {
+    int n = n0 + (i / HN) * (BTN / 2) + ty * HN + (i % HN);
     if (n < N) {
 #pragma unroll
-      for (int j = 0; j < TT; ++j) {
-        int k = k0 + (j / H) * (BT / 2) + tx * H + (j % H);
+      for (int j = 0; j < TK_; ++j) {
+        int k = k0 + (j / HK) * (BTK / 2) + tx * HK + (j % HK);
         if (k < K) out[(long long)n * K + k] = acc[i][j];
       }
       if (want_bias && tx == 0) partial_bias[(long long)split * N + n] = bsum[i];
@@ -297,18 +304,34 @@ __global__ void __launch_bounds__(256) gemm_tn_kernel(const TNProblem p, float* 
   }
 }
 
-// dst[n][(k+rot) % Ktrue] (+)= sum_s partial[s][n][k]   for k < Ktrue   (fixed summation order)
-__global__ void tn_reduce_kernel(const float* __restrict__ partial, int splits, int N, int Ntrue, int K, int Ktrue, int rot,
-                                 float* __restrict__ dst, int ldd, int accumulate, float scale) {
-  long long total = (long long)Ntrue * Ktrue;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    int n = (int)(e / Ktrue), k = (int)(e % Ktrue);
+// dst[n][(k+rot) % Ktrue] (+)= sum_s partial[s][n][k]   for k < Ktrue.  Block = 32 outputs x 8 split lanes: lane g
+// sums splits g, g+8, ... (coalesced over the 32 outputs), then the 8 lane sums are added in a fixed order.
+__global__ void __launch_bounds__(256) tn_reduce_kernel(const float* __restrict__ partial, int splits, int N, int Ntrue, int K,
+                                                        int Ktrue, int rot, float* __restrict__ dst, int ldd, int accumulate,
+                                                        float scale) {
+  __shared__ float red[8][33];
+  const int ox = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const long long total = (long long)Ntrue * Ktrue;
+  for (long long e0 = (long long)blockIdx.x * 32; e0 < total; e0 += (long long)gridDim.x * 32) {
+    const long long e = e0 + ox;
     float s = 0.f;
-    for (int sp = 0; sp < splits; ++sp) s += partial[((long long)sp * N + n) * K + k];
-    int kd = k + rot;
-    if (kd >= Ktrue) kd -= Ktrue;
-    float* d = dst + (long long)n * ldd + kd;
-    *d = (accumulate ? *d : 0.f) + s * scale;
+    int n = 0, k = 0;
+    if (e < total) {
+      n = (int)(e / Ktrue);
+      k = (int)(e % Ktrue);
+      const float* src = partial + (long long)n * K + k;
+      for (int sp = g; sp < splits; sp += 8) s += src[(long long)sp * N * K];
+    }
+    red[g][ox] = s;
+    __syncthreads();
+    if (g == 0 && e < total) {
+      float t = ((red[0][ox] + red[1][ox]) + (red[2][ox] + red[3][ox])) + ((red[4][ox] + red[5][ox]) + (red[6][ox] + red[7][ox]));
+      int kd = k + rot;
+      if (kd >= Ktrue) kd -= Ktrue;
+      float* d = dst + (long long)n * ldd + kd;
+      *d = (accumulate ? *d : 0.f) + t * scale;
+    }
+    __syncthreads();
   }
 }
 __global__ void bias_reduce_kernel(const float* __restrict__ partial, int splits, int N, int Ntrue, float* __restrict__ dst,
@@ -324,28 +347,39 @@ __global__ void bias_reduce_kernel(const float* __restrict__ partial, int splits
 // forward: slots of (sum w*y, sum w*y^2) -> batch mean / biased var -> scale, shift (+ mean, rstd for
 // backward) and the running-stat update PyTorch performs (momentum 0.1, UNBIASED var, counter += 1;
 // torch.nn.BatchNorm2d defaults as instantiated by upstream build_shared_mlp / networks.py:86,89).
-__global__ void bn_finalize_fwd_kernel(const float* __restrict__ stats, int C, double count, const float* __restrict__ gamma,
-                                       const float* __restrict__ beta, float eps, float momentum,
-                                       float* __restrict__ running_mean, float* __restrict__ running_var,
-                                       long long* __restrict__ num_batches_tracked, int training,
-                                       float* __restrict__ scale, float* __restrict__ shift,
-                                       float* __restrict__ mean_out, float* __restrict__ rstd_out) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0 && training && num_batches_tracked) *num_batches_tracked += 1;
+// one warp per channel: lanes stride over the slots with FP64 partials, then a fixed-order shuffle tree
+__device__ __forceinline__ void slot_sums(const float* __restrict__ stats, int C, int c, int lane, double& s, double& q) {
+  s = 0.0;
+  q = 0.0;
+  for (int slot = lane; slot < GADDPG_STAT_SLOTS; slot += 32) {
+    s += (double)stats[(long long)slot * 2 * C + c];
+    q += (double)stats[(long long)slot * 2 * C + C + c];
+  }
+  s = warp_sum_d(s);
+  q = warp_sum_d(q);
+}
+
+__global__ void __launch_bounds__(256) bn_finalize_fwd_kernel(const float* __restrict__ stats, int C, double count,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              float eps, float momentum, float* __restrict__ running_mean,
+                                                              float* __restrict__ running_var,
+                                                              long long* __restrict__ num_batches_tracked, int training,
+                                                              float* __restrict__ scale, float* __restrict__ shift,
+                                                              float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (c == 0 && lane == 0 && training && num_batches_tracked) *num_batches_tracked += 1;
   if (c >= C) return;
   float mean, var;
   if (training) {
-    double s = 0.0, q = 0.0;
-    for (int slot = 0; slot < GADDPG_STAT_SLOTS; ++slot) {
-      s += (double)stats[(long long)slot * 2 * C + c];
-      q += (double)stats[(long long)slot * 2 * C + C + c];
-    }
+    double s, q;
+    slot_sums(stats, C, c, lane, s, q);
     double m = s / count;
     double v = q / count - m * m;
     if (v < 0.0) v = 0.0;
     mean = (float)m;
     var = (float)v;
-    if (running_mean) {
+    if (running_mean && lane == 0) {
       double unbiased = count > 1.0 ? v * (count / (count - 1.0)) : v;
       running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
       running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
@@ -354,6 +388,7 @@ __global__ void bn_finalize_fwd_kernel(const float* __restrict__ stats, int C, d
     mean = running_mean[c];
     var = running_var[c];
   }
+  if (lane != 0) return;
   float rstd = 1.0f / sqrtf(var + eps);
   float sc = gamma[c] * rstd;
   scale[c] = sc;
@@ -363,17 +398,17 @@ __global__ void bn_finalize_fwd_kernel(const float* __restrict__ stats, int C, d
 }
 
 // backward: slots of (sum D, sum D*xhat) -> m1, m2, g = gamma*rstd, and dgamma / dbeta
-__global__ void bn_finalize_bwd_kernel(const float* __restrict__ stats, int C, double count, const float* __restrict__ gamma,
-                                       const float* __restrict__ rstd, float* __restrict__ g, float* __restrict__ m1,
-                                       float* __restrict__ m2, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                       int accumulate) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) bn_finalize_bwd_kernel(const float* __restrict__ stats, int C, double count,
+                                                              const float* __restrict__ gamma, const float* __restrict__ rstd,
+                                                              float* __restrict__ g, float* __restrict__ m1,
+                                                              float* __restrict__ m2, float* __restrict__ dgamma,
+                                                              float* __restrict__ dbeta, int accumulate) {
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (c >= C) return;
-  double s = 0.0, q = 0.0;
-  for (int slot = 0; slot < GADDPG_STAT_SLOTS; ++slot) {
-    s += (double)stats[(long long)slot * 2 * C + c];
-    q += (double)stats[(long long)slot * 2 * C + C + c];
-  }
+  double s, q;
+  slot_sums(stats, C, c, lane, s, q);
+  if (lane != 0) return;
   m1[c] = (float)(s / count);
   m2[c] = (float)(q / count);
   g[c] = gamma[c] * rstd[c];
@@ -476,11 +511,10 @@ int gaddpg_gemm_tn_impl(const TNProblem* p, int pmode, int qmode, float* dW, int
   if (rc) return rc;
   if (p->M_max == 0) return GADDPG_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  const bool small = (p->N <= 64 && p->K <= 64);
-  const int BT = small ? 64 : 128;
-  int tiles = ceil_div(p->N, BT) * ceil_div(p->K, BT);
+  const int BTN = p->N <= 64 ? 64 : 128, BTK = p->K <= 64 ? 64 : 128;
+  int tiles = ceil_div(p->N, BTN) * ceil_div(p->K, BTK);
   int chunks = ceil_div(p->M_max, 16);
-  int splits = (2 * GADDPG_STAT_SLOTS) / tiles;
+  int splits = GADDPG_STAT_SLOTS / tiles;
   if (splits > chunks) splits = chunks;
   if (splits > 64 * 1024 / p->N) splits = 64 * 1024 / p->N;
   if (splits < 1) splits = 1;
@@ -492,10 +526,15 @@ int gaddpg_gemm_tn_impl(const TNProblem* p, int pmode, int qmode, float* dW, int
   dim3 grid(tiles, splits);
 #define TN_CASE(PM, QM)                                                                                         \
   if (pmode == PM && qmode == QM) {                                                                             \
-    if (small)                                                                                                  \
-      gemm_tn_kernel<64, 4, PM, QM><<<grid, 256, 0, st>>>(*p, ws, dbias ? ws_bias : nullptr, splits);           \
+    float* wb = dbias ? ws_bias : nullptr;                                                                      \
+    if (BTN == 64 && BTK == 64)                                                                                 \
+      gemm_tn_kernel<64, 64, PM, QM><<<grid, 256, 0, st>>>(*p, ws, wb, splits);                                 \
+    else if (BTN == 64)                                                                                         \
+      gemm_tn_kernel<64, 128, PM, QM><<<grid, 256, 0, st>>>(*p, ws, wb, splits);                                \
+    else if (BTK == 64)                                                                                         \
+      gemm_tn_kernel<128, 64, PM, QM><<<grid, 256, 0, st>>>(*p, ws, wb, splits);                                \
     else                                                                                                        \
-      gemm_tn_kernel<128, 8, PM, QM><<<grid, 256, 0, st>>>(*p, ws, dbias ? ws_bias : nullptr, splits);          \
+      gemm_tn_kernel<128, 128, PM, QM><<<grid, 256, 0, st>>>(*p, ws, wb, splits);                               \
   } else
   TN_CASE(OP_PLAIN, OP_PLAIN)
   TN_CASE(OP_PLAIN, OP_BNRELU)
@@ -507,7 +546,7 @@ int gaddpg_gemm_tn_impl(const TNProblem* p, int pmode, int qmode, float* dW, int
 #undef TN_CASE
   GADDPG_CHECK_LAUNCH("gemm_tn_kernel");
   long long total = (long long)Ntrue * Ktrue;
-  int rgrid = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+  int rgrid = (int)((total + 31) / 32 < 1184 ? (total + 31) / 32 : 1184);
   tn_reduce_kernel<<<rgrid, 256, 0, st>>>(ws, splits, p->N, Ntrue, p->K, Ktrue, rot, dW, ldd, accumulate, 1.0f);
   GADDPG_CHECK_LAUNCH("tn_reduce_kernel");
   if (dbias) {
@@ -523,7 +562,7 @@ int gaddpg_bn_finalize_fwd_impl(const float* stats, int C, double count, const f
   GADDPG_CHECK_ARG(C >= 1 && gamma && beta && scale && shift, "bn_finalize_fwd: null pointer");
   GADDPG_CHECK_ARG(training ? (stats != nullptr && count >= 1.0) : (running_mean && running_var),
                    "bn_finalize_fwd: missing statistics source");
-  bn_finalize_fwd_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(stats, C, count, gamma, beta, eps, momentum,
+  bn_finalize_fwd_kernel<<<ceil_div(C, 8), 256, 0, (cudaStream_t)stream>>>(stats, C, count, gamma, beta, eps, momentum,
                                                                             running_mean, running_var, nbt, training,
                                                                             scale, shift, mean_out, rstd_out);
   GADDPG_CHECK_LAUNCH("bn_finalize_fwd_kernel");
@@ -533,7 +572,7 @@ int gaddpg_bn_finalize_fwd_impl(const float* stats, int C, double count, const f
 int gaddpg_bn_finalize_bwd_impl(const float* stats, int C, double count, const float* gamma, const float* rstd, float* g,
                                 float* m1, float* m2, float* dgamma, float* dbeta, int accumulate, void* stream) {
   GADDPG_CHECK_ARG(C >= 1 && stats && gamma && rstd && g && m1 && m2 && count >= 1.0, "bn_finalize_bwd: bad argument");
-  bn_finalize_bwd_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(stats, C, count, gamma, rstd, g, m1, m2,
+  bn_finalize_bwd_kernel<<<ceil_div(C, 8), 256, 0, (cudaStream_t)stream>>>(stats, C, count, gamma, rstd, g, m1, m2,
                                                                             dgamma, dbeta, accumulate);
   GADDPG_CHECK_LAUNCH("bn_finalize_bwd_kernel");
   return GADDPG_OK;
