@@ -279,7 +279,7 @@ def profile(agent, devb, args):
     rows = sorted(tab.items(), key=lambda kv: -kv[1]["ms"])
     kernels = [dict(entry=k, ms_per_step=r["ms"] / 2, share=r["ms"] / total, calls_per_step=r["calls"] / 2,
                     tflops=(r["flops"] / (r["ms"] * 1e-3) / 1e12) if r["ms"] > 0 else 0.0,
-                    gbs=(r["bytes"] / (r["ms"] * 1e-3) / 1e9) if r["ms"] > 0 else 0.0) for k, r in rows[:12]]
+                    gbs=(r["bytes"] / (r["ms"] * 1e-3) / 1e9) if r["ms"] > 0 else 0.0) for k, r in rows[:60]]
     # group all row-GEMM launches: they are one kernel family and dominate the step
     fam = {"nt": dict(ms=0.0, flops=0.0, bytes=0.0, calls=0), "tn": dict(ms=0.0, flops=0.0, bytes=0.0, calls=0)}
     for k, r in tab.items():

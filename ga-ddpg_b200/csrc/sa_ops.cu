@@ -46,35 +46,55 @@ __global__ void __launch_bounds__(256) sa1_l1_fwd_kernel(const float* __restrict
   int M = M_dev ? *M_dev : M_max;
   M = M < M_max ? M : M_max;
   float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int r = blockIdx.x * 16 + rl; r < M; r += gridDim.x * 16) {
-    const int seg = row_seg[r], src = row_src[r];
-    const int b = seg / npoint;
-    const float* pc = cloud + (long long)b * cloud_sb + skip + src;
-    float in[SA1_KMAX];
+  constexpr int UR = 4;  // rows in flight per thread: indices -> cloud gathers -> FMAs, each stage issued for all UR rows
+  const int rstep = gridDim.x * 16;
+  for (int r0 = blockIdx.x * 16 + rl; r0 < M; r0 += rstep * UR) {
+    int seg[UR], src[UR];
 #pragma unroll
-    for (int k = 0; k < SA1_KMAX; ++k) in[k] = 0.f;
-#pragma unroll
-    for (int k = 0; k < SA1_KMAX - 3; ++k)
-      if (k < Cp) in[3 + k] = pc[(long long)k * cloud_sc];
-    in[0] = in[3] - ctr[(long long)seg * 3 + 0];
-    in[1] = in[4] - ctr[(long long)seg * 3 + 1];
-    in[2] = in[5] - ctr[(long long)seg * 3 + 2];
-    float4 o;
-    float* op = &o.x;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      float a = bcbias ? bcbias[(long long)b * SA1_CO + q * 4 + c] : 0.f;
-#pragma unroll
-      for (int k = 0; k < SA1_KMAX; ++k) a = fmaf(w[c][k], in[k], a);
-      op[c] = a;
+    for (int u = 0; u < UR; ++u) {
+      const int r = r0 + u * rstep;
+      seg[u] = r < M ? row_seg[r] : 0;
+      src[u] = r < M ? row_src[r] : 0;
     }
-    *reinterpret_cast<float4*>(Y + (long long)r * SA1_CO + q * 4) = o;
-    if (stats) {
-      const float rw = row_w[r];
+    float in[UR][SA1_KMAX];
+    float cx[UR][3], rwv[UR];
+#pragma unroll
+    for (int u = 0; u < UR; ++u) {
+      const int b = seg[u] / npoint;
+      const float* pc = cloud + (long long)b * cloud_sb + skip + src[u];
+#pragma unroll
+      for (int k = 0; k < SA1_KMAX; ++k) in[u][k] = 0.f;
+#pragma unroll
+      for (int k = 0; k < SA1_KMAX - 3; ++k)
+        if (k < Cp) in[u][3 + k] = pc[(long long)k * cloud_sc];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) cx[u][d] = ctr[(long long)seg[u] * 3 + d];
+      rwv[u] = (stats && r0 + u * rstep < M) ? row_w[r0 + u * rstep] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < UR; ++u) {
+      const int r = r0 + u * rstep;
+      if (r >= M) continue;
+      const int b = seg[u] / npoint;
+      in[u][0] = in[u][3] - cx[u][0];
+      in[u][1] = in[u][4] - cx[u][1];
+      in[u][2] = in[u][5] - cx[u][2];
+      float4 o;
+      float* op = &o.x;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        s0[c] = fmaf(rw, op[c], s0[c]);
-        s1[c] = fmaf(rw * op[c], op[c], s1[c]);
+        float a = bcbias ? bcbias[(long long)b * SA1_CO + q * 4 + c] : 0.f;
+#pragma unroll
+        for (int k = 0; k < SA1_KMAX; ++k) a = fmaf(w[c][k], in[u][k], a);
+        op[c] = a;
+      }
+      *reinterpret_cast<float4*>(Y + (long long)r * SA1_CO + q * 4) = o;
+      if (stats) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          s0[c] = fmaf(rwv[u], op[c], s0[c]);
+          s1[c] = fmaf(rwv[u] * op[c], op[c], s1[c]);
+        }
       }
     }
   }
@@ -125,24 +145,41 @@ __global__ void __launch_bounds__(256) sa1_l1_bwd_kernel(const float* __restrict
   float acc[SA1_KMAX];
 #pragma unroll
   for (int k = 0; k < SA1_KMAX; ++k) acc[k] = 0.f;
-  for (int r = blockIdx.x * 4 + rl; r < M; r += gridDim.x * 4) {
-    const int seg = row_seg[r], src = row_src[r];
-    const int b = seg / npoint;
-    const float* pc = cloud + (long long)b * cloud_sb + skip + src;
-    float in[SA1_KMAX];
+  constexpr int UR = 8;  // rows in flight per thread
+  const int rstep = gridDim.x * 4;
+  for (int r0 = blockIdx.x * 4 + rl; r0 < M; r0 += rstep * UR) {
+    int seg[UR], src[UR];
+    float d[UR], y[UR], rwv[UR];
 #pragma unroll
-    for (int k = 0; k < SA1_KMAX; ++k) in[k] = 0.f;
+    for (int u = 0; u < UR; ++u) {
+      const int r = r0 + u * rstep;
+      const bool ok = r < M;
+      seg[u] = ok ? row_seg[r] : 0;
+      src[u] = ok ? row_src[r] : 0;
+      d[u] = ok ? D[(long long)r * SA1_CO + n] : 0.f;
+      y[u] = ok ? Y[(long long)r * SA1_CO + n] : 0.f;
+      rwv[u] = ok ? row_w[r] : 0.f;
+    }
 #pragma unroll
-    for (int k = 0; k < SA1_KMAX - 3; ++k)
-      if (k < Cp) in[3 + k] = pc[(long long)k * cloud_sc];
-    in[0] = in[3] - ctr[(long long)seg * 3 + 0];
-    in[1] = in[4] - ctr[(long long)seg * 3 + 1];
-    in[2] = in[5] - ctr[(long long)seg * 3 + 2];
-    const float d = D[(long long)r * SA1_CO + n], y = Y[(long long)r * SA1_CO + n];
-    const float dy = gn * (d - row_w[r] * (m1n + (y - mun) * rsn * m2n));
-    if (dY_out) dY_out[(long long)r * SA1_CO + n] = dy;
+    for (int u = 0; u < UR; ++u) {
+      const int r = r0 + u * rstep;
+      if (r >= M) continue;
+      const int b = seg[u] / npoint;
+      const float* pc = cloud + (long long)b * cloud_sb + skip + src[u];
+      float in[SA1_KMAX];
 #pragma unroll
-    for (int k = 0; k < SA1_KMAX; ++k) acc[k] = fmaf(dy, in[k], acc[k]);
+      for (int k = 0; k < SA1_KMAX; ++k) in[k] = 0.f;
+#pragma unroll
+      for (int k = 0; k < SA1_KMAX - 3; ++k)
+        if (k < Cp) in[3 + k] = pc[(long long)k * cloud_sc];
+      in[0] = in[3] - ctr[(long long)seg[u] * 3 + 0];
+      in[1] = in[4] - ctr[(long long)seg[u] * 3 + 1];
+      in[2] = in[5] - ctr[(long long)seg[u] * 3 + 2];
+      const float dy = gn * (d[u] - rwv[u] * (m1n + (y[u] - mun) * rsn * m2n));
+      if (dY_out) dY_out[(long long)r * SA1_CO + n] = dy;
+#pragma unroll
+      for (int k = 0; k < SA1_KMAX; ++k) acc[k] = fmaf(dy, in[k], acc[k]);
+    }
   }
 #pragma unroll
   for (int k = 0; k < SA1_KMAX; ++k) red[(rl * SA1_CO + n) * SA1_KMAX + k] = acc[k];
@@ -277,47 +314,80 @@ __global__ void pool_fwd_kernel(const float* __restrict__ Y, int C, const float*
 }
 
 // D[r][c] = dOut[seg][c] if r is the arg-max row and the pooled value is > 0, else 0; BN-backward sums.
-// Block = 256 threads = 4 row lanes x 64 channels; persistent over (row chunk, channel block) pairs.
+// A thread owns 4 consecutive channels (float4) of a fixed channel group and walks rows; CL = C/4 lanes cover a row,
+// 256/CL rows are processed per pass and UR passes are in flight.  Per-thread partial sums are combined in a fixed
+// order at the end (one slot per CTA).
 __global__ void __launch_bounds__(256) pool_bwd_kernel(const float* __restrict__ dOut, int ldo, const float* __restrict__ out,
                                                        const int32_t* __restrict__ arg, const float* __restrict__ Y,
                                                        int C, const int32_t* __restrict__ row_seg, int fixed_len,
                                                        int M_max, const int* __restrict__ M_dev,
                                                        const float* __restrict__ mean, const float* __restrict__ rstd,
                                                        float* __restrict__ D, float* __restrict__ stats) {
-  extern __shared__ float sst[];  // 2*C running sums + 2*4*64 reduction scratch
-  float* red = sst + 2 * C;
-  const int tid = threadIdx.x, cl = tid & 63, rl = tid >> 6;
+  extern __shared__ float sst[];  // [256 threads][8] partial sums
+  const int tid = threadIdx.x;
   int M = M_dev ? *M_dev : M_max;
   M = M < M_max ? M : M_max;
-  for (int c = tid; c < 2 * C; c += 256) sst[c] = 0.f;
-  __syncthreads();
-  const int cblocks = C / 64, rchunks = (M + 63) / 64;
-  for (int t = blockIdx.x; t < rchunks * cblocks; t += gridDim.x) {
-    const int c = (t % cblocks) * 64 + cl, rbase = (t / cblocks) * 64;
-    const float mu = mean[c], rs = rstd[c];
-    float a0 = 0.f, a1 = 0.f;
-    for (int i = rl; i < 64; i += 4) {
-      int r = rbase + i;
-      if (r < M) {
-        int seg = row_seg ? row_seg[r] : r / fixed_len;
-        long long pe = (long long)seg * C + c;
-        float d = (arg[pe] == r && out[pe] > 0.f) ? dOut[(long long)seg * ldo + c] : 0.f;
-        D[(long long)r * C + c] = d;
-        a0 += d;
-        a1 = fmaf(d, (Y[(long long)r * C + c] - mu) * rs, a1);
+  const int CL = C >> 2;            // float4 lanes per row (C % 64 == 0 -> CL in {16,32,64,128,256})
+  const int cl = tid % CL, rl = tid / CL;
+  const int RPP = 256 / CL;         // rows per pass per CTA (CL <= 256)
+  float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
+  if (rl < RPP) {
+    const int c = cl << 2;
+    const float4 mu = *reinterpret_cast<const float4*>(mean + c), rs = *reinterpret_cast<const float4*>(rstd + c);
+    constexpr int UR = 4;
+    const int rstep = gridDim.x * RPP;
+    for (int r0 = blockIdx.x * RPP + rl; r0 < M; r0 += rstep * UR) {
+      int seg[UR];
+      float4 y[UR];
+#pragma unroll
+      for (int u = 0; u < UR; ++u) {
+        const int r = r0 + u * rstep;
+        seg[u] = r < M ? (row_seg ? row_seg[r] : r / fixed_len) : 0;
+        y[u] = r < M ? *reinterpret_cast<const float4*>(Y + (long long)r * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      int4 ag[UR];
+      float4 po[UR], dg[UR];
+#pragma unroll
+      for (int u = 0; u < UR; ++u) {
+        const long long pe = (long long)seg[u] * C + c;
+        ag[u] = *reinterpret_cast<const int4*>(arg + pe);
+        po[u] = *reinterpret_cast<const float4*>(out + pe);
+        dg[u] = *reinterpret_cast<const float4*>(dOut + (long long)seg[u] * ldo + c);
+      }
+#pragma unroll
+      for (int u = 0; u < UR; ++u) {
+        const int r = r0 + u * rstep;
+        if (r >= M) continue;
+        float4 d;
+        d.x = (ag[u].x == r && po[u].x > 0.f) ? dg[u].x : 0.f;
+        d.y = (ag[u].y == r && po[u].y > 0.f) ? dg[u].y : 0.f;
+        d.z = (ag[u].z == r && po[u].z > 0.f) ? dg[u].z : 0.f;
+        d.w = (ag[u].w == r && po[u].w > 0.f) ? dg[u].w : 0.f;
+        *reinterpret_cast<float4*>(D + (long long)r * C + c) = d;
+        a0[0] += d.x; a0[1] += d.y; a0[2] += d.z; a0[3] += d.w;
+        a1[0] = fmaf(d.x, (y[u].x - mu.x) * rs.x, a1[0]);
+        a1[1] = fmaf(d.y, (y[u].y - mu.y) * rs.y, a1[1]);
+        a1[2] = fmaf(d.z, (y[u].z - mu.z) * rs.z, a1[2]);
+        a1[3] = fmaf(d.w, (y[u].w - mu.w) * rs.w, a1[3]);
       }
     }
-    red[rl * 64 + cl] = a0;
-    red[256 + rl * 64 + cl] = a1;
-    __syncthreads();
-    if (tid < 64) {
-      sst[c] += red[cl] + red[64 + cl] + red[128 + cl] + red[192 + cl];
-      sst[C + c] += red[256 + cl] + red[320 + cl] + red[384 + cl] + red[448 + cl];
-    }
-    __syncthreads();
   }
-  for (int slot = blockIdx.x; slot < GADDPG_STAT_SLOTS; slot += gridDim.x)
-    for (int c = tid; c < 2 * C; c += 256) stats[(long long)slot * 2 * C + c] = (slot == (int)blockIdx.x) ? sst[c] : 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    sst[tid * 8 + i] = a0[i];
+    sst[tid * 8 + 4 + i] = a1[i];
+  }
+  __syncthreads();
+  // column c = 4*cl + i is held by threads (rl', cl) for rl' < RPP: sum them in rl' order
+  for (int e = tid; e < 2 * C; e += 256) {
+    const int which = e / C, c = e % C;
+    const int l = c >> 2, i = c & 3;
+    float v = 0.f;
+    for (int rr = 0; rr < RPP; ++rr) v += sst[(rr * CL + l) * 8 + which * 4 + i];
+    stats[(long long)blockIdx.x * 2 * C + e] = v;
+  }
+  for (int slot = blockIdx.x + gridDim.x; slot < GADDPG_STAT_SLOTS; slot += gridDim.x)
+    for (int e = tid; e < 2 * C; e += 256) stats[(long long)slot * 2 * C + e] = 0.f;
 }
 
 // feat[b][0:C] = relu(y*scale+shift), feat[b][C] = time[b], feat[b][C+1:ld] = 0
@@ -478,9 +548,11 @@ int gaddpg_pool_bwd_impl(const float* dOut, int ldo, const float* out, const int
   GADDPG_CHECK_ARG(dOut && out && arg && Y && mean && rstd && D && stats, "pool_bwd: null pointer");
   GADDPG_CHECK_ARG((C % 64) == 0 && C <= 1024 && ldo >= C && (row_seg || fixed_len >= 1), "pool_bwd: bad shape C=%d", C);
   if (M_max == 0) return GADDPG_OK;
-  int tiles = ceil_div(M_max, 64) * (C / 64);
+  GADDPG_CHECK_ARG(ldo % 4 == 0 && ((uintptr_t)dOut % 16) == 0, "pool_bwd: dOut must be 16-byte aligned with ld %% 4 == 0");
+  int rpp = 256 / (C / 4);
+  int tiles = ceil_div(M_max, rpp * 4);
   int grid = tiles < GADDPG_STAT_SLOTS ? tiles : GADDPG_STAT_SLOTS;
-  size_t smem = (2 * (size_t)C + 512) * sizeof(float);
+  size_t smem = 256 * 8 * sizeof(float);
   pool_bwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(dOut, ldo, out, arg, Y, C, row_seg, fixed_len, M_max, M_dev, mean, rstd,
                                                             D, stats);
   GADDPG_CHECK_LAUNCH("pool_bwd_kernel");

@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
     constexpr int KQ4 = K / 4;        // float4 per row
     constexpr int RPI = 128 / KQ4;    // rows covered by the 128 producer threads per iteration
     constexpr int ITERS = TC_BM / RPI;
-    constexpr int U = 8;              // loads in flight per thread
+    constexpr int U = (AMODE == OP_BNBWD) ? 4 : 8;  // row-iterations per pipeline unit (two register sets in flight)
     static_assert(128 % KQ4 == 0 && ITERS % U == 0, "K must be 32, 64 or 128");
     for (int idx = tid; idx < N * KQ4; idx += 128) {
       int n = idx / KQ4, k = (idx % KQ4) << 2;
@@ -247,41 +247,60 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
     const int kcol = (tid % KQ4) << 2, rsub = tid / KQ4;
     ColConsts<AMODE> cc;
     cc.load(p.A, kcol);
-    int it = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-      const int s = it % stages;
-      const uint32_t ph = (uint32_t)(it / stages) & 1u;
-      mbar_wait(&a_empty[s], ph ^ 1u);
-      const int row0 = t * TC_BM;
-      unsigned char* ah = smem + L.a_hi[s];
-      unsigned char* al = smem + L.a_lo[s];
-#pragma unroll 1
-      for (int i0 = 0; i0 < ITERS; i0 += U) {
-        float4 x[U], y[U];
-        float w[U];
+    // Software pipeline over "units" of U row-iterations: the global loads of unit u+1 are issued into a second
+    // register set before unit u is transformed and stored, so HBM latency overlaps the prologue math and the
+    // shared-memory stores (and runs ahead across tile boundaries, independent of the smem-stage barriers).
+    constexpr int UPT = ITERS / U;  // units per tile
+    struct Regs {
+      float4 x[U], y[U];
+      float w[U];
+    };
+    const int my_tiles = (ntiles > (int)blockIdx.x) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int total_units = my_tiles * UPT;
+    auto issue = [&](Regs& R, int u) {
+      const int it = u / UPT, i0 = (u % UPT) * U;
+      const int row0 = ((int)blockIdx.x + it * (int)gridDim.x) * TC_BM;
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int r = rsub + (i0 + u) * RPI, row = row0 + r;
-          x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          y[u] = x[u];
-          w[u] = 1.f;
-          if (row < M) {
-            x[u] = ldg4(p.A.X + (long long)row * p.A.ldx + kcol);
-            if (AMODE == OP_BNBWD) {
-              y[u] = ldg4(p.A.Y + (long long)row * p.A.ldy + kcol);
-              if (p.A.rw) w[u] = p.A.rw[row];
-            }
+      for (int k = 0; k < U; ++k) {
+        const int row = row0 + rsub + (i0 + k) * RPI;
+        R.x[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        R.y[k] = R.x[k];
+        R.w[k] = 1.f;
+        if (row < M) {
+          R.x[k] = ldg4(p.A.X + (long long)row * p.A.ldx + kcol);
+          if (AMODE == OP_BNBWD) {
+            R.y[k] = ldg4(p.A.Y + (long long)row * p.A.ldy + kcol);
+            if (p.A.rw) R.w[k] = p.A.rw[row];
           }
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int r = rsub + (i0 + u) * RPI;
-          float4 v = (row0 + r < M) ? cc.apply(x[u], y[u], w[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
-          split_store(ah, al, sw128_off(r, kcol, TC_BM), v);
-        }
       }
-      fence_proxy_async();
-      mbar_arrive(&a_full[s]);
+    };
+    auto process = [&](const Regs& R, int u) {
+      const int it = u / UPT, i0 = (u % UPT) * U;
+      const int s = it % stages;
+      const int row0 = ((int)blockIdx.x + it * (int)gridDim.x) * TC_BM;
+      if (i0 == 0) mbar_wait(&a_empty[s], ((uint32_t)(it / stages) & 1u) ^ 1u);
+      unsigned char* ah = smem + L.a_hi[s];
+      unsigned char* al = smem + L.a_lo[s];
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        const int r = rsub + (i0 + k) * RPI;
+        float4 v = (row0 + r < M) ? cc.apply(R.x[k], R.y[k], R.w[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        split_store(ah, al, sw128_off(r, kcol, TC_BM), v);
+      }
+      if (i0 + U == ITERS) {
+        fence_proxy_async();
+        mbar_arrive(&a_full[s]);
+      }
+    };
+    Regs RA, RB;
+    if (total_units > 0) issue(RA, 0);
+#pragma unroll 1
+    for (int u = 0; u < total_units; u += 2) {
+      if (u + 1 < total_units) issue(RB, u + 1);
+      process(RA, u);
+      if (u + 2 < total_units) issue(RA, u + 2);
+      if (u + 1 < total_units) process(RB, u + 1);
     }
   } else if (warp == 4) {
     // ===================== MMA issuer =====================
