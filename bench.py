@@ -264,6 +264,7 @@ def profile(agent, devb, args):
 
     pk = peaks()
     agent.use_graph = False
+    agent.world = None  # rank 0 profiles alone: no collectives in this leg (the other ranks wait at the barrier)
     prof = KernelProfile()
     with prof:
         for i in range(2):

@@ -315,7 +315,8 @@ class AgentB200:
             # stream without executing (torch.cuda.graph records, it does not run)
             graph = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
-            with torch.cuda.graph(graph):
+            # thread_local: the NCCL watchdog thread of a sharded run keeps polling CUDA events while we capture
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 fn()
             self._graphs[key] = graph
             g = graph
