@@ -74,6 +74,8 @@ class PointNetFeatureB200(nn.Module):
             if dev.type != "cuda":
                 raise RuntimeError("PointNetFeatureB200 runs on CUDA only (no CPU fallback)")
             ef = engine.EncoderFlat(mod, dev)
+            for prm in mod.parameters():
+                prm.grad = None  # autograd owns .grad in plug-in mode; the arena's grad region is kernel scratch
             ef.arena.gview_of = lambda p, A=ef.arena: A.g[(p.data_ptr() - A.p.data_ptr()) // 4: (p.data_ptr() - A.p.data_ptr()) // 4 + p.numel()].view(p.shape)
             self._flats[key] = ef
         return self._flats[key]
