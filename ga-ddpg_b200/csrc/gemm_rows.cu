@@ -453,11 +453,13 @@ int check_operand(const Operand& o, int mode, int W, const char* what) {
 }  // namespace
 
 static int g_tc_enabled = -1;
-void gaddpg_set_tensor_core_impl(int enable) { g_tc_enabled = enable ? 1 : 0; }
+// level: 0 = FP32 FFMA only; 1 = + resident-weight tcgen05 NT (tc_gemm.cu); 2 = + K-chunked tcgen05 NT; 3 = + tcgen05 TN
+// (default); 4 = like 3 but the K-chunked kernel also takes the shapes of the resident-weight kernel (A/B testing)
+void gaddpg_set_tensor_core_impl(int level) { g_tc_enabled = level < 0 ? 0 : (level > 4 ? 4 : level); }
 int gaddpg_get_tensor_core_impl() {
   if (g_tc_enabled < 0) {
     const char* e = getenv("GADDPG_TC");
-    g_tc_enabled = (e && e[0] == '0') ? 0 : 1;
+    g_tc_enabled = (e && e[0] >= '0' && e[0] <= '4') ? (e[0] - '0') : 3;
   }
   return g_tc_enabled;
 }
@@ -479,8 +481,11 @@ int gaddpg_gemm_nt_impl(const NTGroup* g, int nprob, int amode, int emode, void*
       GADDPG_CHECK_ARG(!p.psc || p.psh, "gemm_nt[%d]: psc without psh", i);
     }
   }
-  if (nprob == 1 && gaddpg_get_tensor_core_impl() && gaddpg_tc_gemm_supported(g->p[0], amode, emode))
+  if (nprob == 1 && gaddpg_get_tensor_core_impl() >= 1 && gaddpg_get_tensor_core_impl() <= 3 &&
+      gaddpg_tc_gemm_supported(g->p[0], amode, emode))
     return gaddpg_tc_gemm_nt_impl(&g->p[0], amode, emode, stream);  // tcgen05 3xTF32 path for the wide SA layers
+  if (nprob == 1 && gaddpg_get_tensor_core_impl() >= 2 && gaddpg_tc_nt_kc_supported(g->p[0], amode, emode))
+    return gaddpg_tc_nt_kc_impl(&g->p[0], amode, emode, stream);   // K-chunked tcgen05 path (SA2 / SA3 / FC / heads)
   cudaStream_t st = (cudaStream_t)stream;
 #define NT_CASE(A, E) \
   if (amode == A && emode == E) return launch_nt<A, E>(*g, nprob, st)
@@ -511,6 +516,22 @@ int gaddpg_gemm_tn_impl(const TNProblem* p, int pmode, int qmode, float* dW, int
   if (rc) return rc;
   if (p->M_max == 0) return GADDPG_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  if (gaddpg_get_tensor_core_impl() >= 3 && gaddpg_tc_tn_supported(*p, pmode, qmode)) {
+    GADDPG_CHECK_ARG(ws_bytes >= gaddpg_gemm_tn_workspace_bytes_impl(), "gemm_tn: workspace too small (%zu bytes given)", ws_bytes);
+    float* wsb = ws + (size_t)2 * GADDPG_STAT_SLOTS * 128 * 128;
+    int sp = 1;
+    rc = gaddpg_tc_tn_impl(p, pmode, qmode, ws, (size_t)2 * GADDPG_STAT_SLOTS * 128 * 128, dbias ? wsb : nullptr, &sp, stream);
+    if (rc) return rc;
+    long long tot = (long long)Ntrue * Ktrue;
+    int rg = (int)((tot + 31) / 32 < 1184 ? (tot + 31) / 32 : 1184);
+    tn_reduce_kernel<<<rg, 256, 0, st>>>(ws, sp, p->N, Ntrue, p->K, Ktrue, rot, dW, ldd, accumulate, 1.0f);
+    GADDPG_CHECK_LAUNCH("tn_reduce_kernel");
+    if (dbias) {
+      bias_reduce_kernel<<<ceil_div(Ntrue, 128), 128, 0, st>>>(wsb, sp, p->N, Ntrue, dbias, accumulate);
+      GADDPG_CHECK_LAUNCH("bias_reduce_kernel");
+    }
+    return GADDPG_OK;
+  }
   const int BTN = p->N <= 64 ? 64 : 128, BTK = p->K <= 64 ? 64 : 128;
   int tiles = ceil_div(p->N, BTN) * ceil_div(p->K, BTK);
   int chunks = ceil_div(p->M_max, 16);

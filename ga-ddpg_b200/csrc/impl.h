@@ -89,5 +89,11 @@ int gaddpg_f64_to_f32_impl(const double* src, float* dst, long long n, void* str
 // tc_gemm.cu
 bool gaddpg_tc_gemm_supported(const NTProblem& p, int amode, int emode);
 int gaddpg_tc_gemm_nt_impl(const NTProblem* p, int amode, int emode, void* stream);
+// tc_gemm_kc.cu
+bool gaddpg_tc_nt_kc_supported(const NTProblem& p, int amode, int emode);
+int gaddpg_tc_nt_kc_impl(const NTProblem* p, int amode, int emode, void* stream);
+bool gaddpg_tc_tn_supported(const TNProblem& p, int pmode, int qmode);
+int gaddpg_tc_tn_impl(const TNProblem* p, int pmode, int qmode, float* ws, size_t ws_floats, float* ws_bias, int* splits_out,
+                      void* stream);
 void gaddpg_set_tensor_core_impl(int enable);
 int gaddpg_get_tensor_core_impl();

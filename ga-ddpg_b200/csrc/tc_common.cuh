@@ -1,0 +1,121 @@
+// tc_common.cuh — PTX wrappers shared by the tcgen05 kernels (tc_gemm.cu, tc_gemm_kc.cu): mbarriers, TMEM
+// allocation, tcgen05.mma/commit/ld, the SWIZZLE_128B shared-memory descriptors and the 3xTF32 hi/lo split.
+#pragma once
+#include "common.cuh"
+#include "gemm_rows.cuh"
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const uint32_t addr = smem_u32(bar);
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] . B[smem desc]^T, kind::tf32, one thread issues for the CTA
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* r) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(r);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]),
+        "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]), "=r"(u[17]), "=r"(u[18]),
+        "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]),
+        "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO>>4 <<16 |
+// SBO>>4 <<32 | version 1 <<46 | layout SWIZZLE_128B(2) <<61.  SBO = 1024 B (8 rows x 128 B); LBO unused (=1).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// byte offset of the 16-byte chunk holding (row r, k..k+3) inside an operand stored as K/32 blocks of [rows x 128 B]
+__device__ __forceinline__ uint32_t sw128_off(int r, int k, int rows) {
+  const int kb = k >> 5, chunk = (k & 31) >> 2;
+  return (uint32_t)(kb * rows * 128 + (r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4));
+}
+__device__ __forceinline__ void split_store(unsigned char* hi_base, unsigned char* lo_base, uint32_t off, float4 v) {
+  float4 h, l;
+  h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+  h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+  h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+  h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+  l.x = v.x - h.x;
+  l.y = v.y - h.y;
+  l.z = v.z - h.z;
+  l.w = v.w - h.w;
+  *reinterpret_cast<float4*>(hi_base + off) = h;
+  *reinterpret_cast<float4*>(lo_base + off) = l;
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+template <int MODE>
+__device__ __forceinline__ float4 load_operand4(const Operand& d, int row, int col, int M, int W) {
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (row >= M || col >= W) return r;
+  float4 x = ldg4(d.X + (long long)row * d.ldx + col);
+  if (MODE == OP_PLAIN) {
+    r = x;
+  } else if (MODE == OP_BNRELU) {
+    float4 s = ldg4(d.c0 + col), t = ldg4(d.c1 + col);
+    r.x = fmaxf(fmaf(x.x, s.x, t.x), 0.f);
+    r.y = fmaxf(fmaf(x.y, s.y, t.y), 0.f);
+    r.z = fmaxf(fmaf(x.z, s.z, t.z), 0.f);
+    r.w = fmaxf(fmaf(x.w, s.w, t.w), 0.f);
+  } else {
+    float4 y = ldg4(d.Y + (long long)row * d.ldy + col);
+    float4 g = ldg4(d.c0 + col), m1 = ldg4(d.c1 + col), m2 = ldg4(d.c2 + col), mu = ldg4(d.c3 + col), rs = ldg4(d.c4 + col);
+    float w = d.rw ? d.rw[row] : 1.f;
+    r.x = g.x * (x.x - w * (m1.x + (y.x - mu.x) * rs.x * m2.x));
+    r.y = g.y * (x.y - w * (m1.y + (y.y - mu.y) * rs.y * m2.y));
+    r.z = g.z * (x.z - w * (m1.z + (y.z - mu.z) * rs.z * m2.z));
+    r.w = g.w * (x.w - w * (m1.w + (y.w - mu.w) * rs.w * m2.w));
+  }
+  return r;
+}
+
+
+}  // namespace

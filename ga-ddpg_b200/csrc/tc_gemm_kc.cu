@@ -1,0 +1,665 @@
+// tc_gemm_kc.cu — K-chunked tcgen05 (3xTF32) row-GEMMs for every shape tc_gemm.cu does not take (sm_100a only).
+//
+//   NT:  C[M,N]  = epi( pro(A)[M,K] . W[N,K]^T )            any K (multiple of 4), any N, M >= 128
+//   TN:  dW[N,K] = sum_r pro1(P)[r,:]^T pro2(Q)[r,:]         weight gradients (split over rows, fixed-order reduce)
+//
+// These carry SA2 / SA3 / the FC-BN head / the actor-critic Linear layers (K = 132 ... 1024) and ALL weight
+// gradients, i.e. what upstream build_shared_mlp / nn.Linear do through cuDNN / cuBLAS for
+// /root/reference/core/networks.py:65-92,265-300,315-351.  Same operand prologues / epilogues and the same
+// deterministic statistics slots as gemm_rows.cu; same 3xTF32 split as tc_gemm.cu (x = hi + lo, three MMAs).
+//
+// NT kernel: grid (m-tiles (persistent), n-tiles).  288 threads: warps 0-3 stream A[128 x 32] and W[BN x 32] K-chunks
+// (prologue in registers, hi/lo split, st.shared into the K-major SWIZZLE_128B UMMA layout) through an mbarrier
+// ring; warp 4 issues 12 tcgen05.mma per chunk into a double-buffered TMEM accumulator; warps 5-8 run the
+// epilogue (tcgen05.ld -> smem transpose -> coalesced stores, mask reads, BN statistics).
+//
+// TN kernel: grid (output tiles [128 x BKT], row splits).  The reduction runs over ROWS, so both operands are fed
+// to the tensor core MN-major: the natural [rows x channels] staging (rows 128 B apart) is the canonical MN-major
+// SWIZZLE_128B_BASE32B layout (4-row K atoms, two per K = 8 instruction); no transpose anywhere.  The accumulator
+// (dW tile) stays in TMEM for the whole kernel and is written once as a per-split partial.
+#include "tc_common.cuh"
+#include "impl.h"
+
+namespace {
+
+constexpr int KC_BM = 128;
+constexpr int KC_THREADS = 288;  // 4 producer warps + 1 MMA warp + 4 epilogue warps
+
+// byte offset of (row r, float4 index q) inside one [rows x 128 B] SWIZZLE_128B block
+__device__ __forceinline__ uint32_t blk_off(int r, int q) {
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((q ^ (r & 7)) << 4));
+}
+// MN-major operands of kind::tf32 have exactly one legal shared-memory layout: SWIZZLE_128B_BASE32B (layout type 1;
+// cutlass sm100_common.inl: "for mn-major tf32 operands, SW128_32B is the only available smem layout").  Rows of the
+// reduction index are 128 B (32 channels) apart, the swizzle XORs the 32-byte unit index (address bits [5,7)) with the
+// row index mod 4 (bits [7,9)), the K atom is 4 rows: LBO = byte stride between 32-channel blocks, SBO = byte stride
+// between 4-row groups (cute::UMMA::make_umma_desc<Major::MN>: ((8,n),(4,k)) in uint128 units).
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46) |
+         (1ull << 61);
+}
+// byte offset of (row r, float4 index q) inside one [rows x 128 B] SWIZZLE_128B_BASE32B block
+__device__ __forceinline__ uint32_t blk_off_mn(int r, int q) {
+  return (uint32_t)(r * 128 + ((((q >> 1) ^ (r & 3)) << 5) | ((q & 1) << 4)));
+}
+
+template <int MODE>
+struct Consts4 {
+  float4 c0, c1, c2, c3, c4;
+  __device__ __forceinline__ void load(const Operand& d, int col, bool ok) {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    c0 = c1 = c2 = c3 = c4 = z;
+    if (!ok) return;
+    if (MODE == OP_BNRELU) {
+      c0 = ldg4(d.c0 + col);
+      c1 = ldg4(d.c1 + col);
+    } else if (MODE == OP_BNBWD) {
+      c0 = ldg4(d.c0 + col);
+      c1 = ldg4(d.c1 + col);
+      c2 = ldg4(d.c2 + col);
+      c3 = ldg4(d.c3 + col);
+      c4 = ldg4(d.c4 + col);
+    }
+  }
+  __device__ __forceinline__ float4 apply(float4 x, float4 y, float w) const {
+    float4 r;
+    if (MODE == OP_PLAIN) {
+      r = x;
+    } else if (MODE == OP_BNRELU) {
+      r.x = fmaxf(fmaf(x.x, c0.x, c1.x), 0.f);
+      r.y = fmaxf(fmaf(x.y, c0.y, c1.y), 0.f);
+      r.z = fmaxf(fmaf(x.z, c0.z, c1.z), 0.f);
+      r.w = fmaxf(fmaf(x.w, c0.w, c1.w), 0.f);
+    } else {
+      r.x = c0.x * (x.x - w * (c1.x + (y.x - c3.x) * c4.x * c2.x));
+      r.y = c0.y * (x.y - w * (c1.y + (y.y - c3.y) * c4.y * c2.y));
+      r.z = c0.z * (x.z - w * (c1.z + (y.z - c3.z) * c4.z * c2.z));
+      r.w = c0.w * (x.w - w * (c1.w + (y.w - c3.w) * c4.w * c2.w));
+    }
+    return r;
+  }
+};
+
+// =====================================================================================================
+// NT, K-chunked
+// =====================================================================================================
+template <int BN>
+struct KcLayout {
+  static constexpr int NSTAGE = (BN == 128) ? 3 : 4;
+  static constexpr uint32_t A_BYTES = KC_BM * 128;          // one of hi / lo
+  static constexpr uint32_t W_BYTES = BN * 128;
+  static constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
+  static constexpr uint32_t OFF_STAGEBUF = NSTAGE * STAGE_BYTES;
+  static constexpr uint32_t OFF_BARS = OFF_STAGEBUF + 4 * 32 * 33 * 4;
+  static constexpr uint32_t OFF_COMB = OFF_BARS + 256;
+  static constexpr uint32_t TOTAL = OFF_COMB + 2 * 4 * BN * 4;
+};
+
+template <int BN, int AMODE, int EMODE>
+__global__ void __launch_bounds__(KC_THREADS, 1) tc_nt_kc_kernel(const NTProblem p) {
+  using L = KcLayout<BN>;
+  constexpr int NSTAGE = L::NSTAGE;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BARS);
+  uint64_t* full = bars;                 // [NSTAGE]
+  uint64_t* empty = bars + NSTAGE;       // [NSTAGE]
+  uint64_t* acc_full = bars + 2 * NSTAGE;      // [2]
+  uint64_t* acc_empty = bars + 2 * NSTAGE + 2; // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 4);
+  float* stat_comb = reinterpret_cast<float*>(smem + L::OFF_COMB);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int M = p.M_dev ? *p.M_dev : p.M_max;
+  M = M < p.M_max ? M : p.M_max;
+  const int N = p.N, K = p.K;
+  const int ntiles = (M + KC_BM - 1) / KC_BM;
+  const int nk = (K + 31) >> 5;
+  const int n0 = blockIdx.y * BN;
+  constexpr uint32_t tmem_cols = 2 * BN;  // 128 or 256: power of two >= 32
+
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(&full[s], 128);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int my_tiles = (ntiles > (int)blockIdx.x) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  if (warp < 4) {
+    // ===================== producers =====================
+    constexpr int U = (AMODE == OP_BNBWD) ? 4 : 8;  // A row-iterations per pipeline unit
+    constexpr int HPC = 8 / U;                      // units per K chunk
+    constexpr int WU = (BN / 16) / HPC;             // W row-iterations per unit
+    const int kq = tid & 7, r0 = tid >> 3;          // float4 inside the 32-wide chunk; first row served
+    struct Regs {
+      float4 x[U], y[U];
+      float w[U];
+      float4 b[WU];
+      Consts4<AMODE> cc;
+    };
+    struct Cursor {
+      int it, kc, h, g;  // tile iteration, K chunk, half, global chunk counter
+    };
+    const int total_units = my_tiles * nk * HPC;
+    auto advance = [&](Cursor& c) {
+      if (++c.h == HPC) {
+        c.h = 0;
+        ++c.g;
+        if (++c.kc == nk) {
+          c.kc = 0;
+          ++c.it;
+        }
+      }
+    };
+    auto issue = [&](Regs& R, const Cursor& c) {
+      const int row0 = ((int)blockIdx.x + c.it * (int)gridDim.x) * KC_BM;
+      const int col = (c.kc << 5) + (kq << 2);
+      const bool colok = col < K;
+      R.cc.load(p.A, col, colok);
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        const int row = row0 + r0 + 16 * (c.h * U + k);
+        R.x[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        R.y[k] = R.x[k];
+        R.w[k] = 1.f;
+        if (row < M && colok) {
+          R.x[k] = ldg4(p.A.X + (long long)row * p.A.ldx + col);
+          if (AMODE == OP_BNBWD) {
+            R.y[k] = ldg4(p.A.Y + (long long)row * p.A.ldy + col);
+            if (p.A.rw) R.w[k] = p.A.rw[row];
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < WU; ++k) {
+        const int n = n0 + r0 + 16 * (c.h * WU + k);
+        R.b[k] = (n < N && colok) ? ldg4(p.Bw + (long long)n * p.ldb + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    auto process = [&](const Regs& R, const Cursor& c) {
+      const int s = c.g % NSTAGE;
+      const int row0 = ((int)blockIdx.x + c.it * (int)gridDim.x) * KC_BM;
+      const bool colok = ((c.kc << 5) + (kq << 2)) < K;
+      if (c.h == 0) mbar_wait(&empty[s], ((uint32_t)(c.g / NSTAGE) & 1u) ^ 1u);
+      unsigned char* st = smem + (uint32_t)s * L::STAGE_BYTES;
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        const int r = r0 + 16 * (c.h * U + k);
+        float4 v = (row0 + r < M && colok) ? R.cc.apply(R.x[k], R.y[k], R.w[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        split_store(st, st + L::A_BYTES, blk_off(r, kq), v);
+      }
+#pragma unroll
+      for (int k = 0; k < WU; ++k) {
+        const int r = r0 + 16 * (c.h * WU + k);
+        split_store(st + 2 * L::A_BYTES, st + 2 * L::A_BYTES + L::W_BYTES, blk_off(r, kq), R.b[k]);
+      }
+      if (c.h == HPC - 1) {
+        fence_proxy_async();
+        mbar_arrive(&full[s]);
+      }
+    };
+    Regs RA, RB;
+    Cursor ci = {0, 0, 0, 0}, cp = {0, 0, 0, 0};
+    if (total_units > 0) {
+      issue(RA, ci);
+      advance(ci);
+    }
+#pragma unroll 1
+    for (int u = 0; u < total_units; u += 2) {
+      if (u + 1 < total_units) {
+        issue(RB, ci);
+        advance(ci);
+      }
+      process(RA, cp);
+      advance(cp);
+      if (u + 2 < total_units) {
+        issue(RA, ci);
+        advance(ci);
+      }
+      if (u + 1 < total_units) {
+        process(RB, cp);
+        advance(cp);
+      }
+    }
+  } else if (warp == 4) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(KC_BM >> 4) << 24);
+      const uint32_t sbase = smem_u32(smem);
+      int g = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        const int b = it & 1;
+        mbar_wait(&acc_empty[b], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(b * BN);
+        uint32_t acc = 0;
+        for (int kc = 0; kc < nk; ++kc, ++g) {
+          const int s = g % NSTAGE;
+          mbar_wait(&full[s], (uint32_t)(g / NSTAGE) & 1u);
+          tc_fence_after();
+          const uint32_t st = sbase + (uint32_t)s * L::STAGE_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t a_hi = make_desc(st + ks * 32), a_lo = make_desc(st + L::A_BYTES + ks * 32);
+            const uint64_t b_hi = make_desc(st + 2 * L::A_BYTES + ks * 32), b_lo = make_desc(st + 2 * L::A_BYTES + L::W_BYTES + ks * 32);
+            umma_tf32(d_tmem, a_lo, b_hi, idesc, acc);
+            umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
+            umma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
+            acc = 1u;
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&acc_full[b]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int ew = warp - 5;
+    float* stage = reinterpret_cast<float*>(smem + L::OFF_STAGEBUF) + ew * 32 * 33;
+    const bool do_stats = (p.stats != nullptr);
+    constexpr int NCB = BN / 32;
+    float s0[NCB], s1[NCB];
+#pragma unroll
+    for (int c = 0; c < NCB; ++c) s0[c] = s1[c] = 0.f;
+    for (int it = 0; it < my_tiles; ++it) {
+      const int t = (int)blockIdx.x + it * (int)gridDim.x;
+      const int b = it & 1;
+      const int row_base = t * KC_BM + q * 32;
+      float wrow = 1.f;
+      if (EMODE == EPI_STORE && do_stats && p.srw) wrow = (row_base + lane < M) ? p.srw[row_base + lane] : 0.f;
+      mbar_wait(&acc_full[b], (uint32_t)(it >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll
+      for (int cb = 0; cb < NCB; ++cb) {
+        if (n0 + cb * 32 < N) {
+          const int col = n0 + cb * 32 + lane;
+          const bool cval = col < N;
+          float yp[32];
+          if (EMODE == EPI_DMASK) {
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr)
+              yp[rr] = (cval && row_base + rr < M) ? p.Yprev[(long long)(row_base + rr) * p.ldyp + col] : 0.f;
+          }
+          float r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * BN + cb * 32), r);
+#pragma unroll
+          for (int c = 0; c < 32; ++c) stage[lane * 33 + c] = r[c];
+          __syncwarp();
+          float bias = 0.f, psc = 1.f, psh = 0.f, pmu = 0.f, prs = 0.f;
+          if (cval) {
+            if (EMODE == EPI_STORE) {
+              if (p.bias) bias = p.bias[col];
+            } else {
+              if (p.psc) {
+                psc = p.psc[col];
+                psh = p.psh[col];
+              }
+              if (do_stats) {
+                pmu = p.pmean[col];
+                prs = p.prstd[col];
+              }
+            }
+          }
+          float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) {
+            const int row = row_base + rr;
+            float v = stage[rr * 33 + lane];
+            const float w = __shfl_sync(0xffffffffu, wrow, rr);
+            if (cval && row < M) {
+              if (EMODE == EPI_STORE) {
+                v += bias;
+                if (p.relu) v = fmaxf(v, 0.f);
+                p.C[(long long)row * p.ldc + col] = v;
+                a0 = fmaf(w, v, a0);
+                a1 = fmaf(w * v, v, a1);
+              } else {
+                const float z = p.psc ? fmaf(yp[rr], psc, psh) : yp[rr];
+                v = z > 0.f ? v : 0.f;
+                p.C[(long long)row * p.ldc + col] = v;
+                a0 += v;
+                a1 = fmaf(v, (yp[rr] - pmu) * prs, a1);
+              }
+            }
+          }
+          s0[cb] += a0;
+          s1[cb] += a1;
+          __syncwarp();
+        }
+      }
+      tc_fence_before();
+      if (lane == 0) mbar_arrive(&acc_empty[b]);
+    }
+    if (do_stats) {
+#pragma unroll
+      for (int cb = 0; cb < NCB; ++cb) {
+        stat_comb[ew * BN + cb * 32 + lane] = s0[cb];
+        stat_comb[4 * BN + ew * BN + cb * 32 + lane] = s1[cb];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (p.stats) {
+    for (int c = tid; c < BN; c += KC_THREADS) {
+      if (n0 + c < N) {
+        float a0 = stat_comb[c] + stat_comb[BN + c] + stat_comb[2 * BN + c] + stat_comb[3 * BN + c];
+        float a1 = stat_comb[4 * BN + c] + stat_comb[5 * BN + c] + stat_comb[6 * BN + c] + stat_comb[7 * BN + c];
+        p.stats[(long long)blockIdx.x * 2 * N + n0 + c] = a0;
+        p.stats[(long long)blockIdx.x * 2 * N + N + n0 + c] = a1;
+      }
+    }
+    for (int slot = blockIdx.x + gridDim.x; slot < GADDPG_STAT_SLOTS; slot += gridDim.x)
+      for (int c = tid; c < 2 * BN; c += KC_THREADS) {
+        const int cc = (c < BN) ? c : c - BN;
+        if (n0 + cc < N) p.stats[(long long)slot * 2 * N + (c < BN ? 0 : N) + n0 + cc] = 0.f;
+      }
+  }
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// =====================================================================================================
+// TN (weight gradients): partial[split][N][K] tile [128 x BKT] accumulated in TMEM over this split's row chunks
+// =====================================================================================================
+constexpr int TN_R = 32;  // rows (reduction index) per stage = 4 MMA K-steps of 8
+
+template <int BKT>
+struct TnLayout {
+  static constexpr int NSTAGE = (BKT == 128) ? 3 : 4;
+  static constexpr uint32_t P_BYTES = 4 * TN_R * 128;            // 128 channels = 4 blocks of [32 rows x 128 B]
+  static constexpr uint32_t Q_BYTES = (BKT / 32) * TN_R * 128;
+  static constexpr uint32_t STAGE_BYTES = 2 * P_BYTES + 2 * Q_BYTES;
+  static constexpr uint32_t OFF_BARS = NSTAGE * STAGE_BYTES;
+  static constexpr uint32_t OFF_BIAS = OFF_BARS + 256;
+  static constexpr uint32_t TOTAL = OFF_BIAS + 4 * 128 * 4;
+};
+
+template <int BKT, int PMODE, int QMODE>
+__global__ void __launch_bounds__(KC_THREADS, 1) tc_tn_kernel(const TNProblem p, float* __restrict__ partial,
+                                                               float* __restrict__ partial_bias, int splits, int tiles_k) {
+  using L = TnLayout<BKT>;
+  constexpr int NSTAGE = L::NSTAGE;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BARS);
+  uint64_t* full = bars;             // [NSTAGE]
+  uint64_t* empty = bars + NSTAGE;   // [NSTAGE]
+  uint64_t* acc_full = bars + 2 * NSTAGE;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 1);
+  float* bias_comb = reinterpret_cast<float*>(smem + L::OFF_BIAS);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int M = p.M_dev ? *p.M_dev : p.M_max;
+  M = M < p.M_max ? M : p.M_max;
+  const int N = p.N, K = p.K;
+  const int tile = blockIdx.x, split = blockIdx.y;
+  const int n0 = (tile / tiles_k) * 128, k0 = (tile % tiles_k) * BKT;
+  const bool want_bias = (partial_bias != nullptr) && (tile % tiles_k == 0);
+  const int nchunks = (M + TN_R - 1) / TN_R;
+  const int my_chunks = (nchunks > split) ? (nchunks - 1 - split) / splits + 1 : 0;
+  constexpr uint32_t tmem_cols = BKT;  // 64 or 128
+
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(&full[s], 128);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ===================== producers =====================
+    constexpr int HPC = (PMODE == OP_BNBWD) ? 2 : 1;  // pipeline units per chunk
+    constexpr int PU = 8 / HPC;                       // P row-iterations per unit (128 threads cover 4 rows x 32 float4)
+    constexpr int QROWS = 128 / (BKT / 4);            // rows the 128 threads cover per Q iteration (4 or 8)
+    constexpr int QU = (TN_R / QROWS) / HPC;          // Q row-iterations per unit
+    const int pq = tid & 31, pr = tid >> 5;           // P: float4 column, first row
+    const int qq = tid % (BKT / 4), qr = tid / (BKT / 4);
+    const int pcol = n0 + (pq << 2), qcol = k0 + (qq << 2);
+    const bool pok = pcol < N, qok = qcol < K;
+    Consts4<PMODE> pc;
+    Consts4<QMODE> qc;
+    pc.load(p.P, pcol, pok);
+    qc.load(p.Q, qcol, qok);
+    const uint32_t poff_blk = (uint32_t)(pq >> 3) * (TN_R * 128), qoff_blk = (uint32_t)(qq >> 3) * (TN_R * 128);
+    float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
+    struct Regs {
+      float4 x[PU], y[PU];
+      float w[PU];
+      float4 q[QU];
+    };
+    const int total_units = my_chunks * HPC;
+    auto issue = [&](Regs& R, int u) {
+      const int ci = u / HPC, h = u % HPC;
+      const int rowc = (split + ci * splits) * TN_R;
+#pragma unroll
+      for (int k = 0; k < PU; ++k) {
+        const int row = rowc + pr + 4 * (h * PU + k);
+        R.x[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        R.y[k] = R.x[k];
+        R.w[k] = 1.f;
+        if (row < M && pok) {
+          R.x[k] = ldg4(p.P.X + (long long)row * p.P.ldx + pcol);
+          if (PMODE == OP_BNBWD) {
+            R.y[k] = ldg4(p.P.Y + (long long)row * p.P.ldy + pcol);
+            if (p.P.rw) R.w[k] = p.P.rw[row];
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < QU; ++k) {
+        const int row = rowc + qr + QROWS * (h * QU + k);
+        R.q[k] = (row < M && qok) ? ldg4(p.Q.X + (long long)row * p.Q.ldx + qcol) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    auto process = [&](const Regs& R, int u) {
+      const int ci = u / HPC, h = u % HPC;
+      const int s = ci % NSTAGE;
+      const int rowc = (split + ci * splits) * TN_R;
+      if (h == 0) mbar_wait(&empty[s], ((uint32_t)(ci / NSTAGE) & 1u) ^ 1u);
+      unsigned char* st = smem + (uint32_t)s * L::STAGE_BYTES;
+#pragma unroll
+      for (int k = 0; k < PU; ++k) {
+        const int r = pr + 4 * (h * PU + k);
+        float4 v = (rowc + r < M && pok) ? pc.apply(R.x[k], R.y[k], R.w[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        bsum.x += v.x;
+        bsum.y += v.y;
+        bsum.z += v.z;
+        bsum.w += v.w;
+        split_store(st, st + L::P_BYTES, poff_blk + blk_off_mn(r, pq & 7), v);
+      }
+#pragma unroll
+      for (int k = 0; k < QU; ++k) {
+        const int r = qr + QROWS * (h * QU + k);
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 v = (rowc + r < M && qok) ? qc.apply(R.q[k], z, 1.f) : z;
+        split_store(st + 2 * L::P_BYTES, st + 2 * L::P_BYTES + L::Q_BYTES, qoff_blk + blk_off_mn(r, qq & 7), v);
+      }
+      if (h == HPC - 1) {
+        fence_proxy_async();
+        mbar_arrive(&full[s]);
+      }
+    };
+    Regs RA, RB;
+    if (total_units > 0) issue(RA, 0);
+#pragma unroll 1
+    for (int u = 0; u < total_units; u += 2) {
+      if (u + 1 < total_units) issue(RB, u + 1);
+      process(RA, u);
+      if (u + 2 < total_units) issue(RA, u + 2);
+      if (u + 1 < total_units) process(RB, u + 1);
+    }
+    if (want_bias) *reinterpret_cast<float4*>(bias_comb + pr * 128 + (pq << 2)) = bsum;
+  } else if (warp == 4) {
+    // ===================== MMA issuer =====================
+    if (lane == 0 && my_chunks > 0) {
+      // both operands MN-major (bits 15, 16): the reduction index (rows) is the MMA K dimension
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(BKT >> 3) << 17) |
+                             ((uint32_t)(128 >> 4) << 24);
+      const uint32_t sbase = smem_u32(smem);
+      uint32_t acc = 0;
+      for (int ci = 0; ci < my_chunks; ++ci) {
+        const int s = ci % NSTAGE;
+        mbar_wait(&full[s], (uint32_t)(ci / NSTAGE) & 1u);
+        tc_fence_after();
+        const uint32_t st = sbase + (uint32_t)s * L::STAGE_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < TN_R / 8; ++ks) {
+          const uint32_t o = ks * 1024;
+          const uint64_t a_hi = make_desc_mn(st + o, TN_R * 128, 512), a_lo = make_desc_mn(st + L::P_BYTES + o, TN_R * 128, 512);
+          const uint64_t b_hi = make_desc_mn(st + 2 * L::P_BYTES + o, TN_R * 128, 512);
+          const uint64_t b_lo = make_desc_mn(st + 2 * L::P_BYTES + L::Q_BYTES + o, TN_R * 128, 512);
+          umma_tf32(tmem_base, a_lo, b_hi, idesc, acc);
+          umma_tf32(tmem_base, a_hi, b_lo, idesc, 1u);
+          umma_tf32(tmem_base, a_hi, b_hi, idesc, 1u);
+          acc = 1u;
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(acc_full);
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue: TMEM -> partial[split] =====================
+    const int q = warp & 3;
+    const int n = n0 + q * 32 + lane;
+    float* out = partial + ((long long)split * N + n) * K + k0;
+    if (my_chunks > 0) {
+      mbar_wait(acc_full, 0);
+      tc_fence_after();
+    }
+#pragma unroll
+    for (int cb = 0; cb < BKT / 32; ++cb) {
+      float r[32];
+      if (my_chunks > 0) {
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 32), r);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) r[c] = 0.f;
+      }
+      if (n < N) {
+#pragma unroll
+        for (int c = 0; c < 32; c += 4)
+          if (k0 + cb * 32 + c < K) *reinterpret_cast<float4*>(out + cb * 32 + c) = make_float4(r[c], r[c + 1], r[c + 2], r[c + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (want_bias && tid < 128 && n0 + tid < N)
+    partial_bias[(long long)split * N + n0 + tid] = (bias_comb[tid] + bias_comb[128 + tid]) + (bias_comb[256 + tid] + bias_comb[384 + tid]);
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+}  // namespace
+
+// ----------------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------------
+bool gaddpg_tc_nt_kc_supported(const NTProblem& p, int amode, int emode) {
+  // below ~1k rows a tile grid cannot fill the chip and the serial K loop loses to the FFMA kernel's 32x64 tiles (measured)
+  if (p.M_max < 1024 || p.N < 32 || p.K < 32) return false;
+  if (p.ldb % 4 != 0) return false;
+  (void)amode;
+  (void)emode;
+  return true;
+}
+
+int gaddpg_tc_nt_kc_impl(const NTProblem* p, int amode, int emode, void* stream) {
+  const int mtiles = ceil_div(p->M_max, KC_BM);
+  const bool wide = p->N >= 128 && mtiles * ceil_div(p->N, 128) >= 64;
+  const int BN = wide ? 128 : 64;
+  dim3 grid(mtiles < GADDPG_STAT_SLOTS ? mtiles : GADDPG_STAT_SLOTS, ceil_div(p->N, BN));
+  cudaStream_t st = (cudaStream_t)stream;
+#define KC_LAUNCH(BNN, A, E)                                                                                   \
+  {                                                                                                            \
+    auto kern = tc_nt_kc_kernel<BNN, A, E>;                                                                    \
+    const size_t smem = KcLayout<BNN>::TOTAL + 1024;                                                           \
+    GADDPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
+    kern<<<grid, KC_THREADS, smem, st>>>(*p);                                                                  \
+    GADDPG_CHECK_LAUNCH("tc_nt_kc_kernel");                                                                    \
+    return GADDPG_OK;                                                                                          \
+  }
+#define KC_CASE(A, E)                                                                                          \
+  if (amode == A && emode == E) {                                                                              \
+    if (BN == 128) KC_LAUNCH(128, A, E) else KC_LAUNCH(64, A, E)                                               \
+  }
+  KC_CASE(OP_PLAIN, EPI_STORE)
+  KC_CASE(OP_BNRELU, EPI_STORE)
+  KC_CASE(OP_BNBWD, EPI_DMASK)
+  KC_CASE(OP_BNBWD, EPI_STORE)
+  KC_CASE(OP_PLAIN, EPI_DMASK)
+#undef KC_CASE
+#undef KC_LAUNCH
+  gaddpg_set_error("tc_nt_kc: unsupported mode pair (%d,%d)", amode, emode);
+  return GADDPG_ERR_UNSUPPORTED;
+}
+
+bool gaddpg_tc_tn_supported(const TNProblem& p, int pmode, int qmode) {
+  if (p.N < 32 || p.K < 32 || p.M_max < 64) return false;
+  if (pmode == OP_BNRELU || qmode == OP_BNBWD) return false;
+  return true;
+}
+
+// launches the split kernel only; the caller runs the fixed-order reduction over `*splits_out` partials
+int gaddpg_tc_tn_impl(const TNProblem* p, int pmode, int qmode, float* ws, size_t ws_floats, float* ws_bias, int* splits_out,
+                      void* stream) {
+  const int BKT = (p->K <= 64) ? 64 : 128;
+  const int tiles_k = ceil_div(p->K, BKT);
+  const int tiles = ceil_div(p->N, 128) * tiles_k;
+  const int chunks = ceil_div(p->M_max, TN_R);
+  int splits = gaddpg_sm_count() / tiles;
+  if (splits > chunks) splits = chunks;
+  if ((size_t)splits * p->N * p->K > ws_floats) splits = (int)(ws_floats / ((size_t)p->N * p->K));
+  if (splits > 64 * 1024 / p->N) splits = 64 * 1024 / p->N;
+  if (splits < 1) splits = 1;
+  GADDPG_CHECK_ARG((size_t)splits * p->N * p->K <= ws_floats, "tc_tn: workspace too small");
+  *splits_out = splits;
+  dim3 grid(tiles, splits);
+  cudaStream_t st = (cudaStream_t)stream;
+#define TN_LAUNCH(BK_, PM, QM)                                                                                 \
+  {                                                                                                            \
+    auto kern = tc_tn_kernel<BK_, PM, QM>;                                                                     \
+    const size_t smem = TnLayout<BK_>::TOTAL + 1024;                                                           \
+    GADDPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
+    kern<<<grid, KC_THREADS, smem, st>>>(*p, ws, ws_bias, splits, tiles_k);                                    \
+    GADDPG_CHECK_LAUNCH("tc_tn_kernel");                                                                       \
+    return GADDPG_OK;                                                                                          \
+  }
+#define TN_CASE(PM, QM)                                                                                        \
+  if (pmode == PM && qmode == QM) {                                                                            \
+    if (BKT == 128) TN_LAUNCH(128, PM, QM) else TN_LAUNCH(64, PM, QM)                                          \
+  }
+  TN_CASE(OP_PLAIN, OP_PLAIN)
+  TN_CASE(OP_PLAIN, OP_BNRELU)
+  TN_CASE(OP_BNBWD, OP_PLAIN)
+  TN_CASE(OP_BNBWD, OP_BNRELU)
+#undef TN_CASE
+#undef TN_LAUNCH
+  gaddpg_set_error("tc_tn: unsupported mode pair (%d,%d)", pmode, qmode);
+  return GADDPG_ERR_UNSUPPORTED;
+}

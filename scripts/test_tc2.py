@@ -1,0 +1,114 @@
+"""GPU: the K-chunked tcgen05 NT kernel and the tcgen05 TN (weight-gradient) kernel against a float64 reference and the
+FP32 FFMA kernels: all prologue / epilogue combinations, ragged N / K, device-side row counts, bias sums, rotation."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from types import SimpleNamespace as NS
+from gaddpg_b200 import engine
+from gaddpg_b200.capi import lib
+from gaddpg_b200.engine import nt, nt_problem, tn, op_plain, op_bnrelu, op_bnbwd, OP_PLAIN, OP_BNRELU, OP_BNBWD, EPI_STORE, EPI_DMASK
+from gaddpg_b200.structs import STAT_SLOTS
+
+dev = torch.device("cuda")
+ws = engine.Workspace(dev)
+torch.manual_seed(0)
+def bn(C): return NS(scale=torch.rand(C, device=dev) + 0.5, shift=torch.randn(C, device=dev) * 0.1, mean=torch.randn(C, device=dev) * 0.1, rstd=torch.rand(C, device=dev) + 0.5)
+def bb(C): return NS(g=torch.rand(C, device=dev) + 0.2, m1=torch.randn(C, device=dev) * 0.01, m2=torch.randn(C, device=dev) * 0.01)
+ok = True
+which = os.environ.get("WHICH", "nt,tn")
+TCL = int(os.environ.get("TCL", "4"))
+
+if "nt" in which:
+    for (Mmax, M, N, K) in ((13000, 12973, 128, 132), (8192, 8192, 256, 260), (8192, 8192, 512, 256), (2048, 2048, 1024, 512),
+                            (1024, 1024, 512, 1024), (8192, 8000, 260, 256), (1100, 1100, 256, 516), (20000, 17321, 64, 64),
+                            (40000, 39000, 128, 64), (8192, 8192, 132, 128), (1300, 1290, 32, 36)):
+        Mdev = torch.tensor([M], dtype=torch.int32, device=dev)
+        X = torch.randn(Mmax, K, device=dev); W = torch.randn(N, K, device=dev) * 0.2; rw = torch.rand(Mmax, device=dev) * 3
+        D = torch.randn(Mmax, K, device=dev); Yc = torch.randn(Mmax, K, device=dev); Yp = torch.randn(Mmax, N, device=dev)
+        b, bK, bbK, bN = bn(K), bn(K), bb(K), bn(N)
+        bias = torch.randn(N, device=dev)
+        cases = {
+            "bnrelu+store+stats": lambda Y: nt([nt_problem(op_bnrelu(X, b), W, K, Y, N, Mmax, Mdev.data_ptr(), N, K, stats=ws.stats, srw=rw)], OP_BNRELU, EPI_STORE),
+            "plain+bias+relu": lambda Y: nt([nt_problem(op_plain(X), W, K, Y, N, Mmax, Mdev.data_ptr(), N, K, bias=bias, relu=1)], OP_PLAIN, EPI_STORE),
+            "bnbwd+dmask+stats": lambda Y: nt([nt_problem(op_bnbwd(D, Yc, bK, bbK, rw=rw), W, K, Y, N, Mmax, Mdev.data_ptr(), N, K, stats=ws.stats, Yprev=Yp, ldyp=N, pbn=bN)], OP_BNBWD, EPI_DMASK),
+            "bnbwd+store": lambda Y: nt([nt_problem(op_bnbwd(D, Yc, bK, bbK, rw=rw), W, K, Y, N, Mmax, Mdev.data_ptr(), N, K)], OP_BNBWD, EPI_STORE),
+            "plain+dmask(relu)": lambda Y: nt([nt_problem(op_plain(X), W, K, Y, N, Mmax, Mdev.data_ptr(), N, K, Yprev=Yp, ldyp=N)], OP_PLAIN, EPI_DMASK),
+        }
+        A1 = torch.relu(X[:M].double() * b.scale.double() + b.shift.double())
+        ref = {"bnrelu+store+stats": A1 @ W.double().t(), "plain+bias+relu": torch.relu(X[:M].double() @ W.double().t() + bias.double())}
+        dY = bbK.g.double() * (D[:M].double() - rw[:M, None].double() * (bbK.m1.double() + (Yc[:M].double() - bK.mean.double()) * bK.rstd.double() * bbK.m2.double()))
+        z = Yp[:M].double() * bN.scale.double() + bN.shift.double()
+        ref["bnbwd+dmask+stats"] = (dY @ W.double().t()) * (z > 0)
+        ref["bnbwd+store"] = dY @ W.double().t()
+        ref["plain+dmask(relu)"] = (X[:M].double() @ W.double().t()) * (Yp[:M].double() > 0)
+        for name, fn in cases.items():
+            out = {}
+            for tc in (0, TCL):
+                lib.gaddpg_set_tensor_core(tc)
+                Y = torch.full((Mmax, N), 7.0, device=dev)
+                ws.stats.fill_(123.0)
+                fn(Y)
+                torch.cuda.synchronize()
+                st = ws.stats[: STAT_SLOTS * 2 * N].view(STAT_SLOTS, 2, N).double().sum(0).clone()
+                out[tc] = (Y, st)
+            r = ref[name]
+            e0 = float((out[0][0][:M].double() - r).abs().max() / r.abs().max())
+            e1 = float((out[TCL][0][:M].double() - r).abs().max() / r.abs().max())
+            untouched = bool((out[TCL][0][M:] == 7.0).all())
+            line = "NT M=%d N=%d K=%d %-20s ffma %.2e tcgen05 %.2e untouched %s" % (M, N, K, name, e0, e1, untouched)
+            good = e1 < (5e-6 if K <= 256 else 2e-5) and untouched
+            if "stats" in name:
+                if name.startswith("bnrelu"):
+                    rs = torch.stack([(rw[:M, None].double() * r).sum(0), (rw[:M, None].double() * r * r).sum(0)])
+                else:
+                    xh = (Yp[:M].double() - bN.mean.double()) * bN.rstd.double()
+                    rs = torch.stack([r.sum(0), (r * xh).sum(0)])
+                se0 = float((out[0][1] - rs).abs().max() / rs.abs().max()); se1 = float((out[TCL][1] - rs).abs().max() / rs.abs().max())
+                line += " stats ffma %.2e tc %.2e" % (se0, se1)
+                good = good and se1 < (2e-5 if K <= 256 else 4e-5)
+            print(line, "OK" if good else "FAIL")
+            ok = ok and good
+
+if "tn" in which:
+    # dW[N,K] = sum_r pro1(P)[r,:N]^T pro2(Q)[r,:K]
+    for (Mmax, M, N, K, Ktrue, rot, wb) in ((20000, 17321, 128, 64, 64, 0, False), (20000, 20000, 64, 64, 64, 0, False),
+                                            (13000, 12973, 128, 132, 131, 3, False), (8192, 8192, 512, 256, 256, 0, False),
+                                            (8192, 8000, 256, 260, 259, 3, False), (256, 256, 1024, 512, 512, 0, True),
+                                            (256, 256, 512, 1024, 1024, 0, True), (256, 256, 256, 516, 513, 0, True),
+                                            (100, 70, 32, 32, 32, 0, True), (50000, 50000, 256, 128, 128, 0, False)):
+        Mdev = torch.tensor([M], dtype=torch.int32, device=dev)
+        D = torch.randn(Mmax, N, device=dev); Yc = torch.randn(Mmax, N, device=dev); rw = torch.rand(Mmax, device=dev) * 3
+        Xq = torch.randn(Mmax, K, device=dev)
+        bNn, bbN, bKk = bn(N), bb(N), bn(K)
+        dYd = bbN.g.double() * (D[:M].double() - rw[:M, None].double() * (bbN.m1.double() + (Yc[:M].double() - bNn.mean.double()) * bNn.rstd.double() * bbN.m2.double()))
+        Qrelu = torch.relu(Xq[:M].double() * bKk.scale.double() + bKk.shift.double())
+        modes = {
+            "bnbwd x bnrelu": (op_bnbwd(D, Yc, bNn, bbN, rw=rw), op_bnrelu(Xq, bKk), OP_BNBWD, OP_BNRELU, dYd, Qrelu),
+            "bnbwd x plain": (op_bnbwd(D, Yc, bNn, bbN, rw=rw), op_plain(Xq), OP_BNBWD, OP_PLAIN, dYd, Xq[:M].double()),
+            "plain x plain": (op_plain(D), op_plain(Xq), OP_PLAIN, OP_PLAIN, D[:M].double(), Xq[:M].double()),
+            "plain x bnrelu": (op_plain(D), op_bnrelu(Xq, bKk), OP_PLAIN, OP_BNRELU, D[:M].double(), Qrelu),
+        }
+        for name, (P, Q, pm, qm, Pd, Qd) in modes.items():
+            full = Pd.t() @ Qd                      # [N, K]
+            refW = torch.roll(full[:, :Ktrue], rot, dims=1) if rot else full[:, :Ktrue]
+            refb = Pd.sum(0)
+            res = {}
+            for tc in (0, TCL):
+                lib.gaddpg_set_tensor_core(tc)
+                dW = torch.full((N, Ktrue), 5.0, device=dev)
+                db = torch.full((N,), 5.0, device=dev)
+                tn(ws, P, Q, pm, qm, Mmax, Mdev.data_ptr(), N, K, dW, Ktrue, N, Ktrue, rot=rot, dbias=db if wb else None)
+                torch.cuda.synchronize()
+                res[tc] = (dW.clone(), db.clone())
+            e0 = float((res[0][0].double() - refW).abs().max() / refW.abs().max())
+            e1 = float((res[TCL][0].double() - refW).abs().max() / refW.abs().max())
+            line = "TN M=%d N=%d K=%d(%d,rot%d) %-15s ffma %.2e tcgen05 %.2e" % (M, N, K, Ktrue, rot, name, e0, e1)
+            good = e1 < 1e-5
+            if wb:
+                b1 = float((res[TCL][1].double() - refb).abs().max() / refb.abs().max())
+                line += " bias %.2e" % b1
+                good = good and b1 < 5e-6
+            print(line, "OK" if good else "FAIL")
+            ok = ok and good
+lib.gaddpg_set_tensor_core(3)
+print("ALL OK" if ok else "SOME FAILED")

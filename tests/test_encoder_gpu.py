@@ -42,11 +42,11 @@ def _oracle_forward(ora, cloud, action):
     return PointFeature.encode(ora, xyz, x)
 
 
-@pytest.mark.parametrize("B,N,with_action,tc", [(16, 256, False, 1), (16, 256, True, 1), (6, 1024, True, 1), (16, 256, True, 0),
-                                                  (4, 512, False, 0)])
+@pytest.mark.parametrize("B,N,with_action,tc", [(16, 256, False, 3), (16, 256, True, 3), (6, 1024, True, 3), (16, 256, True, 1),
+                                                  (16, 256, True, 0), (4, 512, False, 0)])
 def test_encoder_forward_backward_matches_oracle(cuda, B, N, with_action, tc):
-    """tc=1: the wide SA1 layers run on the tcgen05 3xTF32 kernel (their row count is >= 8192); tc=0 forces the FP32
-    FFMA kernel everywhere.  Batches of >= 6 keep the BatchNorm1d head well enough conditioned that the two FP32
+    """tc=3: every row-GEMM (NT and TN) with N,K >= 32 runs on the tcgen05 3xTF32 kernels; tc=1: only the wide SA1 layers
+    (resident-weight kernel, row count >= 8192); tc=0 forces the FP32 FFMA kernels everywhere.  Batches of >= 6 keep the BatchNorm1d head well enough conditioned that the two FP32
     evaluations take the same side of (almost) every ReLU / max-pool kink; gradients are still compared with a
     kink-tolerant pair of bounds: tight on the typical tensor, loose on the worst one (DESIGN.md "Parity")."""
     from gaddpg_b200 import engine, synthetic
@@ -118,7 +118,7 @@ def test_encoder_forward_backward_matches_oracle(cuda, B, N, with_action, tc):
     for k in sd_o:
         if "num_batches_tracked" in k:
             assert int(mine.state_dict()[k]) == 1, k
-    lib.gaddpg_set_tensor_core(1)
+    lib.gaddpg_set_tensor_core(3)
 
 
 def test_duplicate_folding_matches_dense_semantics(cuda):
