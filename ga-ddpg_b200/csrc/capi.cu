@@ -6,7 +6,7 @@
 #include "common.cuh"
 #include "impl.h"
 
-#define GADDPG_ABI_VERSION 1
+#define GADDPG_ABI_VERSION 2
 
 static thread_local char g_err[512] = "";
 long long g_gaddpg_launches = 0;
@@ -101,19 +101,19 @@ int gaddpg_bn_finalize_bwd(const float* stats, int C, double count, const float*
   return gaddpg_bn_finalize_bwd_impl(stats, C, count, gamma, rstd, g, m1, m2, dgamma, dbeta, accumulate, stream);
 }
 int gaddpg_sa1_l1_fwd(const float* cloud, long long cloud_stride_b, int cloud_stride_c, int skip, int Cp, const float* bc, int Cb,
-                      int B, const float* ctr, int npoint, const int32_t* row_seg, const int32_t* row_src, const float* row_w,
-                      int M_max, const int* M_dev, const float* W, int ldw, float* bcbias_ws, float* Y, float* stats,
-                      void* stream) {
-  return gaddpg_sa1_l1_fwd_impl(cloud, cloud_stride_b, cloud_stride_c, skip, Cp, bc, Cb, B, ctr, npoint, row_seg, row_src, row_w,
-                                M_max, M_dev, W, ldw, bcbias_ws, Y, stats, stream);
+                      int B, const float* ctr, int npoint, const int32_t* seg_off, const int32_t* row_seg, const int32_t* row_src,
+                      const float* row_w, int M_max, const int* M_dev, const float* W, int ldw, float* bcbias_ws, float* Y,
+                      float* stats, void* stream) {
+  return gaddpg_sa1_l1_fwd_impl(cloud, cloud_stride_b, cloud_stride_c, skip, Cp, bc, Cb, B, ctr, npoint, seg_off, row_seg, row_src,
+                                row_w, M_max, M_dev, W, ldw, bcbias_ws, Y, stats, stream);
 }
 int gaddpg_sa1_l1_bwd(const float* cloud, long long cloud_stride_b, int cloud_stride_c, int skip, int Cp, const float* bc, int Cb,
                       int B, const float* ctr, int npoint, const int32_t* seg_off, const int32_t* row_seg, const int32_t* row_src,
                       const float* row_w, int M_max, const int* M_dev, const float* D, const float* Y, const float* g,
                       const float* m1, const float* m2, const float* mean, const float* rstd, const float* W, int ldw, float* dW,
-                      int accumulate, float* dbc, float* dY_ws, float* ws, long long ws_bytes, void* stream) {
+                      int accumulate, float* dbc, float* ws, long long ws_bytes, void* stream) {
   return gaddpg_sa1_l1_bwd_impl(cloud, cloud_stride_b, cloud_stride_c, skip, Cp, bc, Cb, B, ctr, npoint, seg_off, row_seg, row_src,
-                                row_w, M_max, M_dev, D, Y, g, m1, m2, mean, rstd, W, ldw, dW, accumulate, dbc, dY_ws, ws,
+                                row_w, M_max, M_dev, D, Y, g, m1, m2, mean, rstd, W, ldw, dW, accumulate, dbc, ws,
                                 (size_t)ws_bytes, stream);
 }
 int gaddpg_gather_rows(const float* feats, int C, const float* xyz, int n_src, const float* ctr, int npoint,

@@ -35,15 +35,15 @@ int gaddpg_bn_finalize_bwd_impl(const float* stats, int C, double count, const f
                                 float* m1, float* m2, float* dgamma, float* dbeta, int accumulate, void* stream);
 // sa_ops.cu
 int gaddpg_sa1_l1_fwd_impl(const float* cloud, long long cloud_sb, int cloud_sc, int skip, int Cp, const float* bc, int Cb,
-                           int B, const float* ctr, int npoint, const int32_t* row_seg, const int32_t* row_src,
-                           const float* row_w, int M_max, const int* M_dev, const float* W, int ldw, float* bcbias_ws,
-                           float* Y, float* stats, void* stream);
+                           int B, const float* ctr, int npoint, const int32_t* seg_off, const int32_t* row_seg,
+                           const int32_t* row_src, const float* row_w, int M_max, const int* M_dev, const float* W, int ldw,
+                           float* bcbias_ws, float* Y, float* stats, void* stream);
 int gaddpg_sa1_l1_bwd_impl(const float* cloud, long long cloud_sb, int cloud_sc, int skip, int Cp, const float* bc, int Cb,
                            int B, const float* ctr, int npoint, const int32_t* seg_off, const int32_t* row_seg,
                            const int32_t* row_src, const float* row_w, int M_max, const int* M_dev, const float* D,
                            const float* Y, const float* g, const float* m1, const float* m2, const float* mean,
-                           const float* rstd, const float* W, int ldw, float* dW, int accumulate, float* dbc, float* dY_ws,
-                           float* ws, size_t ws_bytes, void* stream);
+                           const float* rstd, const float* W, int ldw, float* dW, int accumulate, float* dbc, float* ws,
+                           size_t ws_bytes, void* stream);
 int gaddpg_gather_rows_impl(const float* feats, int C, const float* xyz, int n_src, const float* ctr, int npoint,
                             const int32_t* row_seg, const int32_t* row_src, int M_max, const int* M_dev, float* G, int ldg,
                             void* stream);

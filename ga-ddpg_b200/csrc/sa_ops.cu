@@ -20,96 +20,113 @@ namespace {
 constexpr int SA1_CO = 64;   // SA1 first-layer width (networks.py:70: mlp=[in, 64, 64, 128])
 constexpr int SA1_KMAX = 16; // 3 + per-point channels
 
-// One CTA = 256 threads = 16 rows x 16 channel-quads per pass.  W row n holds [dxyz(3) | per-point(Cp) | bcast(Cb)].
-__global__ void __launch_bounds__(256) sa1_l1_fwd_kernel(const float* __restrict__ cloud, long long cloud_sb, int cloud_sc,
-                                                         int skip, int Cp, const float* __restrict__ ctr, int npoint,
-                                                         const int32_t* __restrict__ row_seg,
-                                                         const int32_t* __restrict__ row_src,
-                                                         const float* __restrict__ row_w, int M_max,
-                                                         const int* __restrict__ M_dev, const float* __restrict__ W,
-                                                         int ldw, const float* __restrict__ bcbias,
-                                                         float* __restrict__ Y, float* __restrict__ stats) {
-  __shared__ float sW[SA1_CO * SA1_KMAX];
-  __shared__ float red[2 * 16 * SA1_CO];
-  const int tid = threadIdx.x, q = tid & 15, rl = tid >> 4;
-  const int K1 = 3 + Cp;
-  for (int e = tid; e < SA1_CO * SA1_KMAX; e += 256) {
-    int n = e / SA1_KMAX, k = e % SA1_KMAX;
-    sW[e] = k < K1 ? W[n * ldw + k] : 0.f;
+// Work decomposition shared by the forward and backward kernels of this layer: an ITEM is (sample b, block j of 256
+// consecutive compact rows of that sample) -- rows of one sample are contiguous in the row table -- so everything that
+// is constant per sample (the broadcast-channel bias, the per-sample gradient column sums) is CTA-uniform.  Persistent
+// CTAs (grid <= GADDPG_STAT_SLOTS) stride over B*jmax items; inside an item each of the 8 warps owns 32 rows:
+//   phase 1  lane = row     : coalesced row-table reads, the 3+Cp scattered cloud reads of that row (L2-resident
+//                             cloud, one 4-byte gather per channel), centroid subtraction -> padded smem tile [32][20]
+//   phase 2  lane = 2 chans : walks the 32 staged rows (LDS.128 broadcasts), 2x16 FMAs per row against register
+//                             weights, one coalesced 256-byte store per row; statistics stay in registers.
+constexpr int SA1_ITEM = 256;  // rows per item
+constexpr int SA1_LDI = 20;    // staged-input row stride (floats): conflict-free float4 stores for 8 consecutive lanes
+
+__device__ __forceinline__ void sa1_stage_row(const float* __restrict__ cloud, long long cloud_sb, int cloud_sc, int skip, int Cp,
+                                              const float* __restrict__ ctr, const int32_t* __restrict__ row_seg,
+                                              const int32_t* __restrict__ row_src, const float* __restrict__ row_w, int b, int r,
+                                              bool valid, float* __restrict__ dst, float* __restrict__ wdst) {
+  float in[SA1_KMAX];
+#pragma unroll
+  for (int k = 0; k < SA1_KMAX; ++k) in[k] = 0.f;
+  float w = 0.f;
+  if (valid) {
+    const int seg = row_seg[r], src = row_src[r];
+    w = row_w[r];
+    const float* pc = cloud + (long long)b * cloud_sb + skip + src;
+#pragma unroll
+    for (int k = 0; k < SA1_KMAX - 3; ++k)
+      if (k < Cp) in[3 + k] = pc[(long long)k * cloud_sc];
+    in[0] = in[3] - ctr[(long long)seg * 3 + 0];
+    in[1] = in[4] - ctr[(long long)seg * 3 + 1];
+    in[2] = in[5] - ctr[(long long)seg * 3 + 2];
   }
-  __syncthreads();
-  float w[4][SA1_KMAX];
 #pragma unroll
-  for (int c = 0; c < 4; ++c)
+  for (int k = 0; k < SA1_KMAX; k += 4) *reinterpret_cast<float4*>(dst + k) = make_float4(in[k], in[k + 1], in[k + 2], in[k + 3]);
+  *wdst = w;
+}
+
+__global__ void __launch_bounds__(256, 2) sa1_l1_fwd_kernel(const float* __restrict__ cloud, long long cloud_sb, int cloud_sc,
+                                                            int skip, int Cp, const float* __restrict__ ctr, int npoint,
+                                                            const int32_t* __restrict__ seg_off,
+                                                            const int32_t* __restrict__ row_seg,
+                                                            const int32_t* __restrict__ row_src,
+                                                            const float* __restrict__ row_w, int B, int jmax,
+                                                            const float* __restrict__ W, int ldw,
+                                                            const float* __restrict__ bcbias, float* __restrict__ Y,
+                                                            float* __restrict__ stats) {
+  __shared__ __align__(16) float sIn[8 * 32 * SA1_LDI];
+  __shared__ float sRw[8 * 32];
+  __shared__ float red[8 * 2 * SA1_CO];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int K1 = 3 + Cp;
+  float w0[SA1_KMAX], w1[SA1_KMAX];
 #pragma unroll
-    for (int k = 0; k < SA1_KMAX; ++k) w[c][k] = sW[(q * 4 + c) * SA1_KMAX + k];
-  int M = M_dev ? *M_dev : M_max;
-  M = M < M_max ? M : M_max;
-  float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
-  constexpr int UR = 4;  // rows in flight per thread: indices -> cloud gathers -> FMAs, each stage issued for all UR rows
-  const int rstep = gridDim.x * 16;
-  for (int r0 = blockIdx.x * 16 + rl; r0 < M; r0 += rstep * UR) {
-    int seg[UR], src[UR];
+  for (int k = 0; k < SA1_KMAX; ++k) {
+    w0[k] = k < K1 ? W[(2 * lane) * ldw + k] : 0.f;
+    w1[k] = k < K1 ? W[(2 * lane + 1) * ldw + k] : 0.f;
+  }
+  float s00 = 0.f, s01 = 0.f, s10 = 0.f, s11 = 0.f;
+  float* myIn = sIn + warp * 32 * SA1_LDI;
+  float* myRw = sRw + warp * 32;
+  for (int item = blockIdx.x; item < B * jmax; item += gridDim.x) {
+    const int b = item / jmax, j = item - b * jmax;
+    const int rend = seg_off[(b + 1) * npoint];
+    const int base = seg_off[b * npoint] + j * SA1_ITEM + warp * 32;
+    int nrows = rend - base;
+    nrows = nrows > 32 ? 32 : nrows;
+    if (nrows <= 0) continue;  // warp-uniform
+    sa1_stage_row(cloud, cloud_sb, cloud_sc, skip, Cp, ctr, row_seg, row_src, row_w, b, base + lane, lane < nrows,
+                  myIn + lane * SA1_LDI, myRw + lane);
+    float2 bias = make_float2(0.f, 0.f);
+    if (bcbias) bias = *reinterpret_cast<const float2*>(bcbias + (long long)b * SA1_CO + 2 * lane);
+    __syncwarp();
+#pragma unroll 4
+    for (int rr = 0; rr < nrows; ++rr) {
+      float in[SA1_KMAX];
 #pragma unroll
-    for (int u = 0; u < UR; ++u) {
-      const int r = r0 + u * rstep;
-      seg[u] = r < M ? row_seg[r] : 0;
-      src[u] = r < M ? row_src[r] : 0;
-    }
-    float in[UR][SA1_KMAX];
-    float cx[UR][3], rwv[UR];
-#pragma unroll
-    for (int u = 0; u < UR; ++u) {
-      const int b = seg[u] / npoint;
-      const float* pc = cloud + (long long)b * cloud_sb + skip + src[u];
-#pragma unroll
-      for (int k = 0; k < SA1_KMAX; ++k) in[u][k] = 0.f;
-#pragma unroll
-      for (int k = 0; k < SA1_KMAX - 3; ++k)
-        if (k < Cp) in[u][3 + k] = pc[(long long)k * cloud_sc];
-#pragma unroll
-      for (int d = 0; d < 3; ++d) cx[u][d] = ctr[(long long)seg[u] * 3 + d];
-      rwv[u] = (stats && r0 + u * rstep < M) ? row_w[r0 + u * rstep] : 0.f;
-    }
-#pragma unroll
-    for (int u = 0; u < UR; ++u) {
-      const int r = r0 + u * rstep;
-      if (r >= M) continue;
-      const int b = seg[u] / npoint;
-      in[u][0] = in[u][3] - cx[u][0];
-      in[u][1] = in[u][4] - cx[u][1];
-      in[u][2] = in[u][5] - cx[u][2];
-      float4 o;
-      float* op = &o.x;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float a = bcbias ? bcbias[(long long)b * SA1_CO + q * 4 + c] : 0.f;
-#pragma unroll
-        for (int k = 0; k < SA1_KMAX; ++k) a = fmaf(w[c][k], in[u][k], a);
-        op[c] = a;
+      for (int k = 0; k < SA1_KMAX; k += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(myIn + rr * SA1_LDI + k);
+        in[k] = v.x;
+        in[k + 1] = v.y;
+        in[k + 2] = v.z;
+        in[k + 3] = v.w;
       }
-      *reinterpret_cast<float4*>(Y + (long long)r * SA1_CO + q * 4) = o;
+      float a0 = bias.x, a1 = bias.y;
+#pragma unroll
+      for (int k = 0; k < SA1_KMAX; ++k) {
+        a0 = fmaf(w0[k], in[k], a0);
+        a1 = fmaf(w1[k], in[k], a1);
+      }
+      *reinterpret_cast<float2*>(Y + (long long)(base + rr) * SA1_CO + 2 * lane) = make_float2(a0, a1);
       if (stats) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          s0[c] = fmaf(rwv[u], op[c], s0[c]);
-          s1[c] = fmaf(rwv[u] * op[c], op[c], s1[c]);
-        }
+        const float w = myRw[rr];
+        s00 = fmaf(w, a0, s00);
+        s01 = fmaf(w * a0, a0, s01);
+        s10 = fmaf(w, a1, s10);
+        s11 = fmaf(w * a1, a1, s11);
       }
     }
+    __syncwarp();
   }
   if (stats) {
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      red[rl * SA1_CO + q * 4 + c] = s0[c];
-      red[16 * SA1_CO + rl * SA1_CO + q * 4 + c] = s1[c];
-    }
+    red[warp * 2 * SA1_CO + 2 * lane] = s00;
+    red[warp * 2 * SA1_CO + 2 * lane + 1] = s10;
+    red[warp * 2 * SA1_CO + SA1_CO + 2 * lane] = s01;
+    red[warp * 2 * SA1_CO + SA1_CO + 2 * lane + 1] = s11;
     __syncthreads();
     float v = 0.f;
-    if (tid < 2 * SA1_CO) {
-      int which = tid / SA1_CO, c = tid % SA1_CO;
-      for (int y = 0; y < 16; ++y) v += red[which * 16 * SA1_CO + y * SA1_CO + c];
-    }
+    if (tid < 2 * SA1_CO)
+      for (int y = 0; y < 8; ++y) v += red[y * 2 * SA1_CO + tid];
     for (int slot = blockIdx.x; slot < GADDPG_STAT_SLOTS; slot += gridDim.x)
       if (tid < 2 * SA1_CO) stats[(long long)slot * 2 * SA1_CO + tid] = (slot == (int)blockIdx.x) ? v : 0.f;
   }
@@ -126,66 +143,103 @@ __global__ void sa1_bcbias_kernel(const float* __restrict__ bc, int Cb, int B, c
   bcbias[e] = a;
 }
 
-// dW1[n][k] partials: thread = (channel n, row lane rl of 4); dY1 = BN-backward of (D1, Y1) on the fly
-__global__ void __launch_bounds__(256) sa1_l1_bwd_kernel(const float* __restrict__ cloud, long long cloud_sb, int cloud_sc,
-                                                         int skip, int Cp, const float* __restrict__ ctr, int npoint,
-                                                         const int32_t* __restrict__ row_seg,
-                                                         const int32_t* __restrict__ row_src,
-                                                         const float* __restrict__ row_w, int M_max,
-                                                         const int* __restrict__ M_dev, const float* __restrict__ D,
-                                                         const float* __restrict__ Y, const float* __restrict__ g,
-                                                         const float* __restrict__ m1, const float* __restrict__ m2,
-                                                         const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                         float* __restrict__ dY_out, float* __restrict__ partial) {
-  __shared__ float red[4 * SA1_CO * SA1_KMAX];
-  const int tid = threadIdx.x, n = tid & 63, rl = tid >> 6;
-  const float gn = g[n], m1n = m1[n], m2n = m2[n], mun = mean[n], rsn = rstd[n];
-  int M = M_dev ? *M_dev : M_max;
-  M = M < M_max ? M : M_max;
-  float acc[SA1_KMAX];
+// Backward of the same layer, same item decomposition: dY1 = BN-backward of (D1, Y1) on the fly (never stored),
+// dW1[n][k] += dY1[r][n] * in[r][k] in 2x16 register accumulators per lane, and -- when the layer has broadcast
+// channels -- the per-sample column sums of dY1 as one [64] partial per item (fixed-order sum in sa1_dbc_kernel).
+__global__ void __launch_bounds__(256, 2) sa1_l1_bwd_kernel(const float* __restrict__ cloud, long long cloud_sb, int cloud_sc,
+                                                            int skip, int Cp, const float* __restrict__ ctr, int npoint,
+                                                            const int32_t* __restrict__ seg_off,
+                                                            const int32_t* __restrict__ row_seg,
+                                                            const int32_t* __restrict__ row_src,
+                                                            const float* __restrict__ row_w, int B, int jmax,
+                                                            const float* __restrict__ D, const float* __restrict__ Y,
+                                                            const float* __restrict__ g, const float* __restrict__ m1,
+                                                            const float* __restrict__ m2, const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd, float* __restrict__ colsum_part,
+                                                            float* __restrict__ partial) {
+  __shared__ __align__(16) float sbuf[8 * SA1_CO * SA1_KMAX];  // staged inputs (8*32*20 floats) / final dW reduction
+  __shared__ float sRw[8 * 32];
+  __shared__ float red[8 * SA1_CO];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float2 gn = *reinterpret_cast<const float2*>(g + 2 * lane), m1n = *reinterpret_cast<const float2*>(m1 + 2 * lane),
+               m2n = *reinterpret_cast<const float2*>(m2 + 2 * lane), mun = *reinterpret_cast<const float2*>(mean + 2 * lane),
+               rsn = *reinterpret_cast<const float2*>(rstd + 2 * lane);
+  float acc0[SA1_KMAX], acc1[SA1_KMAX];
 #pragma unroll
-  for (int k = 0; k < SA1_KMAX; ++k) acc[k] = 0.f;
-  constexpr int UR = 8;  // rows in flight per thread
-  const int rstep = gridDim.x * 4;
-  for (int r0 = blockIdx.x * 4 + rl; r0 < M; r0 += rstep * UR) {
-    int seg[UR], src[UR];
-    float d[UR], y[UR], rwv[UR];
-#pragma unroll
-    for (int u = 0; u < UR; ++u) {
-      const int r = r0 + u * rstep;
-      const bool ok = r < M;
-      seg[u] = ok ? row_seg[r] : 0;
-      src[u] = ok ? row_src[r] : 0;
-      d[u] = ok ? D[(long long)r * SA1_CO + n] : 0.f;
-      y[u] = ok ? Y[(long long)r * SA1_CO + n] : 0.f;
-      rwv[u] = ok ? row_w[r] : 0.f;
+  for (int k = 0; k < SA1_KMAX; ++k) acc0[k] = acc1[k] = 0.f;
+  float* myIn = sbuf + warp * 32 * SA1_LDI;
+  float* myRw = sRw + warp * 32;
+  for (int item = blockIdx.x; item < B * jmax; item += gridDim.x) {
+    const int b = item / jmax, j = item - b * jmax;
+    const int rend = seg_off[(b + 1) * npoint];
+    const int start = seg_off[b * npoint] + j * SA1_ITEM;
+    if (start >= rend) {  // CTA-uniform: empty item
+      if (colsum_part && tid < SA1_CO) colsum_part[(long long)item * SA1_CO + tid] = 0.f;
+      continue;
     }
+    const int base = start + warp * 32;
+    int nrows = rend - base;
+    nrows = nrows > 32 ? 32 : nrows;
+    float cs0 = 0.f, cs1 = 0.f;
+    if (nrows > 0) {
+      sa1_stage_row(cloud, cloud_sb, cloud_sc, skip, Cp, ctr, row_seg, row_src, row_w, b, base + lane, lane < nrows,
+                    myIn + lane * SA1_LDI, myRw + lane);
+      __syncwarp();
+      for (int r4 = 0; r4 < nrows; r4 += 4) {
+        float2 d[4], y[4];
 #pragma unroll
-    for (int u = 0; u < UR; ++u) {
-      const int r = r0 + u * rstep;
-      if (r >= M) continue;
-      const int b = seg[u] / npoint;
-      const float* pc = cloud + (long long)b * cloud_sb + skip + src[u];
-      float in[SA1_KMAX];
+        for (int u = 0; u < 4; ++u) {
+          const bool ok = r4 + u < nrows;
+          d[u] = ok ? *reinterpret_cast<const float2*>(D + (long long)(base + r4 + u) * SA1_CO + 2 * lane) : make_float2(0.f, 0.f);
+          y[u] = ok ? *reinterpret_cast<const float2*>(Y + (long long)(base + r4 + u) * SA1_CO + 2 * lane) : make_float2(0.f, 0.f);
+        }
 #pragma unroll
-      for (int k = 0; k < SA1_KMAX; ++k) in[k] = 0.f;
+        for (int u = 0; u < 4; ++u) {
+          if (r4 + u < nrows) {
+            const float w = myRw[r4 + u];
+            const float dy0 = gn.x * (d[u].x - w * (m1n.x + (y[u].x - mun.x) * rsn.x * m2n.x));
+            const float dy1 = gn.y * (d[u].y - w * (m1n.y + (y[u].y - mun.y) * rsn.y * m2n.y));
+            cs0 += dy0;
+            cs1 += dy1;
 #pragma unroll
-      for (int k = 0; k < SA1_KMAX - 3; ++k)
-        if (k < Cp) in[3 + k] = pc[(long long)k * cloud_sc];
-      in[0] = in[3] - ctr[(long long)seg[u] * 3 + 0];
-      in[1] = in[4] - ctr[(long long)seg[u] * 3 + 1];
-      in[2] = in[5] - ctr[(long long)seg[u] * 3 + 2];
-      const float dy = gn * (d[u] - rwv[u] * (m1n + (y[u] - mun) * rsn * m2n));
-      if (dY_out) dY_out[(long long)r * SA1_CO + n] = dy;
-#pragma unroll
-      for (int k = 0; k < SA1_KMAX; ++k) acc[k] = fmaf(dy, in[k], acc[k]);
+            for (int k = 0; k < SA1_KMAX; k += 4) {
+              const float4 v = *reinterpret_cast<const float4*>(myIn + (r4 + u) * SA1_LDI + k);
+              acc0[k] = fmaf(dy0, v.x, acc0[k]);
+              acc0[k + 1] = fmaf(dy0, v.y, acc0[k + 1]);
+              acc0[k + 2] = fmaf(dy0, v.z, acc0[k + 2]);
+              acc0[k + 3] = fmaf(dy0, v.w, acc0[k + 3]);
+              acc1[k] = fmaf(dy1, v.x, acc1[k]);
+              acc1[k + 1] = fmaf(dy1, v.y, acc1[k + 1]);
+              acc1[k + 2] = fmaf(dy1, v.z, acc1[k + 2]);
+              acc1[k + 3] = fmaf(dy1, v.w, acc1[k + 3]);
+            }
+          }
+        }
+      }
+      __syncwarp();
+    }
+    if (colsum_part) {
+      red[warp * SA1_CO + 2 * lane] = cs0;
+      red[warp * SA1_CO + 2 * lane + 1] = cs1;
+      __syncthreads();
+      if (tid < SA1_CO) {
+        float v = 0.f;
+        for (int y = 0; y < 8; ++y) v += red[y * SA1_CO + tid];
+        colsum_part[(long long)item * SA1_CO + tid] = v;
+      }
+      __syncthreads();
     }
   }
+  __syncthreads();
 #pragma unroll
-  for (int k = 0; k < SA1_KMAX; ++k) red[(rl * SA1_CO + n) * SA1_KMAX + k] = acc[k];
+  for (int k = 0; k < SA1_KMAX; k += 4) {
+    *reinterpret_cast<float4*>(sbuf + (warp * SA1_CO + 2 * lane) * SA1_KMAX + k) = make_float4(acc0[k], acc0[k + 1], acc0[k + 2], acc0[k + 3]);
+    *reinterpret_cast<float4*>(sbuf + (warp * SA1_CO + 2 * lane + 1) * SA1_KMAX + k) = make_float4(acc1[k], acc1[k + 1], acc1[k + 2], acc1[k + 3]);
+  }
   __syncthreads();
   for (int e = tid; e < SA1_CO * SA1_KMAX; e += 256) {
-    float v = red[e] + red[SA1_CO * SA1_KMAX + e] + red[2 * SA1_CO * SA1_KMAX + e] + red[3 * SA1_CO * SA1_KMAX + e];
+    float v = 0.f;
+    for (int y = 0; y < 8; ++y) v += sbuf[y * SA1_CO * SA1_KMAX + e];
     partial[(long long)blockIdx.x * SA1_CO * SA1_KMAX + e] = v;
   }
 }
@@ -200,15 +254,14 @@ __global__ void sa1_dw_reduce_kernel(const float* __restrict__ partial, int nblk
   *d = (accumulate ? *d : 0.f) + s;
 }
 
-// per-sample column sums of dY1 (rows of a sample are contiguous), then dbc = Wbc^T colsum, dWbc += colsum (x) bc
-__global__ void __launch_bounds__(64) sa1_dbc_kernel(const float* __restrict__ dY, const int32_t* __restrict__ seg_off,
-                                                     int npoint, const float* __restrict__ W, int ldw, int koff, int Cb,
-                                                     float* __restrict__ colsum, float* __restrict__ dbc) {
+// per-sample column sums of dY1 from the per-item partials (fixed order), then dbc = Wbc^T colsum
+__global__ void __launch_bounds__(64) sa1_dbc_kernel(const float* __restrict__ colsum_part, int jmax, const float* __restrict__ W,
+                                                     int ldw, int koff, int Cb, float* __restrict__ colsum,
+                                                     float* __restrict__ dbc) {
   __shared__ float s[SA1_CO];
   const int b = blockIdx.x, n = threadIdx.x;
-  const int r0 = seg_off[b * npoint], r1 = seg_off[(b + 1) * npoint];
   float a = 0.f;
-  for (int r = r0; r < r1; ++r) a += dY[(long long)r * SA1_CO + n];
+  for (int j = 0; j < jmax; ++j) a += colsum_part[((long long)b * jmax + j) * SA1_CO + n];
   s[n] = a;
   if (colsum) colsum[(long long)b * SA1_CO + n] = a;
   __syncthreads();
@@ -449,23 +502,27 @@ int gaddpg_dmask_stats_impl(const float* dX, int ldx, const float* Yprev, int C,
   return GADDPG_OK;
 }
 
+static int sa1_jmax(int M_max, int B) { return ceil_div(ceil_div(M_max, B > 0 ? B : 1), SA1_ITEM); }
+
 int gaddpg_sa1_l1_fwd_impl(const float* cloud, long long cloud_sb, int cloud_sc, int skip, int Cp, const float* bc, int Cb,
-                           int B, const float* ctr, int npoint, const int32_t* row_seg, const int32_t* row_src,
-                           const float* row_w, int M_max, const int* M_dev, const float* W, int ldw, float* bcbias_ws,
-                           float* Y, float* stats, void* stream) {
-  GADDPG_CHECK_ARG(cloud && ctr && row_seg && row_src && row_w && W && Y, "sa1_l1_fwd: null pointer");
+                           int B, const float* ctr, int npoint, const int32_t* seg_off, const int32_t* row_seg,
+                           const int32_t* row_src, const float* row_w, int M_max, const int* M_dev, const float* W, int ldw,
+                           float* bcbias_ws, float* Y, float* stats, void* stream) {
+  GADDPG_CHECK_ARG(cloud && ctr && seg_off && row_seg && row_src && row_w && W && Y, "sa1_l1_fwd: null pointer");
   GADDPG_CHECK_ARG(Cp >= 3 && 3 + Cp <= SA1_KMAX && Cb >= 0 && ldw >= 3 + Cp + Cb, "sa1_l1_fwd: bad channels Cp=%d Cb=%d", Cp, Cb);
   GADDPG_CHECK_ARG(Cb == 0 || (bc && bcbias_ws), "sa1_l1_fwd: broadcast channels need bc and workspace");
+  (void)M_dev;  // the live row count is seg_off[B*npoint]
   cudaStream_t st = (cudaStream_t)stream;
   if (Cb > 0) {
     sa1_bcbias_kernel<<<ceil_div(B * SA1_CO, 256), 256, 0, st>>>(bc, Cb, B, W, ldw, 3 + Cp, bcbias_ws);
     GADDPG_CHECK_LAUNCH("sa1_bcbias_kernel");
   }
-  if (M_max == 0) return GADDPG_OK;
-  int grid = ceil_div(M_max, 16);
+  if (M_max == 0 || B == 0) return GADDPG_OK;
+  const int jmax = sa1_jmax(M_max, B);
+  int grid = B * jmax;
   grid = grid < GADDPG_STAT_SLOTS ? grid : GADDPG_STAT_SLOTS;
-  sa1_l1_fwd_kernel<<<grid, 256, 0, st>>>(cloud, cloud_sb, cloud_sc, skip, Cp, ctr, npoint, row_seg, row_src, row_w, M_max,
-                                          M_dev, W, ldw, Cb > 0 ? bcbias_ws : nullptr, Y, stats);
+  sa1_l1_fwd_kernel<<<grid, 256, 0, st>>>(cloud, cloud_sb, cloud_sc, skip, Cp, ctr, npoint, seg_off, row_seg, row_src, row_w, B, jmax,
+                                          W, ldw, Cb > 0 ? bcbias_ws : nullptr, Y, stats);
   GADDPG_CHECK_LAUNCH("sa1_l1_fwd_kernel");
   return GADDPG_OK;
 }
@@ -474,27 +531,31 @@ int gaddpg_sa1_l1_bwd_impl(const float* cloud, long long cloud_sb, int cloud_sc,
                            int B, const float* ctr, int npoint, const int32_t* seg_off, const int32_t* row_seg,
                            const int32_t* row_src, const float* row_w, int M_max, const int* M_dev, const float* D,
                            const float* Y, const float* g, const float* m1, const float* m2, const float* mean,
-                           const float* rstd, const float* W, int ldw, float* dW, int accumulate, float* dbc, float* dY_ws,
-                           float* ws, size_t ws_bytes, void* stream) {
+                           const float* rstd, const float* W, int ldw, float* dW, int accumulate, float* dbc, float* ws,
+                           size_t ws_bytes, void* stream) {
   GADDPG_CHECK_ARG(cloud && ctr && seg_off && row_seg && row_src && row_w && D && Y && g && m1 && m2 && mean && rstd && W && ws,
                    "sa1_l1_bwd: null pointer");
   GADDPG_CHECK_ARG(Cp >= 3 && 3 + Cp <= SA1_KMAX && Cb >= 0, "sa1_l1_bwd: bad channels");
-  GADDPG_CHECK_ARG(Cb == 0 || dY_ws, "sa1_l1_bwd: broadcast channels need the dY workspace");
+  (void)M_dev;
   const int nblk = GADDPG_STAT_SLOTS;
-  size_t need = ((size_t)nblk * SA1_CO * SA1_KMAX + (size_t)B * SA1_CO) * sizeof(float);
-  GADDPG_CHECK_ARG(ws_bytes >= need, "sa1_l1_bwd: workspace too small");
+  if (M_max == 0 || B == 0) return GADDPG_OK;
+  const int jmax = sa1_jmax(M_max, B);
+  size_t need = ((size_t)nblk * SA1_CO * SA1_KMAX + (size_t)B * SA1_CO * (1 + jmax)) * sizeof(float);
+  GADDPG_CHECK_ARG(ws_bytes >= need, "sa1_l1_bwd: workspace too small (%zu < %zu)", ws_bytes, need);
   cudaStream_t st = (cudaStream_t)stream;
-  if (M_max == 0) return GADDPG_OK;
   float* colsum = ws + (size_t)nblk * SA1_CO * SA1_KMAX;
-  sa1_l1_bwd_kernel<<<nblk, 256, 0, st>>>(cloud, cloud_sb, cloud_sc, skip, Cp, ctr, npoint, row_seg, row_src, row_w, M_max,
-                                          M_dev, D, Y, g, m1, m2, mean, rstd, Cb > 0 ? dY_ws : nullptr, ws);
+  float* colsum_part = colsum + (size_t)B * SA1_CO;
+  int grid = B * jmax;
+  grid = grid < nblk ? grid : nblk;
+  sa1_l1_bwd_kernel<<<grid, 256, 0, st>>>(cloud, cloud_sb, cloud_sc, skip, Cp, ctr, npoint, seg_off, row_seg, row_src, row_w, B, jmax,
+                                          D, Y, g, m1, m2, mean, rstd, Cb > 0 ? colsum_part : nullptr, ws);
   GADDPG_CHECK_LAUNCH("sa1_l1_bwd_kernel");
   if (dW) {
-    sa1_dw_reduce_kernel<<<ceil_div(SA1_CO * (3 + Cp), 128), 128, 0, st>>>(ws, nblk, 3 + Cp, dW, ldw, accumulate);
+    sa1_dw_reduce_kernel<<<ceil_div(SA1_CO * (3 + Cp), 128), 128, 0, st>>>(ws, grid, 3 + Cp, dW, ldw, accumulate);
     GADDPG_CHECK_LAUNCH("sa1_dw_reduce_kernel");
   }
   if (Cb > 0) {
-    sa1_dbc_kernel<<<B, 64, 0, st>>>(dY_ws, seg_off, npoint, W, ldw, 3 + Cp, Cb, colsum, dbc);
+    sa1_dbc_kernel<<<B, 64, 0, st>>>(colsum_part, jmax, W, ldw, 3 + Cp, Cb, colsum, dbc);
     GADDPG_CHECK_LAUNCH("sa1_dbc_kernel");
     if (dW) {
       sa1_dwbc_kernel<<<ceil_div(SA1_CO * Cb, 128), 128, 0, st>>>(colsum, bc, B, Cb, dW, ldw, 3 + Cp, accumulate);

@@ -66,8 +66,9 @@ class Workspace:
         self.sa1_ws_bytes = 0
         self.sa1_ws = None
 
-    def sa1(self, B):
-        need = (STAT_SLOTS * 64 * 16 + B * 64) * 4
+    def sa1(self, B, cap):
+        jmax = -(-(-(-cap // max(B, 1))) // 256)
+        need = (STAT_SLOTS * 64 * 16 + B * 64 * (1 + jmax)) * 4
         if self.sa1_ws is None or self.sa1_ws_bytes < need:
             self.sa1_ws = _f(self.device, need // 4)
             self.sa1_ws_bytes = need
@@ -292,7 +293,6 @@ class BwdScratch:
         self.dout = [_f(device, B * 32, widths[0][2]), None, _f(device, B, 512)]  # SA1 pooled grad, -, SA3 pooled grad
         self.Dfc = [_f(device, B, 1024), _f(device, B, 512)]
         self.bbfc = [_bnbwd(device, 1024), _bnbwd(device, 512)]
-        self.dY1 = _f(device, caps[0], 64)
         self.dbc = _f(device, B, 8)
 
 
@@ -316,9 +316,9 @@ def encoder_forward(ws, ef, geom, cloud, skip, Cp, bc, ctx, time=None, time_offs
     s = ctx.sa[0]
     W0 = L["sa0.0"]
     assert W0.K == 3 + Cp + Cb, (W0.K, Cp, Cb)
-    lib.gaddpg_sa1_l1_fwd(dp(cloud), C * Np, Np, skip, Cp, dp(bc), Cb, B, dp(l1.new_xyz), geom.npoint, dp(l1.row_seg),
-                          dp(l1.row_src), dp(l1.row_w), l1.cap, l1.M_dev, dp(W0.W), W0.K, dp(ctx.bcbias), dp(s.Y[0]),
-                          dp(ws.stats) if train else None, st)
+    lib.gaddpg_sa1_l1_fwd(dp(cloud), C * Np, Np, skip, Cp, dp(bc), Cb, B, dp(l1.new_xyz), geom.npoint, dp(l1.seg_off),
+                          dp(l1.row_seg), dp(l1.row_src), dp(l1.row_w), l1.cap, l1.M_dev, dp(W0.W), W0.K, dp(ctx.bcbias),
+                          dp(s.Y[0]), dp(ws.stats) if train else None, st)
     bn_fwd(ws, 64, B * geom.npoint * l1.ns, W0, s.bn[0], train)
     _mlp_tail_forward(ws, [L["sa0.1"], L["sa0.2"]], s, 1, l1.cap, l1.M_dev, l1.row_w, B * geom.npoint * l1.ns, train)
     lib.gaddpg_pool_fwd(dp(s.Y[2]), 128, dp(s.bn[2].scale), dp(s.bn[2].shift), dp(l1.seg_off), 0, l1.S, dp(s.out), dp(s.arg), st)
@@ -417,8 +417,7 @@ def encoder_backward(ws, ef, ctx, sc, want_dw=True, want_dbc=False, accumulate=0
                           dp(ctx.bc), ctx.Cb, B, dp(l1.new_xyz), geom.npoint, dp(l1.seg_off), dp(l1.row_seg), dp(l1.row_src),
                           dp(l1.row_w), l1.cap, l1.M_dev, dp(sc.D[0][0]), dp(s.Y[0]), dp(bb0.g), dp(bb0.m1), dp(bb0.m2),
                           dp(s.bn[0].mean), dp(s.bn[0].rstd), dp(W0.W), W0.K, dp(W0.dW) if want_dw else None, accumulate,
-                          dp(sc.dbc) if (want_dbc and ctx.Cb > 0) else None, dp(sc.dY1) if ctx.Cb > 0 else None,
-                          dp(ws.sa1(B)), ws.sa1_ws_bytes, st)
+                          dp(sc.dbc) if (want_dbc and ctx.Cb > 0) else None, dp(ws.sa1(B, l1.cap)), ws.sa1_ws_bytes, st)
     return sc.dbc.view(-1)[: B * ctx.Cb].view(B, ctx.Cb) if (want_dbc and ctx.Cb > 0) else None
 
 

@@ -157,18 +157,20 @@ GADDPG_API int gaddpg_bn_finalize_bwd(const float* stats, int C, double count, c
 
 /* ---- set-abstraction glue (SURVEY.md §8 Spec S3; upstream QueryAndGroup / GroupAll / F.max_pool2d) ------------- */
 /* SA1 first layer straight from the channel-major cloud (B, *, skip+N): W[64][3+Cp+Cb] = [dxyz | per-point | broadcast];
- * bc (B,Cb) are per-sample constant channels (the action, utils.py:291-297); bcbias_ws (B,64) scratch. */
+ * bc (B,Cb) are per-sample constant channels (the action, utils.py:291-297); bcbias_ws (B,64) scratch;
+ * seg_off[B*npoint+1] of gaddpg_row_table (rows of one sample are contiguous: work is split per sample). */
 GADDPG_API int gaddpg_sa1_l1_fwd(const float* cloud, long long cloud_stride_b, int cloud_stride_c, int skip, int Cp, const float* bc,
-                                 int Cb, int B, const float* ctr, int npoint, const int32_t* row_seg, const int32_t* row_src,
-                                 const float* row_w, int M_max, const int* M_dev, const float* W, int ldw, float* bcbias_ws,
-                                 float* Y, float* stats, void* stream);
-/* backward of the same layer: dW (may be NULL), dbc (B,Cb) (may be NULL); dY_ws (M,64) scratch needed when Cb > 0 */
+                                 int Cb, int B, const float* ctr, int npoint, const int32_t* seg_off, const int32_t* row_seg,
+                                 const int32_t* row_src, const float* row_w, int M_max, const int* M_dev, const float* W, int ldw,
+                                 float* bcbias_ws, float* Y, float* stats, void* stream);
+/* backward of the same layer: dW (may be NULL), dbc (B,Cb) (may be NULL); dY1 is never materialised.
+ * ws: (GADDPG_STAT_SLOTS*64*16 + B*64*(1 + ceil(M_max/B/256))) floats */
 GADDPG_API int gaddpg_sa1_l1_bwd(const float* cloud, long long cloud_stride_b, int cloud_stride_c, int skip, int Cp, const float* bc,
                                  int Cb, int B, const float* ctr, int npoint, const int32_t* seg_off, const int32_t* row_seg,
                                  const int32_t* row_src, const float* row_w, int M_max, const int* M_dev, const float* D,
                                  const float* Y, const float* g, const float* m1, const float* m2, const float* mean,
-                                 const float* rstd, const float* W, int ldw, float* dW, int accumulate, float* dbc, float* dY_ws,
-                                 float* ws, long long ws_bytes, void* stream);
+                                 const float* rstd, const float* W, int ldw, float* dW, int accumulate, float* dbc, float* ws,
+                                 long long ws_bytes, void* stream);
 /* G[r] = [feats[src] (C) | xyz[src]-ctr[seg] (3) | 0-pad]; row tables NULL: identity rows, absolute xyz (GroupAll) */
 GADDPG_API int gaddpg_gather_rows(const float* feats, int C, const float* xyz, int n_src, const float* ctr, int npoint,
                                   const int32_t* row_seg, const int32_t* row_src, int M_max, const int* M_dev, float* G, int ldg,
