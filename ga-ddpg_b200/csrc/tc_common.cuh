@@ -118,4 +118,112 @@ __device__ __forceinline__ float4 load_operand4(const Operand& d, int row, int c
 }
 
 
+// ---------------------------------------------------------------------------------------------------------
+// Shared NT epilogue: one 32-row x 32-column accumulator block of one epilogue warp.
+//   tcgen05.ld (lane = row, 32 columns in registers) -> 8 x STS.128 into a [32][36] staging tile -> 8 x LDS.128 in
+//   the store layout (lane -> row 4i + (lane>>3), columns 4*(lane&7)..+3) -> 8 x STG.128, each covering four complete
+//   128-byte row segments.  Everything the block needs from global memory (mask source, row weights) is loaded
+//   before the TMEM wait; the body is branch-free so the loads, shared-memory traffic and stores of a block overlap.
+// BatchNorm statistics are kept per lane for its 4 columns (s0/s1) across all tiles of the CTA and reduced once at
+// the end of the kernel (epi_reduce_stats), always in the same order.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int EPI_LD = 36;  // staging row pitch in floats: 16-byte aligned rows, conflict-free STS.128 / LDS.128
+
+template <int EMODE>
+__device__ __forceinline__ void epi_block32(const NTProblem& p, uint32_t taddr, float* stage, int lane, int row_base, int col0,
+                                            int M, int N, const float (&wr)[8], bool do_stats, float (&s0)[4], float (&s1)[4]) {
+  const int rsub = lane >> 3, c4 = (lane & 7) << 2;
+  const int col = col0 + c4;
+  const bool cval = col < N;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 yp[8];
+  if (EMODE == EPI_DMASK) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = row_base + 4 * i + rsub;
+      yp[i] = (cval && row < M) ? ldg4(p.Yprev + (long long)row * p.ldyp + col) : zero4;
+    }
+  }
+  float4 k0 = zero4, k1 = zero4, k2 = zero4, k3 = zero4;  // STORE: bias | DMASK: scale, shift, mean, rstd of the mask source
+  bool has_psc = false;
+  if (cval) {
+    if (EMODE == EPI_STORE) {
+      if (p.bias) k0 = make_float4(p.bias[col], p.bias[col + 1], p.bias[col + 2], p.bias[col + 3]);
+    } else {
+      has_psc = p.psc != nullptr;
+      if (has_psc) {
+        k0 = ldg4(p.psc + col);
+        k1 = ldg4(p.psh + col);
+      }
+      if (do_stats) {
+        k2 = ldg4(p.pmean + col);
+        k3 = ldg4(p.prstd + col);
+      }
+    }
+  }
+  float r[32];
+  tmem_ld32(taddr, r);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(stage + lane * EPI_LD + 4 * j) = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+  __syncwarp();
+  float4 v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const float4*>(stage + (4 * i + rsub) * EPI_LD + c4);
+  __syncwarp();
+  const bool relu = (EMODE == EPI_STORE) && p.relu;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = row_base + 4 * i + rsub;
+    const bool ok = cval && row < M;
+    float4 x = v[i];
+    if (EMODE == EPI_STORE) {
+      x.x += k0.x; x.y += k0.y; x.z += k0.z; x.w += k0.w;
+      if (relu) {
+        x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
+      }
+      if (ok) *reinterpret_cast<float4*>(p.C + (long long)row * p.ldc + col) = x;
+      if (!ok) x = zero4;  // TMEM columns >= N / rows >= M may hold anything (0 * NaN would poison the sums)
+      const float w = ok ? wr[i] : 0.f;
+      s0[0] = fmaf(w, x.x, s0[0]); s1[0] = fmaf(w * x.x, x.x, s1[0]);
+      s0[1] = fmaf(w, x.y, s0[1]); s1[1] = fmaf(w * x.y, x.y, s1[1]);
+      s0[2] = fmaf(w, x.z, s0[2]); s1[2] = fmaf(w * x.z, x.z, s1[2]);
+      s0[3] = fmaf(w, x.w, s0[3]); s1[3] = fmaf(w * x.w, x.w, s1[3]);
+    } else {
+      const float4 y = yp[i];
+      const float zx = has_psc ? fmaf(y.x, k0.x, k1.x) : y.x, zy = has_psc ? fmaf(y.y, k0.y, k1.y) : y.y;
+      const float zz = has_psc ? fmaf(y.z, k0.z, k1.z) : y.z, zw = has_psc ? fmaf(y.w, k0.w, k1.w) : y.w;
+      x.x = (ok && zx > 0.f) ? x.x : 0.f;
+      x.y = (ok && zy > 0.f) ? x.y : 0.f;
+      x.z = (ok && zz > 0.f) ? x.z : 0.f;
+      x.w = (ok && zw > 0.f) ? x.w : 0.f;
+      if (ok) *reinterpret_cast<float4*>(p.C + (long long)row * p.ldc + col) = x;
+      s0[0] += x.x; s1[0] = fmaf(x.x, (y.x - k2.x) * k3.x, s1[0]);
+      s0[1] += x.y; s1[1] = fmaf(x.y, (y.y - k2.y) * k3.y, s1[1]);
+      s0[2] += x.z; s1[2] = fmaf(x.z, (y.z - k2.z) * k3.z, s1[2]);
+      s0[3] += x.w; s1[3] = fmaf(x.w, (y.w - k2.w) * k3.w, s1[3]);
+    }
+  }
+}
+
+// fold the four row-phase lanes (lane>>3) of each column quad; afterwards every lane holds the warp's column sums
+__device__ __forceinline__ void epi_reduce_stats(float (&s)[4]) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    s[k] += __shfl_xor_sync(0xffffffffu, s[k], 8);
+    s[k] += __shfl_xor_sync(0xffffffffu, s[k], 16);
+  }
+}
+
+// the NT epilogue needs 16-byte aligned rows of C (and of the mask source): everything else stays on gemm_rows.cu
+static inline bool tc_epilogue_ok(const NTProblem& p, int emode) {
+  if (p.N % 4 != 0 || p.ldc % 4 != 0 || ((uintptr_t)p.C & 15u) != 0) return false;
+  if (emode == EPI_DMASK) {
+    if (p.ldyp % 4 != 0 || ((uintptr_t)p.Yprev & 15u) != 0) return false;
+    if (p.psc && ((((uintptr_t)p.psc) | ((uintptr_t)p.psh)) & 15u) != 0) return false;
+    if (p.stats && ((((uintptr_t)p.pmean) | ((uintptr_t)p.prstd)) & 15u) != 0) return false;
+  }
+  return true;
+}
+
 }  // namespace

@@ -14,8 +14,9 @@
 //                          (the weights are staged the same way once per CTA), fence.proxy.async, mbarrier arrive
 //   warp  4    MMA issuer: one thread issues 3*K/8 tcgen05.mma.kind::tf32 (M=128, N=N, K=8) per tile into a
 //                          double-buffered TMEM accumulator and tcgen05.commit's the smem stage / accumulator barriers
-//   warps 5-8  epilogue  : tcgen05.ld 32x32b -> registers -> padded smem transpose -> coalesced global stores, mask
-//                          epilogue reads and per-column BatchNorm statistics (fixed order, one slot per CTA)
+//   warps 5-8  epilogue  : tcgen05.ld 32x32b -> registers -> smem re-layout -> 16-byte global stores (four full 128-byte
+//                          row segments per instruction), mask reads and per-column BatchNorm statistics (fixed order,
+//                          one slot per CTA); shared with tc_gemm_kc.cu (tc_common.cuh: epi_block32)
 // No TMA here by design: every A element passes through a per-element prologue before it may reach the tensor
 // core, so the producer warps ARE the copy engine; W is 16-64 KB and loaded once per CTA.
 #include "tc_common.cuh"
@@ -38,7 +39,7 @@ __host__ __device__ inline TcSmemLayout tc_layout(int N, int K, int stages) {
     L.a_hi[s] = off; if (s < stages) off += (uint32_t)TC_BM * K * 4;
     L.a_lo[s] = off; if (s < stages) off += (uint32_t)TC_BM * K * 4;
   }
-  L.stage_buf = off; off += 4 * 32 * 33 * 4;   // per-epilogue-warp transpose buffers
+  L.stage_buf = off; off += 4 * 32 * EPI_LD * 4;   // per-epilogue-warp transpose buffers
   L.bars = off; off += 256;                     // mbarriers + tmem address + stats scratch header
   off += 2 * 4 * 256 * 4;                       // cross-warp stats combine: [2][4 warps][N<=256]
   L.total = off;
@@ -229,78 +230,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
   } else {
     // ===================== epilogue =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    float* stage = reinterpret_cast<float*>(smem + L.stage_buf) + (warp - 5) * 32 * 33;
+    float* stage = reinterpret_cast<float*>(smem + L.stage_buf) + (warp - 5) * 32 * EPI_LD;
     const bool do_stats = (p.stats != nullptr);
-    float s0[8], s1[8];
+    const int rsub = lane >> 3;
+    float s0[8][4], s1[8][4];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) s0[c] = s1[c] = 0.f;
+    for (int c = 0; c < 8; ++c)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s0[c][k] = s1[c][k] = 0.f;
     int it = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
       const int b = it & 1;
       const uint32_t bph = (uint32_t)(it >> 1) & 1u;
       const int row_base = t * TC_BM + q * 32;
-      // row weight of "my" row (lane = row), broadcast by shuffle inside the row loop
-      float wrow = 1.f;
-      if (EMODE == EPI_STORE && do_stats && p.srw) wrow = (row_base + lane < M) ? p.srw[row_base + lane] : 0.f;
+      // duplicate-row multiplicities of the 8 rows this lane stores (statistics weights)
+      float wr[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) wr[i] = 1.f;
+      if (EMODE == EPI_STORE && do_stats && p.srw) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = row_base + 4 * i + rsub;
+          wr[i] = (row < M) ? p.srw[row] : 0.f;
+        }
+      }
       mbar_wait(&acc_full[b], bph);
       tc_fence_after();
 #pragma unroll
       for (int cb = 0; cb < 8; ++cb) {
-        if (cb * 32 < N) {
-          const int col = cb * 32 + lane;
-          const bool cval = col < N;
-          float yp[32];
-          if (EMODE == EPI_DMASK) {  // issue all mask-source loads of this 32x32 block before touching TMEM
-#pragma unroll
-            for (int rr = 0; rr < 32; ++rr)
-              yp[rr] = (cval && row_base + rr < M) ? p.Yprev[(long long)(row_base + rr) * p.ldyp + col] : 0.f;
-          }
-          float r[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * N + cb * 32), r);
-#pragma unroll
-          for (int c = 0; c < 32; ++c) stage[lane * 33 + c] = r[c];
-          __syncwarp();
-          float bias = 0.f, psc = 1.f, psh = 0.f, pmu = 0.f, prs = 0.f;
-          if (cval) {
-            if (EMODE == EPI_STORE) {
-              if (p.bias) bias = p.bias[col];
-            } else {
-              if (p.psc) {
-                psc = p.psc[col];
-                psh = p.psh[col];
-              }
-              if (do_stats) {
-                pmu = p.pmean[col];
-                prs = p.prstd[col];
-              }
-            }
-          }
-          float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-          for (int rr = 0; rr < 32; ++rr) {
-            const int row = row_base + rr;
-            float v = stage[rr * 33 + lane];
-            const float w = __shfl_sync(0xffffffffu, wrow, rr);
-            if (cval && row < M) {
-              if (EMODE == EPI_STORE) {
-                v += bias;
-                if (p.relu) v = fmaxf(v, 0.f);
-                p.C[(long long)row * p.ldc + col] = v;
-                a0 = fmaf(w, v, a0);
-                a1 = fmaf(w * v, v, a1);
-              } else {
-                const float z = p.psc ? fmaf(yp[rr], psc, psh) : yp[rr];
-                v = z > 0.f ? v : 0.f;
-                p.C[(long long)row * p.ldc + col] = v;
-                a0 += v;
-                a1 = fmaf(v, (yp[rr] - pmu) * prs, a1);
-              }
-            }
-          }
-          s0[cb] += a0;
-          s1[cb] += a1;
-          __syncwarp();
-        }
+        if (cb * 32 < N)
+          epi_block32<EMODE>(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * N + cb * 32), stage, lane, row_base, cb * 32,
+                             M, N, wr, do_stats, s0[cb], s1[cb]);
       }
       tc_fence_before();
       if (lane == 0) mbar_arrive(&acc_empty[b]);
@@ -308,10 +268,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
     if (do_stats) {
 #pragma unroll
       for (int cb = 0; cb < 8; ++cb) {
-        const int col = cb * 32 + lane;
-        if (col < N) {
-          stat_comb[(warp - 5) * 256 + col] = s0[cb];
-          stat_comb[1024 + (warp - 5) * 256 + col] = s1[cb];
+        if (cb * 32 < N) {
+          epi_reduce_stats(s0[cb]);
+          epi_reduce_stats(s1[cb]);
+          if (lane < 8) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int col = cb * 32 + lane * 4 + k;
+              if (col < N) {
+                stat_comb[(warp - 5) * 256 + col] = s0[cb][k];
+                stat_comb[1024 + (warp - 5) * 256 + col] = s1[cb][k];
+              }
+            }
+          }
         }
       }
     }
@@ -341,6 +310,7 @@ bool gaddpg_tc_gemm_supported(const NTProblem& p, int amode, int emode) {
   if (p.M_max < 8192) return false;  // small problems are latency bound either way
   if (p.K != 32 && p.K != 64 && p.K != 128) return false;
   if (p.N % 16 != 0 || p.N < 16 || p.N > 256) return false;
+  if (!tc_epilogue_ok(p, emode)) return false;
   if (p.ldb != p.K) {
     if (p.ldb % 4 != 0) return false;
   }

@@ -90,7 +90,7 @@ struct KcLayout {
   static constexpr uint32_t W_BYTES = BN * 128;
   static constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
   static constexpr uint32_t OFF_STAGEBUF = NSTAGE * STAGE_BYTES;
-  static constexpr uint32_t OFF_BARS = OFF_STAGEBUF + 4 * 32 * 33 * 4;
+  static constexpr uint32_t OFF_BARS = OFF_STAGEBUF + 4 * 32 * EPI_LD * 4;
   static constexpr uint32_t OFF_COMB = OFF_BARS + 256;
   static constexpr uint32_t TOTAL = OFF_COMB + 2 * 4 * BN * 4;
 };
@@ -267,77 +267,36 @@ __global__ void __launch_bounds__(KC_THREADS, 1) tc_nt_kc_kernel(const NTProblem
     // ===================== epilogue =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int ew = warp - 5;
-    float* stage = reinterpret_cast<float*>(smem + L::OFF_STAGEBUF) + ew * 32 * 33;
+    float* stage = reinterpret_cast<float*>(smem + L::OFF_STAGEBUF) + ew * 32 * EPI_LD;
     const bool do_stats = (p.stats != nullptr);
+    const int rsub = lane >> 3;
     constexpr int NCB = BN / 32;
-    float s0[NCB], s1[NCB];
+    float s0[NCB][4], s1[NCB][4];
 #pragma unroll
-    for (int c = 0; c < NCB; ++c) s0[c] = s1[c] = 0.f;
+    for (int c = 0; c < NCB; ++c)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s0[c][k] = s1[c][k] = 0.f;
     for (int it = 0; it < my_tiles; ++it) {
       const int t = (int)blockIdx.x + it * (int)gridDim.x;
       const int b = it & 1;
       const int row_base = t * KC_BM + q * 32;
-      float wrow = 1.f;
-      if (EMODE == EPI_STORE && do_stats && p.srw) wrow = (row_base + lane < M) ? p.srw[row_base + lane] : 0.f;
+      float wr[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) wr[i] = 1.f;
+      if (EMODE == EPI_STORE && do_stats && p.srw) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = row_base + 4 * i + rsub;
+          wr[i] = (row < M) ? p.srw[row] : 0.f;
+        }
+      }
       mbar_wait(&acc_full[b], (uint32_t)(it >> 1) & 1u);
       tc_fence_after();
 #pragma unroll
       for (int cb = 0; cb < NCB; ++cb) {
-        if (n0 + cb * 32 < N) {
-          const int col = n0 + cb * 32 + lane;
-          const bool cval = col < N;
-          float yp[32];
-          if (EMODE == EPI_DMASK) {
-#pragma unroll
-            for (int rr = 0; rr < 32; ++rr)
-              yp[rr] = (cval && row_base + rr < M) ? p.Yprev[(long long)(row_base + rr) * p.ldyp + col] : 0.f;
-          }
-          float r[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * BN + cb * 32), r);
-#pragma unroll
-          for (int c = 0; c < 32; ++c) stage[lane * 33 + c] = r[c];
-          __syncwarp();
-          float bias = 0.f, psc = 1.f, psh = 0.f, pmu = 0.f, prs = 0.f;
-          if (cval) {
-            if (EMODE == EPI_STORE) {
-              if (p.bias) bias = p.bias[col];
-            } else {
-              if (p.psc) {
-                psc = p.psc[col];
-                psh = p.psh[col];
-              }
-              if (do_stats) {
-                pmu = p.pmean[col];
-                prs = p.prstd[col];
-              }
-            }
-          }
-          float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-          for (int rr = 0; rr < 32; ++rr) {
-            const int row = row_base + rr;
-            float v = stage[rr * 33 + lane];
-            const float w = __shfl_sync(0xffffffffu, wrow, rr);
-            if (cval && row < M) {
-              if (EMODE == EPI_STORE) {
-                v += bias;
-                if (p.relu) v = fmaxf(v, 0.f);
-                p.C[(long long)row * p.ldc + col] = v;
-                a0 = fmaf(w, v, a0);
-                a1 = fmaf(w * v, v, a1);
-              } else {
-                const float z = p.psc ? fmaf(yp[rr], psc, psh) : yp[rr];
-                v = z > 0.f ? v : 0.f;
-                p.C[(long long)row * p.ldc + col] = v;
-                a0 += v;
-                a1 = fmaf(v, (yp[rr] - pmu) * prs, a1);
-              }
-            }
-          }
-          s0[cb] += a0;
-          s1[cb] += a1;
-          __syncwarp();
-        }
+        if (n0 + cb * 32 < N)
+          epi_block32<EMODE>(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * BN + cb * 32), stage, lane, row_base,
+                             n0 + cb * 32, M, N, wr, do_stats, s0[cb], s1[cb]);
       }
       tc_fence_before();
       if (lane == 0) mbar_arrive(&acc_empty[b]);
@@ -345,8 +304,15 @@ __global__ void __launch_bounds__(KC_THREADS, 1) tc_nt_kc_kernel(const NTProblem
     if (do_stats) {
 #pragma unroll
       for (int cb = 0; cb < NCB; ++cb) {
-        stat_comb[ew * BN + cb * 32 + lane] = s0[cb];
-        stat_comb[4 * BN + ew * BN + cb * 32 + lane] = s1[cb];
+        epi_reduce_stats(s0[cb]);
+        epi_reduce_stats(s1[cb]);
+        if (lane < 8) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            stat_comb[ew * BN + cb * 32 + lane * 4 + k] = s0[cb][k];
+            stat_comb[4 * BN + ew * BN + cb * 32 + lane * 4 + k] = s1[cb][k];
+          }
+        }
       }
     }
   }
@@ -584,8 +550,8 @@ bool gaddpg_tc_nt_kc_supported(const NTProblem& p, int amode, int emode) {
   // below ~1k rows a tile grid cannot fill the chip and the serial K loop loses to the FFMA kernel's 32x64 tiles (measured)
   if (p.M_max < 1024 || p.N < 32 || p.K < 32) return false;
   if (p.ldb % 4 != 0) return false;
+  if (!tc_epilogue_ok(p, emode)) return false;
   (void)amode;
-  (void)emode;
   return true;
 }
 
