@@ -264,6 +264,7 @@ def profile(agent, devb, args):
 
     pk = peaks()
     agent.use_graph = False
+    agent.overlap = False  # one stream: per-call CUDA-event times must not overlap each other
     agent.world = None  # rank 0 profiles alone: no collectives in this leg (the other ranks wait at the barrier)
     prof = KernelProfile()
     with prof:

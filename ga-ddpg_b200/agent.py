@@ -8,10 +8,11 @@ updates, k) -> dict[str, float]`` with the 11 keys of get_loss_info_dict (utils.
 no autograd graph, no allocation, no host synchronisation except the single read-back of the scalars.
 
 Step structure (ddpg.py:146-185; F = encoder forward, B = backward):
-  phase 1   geometry(state), geometry(next); F1 value(state,a); F2 policy(next) -> policy_target -> TD3 noise;
-            F3 value(next,a') -> critic_target -> y; critic(F1) -> losses; B1 through critic + value encoder
+  phase 1   state chain: geometry(state); F1 value(state,a); F4 policy(state); critic(F1)   || on a second stream,
+            target chain: geometry(next); F2 policy(next) -> policy_target -> TD3 noise; F3 value(next,a') ->
+            critic_target -> y;  then losses; B1 through critic + value encoder (weight gradients on a third stream)
   [all-reduce of the value-encoder + critic gradient range when sample-sharded over several GPUs]
-  phase 2   clip_grad_norm(critic), Adam(value encoder), Adam(critic); F4 policy(state) -> policy -> pi;
+  phase 2   clip_grad_norm(critic), Adam(value encoder), Adam(critic); policy(F4) -> pi;
             even steps: F5 value(state,pi) -> critic -> -mix*mean(minQ), B through critic + value encoder to dpi;
             actor losses; B2 through policy + policy encoder
   [all-reduce of the policy-encoder + policy gradient range]
@@ -137,10 +138,18 @@ class AgentB200:
         )
         dev = self.device
         self.ws = engine.Workspace(dev)
+        # stream-level overlap inside a step (identical arithmetic, see _phase1): a second encoder chain and the
+        # weight-gradient products run on side streams; ``overlap = False`` issues everything on one stream
+        self.overlap = True
+        self.side_enc = engine.SideStream(dev)
+        self.side_dw = engine.SideStream(dev)
         self.ef_p = engine.EncoderFlat(self._extractor.encoder, dev)
         self.ef_v = engine.EncoderFlat(self._extractor.value_encoder, dev)
         self._extractor._flats[("policy", str(dev))] = self.ef_p
         self._extractor._flats[("value", str(dev))] = self.ef_v
+        # per-pass staging of the BatchNorm running statistics (F1, F3: value encoder | F2, F4: policy encoder)
+        self.bnst = {1: engine.BNStage(self.ef_v, dev), 2: engine.BNStage(self.ef_p, dev), 3: engine.BNStage(self.ef_v, dev),
+                     4: engine.BNStage(self.ef_p, dev)}
         self.pf = engine.PolicyFlat(self.policy, dev)
         self.pft = engine.PolicyFlat(self.policy_target, dev, with_opt=False)
         if self.has_critic:
@@ -227,7 +236,11 @@ class AgentB200:
 
         put_cloud(self.cloud, self.cloud_host, cloud)
         if self.has_critic:
-            put_cloud(self.next_cloud, self.next_cloud_host, batch["next_point_state_batch"])
+            if self.overlap:  # only the target chain (side stream) reads it: its copy overlaps the state chain
+                with torch.cuda.stream(self.side_enc.stream):
+                    put_cloud(self.next_cloud, self.next_cloud_host, batch["next_point_state_batch"])
+            else:
+                put_cloud(self.next_cloud, self.next_cloud_host, batch["next_point_state_batch"])
         on_device = torch.is_tensor(cloud) and cloud.is_cuda
         tgt = self.v if on_device else self.vh   # device-resident batch: D2D straight into the kernel inputs
 
@@ -407,30 +420,65 @@ class DDPGB200(AgentB200):
         self.refresh_all()
 
     # -- phase 1: critic side ------------------------------------------------------------------------------
-    def _phase1(self):
-        B, ws, v, s = self.B, self.ws, self.v, current_stream()
+    # Two independent encoder chains run side by side on two streams:
+    #   state chain  (main): geometry(state), F1 value(state, a), F4 policy(state), critic(F1)
+    #   target chain (side): geometry(next),  F2 policy(next) -> a', F3 value(next, a') -> critic_target -> y
+    # F4 belongs to the actor branch (ddpg.py:164-166) but depends only on the state cloud and the policy-encoder
+    # weights, which nothing touches before phase 3, so it is issued here where it overlaps the target chain.  Each
+    # pass stages its BatchNorm batch statistics; _phase1_critic then updates the running statistics in the
+    # reference's order (value encoder: F1, F3; policy encoder: F2, F4).  The target chain only needs the next-state
+    # cloud, whose H2D copy is issued on the side stream, so it also overlaps the state chain's first kernels.
+    def _phase1_state(self):
+        B, ws, v = self.B, self.ws, self.v
         self.out.zero_()
         self.geom_s.build(self.cloud, self.skip)
-        self.geom_n.build(self.next_cloud, self.skip)
         f1 = engine.encoder_forward(ws, self.ef_v, self.geom_s, self.cloud, self.skip, self.Cp_value, self._bc(v.action, 0), self.ctx_v1,
-                                    time=v.time, time_offset=0.0, train=True)                                    # F1
+                                    time=v.time, time_offset=0.0, train=True, bn_stage=self.bnst[1])              # F1
+        engine.encoder_forward(ws, self.ef_p, self.geom_s, self.cloud, self.skip, self.Cp_policy, None, self.ctx_p,
+                               time=v.time, time_offset=0.0, train=True, bn_stage=self.bnst[4])                   # F4
+        engine.critic_forward(self.cf, f1, self.cc1, B)
+
+    def _phase1_target(self, ws):
+        B, v, s = self.B, self.v, current_stream()
+        self.geom_n.build(self.next_cloud, self.skip)
         f2 = engine.encoder_forward(ws, self.ef_p, self.geom_n, self.next_cloud, self.skip, self.Cp_policy, None, self.ctx_n,
-                                    time=v.time, time_offset=-1.0, train=True)                                   # F2
+                                    time=v.time, time_offset=-1.0, train=True, bn_stage=self.bnst[2])             # F2
         rawt = engine.policy_forward(self.pft, f2, self.pct, B)
         lib.gaddpg_td3_next_action(dp(rawt), self.pft.NHp, dp(v.noise_u), float(self._noise_scale()), B, dp(self.next_action), s)
-        f3 = engine.encoder_forward(ws, self.ef_v, self.geom_n, self.next_cloud, self.skip, self.Cp_value, self._bc(self.next_action, 1),
-                                    self.ctx_n, time=v.time, time_offset=-1.0, train=True)                       # F3
+        f3 = engine.encoder_forward(ws, self.ef_v, self.geom_n, self.next_cloud, self.skip, self.Cp_value,
+                                    self._bc(self.next_action, 1), self.ctx_n, time=v.time, time_offset=-1.0, train=True,
+                                    bn_stage=self.bnst[3])                                                         # F3
         qat = engine.critic_forward(self.cft, f3, self.cct, B, nb=2)
         lib.gaddpg_td3_target(dp(qat), QA_LD, QA_Q2, dp(v.reward), dp(v.done), float(self.gamma), B, dp(self.y), s)
-        qa = engine.critic_forward(self.cf, f1, self.cc1, B)
+
+    def _phase1_critic(self):
+        B, ws, v, s = self.B, self.ws, self.v, current_stream()
+        for k in (1, 3, 2, 4):
+            self.bnst[k].apply()
+        qa, f1 = self.cc1.qa, self.ctx_v1.feat
         lib.gaddpg_critic_loss(dp(qa), QA_LD, QA_Q2, QA_AUX, dp(self.y), dp(v.perturb_flag), dp(v.ret), dp(v.goal),
                                1 if self.critic_aux else 0, B, 1.0, dp(self.cc1.dqa), self.out.data_ptr() + 4 * O_CRITIC, s)
-        engine.critic_backward(ws, self.cf, f1, self.cc1, B, self.cf.nb, self.ctx_v1, self.sc, accumulate=0)         # B1
-        engine.encoder_backward(ws, self.ef_v, self.ctx_v1, self.sc, want_dw=True, want_dbc=False, accumulate=0)
+        with engine.side_dw(self.side_dw if self.overlap else None):
+            engine.critic_backward(ws, self.cf, f1, self.cc1, B, self.cf.nb, self.ctx_v1, self.sc, accumulate=0)     # B1
+            engine.encoder_backward(ws, self.ef_v, self.ctx_v1, self.sc, want_dw=True, want_dbc=False, accumulate=0)
+
+    def _phase1(self, sig):
+        if self.overlap:
+            side = self.side_enc
+            side.fork()  # the side stream sees the vector / state-cloud copies issued on the main stream
+            with torch.cuda.stream(side.stream):
+                self._run(("p1t",) + sig, lambda: self._phase1_target(side.ws))
+            self._run(("p1s",) + sig, self._phase1_state)
+            side.join()
+        else:
+            self._run(("p1s",) + sig, self._phase1_state)
+            self._run(("p1t",) + sig, lambda: self._phase1_target(self.ws))
+        self._run(("p1c",) + sig, self._phase1_critic)
 
     # -- phase 2: critic/value-encoder step, then the actor side -----------------------------------------------
     def _phase2(self, even):
         B, ws, v, s = self.B, self.ws, self.v, current_stream()
+        dw = self.side_dw if self.overlap else None
         cA = self.cf.arena
         lib.gaddpg_clip_coef(dp(cA.g), cA.n, float(self.clip_grad), self.out.data_ptr() + 4 * O_CLIP,
                              self.out.data_ptr() + 4 * O_GNORM, dp(ws.red), s)
@@ -438,8 +486,7 @@ class DDPGB200(AgentB200):
         self._adam(cA, 0, cA.n, "critic", 1e-5, 1e-5, clip=self.out.data_ptr() + 4 * O_CLIP, write_back=1)
         self.ef_v.refresh_derived()
         self.cf.refresh_derived()
-        f4 = engine.encoder_forward(ws, self.ef_p, self.geom_s, self.cloud, self.skip, self.Cp_policy, None, self.ctx_p,
-                                    time=v.time, time_offset=0.0, train=True)                                    # F4
+        f4 = self.ctx_p.feat                                                                                     # F4: phase 1
         raw = engine.policy_forward(self.pf, f4, self.pc, B)
         lib.gaddpg_policy_head_fwd(dp(raw), self.pf.NHp, B, dp(self.pc.pi), s)
         mix = self.get_mix_ratio()[1]
@@ -450,16 +497,18 @@ class DDPGB200(AgentB200):
             qa5 = engine.critic_forward(self.cf, f5, self.cc5, B, nb=2)
             lib.gaddpg_actor_critic_loss(dp(qa5), QA_LD, QA_Q2, dp(v.ret), dp(v.expert_flag), float(mix), B, 1.0, QA_LD,
                                          dp(self.cc5.dqa), self.out.data_ptr() + 4 * O_AC, s)
-            engine.critic_backward(ws, self.cf, f5, self.cc5, B, 2, self.ctx_v5, self.sc, accumulate=1)
-            dpi = engine.encoder_backward(ws, self.ef_v, self.ctx_v5, self.sc, want_dw=False, want_dbc=True)
+            with engine.side_dw(dw):
+                engine.critic_backward(ws, self.cf, f5, self.cc5, B, 2, self.ctx_v5, self.sc, accumulate=1)
+                dpi = engine.encoder_backward(ws, self.ef_v, self.ctx_v5, self.sc, want_dw=False, want_dbc=True)
             self.dpi_ac.zero_()
             self.dpi_ac[:, : self.Cb_value].copy_(dpi)
         ranges, n_grad = self.pf.adam_ranges(self.policy_aux)
         lib.gaddpg_actor_loss(dp(raw), self.pf.NHp, dp(self.pc.pi), dp(v.expert_action), dp(v.expert_flag), dp(v.ret), dp(v.goal),
                               1 if self.policy_aux else 0, float(1.0 - mix), dp(self.dpi_ac) if even else None, B, 1.0,
                               dp(self.pc.draw), self.pf.NHp, self.out.data_ptr() + 4 * O_BC, s)
-        engine.policy_backward(ws, self.pf, f4, self.pc, B, n_grad, self.ctx_p, self.sc, accumulate=0)              # B2
-        engine.encoder_backward(ws, self.ef_p, self.ctx_p, self.sc, want_dw=True, want_dbc=False, accumulate=0)
+        with engine.side_dw(dw):
+            engine.policy_backward(ws, self.pf, f4, self.pc, B, n_grad, self.ctx_p, self.sc, accumulate=0)          # B2
+            engine.encoder_backward(ws, self.ef_p, self.ctx_p, self.sc, want_dw=True, want_dbc=False, accumulate=0)
 
     # -- phase 3: actor step, targets, statistics --------------------------------------------------------------
     def _phase3(self, hard):
@@ -487,7 +536,7 @@ class DDPGB200(AgentB200):
         hard = (self.update_step % self.target_update_interval) == 0
         sig = (self._mix_idx(),)
         self._set_dyn(("critic", "venc", "policy") + (("enc",) if self.train_feature else ()))
-        self._run(("p1",) + sig, self._phase1)
+        self._phase1(sig)
         self._allreduce([self.ef_v.arena, self.cf.arena])
         self._run(("p2", even) + sig, lambda: self._phase2(even))
         self._allreduce([self.ef_p.arena, self.pf.arena])
@@ -519,8 +568,9 @@ class BCB200(AgentB200):
         lib.gaddpg_actor_loss(dp(raw), self.pf.NHp, dp(self.pc.pi), dp(v.expert_action), dp(v.expert_flag), dp(v.ret), dp(v.goal),
                               1 if self.policy_aux else 0, 1.0, None, B, 1.0, dp(self.pc.draw), self.pf.NHp,
                               self.out.data_ptr() + 4 * O_BC, s)
-        engine.policy_backward(ws, self.pf, f, self.pc, B, n_grad, self.ctx_p, self.sc, accumulate=0)
-        engine.encoder_backward(ws, self.ef_p, self.ctx_p, self.sc, want_dw=True, want_dbc=False, accumulate=0)
+        with engine.side_dw(self.side_dw if self.overlap else None):
+            engine.policy_backward(ws, self.pf, f, self.pc, B, n_grad, self.ctx_p, self.sc, accumulate=0)
+            engine.encoder_backward(ws, self.ef_p, self.ctx_p, self.sc, want_dw=True, want_dbc=False, accumulate=0)
 
     def _phase_opt(self):
         ws, s = self.ws, current_stream()

@@ -100,6 +100,10 @@ int gaddpg_bn_finalize_bwd(const float* stats, int C, double count, const float*
                            float* m2, float* dgamma, float* dbeta, int accumulate, void* stream) {
   return gaddpg_bn_finalize_bwd_impl(stats, C, count, gamma, rstd, g, m1, m2, dgamma, dbeta, accumulate, stream);
 }
+int gaddpg_bn_running_update(float* running, const float* staged, long long n, float momentum, long long* num_batches_tracked,
+                             int n_layers, void* stream) {
+  return gaddpg_bn_running_update_impl(running, staged, n, momentum, num_batches_tracked, n_layers, stream);
+}
 int gaddpg_sa1_l1_fwd(const float* cloud, long long cloud_stride_b, int cloud_stride_c, int skip, int Cp, const float* bc, int Cb,
                       int B, const float* ctr, int npoint, const int32_t* seg_off, const int32_t* row_seg, const int32_t* row_src,
                       const float* row_w, int M_max, const int* M_dev, const float* W, int ldw, float* bcbias_ws, float* Y,

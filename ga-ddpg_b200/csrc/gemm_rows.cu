@@ -381,8 +381,9 @@ __global__ void __launch_bounds__(256) bn_finalize_fwd_kernel(const float* __res
     var = (float)v;
     if (running_mean && lane == 0) {
       double unbiased = count > 1.0 ? v * (count / (count - 1.0)) : v;
-      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
-      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+      // momentum == 1: staging mode (deferred update, gaddpg_bn_running_update) — store the batch values verbatim
+      running_mean[c] = (momentum == 1.f) ? mean : (1.f - momentum) * running_mean[c] + momentum * mean;
+      running_var[c] = (momentum == 1.f) ? (float)unbiased : (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
     }
   } else {
     mean = running_mean[c];
@@ -395,6 +396,15 @@ __global__ void __launch_bounds__(256) bn_finalize_fwd_kernel(const float* __res
   shift[c] = beta[c] - mean * sc;
   if (mean_out) mean_out[c] = mean;
   if (rstd_out) rstd_out[c] = rstd;
+}
+
+// deferred running-statistics update over a whole running-stat arena (see gaddpg_bn_running_update)
+__global__ void __launch_bounds__(256) bn_running_update_kernel(float* __restrict__ running, const float* __restrict__ staged,
+                                                                long long n, float momentum, long long* __restrict__ nbt,
+                                                                int n_layers) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) running[i] = (1.f - momentum) * running[i] + momentum * staged[i];
+  if (blockIdx.x == 0 && nbt && (int)threadIdx.x < n_layers) nbt[threadIdx.x] += 1;
 }
 
 // backward: slots of (sum D, sum D*xhat) -> m1, m2, g = gamma*rstd, and dgamma / dbeta
@@ -587,6 +597,14 @@ int gaddpg_bn_finalize_fwd_impl(const float* stats, int C, double count, const f
                                                                             running_mean, running_var, nbt, training,
                                                                             scale, shift, mean_out, rstd_out);
   GADDPG_CHECK_LAUNCH("bn_finalize_fwd_kernel");
+  return GADDPG_OK;
+}
+
+int gaddpg_bn_running_update_impl(float* running, const float* staged, long long n, float momentum, long long* nbt, int n_layers,
+                                  void* stream) {
+  GADDPG_CHECK_ARG(running && staged && n >= 1 && n_layers >= 0 && n_layers <= 256, "bn_running_update: bad argument");
+  bn_running_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(running, staged, n, momentum, nbt, n_layers);
+  GADDPG_CHECK_LAUNCH("bn_running_update_kernel");
   return GADDPG_OK;
 }
 

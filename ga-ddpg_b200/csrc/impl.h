@@ -33,6 +33,8 @@ int gaddpg_bn_finalize_fwd_impl(const float* stats, int C, double count, const f
                                 float* scale, float* shift, float* mean_out, float* rstd_out, void* stream);
 int gaddpg_bn_finalize_bwd_impl(const float* stats, int C, double count, const float* gamma, const float* rstd, float* g,
                                 float* m1, float* m2, float* dgamma, float* dbeta, int accumulate, void* stream);
+int gaddpg_bn_running_update_impl(float* running, const float* staged, long long n, float momentum, long long* nbt, int n_layers,
+                                  void* stream);
 // sa_ops.cu
 int gaddpg_sa1_l1_fwd_impl(const float* cloud, long long cloud_sb, int cloud_sc, int skip, int Cp, const float* bc, int Cb,
                            int B, const float* ctr, int npoint, const int32_t* seg_off, const int32_t* row_seg,

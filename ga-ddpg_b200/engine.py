@@ -75,6 +75,46 @@ class Workspace:
         return self.sa1_ws
 
 
+class SideStream:
+    """A second CUDA stream with its own scratch.  Used (a) for the weight-gradient products of a backward pass, which
+    are off the dX critical path, and (b) for a whole independent encoder chain (F2 -> F3 beside F1 -> F4).  Fork /
+    join are plain stream waits, so the same code runs eagerly and under CUDA-graph capture (parallel graph branches)."""
+
+    def __init__(self, device):
+        self.stream = torch.cuda.Stream(device=device)
+        self.ws = Workspace(device)
+
+    def fork(self):
+        """Make the side stream wait for everything issued so far on the current stream."""
+        self.stream.wait_stream(torch.cuda.current_stream())
+
+    def run(self, fn):
+        self.fork()
+        with torch.cuda.stream(self.stream):
+            fn(self.ws)
+
+    def join(self):
+        torch.cuda.current_stream().wait_stream(self.stream)
+
+
+class BNStage:
+    """Staging copy of one encoder's running-statistics arena for ONE pass: with several passes of the same encoder in
+    flight at once, each pass writes its batch mean / unbiased variance here and ``apply`` folds them into the real
+    running statistics afterwards, pass by pass in the reference's order (F1, F3 | F2, F4) — the values are the
+    ones the in-kernel update would have produced."""
+
+    def __init__(self, ef, device):
+        self.ef = ef
+        self.flat = torch.zeros_like(ef.buffers.p)
+        self.rm = {k: ef.buffers.view(k + ".rm", (L.N,), self.flat) for k, L in ef.layers.items()}
+        self.rv = {k: ef.buffers.view(k + ".rv", (L.N,), self.flat) for k, L in ef.layers.items()}
+
+    def apply(self):
+        ef = self.ef
+        lib.gaddpg_bn_running_update(dp(ef.buffers.p), dp(self.flat), ef.buffers.n, BN_MOMENTUM, dp(ef.nbt), ef.nbt.numel(),
+                                     current_stream())
+
+
 # ------------------------------------------------------------------------------------------------
 # thin launch helpers
 # ------------------------------------------------------------------------------------------------
@@ -109,15 +149,49 @@ def nt_problem(A, Bw, ldb, C, ldc, M_max, M_dev, N, K, bias=None, relu=0, stats=
     return p
 
 
+SIDE = None  # SideStream carrying the weight-gradient products of the backward pass being issued (None: same stream)
+
+
 def tn(ws, P, Q, pmode, qmode, M_max, M_dev, N, K, dW, ldd, Ntrue, Ktrue, rot=0, dbias=None, accumulate=0):
     prob = TNProblem(P=P, Q=Q, M_max=M_max, M_dev=M_dev, N=N, K=K)
-    _tag("tn[%dx%d,p%d,q%d]" % (N, K, pmode, qmode), M_max, M_dev, 2.0 * N * K, 4.0 * (N * (2 if pmode == OP_BNBWD else 1) + K),
-         4.0 * N * K)
-    lib.gaddpg_gemm_tn(ctypes.byref(prob), pmode, qmode, dp(dW), ldd, Ntrue, Ktrue, rot, dp(dbias), accumulate,
-                       dp(ws.tn), ws.tn_bytes, current_stream())
+
+    def launch(w):
+        _tag("tn[%dx%d,p%d,q%d]" % (N, K, pmode, qmode), M_max, M_dev, 2.0 * N * K,
+             4.0 * (N * (2 if pmode == OP_BNBWD else 1) + K), 4.0 * N * K)
+        lib.gaddpg_gemm_tn(ctypes.byref(prob), pmode, qmode, dp(dW), ldd, Ntrue, Ktrue, rot, dp(dbias), accumulate,
+                           dp(w.tn), w.tn_bytes, current_stream())
+
+    if SIDE is None:
+        launch(ws)
+    else:
+        SIDE.run(launch)  # reads only buffers that are complete at this point and that the dX chain never rewrites
 
 
-def bn_fwd(ws, C, count, bnp, st, train):
+class side_dw:
+    """``with side_dw(side): <backward calls>`` — weight gradients of the enclosed backward passes go to ``side``;
+    joined on exit, so gradients are complete (and the scratch reusable) when the block ends."""
+
+    def __init__(self, side):
+        self.side = side
+
+    def __enter__(self):
+        global SIDE
+        self.prev, SIDE = SIDE, self.side
+        return self
+
+    def __exit__(self, *exc):
+        global SIDE
+        if self.side is not None:
+            self.side.join()
+        SIDE = self.prev
+
+
+def bn_fwd(ws, C, count, bnp, st, train, stage=None):
+    if stage is not None and train:  # deferred running-stat update: stage the batch statistics (momentum 1 = verbatim)
+        lib.gaddpg_bn_finalize_fwd(dp(ws.stats), C, float(count), dp(bnp.gamma), dp(bnp.beta), BN_EPS, 1.0, dp(stage.rm[bnp.key]),
+                                   dp(stage.rv[bnp.key]), None, 1, dp(st.scale), dp(st.shift), dp(st.mean), dp(st.rstd),
+                                   current_stream())
+        return
     lib.gaddpg_bn_finalize_fwd(dp(ws.stats), C, float(count), dp(bnp.gamma), dp(bnp.beta), BN_EPS, BN_MOMENTUM, dp(bnp.rm),
                                dp(bnp.rv), dp(bnp.nbt), 1 if train else 0, dp(st.scale), dp(st.shift), dp(st.mean),
                                dp(st.rstd), current_stream())
@@ -302,10 +376,11 @@ WIDTHS = [(64, 64, 128), (128, 128, 256), (256, 256, 512)]
 # ------------------------------------------------------------------------------------------------
 # encoder forward / backward
 # ------------------------------------------------------------------------------------------------
-def encoder_forward(ws, ef, geom, cloud, skip, Cp, bc, ctx, time=None, time_offset=0.0, train=True):
+def encoder_forward(ws, ef, geom, cloud, skip, Cp, bc, ctx, time=None, time_offset=0.0, train=True, bn_stage=None):
     """One pass of an encoder over ``cloud`` (B, C, skip+N).  Per-point input channels are cloud rows [0, Cp);
     ``bc`` (B, Cb) are per-sample constant channels appended after them (the action for the value encoder).
-    Writes ctx.feat (B, 516) = [z(512) | time+offset | 0 0 0] and keeps the activations backward needs."""
+    Writes ctx.feat (B, 516) = [z(512) | time+offset | 0 0 0] and keeps the activations backward needs.
+    ``bn_stage`` (BNStage): defer the running-statistics update of this pass (see BNStage)."""
     B, C, Np = cloud.shape
     st = current_stream()
     l1, l2 = geom.lv
@@ -319,15 +394,15 @@ def encoder_forward(ws, ef, geom, cloud, skip, Cp, bc, ctx, time=None, time_offs
     lib.gaddpg_sa1_l1_fwd(dp(cloud), C * Np, Np, skip, Cp, dp(bc), Cb, B, dp(l1.new_xyz), geom.npoint, dp(l1.seg_off),
                           dp(l1.row_seg), dp(l1.row_src), dp(l1.row_w), l1.cap, l1.M_dev, dp(W0.W), W0.K, dp(ctx.bcbias),
                           dp(s.Y[0]), dp(ws.stats) if train else None, st)
-    bn_fwd(ws, 64, B * geom.npoint * l1.ns, W0, s.bn[0], train)
-    _mlp_tail_forward(ws, [L["sa0.1"], L["sa0.2"]], s, 1, l1.cap, l1.M_dev, l1.row_w, B * geom.npoint * l1.ns, train)
+    bn_fwd(ws, 64, B * geom.npoint * l1.ns, W0, s.bn[0], train, bn_stage)
+    _mlp_tail_forward(ws, [L["sa0.1"], L["sa0.2"]], s, 1, l1.cap, l1.M_dev, l1.row_w, B * geom.npoint * l1.ns, train, bn_stage)
     lib.gaddpg_pool_fwd(dp(s.Y[2]), 128, dp(s.bn[2].scale), dp(s.bn[2].shift), dp(l1.seg_off), 0, l1.S, dp(s.out), dp(s.arg), st)
     # ---- SA2: gather [feats | dxyz | pad] rows, three row-GEMMs, pool
     s2 = ctx.sa[1]
     lib.gaddpg_gather_rows(dp(s.out), 128, dp(l1.new_xyz), geom.npoint, dp(l2.new_xyz), geom.npoint, dp(l2.row_seg),
                            dp(l2.row_src), l2.cap, l2.M_dev, dp(s2.G), s2.G.shape[1], st)
-    _mlp_first_forward(ws, L["sa1.0"], s2, l2.cap, l2.M_dev, l2.row_w, B * geom.npoint * l2.ns, train)
-    _mlp_tail_forward(ws, [L["sa1.1"], L["sa1.2"]], s2, 1, l2.cap, l2.M_dev, l2.row_w, B * geom.npoint * l2.ns, train)
+    _mlp_first_forward(ws, L["sa1.0"], s2, l2.cap, l2.M_dev, l2.row_w, B * geom.npoint * l2.ns, train, bn_stage)
+    _mlp_tail_forward(ws, [L["sa1.1"], L["sa1.2"]], s2, 1, l2.cap, l2.M_dev, l2.row_w, B * geom.npoint * l2.ns, train, bn_stage)
     lib.gaddpg_pool_fwd(dp(s2.Y[2]), 256, dp(s2.bn[2].scale), dp(s2.bn[2].shift), dp(l2.seg_off), 0, l2.S, dp(s2.out),
                         dp(s2.arg), st)
     # ---- SA3: GroupAll over the 32 SA2 centroids (absolute xyz)
@@ -335,35 +410,35 @@ def encoder_forward(ws, ef, geom, cloud, skip, Cp, bc, ctx, time=None, time_offs
     M3 = B * geom.npoint
     lib.gaddpg_gather_rows(dp(s2.out), 256, dp(l2.new_xyz), geom.npoint, None, geom.npoint, None, None, M3, None, dp(s3.G),
                            s3.G.shape[1], st)
-    _mlp_first_forward(ws, L["sa2.0"], s3, M3, None, None, M3, train)
-    _mlp_tail_forward(ws, [L["sa2.1"], L["sa2.2"]], s3, 1, M3, None, None, M3, train)
+    _mlp_first_forward(ws, L["sa2.0"], s3, M3, None, None, M3, train, bn_stage)
+    _mlp_tail_forward(ws, [L["sa2.1"], L["sa2.2"]], s3, 1, M3, None, None, M3, train, bn_stage)
     lib.gaddpg_pool_fwd(dp(s3.Y[2]), 512, dp(s3.bn[2].scale), dp(s3.bn[2].shift), None, geom.npoint, B, dp(s3.out), dp(s3.arg), st)
     # ---- FC head: Linear + BN1d + ReLU twice
     f = ctx.fc
     F0, F1 = L["fc0"], L["fc1"]
     nt([nt_problem(op_plain(s3.out), F0.Wf, F0.Kp, f.Y[0], 1024, B, None, 1024, 512, bias=F0.bias,
                    stats=ws.stats if train else None)], OP_PLAIN, EPI_STORE)
-    bn_fwd(ws, 1024, B, F0, f.bn[0], train)
+    bn_fwd(ws, 1024, B, F0, f.bn[0], train, bn_stage)
     nt([nt_problem(op_bnrelu(f.Y[0], f.bn[0]), F1.Wf, F1.Kp, f.Y[1], 512, B, None, 512, 1024, bias=F1.bias,
                    stats=ws.stats if train else None)], OP_BNRELU, EPI_STORE)
-    bn_fwd(ws, 512, B, F1, f.bn[1], train)
+    bn_fwd(ws, 512, B, F1, f.bn[1], train, bn_stage)
     lib.gaddpg_feat_finish(dp(f.Y[1]), 512, dp(f.bn[1].scale), dp(f.bn[1].shift), dp(time), float(time_offset), B, dp(ctx.feat),
                            516, st)
     return ctx.feat
 
 
-def _mlp_first_forward(ws, Lp, s, M_max, M_dev, rw, count, train):
+def _mlp_first_forward(ws, Lp, s, M_max, M_dev, rw, count, train, bn_stage=None):
     nt([nt_problem(op_plain(s.G), Lp.Wf, Lp.Kp, s.Y[0], Lp.N, M_max, M_dev, Lp.N, Lp.Kp, stats=ws.stats if train else None,
                    srw=rw)], OP_PLAIN, EPI_STORE)
-    bn_fwd(ws, Lp.N, count, Lp, s.bn[0], train)
+    bn_fwd(ws, Lp.N, count, Lp, s.bn[0], train, bn_stage)
 
 
-def _mlp_tail_forward(ws, layers, s, first, M_max, M_dev, rw, count, train):
+def _mlp_tail_forward(ws, layers, s, first, M_max, M_dev, rw, count, train, bn_stage=None):
     for j, Lp in enumerate(layers):
         l = first + j
         nt([nt_problem(op_bnrelu(s.Y[l - 1], s.bn[l - 1]), Lp.Wf, Lp.Kp, s.Y[l], Lp.N, M_max, M_dev, Lp.N, Lp.Kp,
                        stats=ws.stats if train else None, srw=rw)], OP_BNRELU, EPI_STORE)
-        bn_fwd(ws, Lp.N, count, Lp, s.bn[l], train)
+        bn_fwd(ws, Lp.N, count, Lp, s.bn[l], train, bn_stage)
 
 
 def encoder_backward(ws, ef, ctx, sc, want_dw=True, want_dbc=False, accumulate=0, dfeat=None):

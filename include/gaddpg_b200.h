@@ -154,6 +154,13 @@ GADDPG_API int gaddpg_bn_finalize_fwd(const float* stats, int C, double count, c
                                       int training, float* scale, float* shift, float* mean_out, float* rstd_out, void* stream);
 GADDPG_API int gaddpg_bn_finalize_bwd(const float* stats, int C, double count, const float* gamma, const float* rstd, float* g,
                                       float* m1, float* m2, float* dgamma, float* dbeta, int accumulate, void* stream);
+/* Deferred running-statistics update for encoder passes that run concurrently on several streams: each pass stages its
+ * batch mean / unbiased variance (gaddpg_bn_finalize_fwd with momentum = 1 writes them verbatim into a staging copy of the
+ * running-stat arena), and this applies  running = (1-momentum)*running + momentum*staged  over the whole arena (n floats)
+ * plus num_batches_tracked[0..n_layers) += 1 — called once per pass, in the reference's pass order
+ * (torch.nn.BatchNorm2d / BatchNorm1d training-mode forward, reached from core/networks.py:65-92). */
+GADDPG_API int gaddpg_bn_running_update(float* running, const float* staged, long long n, float momentum,
+                                        long long* num_batches_tracked, int n_layers, void* stream);
 
 /* ---- set-abstraction glue (SURVEY.md §8 Spec S3; upstream QueryAndGroup / GroupAll / F.max_pool2d) ------------- */
 /* SA1 first layer straight from the channel-major cloud (B, *, skip+N): W[64][3+Cp+Cb] = [dxyz | per-point | broadcast];
