@@ -35,6 +35,9 @@ def workload(args):
 
 
 AGENT_KW = dict(extra_latent=3, policy_aux=False, critic_aux=False)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch (mean over the captured launches of that kernel) from the
+# `ncu --set full` capture summarised in profiles/ (same workload: cfg2); keyed like profile()'s kernel families
+NCU_TRAFFIC = {}
 
 
 def peaks():
@@ -149,12 +152,12 @@ def cpu_baseline(args):
     batches = [synthetic.make_batch(Bs, args.points, step=i, channels=6) for i in range(2)]
     agent.update_parameters(batches[0])  # warm-up (odd step)
     t0 = time.perf_counter()
-    n = 2
-    for i in range(n):  # one even + one odd step
+    n = args.cpu_steps
+    for i in range(n):  # alternating even / odd steps
         agent.update_parameters(batches[(i + 1) % 2])
     dt = time.perf_counter() - t0
     return dict(value=n / dt * (Bs / float(args.batch)), unit=UNIT, cores=cores, kind="port", torch=torch.__version__,
-                sample="oracle port, %d timed DDPG steps (one even, one odd) on a %d-sample sub-batch (N=%d, 6 ch) after 1 warm-up; "
+                sample="oracle port, %d timed DDPG steps (alternating even / odd) on a %d-sample sub-batch (N=%d, 6 ch) after 1 warm-up; "
                        "scaled by %d/%d to the 256-sample unit; %.1f s of CPU work" % (n, Bs, args.points, Bs, args.batch, dt))
 
 
@@ -167,6 +170,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--points", type=int, default=4096)
     ap.add_argument("--ref-batch", type=int, default=32)
+    ap.add_argument("--cpu-steps", type=int, default=10, help="timed CPU-baseline steps (about 1.3 s each on 16 cores)")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
@@ -282,27 +286,47 @@ def profile(agent, devb, args):
     kernels = [dict(entry=k, ms_per_step=r["ms"] / 2, share=r["ms"] / total, calls_per_step=r["calls"] / 2,
                     tflops=(r["flops"] / (r["ms"] * 1e-3) / 1e12) if r["ms"] > 0 else 0.0,
                     gbs=(r["bytes"] / (r["ms"] * 1e-3) / 1e9) if r["ms"] > 0 else 0.0) for k, r in rows[:60]]
-    # group all row-GEMM launches: they are one kernel family and dominate the step
-    fam = {"nt": dict(ms=0.0, flops=0.0, bytes=0.0, calls=0), "tn": dict(ms=0.0, flops=0.0, bytes=0.0, calls=0)}
+    # group the row-GEMM launches by the kernel that ran them (engine.nt asks the library which path a call takes)
+    FAM = {"gemm_nt:tc:": "tc_gemm_nt_kernel (tcgen05 3xTF32 row-GEMM, SA1 shared-MLP layers fwd + dX, M ~ 423k rows)",
+           "gemm_nt:kc:": "tc_nt_kc_kernel (K-chunked tcgen05 row-GEMM, SA2/SA3 layers)",
+           "gemm_nt:sk:": "skinny_nt_kernel (cp.async ring + mma.sync 3xTF32, FC head + actor/critic layers, M = B)",
+           "gemm_nt:ffma:": "gemm_nt_kernel (FP32 FFMA row-GEMM fallback)",
+           "gemm_tn:": "tc_tn_kernel + tn_reduce (tcgen05 weight gradients)"}
+    fam = {k: dict(ms=0.0, flops=0.0, bytes=0.0, calls=0, shapes={}) for k in FAM}
     for k, r in tab.items():
-        f = "nt" if k.startswith("gemm_nt") else ("tn" if k.startswith("gemm_tn") else None)
-        if f:
-            for kk in ("ms", "flops", "bytes"):
-                fam[f][kk] += r[kk]
-            fam[f]["calls"] += r["calls"]
+        for f in FAM:
+            if k.startswith(f):
+                for kk in ("ms", "flops", "bytes"):
+                    fam[f][kk] += r[kk]
+                fam[f]["calls"] += r["calls"]
+                fam[f]["shapes"][k[len(f):]] = dict(us_per_launch=1e3 * r["ms"] / r["calls"], launches_per_step=r["calls"] / 2,
+                                                    gbs=r["bytes"] / (r["ms"] * 1e-3) / 1e9, tflops=r["flops"] / (r["ms"] * 1e-3) / 1e12)
     dom = max(fam, key=lambda f: fam[f]["ms"])
     d = fam[dom]
-    achieved = d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0
-    roof = dict(kernel="gemm_%s_kernel (all launches of the step)" % dom, bound="tensor", achieved=achieved, peak=pk["tensor_sustained"],
-                unit="TFLOP/s", frac=achieved / pk["tensor_sustained"], traffic=None, peak_source=pk["src"] + ", sustained bf16",
-                share_of_step=d["ms"] / total, avg_launch_ms=d["ms"] / max(d["calls"], 1),
-                algorithmic_gbs=d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else 0.0, hbm_peak_gbs=pk["hbm"],
-                fp32_ffma_peak_tflops=FP32_PEAK_TFLOPS, frac_of_fp32_ffma_peak=achieved / FP32_PEAK_TFLOPS,
-                note="FP32 FFMA row-GEMM (CUDA cores; 1e-4 parity rules out single-pass TF32): the bf16 tensor peak is the contract's "
-                     "denominator, the FP32 FFMA peak is the pipe this kernel actually runs on")
+    gbs = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else 0.0
+    tfl = d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0
+    hbm_bound = gbs / pk["hbm"] >= 3.0 * tfl / pk["tensor_sustained"]   # 3xTF32: three tensor passes per algorithmic flop
+    if hbm_bound:
+        roof = dict(kernel=FAM[dom], bound="hbm", achieved=gbs, peak=pk["hbm"], unit="GB/s", frac=gbs / pk["hbm"],
+                    traffic=NCU_TRAFFIC.get(dom), peak_source=pk["src"] + ", copy bandwidth",
+                    algorithmic_tflops=tfl, tensor_peak_tflops=pk["tensor_sustained"])
+    else:
+        roof = dict(kernel=FAM[dom], bound="tensor", achieved=tfl, peak=pk["tensor_sustained"], unit="TFLOP/s",
+                    frac=tfl / pk["tensor_sustained"], traffic=NCU_TRAFFIC.get(dom), peak_source=pk["src"] + ", sustained bf16",
+                    algorithmic_gbs=gbs, hbm_peak_gbs=pk["hbm"])
+    roof.update(share_of_step=d["ms"] / total, avg_launch_ms=d["ms"] / max(d["calls"], 1), launches_per_step=d["calls"] / 2,
+                algorithmic_bytes_per_launch=d["bytes"] / max(d["calls"], 1), shapes=d["shapes"],
+                note="achieved = algorithmic bytes (A row [+Y row for BN-backward, + mask-source row] read once, C row written "
+                     "once, weights once; DESIGN.md section 4) of all launches of this kernel in one even + one odd step / their "
+                     "CUDA-event time in a single-stream eager pass; 'traffic' = dram bytes per launch from the ncu --set full "
+                     "capture under profiles/ (null if that kernel was not captured)")
+    families = {FAM[f].split(" ")[0]: dict(ms_per_step=fam[f]["ms"] / 2, share=fam[f]["ms"] / total,
+                                           gbs=fam[f]["bytes"] / (fam[f]["ms"] * 1e-3) / 1e9 if fam[f]["ms"] > 0 else 0.0,
+                                           tflops=fam[f]["flops"] / (fam[f]["ms"] * 1e-3) / 1e12 if fam[f]["ms"] > 0 else 0.0)
+                for f in FAM}
     rows_live = {("state" if g is agent.geom_s else "next") + ".sa%d" % (i + 1): int(l.seg_off[-1]) for g in (agent.geom_s, agent.geom_n)
                  for i, l in enumerate(g.lv)}
-    return dict(roofline=roof, kernels=kernels, eager_ms_per_step=total / 2, folded_rows=rows_live,
+    return dict(roofline=roof, kernel_families=families, kernels=kernels, eager_ms_per_step=total / 2, folded_rows=rows_live,
                 dense_rows={"sa1": agent.B * 32 * 64, "sa2": agent.B * 32 * 128})
 
 

@@ -71,7 +71,8 @@ class _Lib:
     def __getattr__(self, name):
         lib = self.load()
         fn = getattr(lib, name)
-        if self.protos[name][0] != "int" or name in ("gaddpg_version", "gaddpg_opt_n_threads", "gaddpg_launch_count", "gaddpg_get_tensor_core"):
+        if self.protos[name][0] != "int" or name in ("gaddpg_version", "gaddpg_opt_n_threads", "gaddpg_launch_count", "gaddpg_get_tensor_core",
+                                                   "gaddpg_gemm_nt_path"):
             return fn
 
         def checked(*a):

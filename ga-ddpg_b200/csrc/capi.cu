@@ -85,6 +85,14 @@ int gaddpg_get_tensor_core(void) { return gaddpg_get_tensor_core_impl(); }
 int gaddpg_gemm_nt(const gaddpg_nt_group* group, int nprob, int amode, int emode, void* stream) {
   return gaddpg_gemm_nt_impl(group, nprob, amode, emode, stream);
 }
+int gaddpg_gemm_nt_path(const gaddpg_nt_group* group, int nprob, int amode, int emode) {
+  if (!group || nprob < 1 || nprob > GADDPG_MAX_GROUP) return GADDPG_ERR_ARG;
+  const int tc = gaddpg_get_tensor_core_impl();
+  if (nprob == 1 && tc >= 1 && tc <= 3 && gaddpg_tc_gemm_supported(group->p[0], amode, emode)) return 1;
+  if (nprob == 1 && tc >= 2 && gaddpg_tc_nt_kc_supported(group->p[0], amode, emode)) return 2;
+  if (gaddpg_skinny_enabled() && gaddpg_skinny_supported(*group, nprob, amode, emode)) return 3;
+  return 0;
+}
 long long gaddpg_gemm_tn_workspace_bytes(void) { return (long long)gaddpg_gemm_tn_workspace_bytes_impl(); }
 int gaddpg_gemm_tn(const gaddpg_tn_problem* prob, int pmode, int qmode, float* dW, int ldd, int Ntrue, int Ktrue, int rot,
                    float* dbias, int accumulate, float* ws, long long ws_bytes, void* stream) {

@@ -466,6 +466,14 @@ static int g_tc_enabled = -1;
 // level: 0 = FP32 FFMA only; 1 = + resident-weight tcgen05 NT (tc_gemm.cu); 2 = + K-chunked tcgen05 NT; 3 = + tcgen05 TN
 // (default); 4 = like 3 but the K-chunked kernel also takes the shapes of the resident-weight kernel (A/B testing)
 void gaddpg_set_tensor_core_impl(int level) { g_tc_enabled = level < 0 ? 0 : (level > 4 ? 4 : level); }
+int gaddpg_skinny_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("GADDPG_SKINNY");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on && gaddpg_get_tensor_core_impl() >= 1;
+}
 int gaddpg_get_tensor_core_impl() {
   if (g_tc_enabled < 0) {
     const char* e = getenv("GADDPG_TC");
@@ -496,6 +504,8 @@ int gaddpg_gemm_nt_impl(const NTGroup* g, int nprob, int amode, int emode, void*
     return gaddpg_tc_gemm_nt_impl(&g->p[0], amode, emode, stream);  // tcgen05 3xTF32 path for the wide SA layers
   if (nprob == 1 && gaddpg_get_tensor_core_impl() >= 2 && gaddpg_tc_nt_kc_supported(g->p[0], amode, emode))
     return gaddpg_tc_nt_kc_impl(&g->p[0], amode, emode, stream);   // K-chunked tcgen05 path (SA2 / SA3 / FC / heads)
+  if (gaddpg_skinny_enabled() && gaddpg_skinny_supported(*g, nprob, amode, emode))
+    return gaddpg_skinny_nt_impl(g, nprob, amode, emode, stream);  // few-hundred-row problems: cp.async ring + mma.sync 3xTF32
   cudaStream_t st = (cudaStream_t)stream;
 #define NT_CASE(A, E) \
   if (amode == A && emode == E) return launch_nt<A, E>(*g, nprob, st)

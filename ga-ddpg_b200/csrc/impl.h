@@ -97,5 +97,9 @@ int gaddpg_tc_nt_kc_impl(const NTProblem* p, int amode, int emode, void* stream)
 bool gaddpg_tc_tn_supported(const TNProblem& p, int pmode, int qmode);
 int gaddpg_tc_tn_impl(const TNProblem* p, int pmode, int qmode, float* ws, size_t ws_floats, float* ws_bias, int* splits_out,
                       void* stream);
+// skinny_gemm.cu
+bool gaddpg_skinny_supported(const NTGroup& g, int nprob, int amode, int emode);
+int gaddpg_skinny_nt_impl(const NTGroup* g, int nprob, int amode, int emode, void* stream);
+int gaddpg_skinny_enabled();
 void gaddpg_set_tensor_core_impl(int enable);
 int gaddpg_get_tensor_core_impl();

@@ -134,7 +134,9 @@ def nt(problems, amode, emode):
     # algorithmic work of the launch: 2*N*K flops per row; bytes = A row (+Y for BN-backward, +Yprev for the mask
     # epilogue) read once + C row written once, weights read once
     rd = p0.K * (2 if amode == OP_BNBWD else 1) + (p0.N if emode == EPI_DMASK else 0)
-    _tag("nt[%dx%d,a%d,e%d]" % (p0.N, p0.K, amode, emode), p0.M_max, p0.M_dev,
+    from . import capi
+    path = ("ffma", "tc", "kc", "sk")[lib.gaddpg_gemm_nt_path(ctypes.byref(g), len(problems), amode, emode)] if capi.PROFILE is not None else ""
+    _tag("%snt[%dx%d,a%d,e%d]" % (path + ":" if path else "", p0.N, p0.K, amode, emode), p0.M_max, p0.M_dev,
          sum(2.0 * q.N * q.K for q in problems), 4.0 * len(problems) * (rd + p0.N), 4.0 * sum(q.N * q.K for q in problems))
     lib.gaddpg_gemm_nt(ctypes.byref(g), len(problems), amode, emode, current_stream())
 

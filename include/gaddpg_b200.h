@@ -140,6 +140,11 @@ GADDPG_API int gaddpg_set_tensor_core(int enable);
 GADDPG_API int gaddpg_get_tensor_core(void);
 /* up to GADDPG_MAX_GROUP independent NT problems in one launch (blockIdx.y = problem) */
 GADDPG_API int gaddpg_gemm_nt(const gaddpg_nt_group* group, int nprob, int amode, int emode, void* stream);
+/* which kernel gaddpg_gemm_nt would launch for this group: 0 = FP32 FFMA (gemm_nt_kernel), 1 = tcgen05 whole-K
+ * (tc_gemm_nt_kernel, the SA1 layers), 2 = tcgen05 K-chunked (tc_nt_kc_kernel), 3 = mma.sync 3xTF32 small-M kernel
+ * (skinny_nt_kernel: FC head, actor / critic layers); < 0 = argument error.  Host-only query
+ * used by bench.py to attribute measured time to kernels. */
+GADDPG_API int gaddpg_gemm_nt_path(const gaddpg_nt_group* group, int nprob, int amode, int emode);
 /* dW[n][(k+rot) % Ktrue] (+)= TN product for n < Ntrue (rows >= Ntrue and columns >= Ktrue are padding);
  * dbias[n] (+)= column sums of P */
 GADDPG_API long long gaddpg_gemm_tn_workspace_bytes(void);

@@ -21,7 +21,10 @@ TCL = int(os.environ.get("TCL", "4"))
 if "nt" in which:
     for (Mmax, M, N, K) in ((13000, 12973, 128, 132), (8192, 8192, 256, 260), (8192, 8192, 512, 256), (2048, 2048, 1024, 512),
                             (1024, 1024, 512, 1024), (8192, 8000, 260, 256), (1100, 1100, 256, 516), (20000, 17321, 64, 64),
-                            (40000, 39000, 128, 64), (8192, 8192, 132, 128), (1300, 1290, 32, 36)):
+                            (40000, 39000, 128, 64), (8192, 8192, 132, 128), (1300, 1290, 32, 36),
+                            # few-hundred-row problems: skinny_nt_kernel (cp.async ring + mma.sync 3xTF32)
+                            (256, 256, 512, 1024), (256, 200, 1024, 516), (256, 256, 19, 256), (512, 500, 768, 516),
+                            (96, 70, 64, 36), (256, 256, 256, 20)):
         Mdev = torch.tensor([M], dtype=torch.int32, device=dev)
         X = torch.randn(Mmax, K, device=dev); W = torch.randn(N, K, device=dev) * 0.2; rw = torch.rand(Mmax, device=dev) * 3
         D = torch.randn(Mmax, K, device=dev); Yc = torch.randn(Mmax, K, device=dev); Yp = torch.randn(Mmax, N, device=dev)
