@@ -9,12 +9,12 @@
 // (dropped term lo.lo ~ 2^-22 relative).
 //
 // Warp-specialised persistent kernel, one CTA per SM, 128-row tiles:
-//   warps 0-3  producers : coalesced float4 loads of the A tile, BN(+ReLU) / BN-backward prologue in registers,
+//   warps 0-7  producers : coalesced float4 loads of the A tile, BN(+ReLU) / BN-backward prologue in registers,
 //                          hi/lo split, st.shared into the canonical K-major SWIZZLE_128B UMMA layout
 //                          (the weights are staged the same way once per CTA), fence.proxy.async, mbarrier arrive
-//   warp  4    MMA issuer: one thread issues 3*K/8 tcgen05.mma.kind::tf32 (M=128, N=N, K=8) per tile into a
+//   warp  8    MMA issuer: one thread issues 3*K/8 tcgen05.mma.kind::tf32 (M=128, N=N, K=8) per tile into a
 //                          double-buffered TMEM accumulator and tcgen05.commit's the smem stage / accumulator barriers
-//   warps 5-8  epilogue  : tcgen05.ld 32x32b -> registers -> smem re-layout -> 16-byte global stores (four full 128-byte
+//   warps 9-12 epilogue  : tcgen05.ld 32x32b -> registers -> smem re-layout -> 16-byte global stores (four full 128-byte
 //                          row segments per instruction), mask reads and per-column BatchNorm statistics (fixed order,
 //                          one slot per CTA); shared with tc_gemm_kc.cu (tc_common.cuh: epi_block32)
 // No TMA here by design: every A element passes through a per-element prologue before it may reach the tensor
@@ -25,7 +25,11 @@
 namespace {
 
 constexpr int TC_BM = 128;
-constexpr int TC_THREADS = 288;  // 4 producer warps + 1 MMA warp + 4 epilogue warps
+// 8 producer warps + 1 MMA warp + 4 epilogue warps.  Two producer warps per scheduler: one warp's stream (prologue, hi/lo
+// split, swizzled STS.128) runs at ~0.2 IPC, which bounded the tile rate before HBM did (see tc_gemm_kc.cu).
+constexpr int TC_PW = 8;
+constexpr int TC_PT = TC_PW * 32;
+constexpr int TC_THREADS = (TC_PW + 1 + 4) * 32;
 
 struct TcSmemLayout {
   uint32_t w_hi, w_lo, a_hi[2], a_lo[2], stage_buf, bars, total;
@@ -81,7 +85,8 @@ struct ColConsts {
   }
 };
 
-template <int K, int AMODE, int EMODE>
+// NCB = 32-column accumulator blocks the epilogue keeps statistics for: 4 (N <= 128, the SA1 layers) or 8 (N <= 256)
+template <int K, int AMODE, int EMODE, int NCB>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProblem p, int stages) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // SWIZZLE_128B operands need 1024-byte aligned bases (the host adds 1024 bytes of slack)
@@ -105,28 +110,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
 
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&a_full[s], 128);
+      mbar_init(&a_full[s], TC_PT);
       mbar_init(&a_empty[s], 1);
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], 4);
     }
-    mbar_init(w_full, 128);
+    mbar_init(w_full, TC_PT);
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(tmem_slot, tmem_cols);
+  if (warp == TC_PW) tmem_alloc(tmem_slot, tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
+  if (warp < TC_PW) {
     // ===================== producers =====================
     constexpr int KQ4 = K / 4;        // float4 per row
-    constexpr int RPI = 128 / KQ4;    // rows covered by the 128 producer threads per iteration
+    constexpr int RPI = TC_PT / KQ4;  // rows covered by the producer threads per iteration
     constexpr int ITERS = TC_BM / RPI;
-    constexpr int U = (AMODE == OP_BNBWD) ? 4 : 8;  // row-iterations per pipeline unit (two register sets in flight)
-    static_assert(128 % KQ4 == 0 && ITERS % U == 0, "K must be 32, 64 or 128");
-    for (int idx = tid; idx < N * KQ4; idx += 128) {
+    constexpr int U = (AMODE == OP_BNBWD) ? 2 : 4;  // row-iterations per pipeline unit (two register sets in flight)
+    static_assert(TC_PT % KQ4 == 0 && ITERS % U == 0, "K must be 32, 64 or 128");
+    for (int idx = tid; idx < N * KQ4; idx += TC_PT) {
       int n = idx / KQ4, k = (idx % KQ4) << 2;
       float4 v = ldg4(p.Bw + (long long)n * p.ldb + k);
       split_store(smem + L.w_hi, smem + L.w_lo, sw128_off(n, k, N), v);
@@ -191,7 +196,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
       if (u + 2 < total_units) issue(RA, u + 2);
       if (u + 1 < total_units) process(RB, u + 1);
     }
-  } else if (warp == 4) {
+  } else if (warp == TC_PW) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 (1<<4), a=b=TF32 (2<<7, 2<<10), K-major A and B,
@@ -230,12 +235,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
   } else {
     // ===================== epilogue =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    float* stage = reinterpret_cast<float*>(smem + L.stage_buf) + (warp - 5) * 32 * EPI_LD;
+    float* stage = reinterpret_cast<float*>(smem + L.stage_buf) + (warp - TC_PW - 1) * 32 * EPI_LD;
     const bool do_stats = (p.stats != nullptr);
     const int rsub = lane >> 3;
-    float s0[8][4], s1[8][4];
+    float s0[NCB][4], s1[NCB][4];
 #pragma unroll
-    for (int c = 0; c < 8; ++c)
+    for (int c = 0; c < NCB; ++c)
 #pragma unroll
       for (int k = 0; k < 4; ++k) s0[c][k] = s1[c][k] = 0.f;
     int it = 0;
@@ -257,7 +262,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
       mbar_wait(&acc_full[b], bph);
       tc_fence_after();
 #pragma unroll
-      for (int cb = 0; cb < 8; ++cb) {
+      for (int cb = 0; cb < NCB; ++cb) {
         if (cb * 32 < N)
           epi_block32<EMODE>(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * N + cb * 32), stage, lane, row_base, cb * 32,
                              M, N, wr, do_stats, s0[cb], s1[cb]);
@@ -267,7 +272,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
     }
     if (do_stats) {
 #pragma unroll
-      for (int cb = 0; cb < 8; ++cb) {
+      for (int cb = 0; cb < NCB; ++cb) {
         if (cb * 32 < N) {
           epi_reduce_stats(s0[cb]);
           epi_reduce_stats(s1[cb]);
@@ -276,8 +281,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
             for (int k = 0; k < 4; ++k) {
               const int col = cb * 32 + lane * 4 + k;
               if (col < N) {
-                stat_comb[(warp - 5) * 256 + col] = s0[cb][k];
-                stat_comb[1024 + (warp - 5) * 256 + col] = s1[cb][k];
+                stat_comb[(warp - TC_PW - 1) * 256 + col] = s0[cb][k];
+                stat_comb[1024 + (warp - TC_PW - 1) * 256 + col] = s1[cb][k];
               }
             }
           }
@@ -297,7 +302,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
     for (int slot = blockIdx.x + gridDim.x; slot < GADDPG_STAT_SLOTS; slot += gridDim.x)
       for (int c = tid; c < 2 * N; c += TC_THREADS) p.stats[(long long)slot * 2 * N + c] = 0.f;
   }
-  if (warp == 4) {
+  if (warp == TC_PW) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
@@ -308,7 +313,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
 // Shapes the tensor-core kernel takes; everything else stays on the FP32 FFMA kernel of gemm_rows.cu.
 bool gaddpg_tc_gemm_supported(const NTProblem& p, int amode, int emode) {
   if (p.M_max < 8192) return false;  // small problems are latency bound either way
-  if (p.K != 32 && p.K != 64 && p.K != 128) return false;
+  if (p.K != 64 && p.K != 128) return false;
   if (p.N % 16 != 0 || p.N < 16 || p.N > 256) return false;
   if (!tc_epilogue_ok(p, emode)) return false;
   if (p.ldb != p.K) {
@@ -328,9 +333,9 @@ int gaddpg_tc_gemm_nt_impl(const NTProblem* p, int amode, int emode, void* strea
   int tiles = ceil_div(p->M_max, TC_BM);
   int grid = tiles < gaddpg_sm_count() ? tiles : gaddpg_sm_count();
   cudaStream_t st = (cudaStream_t)stream;
-#define TC_LAUNCH(KK, A, E)                                                                                    \
+#define TC_LAUNCH(KK, A, E, NCB_)                                                                              \
   {                                                                                                            \
-    auto kern = tc_gemm_nt_kernel<KK, A, E>;                                                                   \
+    auto kern = tc_gemm_nt_kernel<KK, A, E, NCB_>;                                                             \
     GADDPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
     kern<<<grid, TC_THREADS, smem, st>>>(*p, stages);                                                          \
     GADDPG_CHECK_LAUNCH("tc_gemm_nt_kernel");                                                                  \
@@ -338,9 +343,10 @@ int gaddpg_tc_gemm_nt_impl(const NTProblem* p, int amode, int emode, void* strea
   }
 #define TC_CASE(A, E)                                                                                          \
   if (amode == A && emode == E) {                                                                              \
-    if (p->K == 32) TC_LAUNCH(32, A, E)                                                                        \
-    if (p->K == 64) TC_LAUNCH(64, A, E)                                                                        \
-    if (p->K == 128) TC_LAUNCH(128, A, E)                                                                      \
+    if (p->K == 64 && p->N <= 128) TC_LAUNCH(64, A, E, 4)                                                      \
+    if (p->K == 64) TC_LAUNCH(64, A, E, 8)                                                                     \
+    if (p->K == 128 && p->N <= 128) TC_LAUNCH(128, A, E, 4)                                                    \
+    if (p->K == 128) TC_LAUNCH(128, A, E, 8)                                                                   \
   }
   TC_CASE(OP_PLAIN, EPI_STORE)
   TC_CASE(OP_BNRELU, EPI_STORE)

@@ -23,7 +23,12 @@
 namespace {
 
 constexpr int KC_BM = 128;
-constexpr int KC_THREADS = 288;  // 4 producer warps + 1 MMA warp + 4 epilogue warps
+constexpr int KC_THREADS = 288;  // TN kernel: 4 producer warps + 1 MMA warp + 4 epilogue warps
+// NT kernel: 8 producer warps.  A producer warp's instruction stream (address math, prologue, hi/lo split, two STS.128 per
+// float4) has little ILP and runs at ~0.2 IPC, and with one producer warp per scheduler that — not HBM or the tensor
+// pipe — set the time per K chunk (ncu: ~1.4-2.6 us per chunk with 4 warps); two warps per scheduler halve it.
+constexpr int KC_PW = 8;
+constexpr int KC_NT_THREADS = (KC_PW + 1 + 4) * 32;
 
 // byte offset of (row r, float4 index q) inside one [rows x 128 B] SWIZZLE_128B block
 __device__ __forceinline__ uint32_t blk_off(int r, int q) {
@@ -96,7 +101,7 @@ struct KcLayout {
 };
 
 template <int BN, int AMODE, int EMODE>
-__global__ void __launch_bounds__(KC_THREADS, 1) tc_nt_kc_kernel(const NTProblem p) {
+__global__ void __launch_bounds__(KC_NT_THREADS, 1) tc_nt_kc_kernel(const NTProblem p) {
   using L = KcLayout<BN>;
   constexpr int NSTAGE = L::NSTAGE;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -120,7 +125,7 @@ __global__ void __launch_bounds__(KC_THREADS, 1) tc_nt_kc_kernel(const NTProblem
 
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
-      mbar_init(&full[s], 128);
+      mbar_init(&full[s], KC_PW * 32);
       mbar_init(&empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -129,18 +134,21 @@ __global__ void __launch_bounds__(KC_THREADS, 1) tc_nt_kc_kernel(const NTProblem
     }
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(tmem_slot, tmem_cols);
+  if (warp == KC_PW) tmem_alloc(tmem_slot, tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int my_tiles = (ntiles > (int)blockIdx.x) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
-  if (warp < 4) {
+  if (warp < KC_PW) {
     // ===================== producers =====================
-    constexpr int U = (AMODE == OP_BNBWD) ? 4 : 8;  // A row-iterations per pipeline unit
-    constexpr int HPC = 8 / U;                      // units per K chunk
-    constexpr int WU = (BN / 16) / HPC;             // W row-iterations per unit
+    constexpr int RPI = KC_PW * 4;                  // rows the producer threads cover per iteration (8 threads per row)
+    constexpr int ITERS = KC_BM / RPI;              // A row-iterations per K chunk
+    constexpr int U = (AMODE == OP_BNBWD) ? ITERS / 2 : ITERS;  // A row-iterations per pipeline unit
+    constexpr int HPC = ITERS / U;                  // units per K chunk
+    constexpr int WU = (BN / RPI) / HPC;            // W row-iterations per unit
+    static_assert(U >= 1 && WU >= 1, "producer mapping");
     const int kq = tid & 7, r0 = tid >> 3;          // float4 inside the 32-wide chunk; first row served
     struct Regs {
       float4 x[U], y[U];
@@ -169,7 +177,7 @@ __global__ void __launch_bounds__(KC_THREADS, 1) tc_nt_kc_kernel(const NTProblem
       R.cc.load(p.A, col, colok);
 #pragma unroll
       for (int k = 0; k < U; ++k) {
-        const int row = row0 + r0 + 16 * (c.h * U + k);
+        const int row = row0 + r0 + RPI * (c.h * U + k);
         R.x[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         R.y[k] = R.x[k];
         R.w[k] = 1.f;
@@ -183,7 +191,7 @@ __global__ void __launch_bounds__(KC_THREADS, 1) tc_nt_kc_kernel(const NTProblem
       }
 #pragma unroll
       for (int k = 0; k < WU; ++k) {
-        const int n = n0 + r0 + 16 * (c.h * WU + k);
+        const int n = n0 + r0 + RPI * (c.h * WU + k);
         R.b[k] = (n < N && colok) ? ldg4(p.Bw + (long long)n * p.ldb + col) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
@@ -195,13 +203,13 @@ __global__ void __launch_bounds__(KC_THREADS, 1) tc_nt_kc_kernel(const NTProblem
       unsigned char* st = smem + (uint32_t)s * L::STAGE_BYTES;
 #pragma unroll
       for (int k = 0; k < U; ++k) {
-        const int r = r0 + 16 * (c.h * U + k);
+        const int r = r0 + RPI * (c.h * U + k);
         float4 v = (row0 + r < M && colok) ? R.cc.apply(R.x[k], R.y[k], R.w[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
         split_store(st, st + L::A_BYTES, blk_off(r, kq), v);
       }
 #pragma unroll
       for (int k = 0; k < WU; ++k) {
-        const int r = r0 + 16 * (c.h * WU + k);
+        const int r = r0 + RPI * (c.h * WU + k);
         split_store(st + 2 * L::A_BYTES, st + 2 * L::A_BYTES + L::W_BYTES, blk_off(r, kq), R.b[k]);
       }
       if (c.h == HPC - 1) {
@@ -232,7 +240,7 @@ __global__ void __launch_bounds__(KC_THREADS, 1) tc_nt_kc_kernel(const NTProblem
         advance(cp);
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == KC_PW) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(KC_BM >> 4) << 24);
@@ -266,7 +274,7 @@ __global__ void __launch_bounds__(KC_THREADS, 1) tc_nt_kc_kernel(const NTProblem
   } else {
     // ===================== epilogue =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int ew = warp - 5;
+    const int ew = warp - KC_PW - 1;
     float* stage = reinterpret_cast<float*>(smem + L::OFF_STAGEBUF) + ew * 32 * EPI_LD;
     const bool do_stats = (p.stats != nullptr);
     const int rsub = lane >> 3;
@@ -319,7 +327,7 @@ __global__ void __launch_bounds__(KC_THREADS, 1) tc_nt_kc_kernel(const NTProblem
   tc_fence_before();
   __syncthreads();
   if (p.stats) {
-    for (int c = tid; c < BN; c += KC_THREADS) {
+    for (int c = tid; c < BN; c += KC_NT_THREADS) {
       if (n0 + c < N) {
         float a0 = stat_comb[c] + stat_comb[BN + c] + stat_comb[2 * BN + c] + stat_comb[3 * BN + c];
         float a1 = stat_comb[4 * BN + c] + stat_comb[5 * BN + c] + stat_comb[6 * BN + c] + stat_comb[7 * BN + c];
@@ -328,12 +336,12 @@ __global__ void __launch_bounds__(KC_THREADS, 1) tc_nt_kc_kernel(const NTProblem
       }
     }
     for (int slot = blockIdx.x + gridDim.x; slot < GADDPG_STAT_SLOTS; slot += gridDim.x)
-      for (int c = tid; c < 2 * BN; c += KC_THREADS) {
+      for (int c = tid; c < 2 * BN; c += KC_NT_THREADS) {
         const int cc = (c < BN) ? c : c - BN;
         if (n0 + cc < N) p.stats[(long long)slot * 2 * N + (c < BN ? 0 : N) + n0 + cc] = 0.f;
       }
   }
-  if (warp == 4) {
+  if (warp == KC_PW) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
@@ -566,7 +574,7 @@ int gaddpg_tc_nt_kc_impl(const NTProblem* p, int amode, int emode, void* stream)
     auto kern = tc_nt_kc_kernel<BNN, A, E>;                                                                    \
     const size_t smem = KcLayout<BNN>::TOTAL + 1024;                                                           \
     GADDPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
-    kern<<<grid, KC_THREADS, smem, st>>>(*p);                                                                  \
+    kern<<<grid, KC_NT_THREADS, smem, st>>>(*p);                                                                \
     GADDPG_CHECK_LAUNCH("tc_nt_kc_kernel");                                                                    \
     return GADDPG_OK;                                                                                          \
   }
