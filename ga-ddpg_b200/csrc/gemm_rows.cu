@@ -347,16 +347,32 @@ __global__ void bias_reduce_kernel(const float* __restrict__ partial, int splits
 // forward: slots of (sum w*y, sum w*y^2) -> batch mean / biased var -> scale, shift (+ mean, rstd for
 // backward) and the running-stat update PyTorch performs (momentum 0.1, UNBIASED var, counter += 1;
 // torch.nn.BatchNorm2d defaults as instantiated by upstream build_shared_mlp / networks.py:86,89).
-// one warp per channel: lanes stride over the slots with FP64 partials, then a fixed-order shuffle tree
-__device__ __forceinline__ void slot_sums(const float* __restrict__ stats, int C, int c, int lane, double& s, double& q) {
+// 256 threads = 32 consecutive channels (lane) x 8 slot groups (warp): every load instruction reads 32 consecutive
+// floats of one slot (coalesced), each thread keeps FP64 partials over its 37 slots, and warp 0 folds the 8 groups in a
+// fixed order — deterministic, and ~3x faster than one warp per channel striding over the slots.
+__device__ __forceinline__ bool slot_sums(const float* __restrict__ stats, int C, int c, double& s, double& q) {
+  __shared__ double sh[8][2][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double s0 = 0.0, q0 = 0.0;
+  if (c < C) {
+#pragma unroll 4
+    for (int slot = warp; slot < GADDPG_STAT_SLOTS; slot += 8) {
+      s0 += (double)stats[(long long)slot * 2 * C + c];
+      q0 += (double)stats[(long long)slot * 2 * C + C + c];
+    }
+  }
+  sh[warp][0][lane] = s0;
+  sh[warp][1][lane] = q0;
+  __syncthreads();
+  if (warp != 0 || c >= C) return false;
   s = 0.0;
   q = 0.0;
-  for (int slot = lane; slot < GADDPG_STAT_SLOTS; slot += 32) {
-    s += (double)stats[(long long)slot * 2 * C + c];
-    q += (double)stats[(long long)slot * 2 * C + C + c];
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    s += sh[w][0][lane];
+    q += sh[w][1][lane];
   }
-  s = warp_sum_d(s);
-  q = warp_sum_d(q);
+  return true;
 }
 
 __global__ void __launch_bounds__(256) bn_finalize_fwd_kernel(const float* __restrict__ stats, int C, double count,
@@ -366,36 +382,50 @@ __global__ void __launch_bounds__(256) bn_finalize_fwd_kernel(const float* __res
                                                               long long* __restrict__ num_batches_tracked, int training,
                                                               float* __restrict__ scale, float* __restrict__ shift,
                                                               float* __restrict__ mean_out, float* __restrict__ rstd_out) {
-  const int lane = threadIdx.x & 31;
-  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (c == 0 && lane == 0 && training && num_batches_tracked) *num_batches_tracked += 1;
-  if (c >= C) return;
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && training && num_batches_tracked) *num_batches_tracked += 1;
   float mean, var;
   if (training) {
     double s, q;
-    slot_sums(stats, C, c, lane, s, q);
+    if (!slot_sums(stats, C, c, s, q)) return;
     double m = s / count;
     double v = q / count - m * m;
     if (v < 0.0) v = 0.0;
     mean = (float)m;
     var = (float)v;
-    if (running_mean && lane == 0) {
+    if (running_mean) {
       double unbiased = count > 1.0 ? v * (count / (count - 1.0)) : v;
       // momentum == 1: staging mode (deferred update, gaddpg_bn_running_update) — store the batch values verbatim
       running_mean[c] = (momentum == 1.f) ? mean : (1.f - momentum) * running_mean[c] + momentum * mean;
       running_var[c] = (momentum == 1.f) ? (float)unbiased : (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
     }
   } else {
+    if (threadIdx.x >= 32 || c >= C) return;
     mean = running_mean[c];
     var = running_var[c];
   }
-  if (lane != 0) return;
   float rstd = 1.0f / sqrtf(var + eps);
   float sc = gamma[c] * rstd;
   scale[c] = sc;
   shift[c] = beta[c] - mean * sc;
   if (mean_out) mean_out[c] = mean;
   if (rstd_out) rstd_out[c] = rstd;
+}
+
+// backward: slots of (sum D, sum D*xhat) -> m1, m2, g = gamma*rstd, and dgamma / dbeta
+__global__ void __launch_bounds__(256) bn_finalize_bwd_kernel(const float* __restrict__ stats, int C, double count,
+                                                              const float* __restrict__ gamma, const float* __restrict__ rstd,
+                                                              float* __restrict__ g, float* __restrict__ m1,
+                                                              float* __restrict__ m2, float* __restrict__ dgamma,
+                                                              float* __restrict__ dbeta, int accumulate) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  double s, q;
+  if (!slot_sums(stats, C, c, s, q)) return;
+  m1[c] = (float)(s / count);
+  m2[c] = (float)(q / count);
+  g[c] = gamma[c] * rstd[c];
+  if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)q;
+  if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)s;
 }
 
 // deferred running-statistics update over a whole running-stat arena (see gaddpg_bn_running_update)
@@ -405,25 +435,6 @@ __global__ void __launch_bounds__(256) bn_running_update_kernel(float* __restric
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i < n) running[i] = (1.f - momentum) * running[i] + momentum * staged[i];
   if (blockIdx.x == 0 && nbt && (int)threadIdx.x < n_layers) nbt[threadIdx.x] += 1;
-}
-
-// backward: slots of (sum D, sum D*xhat) -> m1, m2, g = gamma*rstd, and dgamma / dbeta
-__global__ void __launch_bounds__(256) bn_finalize_bwd_kernel(const float* __restrict__ stats, int C, double count,
-                                                              const float* __restrict__ gamma, const float* __restrict__ rstd,
-                                                              float* __restrict__ g, float* __restrict__ m1,
-                                                              float* __restrict__ m2, float* __restrict__ dgamma,
-                                                              float* __restrict__ dbeta, int accumulate) {
-  const int lane = threadIdx.x & 31;
-  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (c >= C) return;
-  double s, q;
-  slot_sums(stats, C, c, lane, s, q);
-  if (lane != 0) return;
-  m1[c] = (float)(s / count);
-  m2[c] = (float)(q / count);
-  g[c] = gamma[c] * rstd[c];
-  if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)q;
-  if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)s;
 }
 
 template <int AMODE, int EMODE>
@@ -603,7 +614,7 @@ int gaddpg_bn_finalize_fwd_impl(const float* stats, int C, double count, const f
   GADDPG_CHECK_ARG(C >= 1 && gamma && beta && scale && shift, "bn_finalize_fwd: null pointer");
   GADDPG_CHECK_ARG(training ? (stats != nullptr && count >= 1.0) : (running_mean && running_var),
                    "bn_finalize_fwd: missing statistics source");
-  bn_finalize_fwd_kernel<<<ceil_div(C, 8), 256, 0, (cudaStream_t)stream>>>(stats, C, count, gamma, beta, eps, momentum,
+  bn_finalize_fwd_kernel<<<ceil_div(C, 32), 256, 0, (cudaStream_t)stream>>>(stats, C, count, gamma, beta, eps, momentum,
                                                                             running_mean, running_var, nbt, training,
                                                                             scale, shift, mean_out, rstd_out);
   GADDPG_CHECK_LAUNCH("bn_finalize_fwd_kernel");
@@ -621,7 +632,7 @@ int gaddpg_bn_running_update_impl(float* running, const float* staged, long long
 int gaddpg_bn_finalize_bwd_impl(const float* stats, int C, double count, const float* gamma, const float* rstd, float* g,
                                 float* m1, float* m2, float* dgamma, float* dbeta, int accumulate, void* stream) {
   GADDPG_CHECK_ARG(C >= 1 && stats && gamma && rstd && g && m1 && m2 && count >= 1.0, "bn_finalize_bwd: bad argument");
-  bn_finalize_bwd_kernel<<<ceil_div(C, 8), 256, 0, (cudaStream_t)stream>>>(stats, C, count, gamma, rstd, g, m1, m2,
+  bn_finalize_bwd_kernel<<<ceil_div(C, 32), 256, 0, (cudaStream_t)stream>>>(stats, C, count, gamma, rstd, g, m1, m2,
                                                                             dgamma, dbeta, accumulate);
   GADDPG_CHECK_LAUNCH("bn_finalize_bwd_kernel");
   return GADDPG_OK;

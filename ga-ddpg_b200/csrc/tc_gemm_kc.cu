@@ -23,8 +23,7 @@
 namespace {
 
 constexpr int KC_BM = 128;
-constexpr int KC_THREADS = 288;  // TN kernel: 4 producer warps + 1 MMA warp + 4 epilogue warps
-// NT kernel: 8 producer warps.  A producer warp's instruction stream (address math, prologue, hi/lo split, two STS.128 per
+// 8 producer warps + 1 MMA warp + 4 epilogue warps (NT and TN kernels).  A producer warp's instruction stream (address math, prologue, hi/lo split, two STS.128 per
 // float4) has little ILP and runs at ~0.2 IPC, and with one producer warp per scheduler that — not HBM or the tensor
 // pipe — set the time per K chunk (ncu: ~1.4-2.6 us per chunk with 4 warps); two warps per scheduler halve it.
 constexpr int KC_PW = 8;
@@ -360,11 +359,11 @@ struct TnLayout {
   static constexpr uint32_t STAGE_BYTES = 2 * P_BYTES + 2 * Q_BYTES;
   static constexpr uint32_t OFF_BARS = NSTAGE * STAGE_BYTES;
   static constexpr uint32_t OFF_BIAS = OFF_BARS + 256;
-  static constexpr uint32_t TOTAL = OFF_BIAS + 4 * 128 * 4;
+  static constexpr uint32_t TOTAL = OFF_BIAS + KC_PW * 128 * 4;
 };
 
 template <int BKT, int PMODE, int QMODE>
-__global__ void __launch_bounds__(KC_THREADS, 1) tc_tn_kernel(const TNProblem p, float* __restrict__ partial,
+__global__ void __launch_bounds__(KC_NT_THREADS, 1) tc_tn_kernel(const TNProblem p, float* __restrict__ partial,
                                                                float* __restrict__ partial_bias, int splits, int tiles_k) {
   using L = TnLayout<BKT>;
   constexpr int NSTAGE = L::NSTAGE;
@@ -390,23 +389,24 @@ __global__ void __launch_bounds__(KC_THREADS, 1) tc_tn_kernel(const TNProblem p,
 
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
-      mbar_init(&full[s], 128);
+      mbar_init(&full[s], KC_PW * 32);
       mbar_init(&empty[s], 1);
     }
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(tmem_slot, tmem_cols);
+  if (warp == KC_PW) tmem_alloc(tmem_slot, tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
+  if (warp < KC_PW) {
     // ===================== producers =====================
     constexpr int HPC = (PMODE == OP_BNBWD) ? 2 : 1;  // pipeline units per chunk
-    constexpr int PU = 8 / HPC;                       // P row-iterations per unit (128 threads cover 4 rows x 32 float4)
-    constexpr int QROWS = 128 / (BKT / 4);            // rows the 128 threads cover per Q iteration (4 or 8)
+    constexpr int PROWS = KC_PW;                      // rows the producer threads cover per P iteration (32 float4 per row)
+    constexpr int PU = (TN_R / PROWS) / HPC;          // P row-iterations per unit
+    constexpr int QROWS = (KC_PW * 32) / (BKT / 4);   // rows the producer threads cover per Q iteration (8 or 16)
     constexpr int QU = (TN_R / QROWS) / HPC;          // Q row-iterations per unit
     const int pq = tid & 31, pr = tid >> 5;           // P: float4 column, first row
     const int qq = tid % (BKT / 4), qr = tid / (BKT / 4);
@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(KC_THREADS, 1) tc_tn_kernel(const TNProblem p,
       const int rowc = (split + ci * splits) * TN_R;
 #pragma unroll
       for (int k = 0; k < PU; ++k) {
-        const int row = rowc + pr + 4 * (h * PU + k);
+        const int row = rowc + pr + PROWS * (h * PU + k);
         R.x[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         R.y[k] = R.x[k];
         R.w[k] = 1.f;
@@ -455,7 +455,7 @@ __global__ void __launch_bounds__(KC_THREADS, 1) tc_tn_kernel(const TNProblem p,
       unsigned char* st = smem + (uint32_t)s * L::STAGE_BYTES;
 #pragma unroll
       for (int k = 0; k < PU; ++k) {
-        const int r = pr + 4 * (h * PU + k);
+        const int r = pr + PROWS * (h * PU + k);
         float4 v = (rowc + r < M && pok) ? pc.apply(R.x[k], R.y[k], R.w[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
         bsum.x += v.x;
         bsum.y += v.y;
@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(KC_THREADS, 1) tc_tn_kernel(const TNProblem p,
       if (u + 1 < total_units) process(RB, u + 1);
     }
     if (want_bias) *reinterpret_cast<float4*>(bias_comb + pr * 128 + (pq << 2)) = bsum;
-  } else if (warp == 4) {
+  } else if (warp == KC_PW) {
     // ===================== MMA issuer =====================
     if (lane == 0 && my_chunks > 0) {
       // both operands MN-major (bits 15, 16): the reduction index (rows) is the MMA K dimension
@@ -542,8 +542,10 @@ __global__ void __launch_bounds__(KC_THREADS, 1) tc_tn_kernel(const TNProblem p,
   tc_fence_before();
   __syncthreads();
   if (want_bias && tid < 128 && n0 + tid < N)
-    partial_bias[(long long)split * N + n0 + tid] = (bias_comb[tid] + bias_comb[128 + tid]) + (bias_comb[256 + tid] + bias_comb[384 + tid]);
-  if (warp == 4) {
+    partial_bias[(long long)split * N + n0 + tid] =
+        ((bias_comb[tid] + bias_comb[128 + tid]) + (bias_comb[256 + tid] + bias_comb[384 + tid])) +
+        ((bias_comb[512 + tid] + bias_comb[640 + tid]) + (bias_comb[768 + tid] + bias_comb[896 + tid]));
+  if (warp == KC_PW) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
@@ -620,7 +622,7 @@ int gaddpg_tc_tn_impl(const TNProblem* p, int pmode, int qmode, float* ws, size_
     auto kern = tc_tn_kernel<BK_, PM, QM>;                                                                     \
     const size_t smem = TnLayout<BK_>::TOTAL + 1024;                                                           \
     GADDPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
-    kern<<<grid, KC_THREADS, smem, st>>>(*p, ws, ws_bias, splits, tiles_k);                                    \
+    kern<<<grid, KC_NT_THREADS, smem, st>>>(*p, ws, ws_bias, splits, tiles_k);                                    \
     GADDPG_CHECK_LAUNCH("tc_tn_kernel");                                                                       \
     return GADDPG_OK;                                                                                          \
   }
