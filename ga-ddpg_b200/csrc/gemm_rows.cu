@@ -347,18 +347,27 @@ __global__ void bias_reduce_kernel(const float* __restrict__ partial, int splits
 // forward: slots of (sum w*y, sum w*y^2) -> batch mean / biased var -> scale, shift (+ mean, rstd for
 // backward) and the running-stat update PyTorch performs (momentum 0.1, UNBIASED var, counter += 1;
 // torch.nn.BatchNorm2d defaults as instantiated by upstream build_shared_mlp / networks.py:86,89).
-// 256 threads = 32 consecutive channels (lane) x 8 slot groups (warp): every load instruction reads 32 consecutive
-// floats of one slot (coalesced), each thread keeps FP64 partials over its 37 slots, and warp 0 folds the 8 groups in a
-// fixed order — deterministic, and ~3x faster than one warp per channel striding over the slots.
+// 1024 threads = 32 consecutive channels (lane) x 32 slot groups (warp): every load instruction reads 32 consecutive
+// floats of one slot (coalesced), each thread keeps FP64 partials over its <= 10 slots (independent loads, all in flight
+// together), and warp 0 folds the 32 groups in a fixed order — deterministic.
+constexpr int BNF_GROUPS = 32;
 __device__ __forceinline__ bool slot_sums(const float* __restrict__ stats, int C, int c, double& s, double& q) {
-  __shared__ double sh[8][2][32];
+  __shared__ double sh[BNF_GROUPS][2][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double s0 = 0.0, q0 = 0.0;
   if (c < C) {
-#pragma unroll 4
-    for (int slot = warp; slot < GADDPG_STAT_SLOTS; slot += 8) {
-      s0 += (double)stats[(long long)slot * 2 * C + c];
-      q0 += (double)stats[(long long)slot * 2 * C + C + c];
+    constexpr int NIT = (GADDPG_STAT_SLOTS + BNF_GROUPS - 1) / BNF_GROUPS;
+    float a[NIT], b[NIT];
+#pragma unroll
+    for (int i = 0; i < NIT; ++i) {
+      const int slot = warp + i * BNF_GROUPS;
+      a[i] = slot < GADDPG_STAT_SLOTS ? stats[(long long)slot * 2 * C + c] : 0.f;
+      b[i] = slot < GADDPG_STAT_SLOTS ? stats[(long long)slot * 2 * C + C + c] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < NIT; ++i) {
+      s0 += (double)a[i];
+      q0 += (double)b[i];
     }
   }
   sh[warp][0][lane] = s0;
@@ -367,15 +376,15 @@ __device__ __forceinline__ bool slot_sums(const float* __restrict__ stats, int C
   if (warp != 0 || c >= C) return false;
   s = 0.0;
   q = 0.0;
-#pragma unroll
-  for (int w = 0; w < 8; ++w) {
+#pragma unroll 8
+  for (int w = 0; w < BNF_GROUPS; ++w) {
     s += sh[w][0][lane];
     q += sh[w][1][lane];
   }
   return true;
 }
 
-__global__ void __launch_bounds__(256) bn_finalize_fwd_kernel(const float* __restrict__ stats, int C, double count,
+__global__ void __launch_bounds__(1024) bn_finalize_fwd_kernel(const float* __restrict__ stats, int C, double count,
                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
                                                               float eps, float momentum, float* __restrict__ running_mean,
                                                               float* __restrict__ running_var,
@@ -413,7 +422,7 @@ __global__ void __launch_bounds__(256) bn_finalize_fwd_kernel(const float* __res
 }
 
 // backward: slots of (sum D, sum D*xhat) -> m1, m2, g = gamma*rstd, and dgamma / dbeta
-__global__ void __launch_bounds__(256) bn_finalize_bwd_kernel(const float* __restrict__ stats, int C, double count,
+__global__ void __launch_bounds__(1024) bn_finalize_bwd_kernel(const float* __restrict__ stats, int C, double count,
                                                               const float* __restrict__ gamma, const float* __restrict__ rstd,
                                                               float* __restrict__ g, float* __restrict__ m1,
                                                               float* __restrict__ m2, float* __restrict__ dgamma,
@@ -614,7 +623,7 @@ int gaddpg_bn_finalize_fwd_impl(const float* stats, int C, double count, const f
   GADDPG_CHECK_ARG(C >= 1 && gamma && beta && scale && shift, "bn_finalize_fwd: null pointer");
   GADDPG_CHECK_ARG(training ? (stats != nullptr && count >= 1.0) : (running_mean && running_var),
                    "bn_finalize_fwd: missing statistics source");
-  bn_finalize_fwd_kernel<<<ceil_div(C, 32), 256, 0, (cudaStream_t)stream>>>(stats, C, count, gamma, beta, eps, momentum,
+  bn_finalize_fwd_kernel<<<ceil_div(C, 32), 1024, 0, (cudaStream_t)stream>>>(stats, C, count, gamma, beta, eps, momentum,
                                                                             running_mean, running_var, nbt, training,
                                                                             scale, shift, mean_out, rstd_out);
   GADDPG_CHECK_LAUNCH("bn_finalize_fwd_kernel");
@@ -632,7 +641,7 @@ int gaddpg_bn_running_update_impl(float* running, const float* staged, long long
 int gaddpg_bn_finalize_bwd_impl(const float* stats, int C, double count, const float* gamma, const float* rstd, float* g,
                                 float* m1, float* m2, float* dgamma, float* dbeta, int accumulate, void* stream) {
   GADDPG_CHECK_ARG(C >= 1 && stats && gamma && rstd && g && m1 && m2 && count >= 1.0, "bn_finalize_bwd: bad argument");
-  bn_finalize_bwd_kernel<<<ceil_div(C, 32), 256, 0, (cudaStream_t)stream>>>(stats, C, count, gamma, rstd, g, m1, m2,
+  bn_finalize_bwd_kernel<<<ceil_div(C, 32), 1024, 0, (cudaStream_t)stream>>>(stats, C, count, gamma, rstd, g, m1, m2,
                                                                             dgamma, dbeta, accumulate);
   GADDPG_CHECK_LAUNCH("bn_finalize_bwd_kernel");
   return GADDPG_OK;

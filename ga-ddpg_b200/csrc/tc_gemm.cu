@@ -30,6 +30,12 @@ constexpr int TC_BM = 128;
 constexpr int TC_PW = 8;
 constexpr int TC_PT = TC_PW * 32;
 constexpr int TC_THREADS = (TC_PW + 1 + 4) * 32;
+#ifndef TC_U_FWD
+#define TC_U_FWD 8
+#endif
+#ifndef TC_U_BWD
+#define TC_U_BWD 4
+#endif
 
 struct TcSmemLayout {
   uint32_t w_hi, w_lo, a_hi[2], a_lo[2], stage_buf, bars, total;
@@ -129,7 +135,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
     constexpr int KQ4 = K / 4;        // float4 per row
     constexpr int RPI = TC_PT / KQ4;  // rows covered by the producer threads per iteration
     constexpr int ITERS = TC_BM / RPI;
-    constexpr int U = (AMODE == OP_BNBWD) ? 2 : 4;  // row-iterations per pipeline unit (two register sets in flight)
+    constexpr int U = (AMODE == OP_BNBWD) ? TC_U_BWD : TC_U_FWD;  // row-iterations per pipeline unit (two register sets in flight)
     static_assert(TC_PT % KQ4 == 0 && ITERS % U == 0, "K must be 32, 64 or 128");
     for (int idx = tid; idx < N * KQ4; idx += TC_PT) {
       int n = idx / KQ4, k = (idx % KQ4) << 2;
