@@ -146,6 +146,11 @@ int gaddpg_pool_bwd(const float* dOut, int ld_dout, const float* out, const int3
                     float* D, float* stats, void* stream) {
   return gaddpg_pool_bwd_impl(dOut, ld_dout, out, arg, Y, C, row_seg, fixed_len, M_max, M_dev, mean, rstd, D, stats, stream);
 }
+int gaddpg_pool_bwd_sparse(const float* dOut, int ldo, const float* out, const int32_t* arg, const float* Y, int C, int S,
+                           const float* mean, const float* rstd, float* E, uint32_t* mask, int M_max, float* stats,
+                                void* stream) {
+  return gaddpg_pool_bwd_sparse_impl(dOut, ldo, out, arg, Y, C, S, mean, rstd, E, mask, M_max, stats, stream);
+}
 int gaddpg_feat_finish(const float* Y, int C, const float* scale, const float* shift, const float* time, float time_offset, int B,
                        float* feat, int ld, void* stream) {
   return gaddpg_feat_finish_impl(Y, C, scale, shift, time, time_offset, B, feat, ld, stream);

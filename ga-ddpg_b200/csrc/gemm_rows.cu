@@ -475,8 +475,9 @@ int check_operand(const Operand& o, int mode, int W, const char* what) {
   GADDPG_CHECK_ARG(o.X && (o.ldx % 4) == 0 && o.ldx >= W, "%s: bad source (ld=%d, width=%d)", what, o.ldx, W);
   GADDPG_CHECK_ARG(((uintptr_t)o.X % 16) == 0, "%s: source not 16-byte aligned", what);
   if (mode == OP_BNRELU) GADDPG_CHECK_ARG(o.c0 && o.c1, "%s: BNRELU needs scale/shift", what);
-  if (mode == OP_BNBWD)
+  if (mode == OP_BNBWD || mode == OP_BNBWD_POOL)
     GADDPG_CHECK_ARG(o.Y && (o.ldy % 4) == 0 && o.c0 && o.c1 && o.c2 && o.c3 && o.c4, "%s: BNBWD operand incomplete", what);
+  if (mode == OP_BNBWD_POOL) GADDPG_CHECK_ARG(o.pmask && o.pseg, "%s: BNBWD_POOL needs the arg-max bit mask and the row -> segment map", what);
   return GADDPG_OK;
 }
 
@@ -524,6 +525,10 @@ int gaddpg_gemm_nt_impl(const NTGroup* g, int nprob, int amode, int emode, void*
     return gaddpg_tc_gemm_nt_impl(&g->p[0], amode, emode, stream);  // tcgen05 3xTF32 path for the wide SA layers
   if (nprob == 1 && gaddpg_get_tensor_core_impl() >= 2 && gaddpg_tc_nt_kc_supported(g->p[0], amode, emode))
     return gaddpg_tc_nt_kc_impl(&g->p[0], amode, emode, stream);   // K-chunked tcgen05 path (SA2 / SA3 / FC / heads)
+  if (amode == OP_BNBWD_POOL) {
+    gaddpg_set_error("gemm_nt: GADDPG_OP_BNBWD_POOL is only taken by the tcgen05 whole-K kernel (K = 128, N <= 128, DMASK epilogue)");
+    return GADDPG_ERR_UNSUPPORTED;
+  }
   if (gaddpg_skinny_enabled() && gaddpg_skinny_supported(*g, nprob, amode, emode))
     return gaddpg_skinny_nt_impl(g, nprob, amode, emode, stream);  // few-hundred-row problems: cp.async ring + mma.sync 3xTF32
   cudaStream_t st = (cudaStream_t)stream;
@@ -571,6 +576,10 @@ int gaddpg_gemm_tn_impl(const TNProblem* p, int pmode, int qmode, float* dW, int
       GADDPG_CHECK_LAUNCH("bias_reduce_kernel");
     }
     return GADDPG_OK;
+  }
+  if (pmode == OP_BNBWD_POOL) {
+    gaddpg_set_error("gemm_tn: GADDPG_OP_BNBWD_POOL is only taken by the tcgen05 kernel (Q mode BNRELU)");
+    return GADDPG_ERR_UNSUPPORTED;
   }
   const int BTN = p->N <= 64 ? 64 : 128, BTK = p->K <= 64 ? 64 : 128;
   int tiles = ceil_div(p->N, BTN) * ceil_div(p->K, BTK);

@@ -56,6 +56,9 @@ int gaddpg_pool_fwd_impl(const float* Y, int C, const float* scale, const float*
 int gaddpg_pool_bwd_impl(const float* dOut, int ldo, const float* out, const int32_t* arg, const float* Y, int C,
                          const int32_t* row_seg, int fixed_len, int M_max, const int* M_dev, const float* mean,
                          const float* rstd, float* D, float* stats, void* stream);
+int gaddpg_pool_bwd_sparse_impl(const float* dOut, int ldo, const float* out, const int32_t* arg, const float* Y, int C, int S,
+                                const float* mean, const float* rstd, float* E, uint32_t* mask, int M_max, float* stats,
+                                void* stream);
 int gaddpg_feat_finish_impl(const float* Y, int C, const float* scale, const float* shift, const float* time,
                             float time_offset, int B, float* feat, int ld, void* stream);
 // head_ops.cu

@@ -443,6 +443,57 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const float* __restrict__
     for (int e = tid; e < 2 * C; e += 256) stats[(long long)slot * 2 * C + e] = 0.f;
 }
 
+// Sparse max-pool backward: the dense gradient D (M x C) has one non-zero per (segment, channel) — at the arg-max row, if
+// the pooled value survived the ReLU.  E[s][c] holds that value; the BN-backward sums (sum D, sum D*xhat) only need Y at
+// the S*C arg-max elements.  Consumers rebuild D on the fly (GADDPG_OP_BNBWD_POOL), so neither D nor a second pass over Y
+// ever touches HBM; which rows are arg-max is handed over as one bit per (row, channel) (zeroed by the launcher).
+// 256 threads = 256/C segments x C channels per pass; per-thread partials, fixed-order combine, one slot
+// per CTA.
+__global__ void __launch_bounds__(256) pool_bwd_sparse_kernel(const float* __restrict__ dOut, int ldo, const float* __restrict__ out,
+                                                              const int32_t* __restrict__ arg, const float* __restrict__ Y, int C,
+                                                              int S, const float* __restrict__ mean,
+                                                              const float* __restrict__ rstd, float* __restrict__ E,
+                                                              uint32_t* __restrict__ mask, float* __restrict__ stats) {
+  __shared__ float red[2][256];
+  const int tid = threadIdx.x;
+  const int c = tid % C, sl = tid / C, SPP = 256 / C;  // C in {64, 128, 256}
+  float a0 = 0.f, a1 = 0.f;
+  const float mu = mean[c], rs = rstd[c];
+  for (int s0 = blockIdx.x * SPP + sl; s0 < S; s0 += gridDim.x * SPP * 4) {
+    float e[4], y[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int s = s0 + u * gridDim.x * SPP;
+      e[u] = 0.f;
+      y[u] = mu;
+      if (s < S) {
+        const long long pe = (long long)s * C + c;
+        const int r = arg[pe];
+        e[u] = out[pe] > 0.f ? dOut[(long long)s * ldo + c] : 0.f;
+        y[u] = Y[(long long)r * C + c];
+        E[pe] = e[u];
+        atomicOr(mask + (long long)r * (C >> 5) + (c >> 5), 1u << (c & 31));  // bit set: order-independent, deterministic
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      a0 += e[u];
+      a1 = fmaf(e[u], (y[u] - mu) * rs, a1);
+    }
+  }
+  red[0][tid] = a0;
+  red[1][tid] = a1;
+  __syncthreads();
+  for (int i = tid; i < 2 * C; i += 256) {
+    const int which = i / C, cc = i % C;
+    float v = 0.f;
+    for (int k = 0; k < SPP; ++k) v += red[which][k * C + cc];
+    stats[(long long)blockIdx.x * 2 * C + i] = v;
+  }
+  for (int slot = blockIdx.x + gridDim.x; slot < GADDPG_STAT_SLOTS; slot += gridDim.x)
+    for (int i = tid; i < 2 * C; i += 256) stats[(long long)slot * 2 * C + i] = 0.f;
+}
+
 // feat[b][0:C] = relu(y*scale+shift), feat[b][C] = time[b], feat[b][C+1:ld] = 0
 __global__ void feat_finish_kernel(const float* __restrict__ Y, int C, const float* __restrict__ scale,
                                    const float* __restrict__ shift, const float* __restrict__ time, float time_offset,
@@ -617,6 +668,20 @@ int gaddpg_pool_bwd_impl(const float* dOut, int ldo, const float* out, const int
   pool_bwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(dOut, ldo, out, arg, Y, C, row_seg, fixed_len, M_max, M_dev, mean, rstd,
                                                             D, stats);
   GADDPG_CHECK_LAUNCH("pool_bwd_kernel");
+  return GADDPG_OK;
+}
+
+int gaddpg_pool_bwd_sparse_impl(const float* dOut, int ldo, const float* out, const int32_t* arg, const float* Y, int C, int S,
+                                const float* mean, const float* rstd, float* E, uint32_t* mask, int M_max, float* stats,
+                                void* stream) {
+  GADDPG_CHECK_ARG(dOut && out && arg && Y && mean && rstd && E && mask && stats && M_max >= 1, "pool_bwd_sparse: bad argument");
+  GADDPG_CUDA(cudaMemsetAsync(mask, 0, (size_t)M_max * (C / 32) * sizeof(uint32_t), (cudaStream_t)stream));
+  GADDPG_CHECK_ARG((C == 64 || C == 128 || C == 256) && ldo >= C && S >= 1, "pool_bwd_sparse: bad shape C=%d S=%d", C, S);
+  const int spp = 256 / C;
+  int grid = ceil_div(S, spp * 4);
+  grid = grid < GADDPG_STAT_SLOTS ? grid : GADDPG_STAT_SLOTS;
+  pool_bwd_sparse_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dOut, ldo, out, arg, Y, C, S, mean, rstd, E, mask, stats);
+  GADDPG_CHECK_LAUNCH("pool_bwd_sparse_kernel");
   return GADDPG_OK;
 }
 

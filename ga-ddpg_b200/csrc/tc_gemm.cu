@@ -64,7 +64,7 @@ struct ColConsts {
     if (MODE == OP_BNRELU) {
       c0 = ldg4(d.c0 + col);
       c1 = ldg4(d.c1 + col);
-    } else if (MODE == OP_BNBWD) {
+    } else if (MODE == OP_BNBWD || MODE == OP_BNBWD_POOL) {
       c0 = ldg4(d.c0 + col);
       c1 = ldg4(d.c1 + col);
       c2 = ldg4(d.c2 + col);
@@ -135,7 +135,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
     constexpr int KQ4 = K / 4;        // float4 per row
     constexpr int RPI = TC_PT / KQ4;  // rows covered by the producer threads per iteration
     constexpr int ITERS = TC_BM / RPI;
-    constexpr int U = (AMODE == OP_BNBWD) ? TC_U_BWD : TC_U_FWD;  // row-iterations per pipeline unit (two register sets in flight)
+    constexpr bool BWD = (AMODE == OP_BNBWD || AMODE == OP_BNBWD_POOL);
+    constexpr int U = BWD ? TC_U_BWD : TC_U_FWD;  // row-iterations per pipeline unit (two register sets in flight)
     static_assert(TC_PT % KQ4 == 0 && ITERS % U == 0, "K must be 32, 64 or 128");
     for (int idx = tid; idx < N * KQ4; idx += TC_PT) {
       int n = idx / KQ4, k = (idx % KQ4) << 2;
@@ -154,9 +155,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
     struct Regs {
       float4 x[U], y[U];
       float w[U];
+      uint32_t m[U];  // BNBWD_POOL: arg-max bits of this thread's 4 columns (after the shift in process())
     };
     const int my_tiles = (ntiles > (int)blockIdx.x) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     const int total_units = my_tiles * UPT;
+    int segn[U];  // BNBWD_POOL: segments of the rows of the NEXT unit to be issued
+    auto prefetch_seg = [&](int u) {
+      const int it = u / UPT, i0 = (u % UPT) * U;
+      const int row0 = ((int)blockIdx.x + it * (int)gridDim.x) * TC_BM;
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        const int row = row0 + rsub + (i0 + k) * RPI;
+        segn[k] = (u < total_units && row < M) ? p.A.pseg[row] : 0;
+      }
+    };
     auto issue = [&](Regs& R, int u) {
       const int it = u / UPT, i0 = (u % UPT) * U;
       const int row0 = ((int)blockIdx.x + it * (int)gridDim.x) * TC_BM;
@@ -167,12 +179,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
         R.y[k] = R.x[k];
         R.w[k] = 1.f;
         if (row < M) {
-          R.x[k] = ldg4(p.A.X + (long long)row * p.A.ldx + kcol);
-          if (AMODE == OP_BNBWD) {
+          if (AMODE != OP_BNBWD_POOL) R.x[k] = ldg4(p.A.X + (long long)row * p.A.ldx + kcol);
+          if (BWD) {
             R.y[k] = ldg4(p.A.Y + (long long)row * p.A.ldy + kcol);
             if (p.A.rw) R.w[k] = p.A.rw[row];
           }
         }
+      }
+      if (AMODE == OP_BNBWD_POOL) {
+        // D is the max-pool gradient: non-zero only where this row is the arg-max of its (segment, channel).  It is
+        // rebuilt from the (S, C) masked-gradient table E (L2 resident) and a 16-byte arg-max bit mask per row instead
+        // of being read from a dense (M, C) tensor in HBM.  The row -> segment lookup was issued one unit ahead (segn),
+        // so nothing here waits on a dependent load; the select happens in process().
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+          const int row = row0 + rsub + (i0 + k) * RPI;
+          R.m[k] = 0u;
+          if (row < M) {
+            R.x[k] = ldg4(p.A.X + (long long)segn[k] * p.A.ldx + kcol);
+            R.m[k] = p.A.pmask[(long long)row * (K / 32) + (kcol >> 5)];
+          }
+        }
+        prefetch_seg(u + 1);
       }
     };
     auto process = [&](const Regs& R, int u) {
@@ -185,7 +213,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
 #pragma unroll
       for (int k = 0; k < U; ++k) {
         const int r = rsub + (i0 + k) * RPI;
-        float4 v = (row0 + r < M) ? cc.apply(R.x[k], R.y[k], R.w[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 x = R.x[k];
+        if (AMODE == OP_BNBWD_POOL) {
+          const uint32_t bits = R.m[k] >> (kcol & 31);
+          x.x = (bits & 1u) ? x.x : 0.f;
+          x.y = (bits & 2u) ? x.y : 0.f;
+          x.z = (bits & 4u) ? x.z : 0.f;
+          x.w = (bits & 8u) ? x.w : 0.f;
+        }
+        float4 v = (row0 + r < M) ? cc.apply(x, R.y[k], R.w[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
         split_store(ah, al, sw128_off(r, kcol, TC_BM), v);
       }
       if (i0 + U == ITERS) {
@@ -194,6 +230,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
       }
     };
     Regs RA, RB;
+    if (AMODE == OP_BNBWD_POOL) prefetch_seg(0);
     if (total_units > 0) issue(RA, 0);
 #pragma unroll 1
     for (int u = 0; u < total_units; u += 2) {
@@ -322,6 +359,9 @@ bool gaddpg_tc_gemm_supported(const NTProblem& p, int amode, int emode) {
   if (p.K != 64 && p.K != 128) return false;
   if (p.N % 16 != 0 || p.N < 16 || p.N > 256) return false;
   if (!tc_epilogue_ok(p, emode)) return false;
+  if (amode == OP_BNBWD_POOL &&
+      !(p.K == 128 && p.N <= 128 && emode == EPI_DMASK && p.A.pmask && p.A.pseg && p.A.ldx == 128))
+    return false;
   if (p.ldb != p.K) {
     if (p.ldb % 4 != 0) return false;
   }
@@ -354,6 +394,7 @@ int gaddpg_tc_gemm_nt_impl(const NTProblem* p, int amode, int emode, void* strea
     if (p->K == 128 && p->N <= 128) TC_LAUNCH(128, A, E, 4)                                                    \
     if (p->K == 128) TC_LAUNCH(128, A, E, 8)                                                                   \
   }
+  if (amode == OP_BNBWD_POOL && emode == EPI_DMASK && p->K == 128 && p->N <= 128) TC_LAUNCH(128, OP_BNBWD_POOL, EPI_DMASK, 4)
   TC_CASE(OP_PLAIN, EPI_STORE)
   TC_CASE(OP_BNRELU, EPI_STORE)
   TC_CASE(OP_BNBWD, EPI_DMASK)

@@ -57,7 +57,7 @@ struct Consts4 {
     if (MODE == OP_BNRELU) {
       c0 = ldg4(d.c0 + col);
       c1 = ldg4(d.c1 + col);
-    } else if (MODE == OP_BNBWD) {
+    } else if (MODE == OP_BNBWD || MODE == OP_BNBWD_POOL) {
       c0 = ldg4(d.c0 + col);
       c1 = ldg4(d.c1 + col);
       c2 = ldg4(d.c2 + col);
@@ -403,7 +403,8 @@ __global__ void __launch_bounds__(KC_NT_THREADS, 1) tc_tn_kernel(const TNProblem
 
   if (warp < KC_PW) {
     // ===================== producers =====================
-    constexpr int HPC = (PMODE == OP_BNBWD) ? 2 : 1;  // pipeline units per chunk
+    constexpr bool PBWD = (PMODE == OP_BNBWD || PMODE == OP_BNBWD_POOL);
+    constexpr int HPC = PBWD ? 2 : 1;  // pipeline units per chunk
     constexpr int PROWS = KC_PW;                      // rows the producer threads cover per P iteration (32 float4 per row)
     constexpr int PU = (TN_R / PROWS) / HPC;          // P row-iterations per unit
     constexpr int QROWS = (KC_PW * 32) / (BKT / 4);   // rows the producer threads cover per Q iteration (8 or 16)
@@ -421,9 +422,20 @@ __global__ void __launch_bounds__(KC_NT_THREADS, 1) tc_tn_kernel(const TNProblem
     struct Regs {
       float4 x[PU], y[PU];
       float w[PU];
+      uint32_t m[PU];
       float4 q[QU];
     };
     const int total_units = my_chunks * HPC;
+    int segn[PU];  // BNBWD_POOL: segments of the rows of the NEXT unit to be issued
+    auto prefetch_seg = [&](int u) {
+      const int ci = u / HPC, h = u % HPC;
+      const int rowc = (split + ci * splits) * TN_R;
+#pragma unroll
+      for (int k = 0; k < PU; ++k) {
+        const int row = rowc + pr + PROWS * (h * PU + k);
+        segn[k] = (u < total_units && row < M && pok) ? p.P.pseg[row] : 0;
+      }
+    };
     auto issue = [&](Regs& R, int u) {
       const int ci = u / HPC, h = u % HPC;
       const int rowc = (split + ci * splits) * TN_R;
@@ -434,12 +446,24 @@ __global__ void __launch_bounds__(KC_NT_THREADS, 1) tc_tn_kernel(const TNProblem
         R.y[k] = R.x[k];
         R.w[k] = 1.f;
         if (row < M && pok) {
-          R.x[k] = ldg4(p.P.X + (long long)row * p.P.ldx + pcol);
-          if (PMODE == OP_BNBWD) {
+          if (PMODE != OP_BNBWD_POOL) R.x[k] = ldg4(p.P.X + (long long)row * p.P.ldx + pcol);
+          if (PBWD) {
             R.y[k] = ldg4(p.P.Y + (long long)row * p.P.ldy + pcol);
             if (p.P.rw) R.w[k] = p.P.rw[row];
           }
         }
+      }
+      if (PMODE == OP_BNBWD_POOL) {  // max-pool gradient rebuilt from E + the arg-max bit mask (see tc_gemm.cu)
+#pragma unroll
+        for (int k = 0; k < PU; ++k) {
+          const int row = rowc + pr + PROWS * (h * PU + k);
+          R.m[k] = 0u;
+          if (row < M && pok) {
+            R.x[k] = ldg4(p.P.X + (long long)segn[k] * p.P.ldx + pcol);
+            R.m[k] = p.P.pmask[(long long)row * (p.P.ldx >> 5) + (pcol >> 5)];
+          }
+        }
+        prefetch_seg(u + 1);
       }
 #pragma unroll
       for (int k = 0; k < QU; ++k) {
@@ -456,7 +480,15 @@ __global__ void __launch_bounds__(KC_NT_THREADS, 1) tc_tn_kernel(const TNProblem
 #pragma unroll
       for (int k = 0; k < PU; ++k) {
         const int r = pr + PROWS * (h * PU + k);
-        float4 v = (rowc + r < M && pok) ? pc.apply(R.x[k], R.y[k], R.w[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 x = R.x[k];
+        if (PMODE == OP_BNBWD_POOL) {
+          const uint32_t bits = R.m[k] >> (pcol & 31);
+          x.x = (bits & 1u) ? x.x : 0.f;
+          x.y = (bits & 2u) ? x.y : 0.f;
+          x.z = (bits & 4u) ? x.z : 0.f;
+          x.w = (bits & 8u) ? x.w : 0.f;
+        }
+        float4 v = (rowc + r < M && pok) ? pc.apply(x, R.y[k], R.w[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
         bsum.x += v.x;
         bsum.y += v.y;
         bsum.z += v.z;
@@ -476,6 +508,7 @@ __global__ void __launch_bounds__(KC_NT_THREADS, 1) tc_tn_kernel(const TNProblem
       }
     };
     Regs RA, RB;
+    if (PMODE == OP_BNBWD_POOL) prefetch_seg(0);
     if (total_units > 0) issue(RA, 0);
 #pragma unroll 1
     for (int u = 0; u < total_units; u += 2) {
@@ -558,6 +591,7 @@ __global__ void __launch_bounds__(KC_NT_THREADS, 1) tc_tn_kernel(const TNProblem
 // ----------------------------------------------------------------------------------------------------
 bool gaddpg_tc_nt_kc_supported(const NTProblem& p, int amode, int emode) {
   // below ~1k rows a tile grid cannot fill the chip and the serial K loop loses to the FFMA kernel's 32x64 tiles (measured)
+  if (amode == OP_BNBWD_POOL) return false;  // only tc_gemm.cu and the TN kernel rebuild the pool gradient on the fly
   if (p.M_max < 1024 || p.N < 32 || p.K < 32) return false;
   if (p.ldb % 4 != 0) return false;
   if (!tc_epilogue_ok(p, emode)) return false;
@@ -597,7 +631,9 @@ int gaddpg_tc_nt_kc_impl(const NTProblem* p, int amode, int emode, void* stream)
 
 bool gaddpg_tc_tn_supported(const TNProblem& p, int pmode, int qmode) {
   if (p.N < 32 || p.K < 32 || p.M_max < 64) return false;
-  if (pmode == OP_BNRELU || qmode == OP_BNBWD) return false;
+  if (pmode == OP_BNRELU || qmode == OP_BNBWD || qmode == OP_BNBWD_POOL) return false;
+  if (pmode == OP_BNBWD_POOL && !(qmode == OP_BNRELU && p.P.pmask && p.P.pseg && p.P.ldx % 32 == 0))
+    return false;
   return true;
 }
 
@@ -634,6 +670,7 @@ int gaddpg_tc_tn_impl(const TNProblem* p, int pmode, int qmode, float* ws, size_
   TN_CASE(OP_PLAIN, OP_BNRELU)
   TN_CASE(OP_BNBWD, OP_PLAIN)
   TN_CASE(OP_BNBWD, OP_BNRELU)
+  TN_CASE(OP_BNBWD_POOL, OP_BNRELU)
 #undef TN_CASE
 #undef TN_LAUNCH
   gaddpg_set_error("tc_tn: unsupported mode pair (%d,%d)", pmode, qmode);

@@ -23,8 +23,8 @@ import torch
 
 from . import nets
 from .capi import current_stream, lib
-from .structs import (EPI_DMASK, EPI_STORE, OP_BNBWD, OP_BNRELU, OP_PLAIN, STAT_SLOTS, NTGroup, NTProblem, Operand,
-                      TNProblem, check_sizes, dp, op_bnbwd, op_bnrelu, op_plain)
+from .structs import (EPI_DMASK, EPI_STORE, OP_BNBWD, OP_BNBWD_POOL, OP_BNRELU, OP_PLAIN, STAT_SLOTS, NTGroup, NTProblem, Operand,
+                      TNProblem, check_sizes, dp, op_bnbwd, op_bnbwd_pool, op_bnrelu, op_plain)
 
 BN_EPS, BN_MOMENTUM = 1e-5, 0.1
 _checked = False
@@ -151,6 +151,7 @@ def nt_problem(A, Bw, ldb, C, ldc, M_max, M_dev, N, K, bias=None, relu=0, stats=
     return p
 
 
+SPARSE_POOL = True  # SA1 max-pool backward without the dense gradient tensor (False: dense gaddpg_pool_bwd everywhere)
 SIDE = None  # SideStream carrying the weight-gradient products of the backward pass being issued (None: same stream)
 
 
@@ -370,6 +371,9 @@ class BwdScratch:
         self.Dfc = [_f(device, B, 1024), _f(device, B, 512)]
         self.bbfc = [_bnbwd(device, 1024), _bnbwd(device, 512)]
         self.dbc = _f(device, B, 8)
+        # sparse SA1 pool backward: pooled gradient after the pooled ReLU mask + one arg-max bit per (row, channel)
+        self.E = _f(device, B * 32, widths[0][2])
+        self.mask = torch.zeros(caps[0], widths[0][2] // 32, dtype=torch.int32, device=device)
 
 
 WIDTHS = [(64, 64, 128), (128, 128, 256), (256, 256, 512)]
@@ -506,17 +510,28 @@ def _sa_backward(ws, layers, s, sc, lvl, dOut, ld_dout, row_seg, fixed_len, M_ma
     st = current_stream()
     D, bb = sc.D[lvl], sc.bb[lvl]
     C3 = layers[2].N
-    lib.gaddpg_pool_bwd(dp(dOut), ld_dout, dp(s.out), dp(s.arg), dp(s.Y[2]), C3, dp(row_seg), fixed_len, M_max, M_dev,
-                        dp(s.bn[2].mean), dp(s.bn[2].rstd), dp(D[2]), dp(ws.stats), st)
+    # SA1 (423 k rows x 128 channels at cfg2): the dense pool gradient D[2] has one non-zero per (segment, channel), so it
+    # is never written; its consumers (dX and dW of layer 2) rebuild it from the (S, C) tables (GADDPG_OP_BNBWD_POOL)
+    sparse = (SPARSE_POOL and lvl == 0 and row_seg is not None and C3 == 128 and layers[2].Kp == 64
+              and lib.gaddpg_get_tensor_core() >= 3)
+    if sparse:
+        lib.gaddpg_pool_bwd_sparse(dp(dOut), ld_dout, dp(s.out), dp(s.arg), dp(s.Y[2]), C3, s.out.shape[0], dp(s.bn[2].mean),
+                                   dp(s.bn[2].rstd), dp(sc.E), dp(sc.mask), M_max, dp(ws.stats), st)
+    else:
+        lib.gaddpg_pool_bwd(dp(dOut), ld_dout, dp(s.out), dp(s.arg), dp(s.Y[2]), C3, dp(row_seg), fixed_len, M_max, M_dev,
+                            dp(s.bn[2].mean), dp(s.bn[2].rstd), dp(D[2]), dp(ws.stats), st)
     for l in (2, 1):
         Lp = layers[l]
         bn_bwd(ws, Lp.N, count, Lp, s.bn[l], bb[l], want_dw, accumulate)
-        dy = op_bnbwd(D[l], s.Y[l], s.bn[l], bb[l], rw=rw)
+        if sparse and l == 2:
+            dy, dmode = op_bnbwd_pool(sc.E, sc.mask, row_seg, s.Y[l], s.bn[l], bb[l], rw=rw), OP_BNBWD_POOL
+        else:
+            dy, dmode = op_bnbwd(D[l], s.Y[l], s.bn[l], bb[l], rw=rw), OP_BNBWD
         if want_dw:
-            tn(ws, dy, op_bnrelu(s.Y[l - 1], s.bn[l - 1]), OP_BNBWD, OP_BNRELU, M_max, M_dev, Lp.N, Lp.Kp, Lp.dW, Lp.K, Lp.N,
+            tn(ws, dy, op_bnrelu(s.Y[l - 1], s.bn[l - 1]), dmode, OP_BNRELU, M_max, M_dev, Lp.N, Lp.Kp, Lp.dW, Lp.K, Lp.N,
                Lp.K, accumulate=accumulate)
         nt([nt_problem(dy, Lp.WT, Lp.N, D[l - 1], Lp.Kp, M_max, M_dev, Lp.Kp, Lp.N, stats=ws.stats, Yprev=s.Y[l - 1],
-                       ldyp=Lp.Kp, pbn=s.bn[l - 1])], OP_BNBWD, EPI_DMASK)
+                       ldyp=Lp.Kp, pbn=s.bn[l - 1])], dmode, EPI_DMASK)
     L0 = layers[0]
     bn_bwd(ws, L0.N, count, L0, s.bn[0], bb[0], want_dw, accumulate)
     if generic_l0:

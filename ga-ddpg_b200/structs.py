@@ -7,7 +7,7 @@ import ctypes
 
 from .capi import lib
 
-OP_PLAIN, OP_BNRELU, OP_BNBWD = 0, 1, 2
+OP_PLAIN, OP_BNRELU, OP_BNBWD, OP_BNBWD_POOL = 0, 1, 2, 3
 EPI_STORE, EPI_DMASK = 0, 1
 STAT_SLOTS = 296
 MAX_GROUP = 4
@@ -18,7 +18,7 @@ _I = ctypes.c_int
 
 class Operand(ctypes.Structure):
     _fields_ = [("X", _P), ("ldx", _I), ("Y", _P), ("ldy", _I), ("rw", _P),
-                ("c0", _P), ("c1", _P), ("c2", _P), ("c3", _P), ("c4", _P)]
+                ("c0", _P), ("c1", _P), ("c2", _P), ("c3", _P), ("c4", _P), ("pmask", _P), ("pseg", _P)]
 
 
 class NTProblem(ctypes.Structure):
@@ -56,6 +56,13 @@ def op_plain(x, ld=None):
 def op_bnrelu(y, bn, ld=None):
     """relu(y*scale+shift); bn has .scale/.shift"""
     return Operand(X=dp(y), ldx=ld if ld is not None else y.shape[-1], c0=dp(bn.scale), c1=dp(bn.shift))
+
+
+def op_bnbwd_pool(e, mask, row_seg, y, bn, bb, rw=None):
+    """BN backward of (D, Y) where D is the max-pool gradient, never materialised: D[r][c] = E[seg(r)][c] if bit c of
+    mask[r] is set (r is the arg-max row of (seg(r), c)) else 0 (GADDPG_OP_BNBWD_POOL)"""
+    return Operand(X=dp(e), ldx=e.shape[-1], Y=dp(y), ldy=y.shape[-1], rw=dp(rw), pmask=dp(mask), pseg=dp(row_seg),
+                   c0=dp(bb.g), c1=dp(bb.m1), c2=dp(bb.m2), c3=dp(bn.mean), c4=dp(bn.rstd))
 
 
 def op_bnbwd(d, y, bn, bb, rw=None):

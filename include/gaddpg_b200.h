@@ -100,7 +100,7 @@ GADDPG_API int gaddpg_row_table(const int32_t* bq_cnt, const int32_t* bq_idx, in
  * the finalize calls below (deterministic; no float atomics). */
 #define GADDPG_STAT_SLOTS 296
 #define GADDPG_MAX_GROUP 4
-enum { GADDPG_OP_PLAIN = 0, GADDPG_OP_BNRELU = 1, GADDPG_OP_BNBWD = 2 };
+enum { GADDPG_OP_PLAIN = 0, GADDPG_OP_BNRELU = 1, GADDPG_OP_BNBWD = 2, GADDPG_OP_BNBWD_POOL = 3 };
 enum { GADDPG_EPI_STORE = 0, GADDPG_EPI_DMASK = 1 };
 
 typedef struct gaddpg_operand {
@@ -108,6 +108,12 @@ typedef struct gaddpg_operand {
   const float* Y; int ldy;
   const float* rw;
   const float* c0; const float* c1; const float* c2; const float* c3; const float* c4;
+  /* GADDPG_OP_BNBWD_POOL only: the max-pool gradient is never materialised.  X = E (S, ldx): pooled gradient already
+   * masked by the pooled ReLU, pmask (M, ldx/32) uint32: bit c of row r set iff r is the arg-max row of (segment(r), c)
+   * (both written by gaddpg_pool_bwd_sparse), pseg (M): segment of every row; the operand is BNBWD with
+   * D[r][c] = bit(pmask[r], c) ? E[pseg[r]][c] : 0.  Taken by the tcgen05 kernels only (NT with K = 128, TN); other
+   * shapes must use the dense pool_bwd path. */
+  const uint32_t* pmask; const int32_t* pseg;
 } gaddpg_operand;
 
 typedef struct gaddpg_nt_problem {
@@ -196,6 +202,14 @@ GADDPG_API int gaddpg_pool_fwd(const float* Y, int C, const float* scale, const 
 GADDPG_API int gaddpg_pool_bwd(const float* dOut, int ld_dout, const float* out, const int32_t* arg, const float* Y, int C,
                                const int32_t* row_seg, int fixed_len, int M_max, const int* M_dev, const float* mean,
                                const float* rstd, float* D, float* stats, void* stream);
+/* Sparse form of the max-pool backward for levels whose layer-3 operand is consumed as GADDPG_OP_BNBWD_POOL:
+ * E[s][c] = out[s][c] > 0 ? dOut[s][c] : 0, the arg-max bit mask (M_max, C/32) (zeroed here, then one bit per (s, c)) and
+ * the BatchNorm-backward sums (sum D, sum D*xhat) of the implied dense D, gathered from the S*C arg-max elements of Y only
+ * (the dense kernel reads all of Y and writes all of D).  C in {64,128,256} (mask needs C % 32 == 0).
+ * Replaces the autograd backward of F.max_pool2d(kernel=[1,nsample]) + ReLU in upstream _PointnetSAModuleBase.forward. */
+GADDPG_API int gaddpg_pool_bwd_sparse(const float* dOut, int ldo, const float* out, const int32_t* arg, const float* Y, int C,
+                                      int S, const float* mean, const float* rstd, float* E, uint32_t* mask, int M_max,
+                                      float* stats, void* stream);
 /* feat[b] = [relu(Y*scale+shift) (C) | time[b]+time_offset | 0-pad to ld]  (ddpg.py:56-57 appends the time column) */
 GADDPG_API int gaddpg_feat_finish(const float* Y, int C, const float* scale, const float* shift, const float* time,
                                   float time_offset, int B, float* feat, int ld, void* stream);

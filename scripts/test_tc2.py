@@ -113,5 +113,50 @@ if "tn" in which:
                 good = good and b1 < 5e-6
             print(line, "OK" if good else "FAIL")
             ok = ok and good
+if "pool" in which or which == "nt,tn":
+    # sparse max-pool backward: GADDPG_OP_BNBWD_POOL operands (NT K=128 -> N=64 with mask epilogue, TN 128x64) and
+    # gaddpg_pool_bwd_sparse against the dense pool_bwd path — same arithmetic, so the GEMM outputs must be bit-identical
+    from gaddpg_b200.structs import op_bnbwd_pool, OP_BNBWD_POOL, dp
+    lib.gaddpg_set_tensor_core(3)
+    C, Kout = 128, 64
+    lens = torch.randint(1, 65, (700,))
+    Mtrue = int(lens.sum()); Mmax = Mtrue + 300; S = lens.numel()
+    seg_off = torch.zeros(S + 1, dtype=torch.int32); seg_off[1:] = torch.cumsum(lens, 0)
+    row_seg = torch.repeat_interleave(torch.arange(S, dtype=torch.int32), lens)
+    row_seg = torch.cat([row_seg, torch.zeros(Mmax - Mtrue, dtype=torch.int32)]).to(dev)
+    seg_off = seg_off.to(dev)
+    Mdev = torch.tensor([Mtrue], dtype=torch.int32, device=dev)
+    Y2 = torch.randn(Mmax, C, device=dev); Y1 = torch.randn(Mmax, Kout, device=dev); rw = (torch.rand(Mmax, device=dev) * 3).round() + 1
+    b2, bb2, b1 = bn(C), bb(C), bn(Kout)
+    outp = torch.zeros(S, C, device=dev); arg = torch.zeros(S, C, dtype=torch.int32, device=dev)
+    lib.gaddpg_pool_fwd(dp(Y2), C, dp(b2.scale), dp(b2.shift), dp(seg_off), 0, S, dp(outp), dp(arg), 0)
+    dOut = torch.randn(S, C + 4, device=dev)
+    Dd = torch.zeros(Mmax, C, device=dev); E = torch.zeros(S, C, device=dev); mask = torch.full((Mmax, C // 32), -1, dtype=torch.int32, device=dev)
+    lib.gaddpg_pool_bwd(dp(dOut), C + 4, dp(outp), dp(arg), dp(Y2), C, dp(row_seg), 0, Mmax, Mdev.data_ptr(), dp(b2.mean), dp(b2.rstd), dp(Dd), dp(ws.stats), 0)
+    torch.cuda.synchronize()
+    st_dense = ws.stats[: STAT_SLOTS * 2 * C].view(STAT_SLOTS, 2, C).double().sum(0).clone()
+    lib.gaddpg_pool_bwd_sparse(dp(dOut), C + 4, dp(outp), dp(arg), dp(Y2), C, S, dp(b2.mean), dp(b2.rstd), dp(E), dp(mask), Mmax, dp(ws.stats), 0)
+    torch.cuda.synchronize()
+    st_sparse = ws.stats[: STAT_SLOTS * 2 * C].view(STAT_SLOTS, 2, C).double().sum(0).clone()
+    Dre = torch.zeros(Mmax, C, device=dev)
+    Dre.scatter_(0, arg.long(), E)   # D[arg[s][c]][c] = E[s][c]
+    good = bool(torch.equal(Dre[:Mtrue], Dd[:Mtrue])) and float((st_dense - st_sparse).abs().max() / st_dense.abs().max()) < 1e-5
+    print("pool_bwd_sparse: D rebuilt == dense %s, stats rel diff %.2e" % (torch.equal(Dre[:Mtrue], Dd[:Mtrue]), float((st_dense - st_sparse).abs().max() / st_dense.abs().max())), "OK" if good else "FAIL")
+    ok = ok and good
+    W = torch.randn(Kout, C, device=dev) * 0.2
+    res = {}
+    for name, A, mode in (("dense", op_bnbwd(Dd, Y2, b2, bb2, rw=rw), OP_BNBWD), ("pool", op_bnbwd_pool(E, mask, row_seg, Y2, b2, bb2, rw=rw), OP_BNBWD_POOL)):
+        Yo = torch.full((Mmax, Kout), 7.0, device=dev); ws.stats.fill_(5.0)
+        nt([nt_problem(A, W, C, Yo, Kout, Mmax, Mdev.data_ptr(), Kout, C, stats=ws.stats, Yprev=Y1, ldyp=Kout, pbn=b1)], mode, EPI_DMASK)
+        torch.cuda.synchronize()
+        stn = ws.stats[: STAT_SLOTS * 2 * Kout].clone()
+        dW = torch.full((C, Kout), 3.0, device=dev)
+        tn(ws, A, op_bnrelu(Y1, b1), mode, OP_BNRELU, Mmax, Mdev.data_ptr(), C, Kout, dW, Kout, C, Kout)
+        torch.cuda.synchronize()
+        res[name] = (Yo, stn, dW.clone())
+    for i, what in enumerate(("NT dX", "NT stats", "TN dW")):
+        same = bool(torch.equal(res["dense"][i], res["pool"][i]))
+        print("BNBWD_POOL vs dense BNBWD: %s bit-identical %s" % (what, same), "OK" if same else "FAIL")
+        ok = ok and same
 lib.gaddpg_set_tensor_core(3)
 print("ALL OK" if ok else "SOME FAILED")
