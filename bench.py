@@ -37,7 +37,10 @@ def workload(args):
 AGENT_KW = dict(extra_latent=3, policy_aux=False, critic_aux=False)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch (mean over the captured launches of that kernel) from the
 # `ncu --set full` capture summarised in profiles/ (same workload: cfg2); keyed like profile()'s kernel families
-NCU_TRAFFIC = {}
+NCU_TRAFFIC = {   # profiles/r1_ncu_full_v2.md (SA1 shapes, M = 423 k rows): bytes per launch, by shape label
+    "gemm_nt:tc:": {"nt[64x64,a1,e0]": 171.1e6, "nt[128x64,a1,e0]": 270.3e6, "nt[64x64,a2,e1]": 406.1e6, "nt[64x128,a3,e1]": 425.7e6},
+    "gemm_tn:": {"tn[128x64,p3,q1]": 341.7e6, "tn[64x64,p2,q1]": 328.1e6},
+}
 
 
 def peaks():
@@ -306,20 +309,26 @@ def profile(agent, devb, args):
     gbs = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else 0.0
     tfl = d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0
     hbm_bound = gbs / pk["hbm"] >= 3.0 * tfl / pk["tensor_sustained"]   # 3xTF32: three tensor passes per algorithmic flop
+    # measured DRAM traffic per launch: launch-weighted mean over the shapes of this family that were captured under ncu
+    tr = NCU_TRAFFIC.get(dom, {})
+    tw = [(tr[k], v["launches_per_step"]) for k, v in d["shapes"].items() if k in tr]
+    traffic = sum(b * w for b, w in tw) / sum(w for _, w in tw) if tw else None
+    alg_same = sum(v["gbs"] * 1e9 * v["us_per_launch"] * 1e-6 * v["launches_per_step"] for k, v in d["shapes"].items() if k in tr)
+    alg_same = alg_same / sum(w for _, w in tw) if tw else None
     if hbm_bound:
         roof = dict(kernel=FAM[dom], bound="hbm", achieved=gbs, peak=pk["hbm"], unit="GB/s", frac=gbs / pk["hbm"],
-                    traffic=NCU_TRAFFIC.get(dom), peak_source=pk["src"] + ", copy bandwidth",
+                    traffic=traffic, traffic_algorithmic_same_launches=alg_same, peak_source=pk["src"] + ", copy bandwidth",
                     algorithmic_tflops=tfl, tensor_peak_tflops=pk["tensor_sustained"])
     else:
         roof = dict(kernel=FAM[dom], bound="tensor", achieved=tfl, peak=pk["tensor_sustained"], unit="TFLOP/s",
-                    frac=tfl / pk["tensor_sustained"], traffic=NCU_TRAFFIC.get(dom), peak_source=pk["src"] + ", sustained bf16",
+                    frac=tfl / pk["tensor_sustained"], traffic=traffic, peak_source=pk["src"] + ", sustained bf16",
                     algorithmic_gbs=gbs, hbm_peak_gbs=pk["hbm"])
     roof.update(share_of_step=d["ms"] / total, avg_launch_ms=d["ms"] / max(d["calls"], 1), launches_per_step=d["calls"] / 2,
                 algorithmic_bytes_per_launch=d["bytes"] / max(d["calls"], 1), shapes=d["shapes"],
                 note="achieved = algorithmic bytes (A row [+Y row for BN-backward, + mask-source row] read once, C row written "
                      "once, weights once; DESIGN.md section 4) of all launches of this kernel in one even + one odd step / their "
                      "CUDA-event time in a single-stream eager pass; 'traffic' = dram bytes per launch from the ncu --set full "
-                     "capture under profiles/ (null if that kernel was not captured)")
+                     "capture under profiles/r1_ncu_full_v2.md, launch-weighted over the SA1 shapes of this kernel (null if none was captured); traffic_algorithmic_same_launches = the algorithmic bytes of those same launches")
     families = {FAM[f].split(" ")[0]: dict(ms_per_step=fam[f]["ms"] / 2, share=fam[f]["ms"] / total,
                                            gbs=fam[f]["bytes"] / (fam[f]["ms"] * 1e-3) / 1e9 if fam[f]["ms"] > 0 else 0.0,
                                            tflops=fam[f]["flops"] / (fam[f]["ms"] * 1e-3) / 1e12 if fam[f]["ms"] > 0 else 0.0)

@@ -104,17 +104,26 @@ __global__ void __launch_bounds__(256) reduce_partial_kernel(const float* __rest
   }
 }
 // op 0: out = max(partials)   op 1: out = min(1, max_norm / (sqrt(sum partials) + 1e-6))  [clip coefficient]
-__global__ void reduce_final_kernel(const float* __restrict__ partial, int nblk, int op, float max_norm, float* __restrict__ out,
-                                    float* __restrict__ norm_out) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// one CTA of 256 threads: thread t folds partials t, t+256, ... and thread 0 folds the 256 thread results, both in a
+// fixed order (deterministic); the single-thread loop this replaces took ~28 us for 1184 dependent loads.
+__global__ void __launch_bounds__(256) reduce_final_kernel(const float* __restrict__ partial, int nblk, int op, float max_norm,
+                                                           float* __restrict__ out, float* __restrict__ norm_out) {
+  __shared__ double red[256];
+  const int t = threadIdx.x;
+  double a = 0.0;
+  for (int i = t; i < nblk; i += 256) a = op == 0 ? fmax(a, (double)partial[i]) : a + (double)partial[i];
+  red[t] = a;
+  __syncthreads();
+#pragma unroll
+  for (int w = 128; w >= 1; w >>= 1) {
+    if (t < w) red[t] = op == 0 ? fmax(red[t], red[t + w]) : red[t] + red[t + w];
+    __syncthreads();
+  }
+  if (t != 0) return;
   if (op == 0) {
-    float r = 0.f;
-    for (int i = 0; i < nblk; ++i) r = fmaxf(r, partial[i]);
-    *out = r;
+    *out = (float)red[0];
   } else {
-    double s = 0.0;
-    for (int i = 0; i < nblk; ++i) s += (double)partial[i];
-    float nrm = (float)sqrt(s);
+    float nrm = (float)sqrt(red[0]);
     float c = max_norm / (nrm + 1e-6f);
     *out = c < 1.f ? c : 1.f;
     if (norm_out) *norm_out = nrm;
@@ -152,8 +161,11 @@ __global__ void wprep_kernel(const float* __restrict__ W, int N, int K, int rot,
   }
 }
 
-// batched form: jobs[j] = {W, N, K, rot, Wp, ldp, WT, ldt} as 8 x int64 in device memory (pointers are static)
-__global__ void wprep_batched_kernel(const long long* __restrict__ jobs) {
+// batched form: jobs[j] = {W, N, K, rot, Wp, ldp, WT, ldt} as 8 x int64 in device memory (pointers are static).
+// 32x32 tiles through shared memory: W is read once, coalesced along k; Wp is written from the same registers
+// (coalesced along kp) and WT from the transposed tile (coalesced along n).
+__global__ void __launch_bounds__(256) wprep_batched_kernel(const long long* __restrict__ jobs) {
+  __shared__ float tile[32][33];
   const long long* J = jobs + (long long)blockIdx.y * 8;
   const float* W = reinterpret_cast<const float*>(J[0]);
   const int N = (int)J[1], K = (int)J[2], rot = (int)J[3];
@@ -161,30 +173,32 @@ __global__ void wprep_batched_kernel(const long long* __restrict__ jobs) {
   const int ldp = (int)J[5];
   float* WT = reinterpret_cast<float*>(J[6]);
   const int ldt = (int)J[7];
-  long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
-  if (Wp) {
-    for (long long e = i0; e < (long long)N * ldp; e += stride) {
-      int n = (int)(e / ldp), kp = (int)(e % ldp);
-      float v = 0.f;
-      if (kp < K) {
-        int k = kp + rot;
-        if (k >= K) k -= K;
-        v = W[(long long)n * K + k];
-      }
-      Wp[e] = v;
-    }
-  }
-  if (WT) {
-    for (long long e = i0; e < (long long)ldp * ldt; e += stride) {
-      int kp = (int)(e / ldt), n = (int)(e % ldt);
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int nmax = (WT && ldt > N) ? ldt : N;
+  const int tiles_n = (nmax + 31) >> 5, tiles_k = (ldp + 31) >> 5;
+  for (int t = blockIdx.x; t < tiles_n * tiles_k; t += gridDim.x) {
+    const int n0 = (t / tiles_k) << 5, k0 = (t % tiles_k) << 5;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + ty + 8 * j, kp = k0 + tx;
       float v = 0.f;
       if (n < N && kp < K) {
         int k = kp + rot;
         if (k >= K) k -= K;
         v = W[(long long)n * K + k];
       }
-      WT[e] = v;
+      tile[ty + 8 * j][tx] = v;
+      if (Wp && n < N && kp < ldp) Wp[(long long)n * ldp + kp] = v;
     }
+    __syncthreads();
+    if (WT) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int kp = k0 + ty + 8 * j, n = n0 + tx;
+        if (kp < ldp && n < ldt) WT[(long long)kp * ldt + n] = tile[tx][ty + 8 * j];
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -253,7 +267,7 @@ int gaddpg_absmax_impl(const float* x, long long n, float* out, float* ws, void*
   int grid = stream_grid(n);
   reduce_partial_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, n, 0, ws);
   GADDPG_CHECK_LAUNCH("reduce_partial_kernel");
-  reduce_final_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(ws, grid, 0, 0.f, out, nullptr);
+  reduce_final_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(ws, grid, 0, 0.f, out, nullptr);
   GADDPG_CHECK_LAUNCH("reduce_final_kernel");
   return GADDPG_OK;
 }
@@ -263,7 +277,7 @@ int gaddpg_clip_coef_impl(const float* g, long long n, float max_norm, float* co
   int grid = stream_grid(n);
   reduce_partial_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, n, 1, ws);
   GADDPG_CHECK_LAUNCH("reduce_partial_kernel");
-  reduce_final_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(ws, grid, 1, max_norm, coef_out, norm_out);
+  reduce_final_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(ws, grid, 1, max_norm, coef_out, norm_out);
   GADDPG_CHECK_LAUNCH("reduce_final_kernel");
   return GADDPG_OK;
 }

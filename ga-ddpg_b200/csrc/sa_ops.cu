@@ -335,8 +335,20 @@ __global__ void scatter_rows_kernel(const float* __restrict__ dG, int ldg, int C
   for (int e = threadIdx.x; e < n_src * C; e += blockDim.x) sacc[e] = 0.f;
   __syncthreads();
   const int r0 = seg_off[b * npoint], r1 = seg_off[(b + 1) * npoint];
-  for (int c = threadIdx.x; c < C; c += blockDim.x)
-    for (int r = r0; r < r1; ++r) sacc[row_src[r] * C + c] += dG[(long long)r * ldg + c];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    for (int r = r0; r < r1; r += 8) {  // 8 independent loads in flight, then the adds in row order (deterministic)
+      int src[8];
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        src[u] = r + u < r1 ? row_src[r + u] : -1;
+        v[u] = r + u < r1 ? dG[(long long)(r + u) * ldg + c] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (src[u] >= 0) sacc[src[u] * C + c] += v[u];
+    }
+  }
   __syncthreads();
   for (int e = threadIdx.x; e < n_src * C; e += blockDim.x) dfeats[(long long)b * n_src * C + e] = sacc[e];
 }

@@ -264,3 +264,40 @@ def test_stream_overlap_is_bit_identical(cuda):
         assert hist == base_hist, (key, hist, base_hist)
         for k in base_sd:
             assert torch.equal(sd[k], base_sd[k]), (key, k)
+
+
+@pytest.mark.parametrize("name,B,over", [
+    ("cfg2", 256, dict(extra_latent=3, policy_aux=False, critic_aux=False)),   # BASELINE config 2 (the bench workload)
+    ("cfg3", 512, dict()),                                                       # BASELINE config 3: goal-aux + grasp-aux losses on
+])
+def test_full_size_first_step_matches_oracle(cuda, name, B, over):
+    """BASELINE.json's full-size configurations (4096-point clouds, B = 256 / 512): the first update step from identical
+    weights against the CPU oracle — all 11 returned scalars within 1e-4 relative (north_star), FPS / ball-query indices
+    of the whole batch bit-exact, Q values / TD target / actions within 1e-4.  At these sizes every layer runs on its
+    production kernel (tcgen05 SA1/SA2/SA3, mma.sync FC + heads, sparse pool backward, multi-stream schedule, graphs off
+    for the first step)."""
+    from gaddpg_b200 import agent as ag, synthetic
+    from gaddpg_b200.config import LOSS_KEYS
+    from oracle.ddpg_cpu import OracleAgent
+    from oracle.pointnet2_ops_cpu import pointnet2_utils as U
+
+    N = 4096
+    torch.set_num_threads(os.cpu_count())
+    ora = OracleAgent("DDPG", seed=123456, **over)
+    mine = ag.make_agent("DDPG", seed=123456, **over)
+    batch = synthetic.make_batch(B, N, step=0, channels=6 if over.get("extra_latent") == 3 else 4)
+    u = np.random.RandomState(5).rand(B, 6).astype(np.float32)
+    o = ora.update_parameters(batch, noise_u=u)
+    m = mine.update_parameters(batch, 1, 0, noise_u=u)
+    for k in LOSS_KEYS:
+        assert _close(m[k], o[k], rtol=1e-4), (name, k, m[k], o[k])
+    rel = lambda a, b: float((a.cpu().double() - b.double()).abs().max() / (b.double().abs().max() + 1e-30))  # noqa: E731
+    assert rel(mine.y, ora.last["y"]) < 1e-4
+    assert rel(mine.cc1.qa[:, 0], ora.last["q1"].view(-1)) < 1e-4 and rel(mine.cc1.qa[:, 4], ora.last["q2"].view(-1)) < 1e-4
+    assert rel(mine.pc.pi, ora.last["pi"]) < 1e-4
+    xyz = torch.from_numpy(batch["point_state_batch"])[:, :3, 6:].transpose(1, 2).contiguous()
+    fps = U.fps_raw(xyz, 32)
+    assert torch.equal(mine.geom_s.lv[0].fps_idx.cpu(), fps), "FPS indices differ from the oracle at full size"
+    ctr = torch.gather(xyz, 1, fps.long().unsqueeze(-1).expand(-1, -1, 3))
+    bq = U.ball_query_raw(0.02, 64, xyz, ctr.contiguous())
+    assert torch.equal(mine.geom_s.lv[0].bq_idx.cpu(), bq), "ball-query indices differ from the oracle at full size"
