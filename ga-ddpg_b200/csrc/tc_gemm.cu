@@ -37,39 +37,42 @@ constexpr int TC_THREADS = (TC_PW + 1 + 4) * 32;
 #define TC_U_BWD 4
 #endif
 
+constexpr int TC_KS = 64;  // K width of one shared-memory A stage (a K = 128 tile is two stages: its second half loads
+                           // while the tensor core works on the first)
 struct TcSmemLayout {
-  uint32_t w_hi, w_lo, a_hi[2], a_lo[2], stage_buf, bars, total;
+  uint32_t w_hi, w_lo, a_hi[2], a_lo[2], stage_buf, cc, bars, total;
 };
-__host__ __device__ inline TcSmemLayout tc_layout(int N, int K, int stages) {
+__host__ __device__ inline TcSmemLayout tc_layout(int N, int K) {
   TcSmemLayout L;
   uint32_t off = 0;
   L.w_hi = off; off += (uint32_t)N * K * 4;
   L.w_lo = off; off += (uint32_t)N * K * 4;
   for (int s = 0; s < 2; ++s) {
-    L.a_hi[s] = off; if (s < stages) off += (uint32_t)TC_BM * K * 4;
-    L.a_lo[s] = off; if (s < stages) off += (uint32_t)TC_BM * K * 4;
+    L.a_hi[s] = off; off += (uint32_t)TC_BM * TC_KS * 4;
+    L.a_lo[s] = off; off += (uint32_t)TC_BM * TC_KS * 4;
   }
   L.stage_buf = off; off += 4 * 32 * EPI_LD * 4;   // per-epilogue-warp transpose buffers
+  L.cc = off; off += 5 * 128 * 4;                // per-column prologue constants c0..c4 [5][K <= 128]
   L.bars = off; off += 256;                     // mbarriers + tmem address + stats scratch header
   off += 2 * 4 * 256 * 4;                       // cross-warp stats combine: [2][4 warps][N<=256]
   L.total = off;
   return L;
 }
 
-// per-column prologue constants: each producer thread always serves the same 4 columns, so they live in registers
+// per-column prologue constants: staged once per CTA in shared memory ([5][128] floats), fetched per pipeline unit
 template <int MODE>
 struct ColConsts {
   float4 c0, c1, c2, c3, c4;
-  __device__ __forceinline__ void load(const Operand& d, int col) {
+  __device__ __forceinline__ void load(const float* tab, int col) {
     if (MODE == OP_BNRELU) {
-      c0 = ldg4(d.c0 + col);
-      c1 = ldg4(d.c1 + col);
+      c0 = *reinterpret_cast<const float4*>(tab + col);
+      c1 = *reinterpret_cast<const float4*>(tab + 128 + col);
     } else if (MODE == OP_BNBWD || MODE == OP_BNBWD_POOL) {
-      c0 = ldg4(d.c0 + col);
-      c1 = ldg4(d.c1 + col);
-      c2 = ldg4(d.c2 + col);
-      c3 = ldg4(d.c3 + col);
-      c4 = ldg4(d.c4 + col);
+      c0 = *reinterpret_cast<const float4*>(tab + col);
+      c1 = *reinterpret_cast<const float4*>(tab + 128 + col);
+      c2 = *reinterpret_cast<const float4*>(tab + 256 + col);
+      c3 = *reinterpret_cast<const float4*>(tab + 384 + col);
+      c4 = *reinterpret_cast<const float4*>(tab + 512 + col);
     }
   }
   __device__ __forceinline__ float4 apply(float4 x, float4 y, float w) const {
@@ -93,12 +96,13 @@ struct ColConsts {
 
 // NCB = 32-column accumulator blocks the epilogue keeps statistics for: 4 (N <= 128, the SA1 layers) or 8 (N <= 256)
 template <int K, int AMODE, int EMODE, int NCB>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProblem p, int stages) {
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProblem p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // SWIZZLE_128B operands need 1024-byte aligned bases (the host adds 1024 bytes of slack)
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int N = p.N;
-  const TcSmemLayout L = tc_layout(N, K, stages);
+  const TcSmemLayout L = tc_layout(N, K);
+  constexpr int NH = K / TC_KS;  // A stages per tile
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint64_t* a_full = bars;           // [2]
   uint64_t* a_empty = bars + 2;      // [2]
@@ -125,6 +129,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
     fence_barrier_init();
   }
   if (warp == TC_PW) tmem_alloc(tmem_slot, tmem_cols);
+  {
+    float* cct = reinterpret_cast<float*>(smem + L.cc);
+    constexpr int NC = (AMODE == OP_PLAIN) ? 0 : (AMODE == OP_BNRELU) ? 2 : 5;
+    for (int i = tid; i < NC * K; i += TC_THREADS) {
+      const int a = i / K, c = i % K;
+      const float* sp = a == 0 ? p.A.c0 : a == 1 ? p.A.c1 : a == 2 ? p.A.c2 : a == 3 ? p.A.c3 : p.A.c4;
+      cct[a * 128 + c] = sp[c];
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -132,12 +145,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
 
   if (warp < TC_PW) {
     // ===================== producers =====================
-    constexpr int KQ4 = K / 4;        // float4 per row
-    constexpr int RPI = TC_PT / KQ4;  // rows covered by the producer threads per iteration
-    constexpr int ITERS = TC_BM / RPI;
+    constexpr int KQ4 = K / 4;         // float4 per row of the weight matrix
+    constexpr int SQ4 = TC_KS / 4;     // float4 per row of one A stage
+    constexpr int RPI = TC_PT / SQ4;   // rows covered by the producer threads per iteration (16)
+    constexpr int ITERS = TC_BM / RPI; // row-iterations per stage (8)
     constexpr bool BWD = (AMODE == OP_BNBWD || AMODE == OP_BNBWD_POOL);
     constexpr int U = BWD ? TC_U_BWD : TC_U_FWD;  // row-iterations per pipeline unit (two register sets in flight)
-    static_assert(TC_PT % KQ4 == 0 && ITERS % U == 0, "K must be 32, 64 or 128");
+    static_assert(K % TC_KS == 0 && ITERS % U == 0, "K must be 64 or 128");
     for (int idx = tid; idx < N * KQ4; idx += TC_PT) {
       int n = idx / KQ4, k = (idx % KQ4) << 2;
       float4 v = ldg4(p.Bw + (long long)n * p.ldb + k);
@@ -145,13 +159,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
     }
     fence_proxy_async();
     mbar_arrive(w_full);
-    const int kcol = (tid % KQ4) << 2, rsub = tid / KQ4;
-    ColConsts<AMODE> cc;
-    cc.load(p.A, kcol);
+    const int kc = (tid % SQ4) << 2, rsub = tid / SQ4;  // column inside the 64-wide stage, first row served
+    const float* cct = reinterpret_cast<const float*>(smem + L.cc);
     // Software pipeline over "units" of U row-iterations: the global loads of unit u+1 are issued into a second
     // register set before unit u is transformed and stored, so HBM latency overlaps the prologue math and the
-    // shared-memory stores (and runs ahead across tile boundaries, independent of the smem-stage barriers).
-    constexpr int UPT = ITERS / U;  // units per tile
+    // shared-memory stores (and runs ahead across stage and tile boundaries, independent of the smem-stage barriers).
+    constexpr int UPS = ITERS / U;    // units per stage
+    constexpr int UPT = NH * UPS;     // units per tile
     struct Regs {
       float4 x[U], y[U];
       float w[U];
@@ -161,7 +175,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
     const int total_units = my_tiles * UPT;
     int segn[U];  // BNBWD_POOL: segments of the rows of the NEXT unit to be issued
     auto prefetch_seg = [&](int u) {
-      const int it = u / UPT, i0 = (u % UPT) * U;
+      const int it = u / UPT, i0 = ((u % UPT) % UPS) * U;
       const int row0 = ((int)blockIdx.x + it * (int)gridDim.x) * TC_BM;
 #pragma unroll
       for (int k = 0; k < U; ++k) {
@@ -170,8 +184,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
       }
     };
     auto issue = [&](Regs& R, int u) {
-      const int it = u / UPT, i0 = (u % UPT) * U;
+      const int it = u / UPT, v = u % UPT, h = v / UPS, i0 = (v % UPS) * U;
       const int row0 = ((int)blockIdx.x + it * (int)gridDim.x) * TC_BM;
+      const int kcol = h * TC_KS + kc;
 #pragma unroll
       for (int k = 0; k < U; ++k) {
         const int row = row0 + rsub + (i0 + k) * RPI;
@@ -204,10 +219,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
       }
     };
     auto process = [&](const Regs& R, int u) {
-      const int it = u / UPT, i0 = (u % UPT) * U;
-      const int s = it % stages;
+      const int it = u / UPT, v = u % UPT, h = v / UPS, i0 = (v % UPS) * U;
+      const int g = it * NH + h, s = g & 1;  // stage counter of this CTA, ring slot
       const int row0 = ((int)blockIdx.x + it * (int)gridDim.x) * TC_BM;
-      if (i0 == 0) mbar_wait(&a_empty[s], ((uint32_t)(it / stages) & 1u) ^ 1u);
+      const int kcol = h * TC_KS + kc;
+      ColConsts<AMODE> cc;
+      cc.load(cct, kcol);
+      if (i0 == 0) mbar_wait(&a_empty[s], ((uint32_t)(g >> 1) & 1u) ^ 1u);
       unsigned char* ah = smem + L.a_hi[s];
       unsigned char* al = smem + L.a_lo[s];
 #pragma unroll
@@ -221,8 +239,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
           x.z = (bits & 4u) ? x.z : 0.f;
           x.w = (bits & 8u) ? x.w : 0.f;
         }
-        float4 v = (row0 + r < M) ? cc.apply(x, R.y[k], R.w[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
-        split_store(ah, al, sw128_off(r, kcol, TC_BM), v);
+        float4 vv = (row0 + r < M) ? cc.apply(x, R.y[k], R.w[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        split_store(ah, al, sw128_off(r, kc, TC_BM), vv);
       }
       if (i0 + U == ITERS) {
         fence_proxy_async();
@@ -248,30 +266,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
       const uint32_t sbase = smem_u32(smem);
       mbar_wait(w_full, 0);
       tc_fence_after();
-      int it = 0;
+      int it = 0, g = 0;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-        const int s = it % stages, b = it & 1;
-        const uint32_t ph = (uint32_t)(it / stages) & 1u, bph = (uint32_t)(it >> 1) & 1u;
+        const int b = it & 1;
+        const uint32_t bph = (uint32_t)(it >> 1) & 1u;
         mbar_wait(&acc_empty[b], bph ^ 1u);
-        mbar_wait(&a_full[s], ph);
-        tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(b * N);
         uint32_t acc = 0;
 #pragma unroll
-        for (int kb = 0; kb < (K >> 5); ++kb) {
+        for (int h = 0; h < NH; ++h, ++g) {
+          const int s = g & 1;
+          mbar_wait(&a_full[s], (uint32_t)(g >> 1) & 1u);
+          tc_fence_after();
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint32_t aoff = (uint32_t)(kb * TC_BM * 128 + ks * 32), boff = (uint32_t)(kb * N * 128 + ks * 32);
-            const uint64_t a_hi = make_desc(sbase + L.a_hi[s] + aoff), a_lo = make_desc(sbase + L.a_lo[s] + aoff);
-            const uint64_t b_hi = make_desc(sbase + L.w_hi + boff), b_lo = make_desc(sbase + L.w_lo + boff);
-            umma_tf32(d_tmem, a_lo, b_hi, idesc, acc);
-            umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
-            umma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
-            acc = 1u;
+          for (int kb = 0; kb < (TC_KS >> 5); ++kb) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint32_t aoff = (uint32_t)(kb * TC_BM * 128 + ks * 32);
+              const uint32_t boff = (uint32_t)((h * (TC_KS >> 5) + kb) * N * 128 + ks * 32);
+              const uint64_t a_hi = make_desc(sbase + L.a_hi[s] + aoff), a_lo = make_desc(sbase + L.a_lo[s] + aoff);
+              const uint64_t b_hi = make_desc(sbase + L.w_hi + boff), b_lo = make_desc(sbase + L.w_lo + boff);
+              umma_tf32(d_tmem, a_lo, b_hi, idesc, acc);
+              umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
+              umma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
+              acc = 1u;
+            }
           }
+          umma_commit(&a_empty[s]);  // this smem stage may be refilled once these MMAs have read it
         }
-        umma_commit(&a_empty[s]);   // smem stage may be refilled once these MMAs have read it
-        umma_commit(&acc_full[b]);  // accumulator ready for the epilogue
+        umma_commit(&acc_full[b]);   // accumulator ready for the epilogue
       }
     }
     __syncwarp();
@@ -365,16 +388,14 @@ bool gaddpg_tc_gemm_supported(const NTProblem& p, int amode, int emode) {
   if (p.ldb != p.K) {
     if (p.ldb % 4 != 0) return false;
   }
-  int stages = (p.K <= 64) ? 2 : 1;
-  if (tc_layout(p.N, p.K, stages).total + 1024 > 227 * 1024) return false;
+  if (tc_layout(p.N, p.K).total + 1024 > 227 * 1024) return false;
   (void)amode;
   (void)emode;
   return true;
 }
 
 int gaddpg_tc_gemm_nt_impl(const NTProblem* p, int amode, int emode, void* stream) {
-  const int stages = (p->K <= 64) ? 2 : 1;
-  const TcSmemLayout L = tc_layout(p->N, p->K, stages);
+  const TcSmemLayout L = tc_layout(p->N, p->K);
   const size_t smem = L.total + 1024;  // slack for the 1024-byte alignment of the operand regions
   int tiles = ceil_div(p->M_max, TC_BM);
   int grid = tiles < gaddpg_sm_count() ? tiles : gaddpg_sm_count();
@@ -383,7 +404,7 @@ int gaddpg_tc_gemm_nt_impl(const NTProblem* p, int amode, int emode, void* strea
   {                                                                                                            \
     auto kern = tc_gemm_nt_kernel<KK, A, E, NCB_>;                                                             \
     GADDPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
-    kern<<<grid, TC_THREADS, smem, st>>>(*p, stages);                                                          \
+    kern<<<grid, TC_THREADS, smem, st>>>(*p);                                                          \
     GADDPG_CHECK_LAUNCH("tc_gemm_nt_kernel");                                                                  \
     return GADDPG_OK;                                                                                          \
   }
