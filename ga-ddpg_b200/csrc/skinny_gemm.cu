@@ -19,9 +19,9 @@
 
 namespace {
 
-constexpr int SK_BM = 32, SK_BN = 64, SK_BK = 32, SK_STAGES = 5;
+constexpr int SK_BM = 32, SK_BK = 32, SK_STAGES = 5;  // output tile 32 x BN (BN = 64, or 32 when that is needed to fill the chip)
 constexpr int SK_LD = SK_BK + 4;  // row pitch (floats): 16-byte aligned rows, conflict-free fragment loads (bank = 4g + t)
-constexpr int SK_A_FLOATS = SK_BM * SK_LD, SK_B_FLOATS = SK_BN * SK_LD;
+constexpr int SK_A_FLOATS = SK_BM * SK_LD;
 
 __device__ __forceinline__ float4 sk_ldg4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
@@ -81,14 +81,20 @@ struct SkConsts {
   }
 };
 
-template <int AMODE, int EMODE>
+// 8 warps = NWM x NWN: warp (wm, wn) owns MFW 16-row fragments x the 8 columns [8 wn, 8 wn + 8) of the 32 x BN tile.
+// BN = 64: 1 x 8 warps, two m-fragments each; BN = 32: 2 x 4 warps, one m-fragment each (half the MMAs per CTA, twice the CTAs).
+template <int AMODE, int EMODE, int BN>
 __global__ void __launch_bounds__(256) skinny_nt_kernel(const NTGroup grp) {
   extern __shared__ __align__(16) float sk_smem[];
   __shared__ float s_acc[2 * 1024];  // per-CTA running (sum, sum2) per output column (N <= 1024 when stats on)
+  __shared__ float s_part[2][2][64]; // [row half wm][sum | sum2][tile column]: fixed-order fold when NWM = 2
+  constexpr int SK_BN = BN, SK_B_FLOATS = BN * SK_LD;
+  constexpr int NWN = BN / 8, NWM = 8 / NWN, MFW = 2 / NWM;
   constexpr int STAGE_FLOATS = SK_A_FLOATS * (AMODE == OP_BNBWD ? 2 : 1) + SK_B_FLOATS;
 
   const NTProblem& p = grp.p[blockIdx.y];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int wn = warp % NWN, wm = warp / NWN;
   int M = p.M_dev ? *p.M_dev : p.M_max;
   M = M < p.M_max ? M : p.M_max;
   const int N = p.N, K = p.K;
@@ -118,16 +124,16 @@ __global__ void __launch_bounds__(256) skinny_nt_kernel(const NTGroup grp) {
                    arow_ok && kok);
       float* bs = st + SK_A_FLOATS * (AMODE == OP_BNBWD ? 2 : 1);
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
+      for (int i = 0; i < BN / 32; ++i) {
         const int br = ar + 32 * i, n = col0 + br;
         const bool ok = n < N && kok;
         cp_async16(bs + br * SK_LD + aq, p.Bw + (long long)(n < N ? n : 0) * p.ldb + (kok ? k : 0), ok);
       }
     };
 
-    float acc[2][4];
+    float acc[MFW][4];
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < MFW; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
@@ -158,12 +164,12 @@ __global__ void __launch_bounds__(256) skinny_nt_kernel(const NTGroup grp) {
       cp_async_commit();
 
       const float* As = st;
-      const float* Bs = st + SK_A_FLOATS * (AMODE == OP_BNBWD ? 2 : 1) + (warp * 8) * SK_LD;
+      const float* Bs = st + SK_A_FLOATS * (AMODE == OP_BNBWD ? 2 : 1) + (wn * 8) * SK_LD;
       // the tensor core's FP32 accumulation is not IEEE round-to-nearest (its error grows with the number of
       // accumulated products: ~1e-5 at K = 1024); accumulate one 32-wide chunk there and fold chunks with FP32 adds
-      float d[2][4];
+      float d[MFW][4];
 #pragma unroll
-      for (int i = 0; i < 2; ++i)
+      for (int i = 0; i < MFW; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) d[i][j] = 0.f;
 #pragma unroll
@@ -172,9 +178,9 @@ __global__ void __launch_bounds__(256) skinny_nt_kernel(const NTGroup grp) {
         split_tf32(Bs[g * SK_LD + k8 + t], bh[0], bl[0]);
         split_tf32(Bs[g * SK_LD + k8 + t + 4], bh[1], bl[1]);
 #pragma unroll
-        for (int mf = 0; mf < 2; ++mf) {
+        for (int mf = 0; mf < MFW; ++mf) {
           uint32_t ah[4], al[4];
-          const float* a = As + (16 * mf + g) * SK_LD + k8 + t;
+          const float* a = As + (16 * (wm * MFW + mf) + g) * SK_LD + k8 + t;
           split_tf32(a[0], ah[0], al[0]);
           split_tf32(a[8 * SK_LD], ah[1], al[1]);
           split_tf32(a[4], ah[2], al[2]);
@@ -185,25 +191,25 @@ __global__ void __launch_bounds__(256) skinny_nt_kernel(const NTGroup grp) {
         }
       }
 #pragma unroll
-      for (int i = 0; i < 2; ++i)
+      for (int i = 0; i < MFW; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] += d[i][j];
     }
     cp_async_wait<0>();
 
-    // ---- epilogue: thread holds rows row0 + 16 mf + g (+8), columns col0 + 8 warp + 2t (+1) ----
+    // ---- epilogue: thread holds rows row0 + 16 (wm MFW + mf) + g (+8), columns col0 + 8 wn + 2t (+1) ----
     float s0[2] = {0.f, 0.f}, s1[2] = {0.f, 0.f};
 #pragma unroll
-    for (int mf = 0; mf < 2; ++mf) {
+    for (int mf = 0; mf < MFW; ++mf) {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        const int row = row0 + 16 * mf + g + 8 * h;
+        const int row = row0 + 16 * (wm * MFW + mf) + g + 8 * h;
         if (row < M) {
           float w = 1.f;
           if (EMODE == EPI_STORE && do_stats && p.srw) w = p.srw[row];
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
-            const int col = col0 + 8 * warp + 2 * t + j;
+            const int col = col0 + 8 * wn + 2 * t + j;
             if (col < N) {
               float v = acc[mf][2 * h + j];
               if (EMODE == EPI_STORE) {
@@ -227,7 +233,7 @@ __global__ void __launch_bounds__(256) skinny_nt_kernel(const NTGroup grp) {
         }
       }
     }
-    if (do_stats) {  // fold the 8 row groups (g) of the warp in a fixed order; every column has exactly one owner
+    if (do_stats) {  // fold the 8 row groups (g) of the warp, then the NWM row halves, always in the same order
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
 #pragma unroll
@@ -235,11 +241,20 @@ __global__ void __launch_bounds__(256) skinny_nt_kernel(const NTGroup grp) {
           s0[j] += __shfl_xor_sync(0xffffffffu, s0[j], o);
           s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], o);
         }
-        const int col = col0 + 8 * warp + 2 * t + j;
-        if (g == 0 && col < N) {
-          s_acc[col] += s0[j];
-          s_acc[N + col] += s1[j];
+        if (g == 0) {
+          s_part[wm][0][8 * wn + 2 * t + j] = s0[j];
+          s_part[wm][1][8 * wn + 2 * t + j] = s1[j];
         }
+      }
+      __syncthreads();
+      if (tid < BN && col0 + tid < N) {
+        float a0 = s_part[0][0][tid], a1 = s_part[0][1][tid];
+        if (NWM == 2) {
+          a0 += s_part[1][0][tid];
+          a1 += s_part[1][1][tid];
+        }
+        s_acc[col0 + tid] += a0;
+        s_acc[N + col0 + tid] += a1;
       }
     }
   }
@@ -252,17 +267,25 @@ __global__ void __launch_bounds__(256) skinny_nt_kernel(const NTGroup grp) {
   }
 }
 
-template <int AMODE, int EMODE>
-int launch_skinny(const NTGroup& g, int nprob, int maxM, int maxN, cudaStream_t st) {
-  constexpr int STAGE_FLOATS = SK_A_FLOATS * (AMODE == OP_BNBWD ? 2 : 1) + SK_B_FLOATS;
+template <int AMODE, int EMODE, int BN>
+int launch_skinny_bn(const NTGroup& g, int nprob, int maxM, int maxN, cudaStream_t st) {
+  constexpr int STAGE_FLOATS = SK_A_FLOATS * (AMODE == OP_BNBWD ? 2 : 1) + BN * SK_LD;
   const size_t smem = (size_t)SK_STAGES * STAGE_FLOATS * sizeof(float);
-  auto kern = skinny_nt_kernel<AMODE, EMODE>;
+  auto kern = skinny_nt_kernel<AMODE, EMODE, BN>;
   GADDPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int tiles = ceil_div(maxM, SK_BM) * ceil_div(maxN, SK_BN);
+  const int tiles = ceil_div(maxM, SK_BM) * ceil_div(maxN, BN);
   dim3 grid(tiles < GADDPG_STAT_SLOTS ? tiles : GADDPG_STAT_SLOTS, nprob);
   kern<<<grid, 256, smem, st>>>(g);
   GADDPG_CHECK_LAUNCH("skinny_nt_kernel");
   return GADDPG_OK;
+}
+
+template <int AMODE, int EMODE>
+int launch_skinny(const NTGroup& g, int nprob, int maxM, int maxN, cudaStream_t st) {
+  // 32 x 64 tiles unless that leaves most of the 148 SMs without a CTA
+  if (ceil_div(maxM, SK_BM) * ceil_div(maxN, 64) * nprob < gaddpg_sm_count() && maxN > 32)
+    return launch_skinny_bn<AMODE, EMODE, 32>(g, nprob, maxM, maxN, st);
+  return launch_skinny_bn<AMODE, EMODE, 64>(g, nprob, maxM, maxN, st);
 }
 
 }  // namespace
