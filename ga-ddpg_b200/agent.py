@@ -373,7 +373,7 @@ class AgentB200:
         st.eps.copy_(torch.randn(B, 6) if eps is None else torch.as_tensor(eps, dtype=torch.float32).view(B, 6))
         st.geom.build(cloud, skip)
         feat = engine.encoder_forward(self.ws, self.ef_p, st.geom, cloud, skip, self.Cp_policy, None, st.ctx, time=st.time,
-                                      train=False)
+                                      train=False, keep=False)
         raw = engine.policy_forward(self.pf, feat, st.pc, B)
         s = current_stream()
         lib.gaddpg_policy_head_fwd(dp(raw), self.pf.NHp, B, dp(st.pc.pi), s)
@@ -442,12 +442,12 @@ class DDPGB200(AgentB200):
         B, v, s = self.B, self.v, current_stream()
         self.geom_n.build(self.next_cloud, self.skip)
         f2 = engine.encoder_forward(ws, self.ef_p, self.geom_n, self.next_cloud, self.skip, self.Cp_policy, None, self.ctx_n,
-                                    time=v.time, time_offset=-1.0, train=True, bn_stage=self.bnst[2])             # F2
+                                    time=v.time, time_offset=-1.0, train=True, bn_stage=self.bnst[2], keep=False)  # F2
         rawt = engine.policy_forward(self.pft, f2, self.pct, B)
         lib.gaddpg_td3_next_action(dp(rawt), self.pft.NHp, dp(v.noise_u), float(self._noise_scale()), B, dp(self.next_action), s)
         f3 = engine.encoder_forward(ws, self.ef_v, self.geom_n, self.next_cloud, self.skip, self.Cp_value,
                                     self._bc(self.next_action, 1), self.ctx_n, time=v.time, time_offset=-1.0, train=True,
-                                    bn_stage=self.bnst[3])                                                         # F3
+                                    bn_stage=self.bnst[3], keep=False)                                             # F3
         qat = engine.critic_forward(self.cft, f3, self.cct, B, nb=2)
         lib.gaddpg_td3_target(dp(qat), QA_LD, QA_Q2, dp(v.reward), dp(v.done), float(self.gamma), B, dp(self.y), s)
 

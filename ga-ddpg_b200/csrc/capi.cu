@@ -151,6 +151,10 @@ int gaddpg_pool_bwd_sparse(const float* dOut, int ldo, const float* out, const i
                                 void* stream) {
   return gaddpg_pool_bwd_sparse_impl(dOut, ldo, out, arg, Y, C, S, mean, rstd, E, mask, M_max, stats, stream);
 }
+int gaddpg_pool_keys_finalize(unsigned long long* keys, int S, int C, const float* gamma, const float* scale, const float* shift, float* out,
+                              int32_t* arg, void* stream) {
+  return gaddpg_pool_keys_finalize_impl(keys, S, C, gamma, scale, shift, out, arg, stream);
+}
 int gaddpg_feat_finish(const float* Y, int C, const float* scale, const float* shift, const float* time, float time_offset, int B,
                        float* feat, int ld, void* stream) {
   return gaddpg_feat_finish_impl(Y, C, scale, shift, time, time_offset, B, feat, ld, stream);

@@ -525,6 +525,11 @@ int gaddpg_gemm_nt_impl(const NTGroup* g, int nprob, int amode, int emode, void*
     return gaddpg_tc_gemm_nt_impl(&g->p[0], amode, emode, stream);  // tcgen05 3xTF32 path for the wide SA layers
   if (nprob == 1 && gaddpg_get_tensor_core_impl() >= 2 && gaddpg_tc_nt_kc_supported(g->p[0], amode, emode))
     return gaddpg_tc_nt_kc_impl(&g->p[0], amode, emode, stream);   // K-chunked tcgen05 path (SA2 / SA3 / FC / heads)
+  for (int i = 0; i < nprob; ++i)
+    if (g->p[i].pool_keys || g->p[i].no_store) {
+      gaddpg_set_error("gemm_nt: the fused max-pool epilogue (pool_keys / no_store) is only available on the tcgen05 kernels");
+      return GADDPG_ERR_UNSUPPORTED;
+    }
   if (amode == OP_BNBWD_POOL) {
     gaddpg_set_error("gemm_nt: GADDPG_OP_BNBWD_POOL is only taken by the tcgen05 whole-K kernel (K = 128, N <= 128, DMASK epilogue)");
     return GADDPG_ERR_UNSUPPORTED;

@@ -59,6 +59,8 @@ int gaddpg_pool_bwd_impl(const float* dOut, int ldo, const float* out, const int
 int gaddpg_pool_bwd_sparse_impl(const float* dOut, int ldo, const float* out, const int32_t* arg, const float* Y, int C, int S,
                                 const float* mean, const float* rstd, float* E, uint32_t* mask, int M_max, float* stats,
                                 void* stream);
+int gaddpg_pool_keys_finalize_impl(unsigned long long* keys, int S, int C, const float* gamma, const float* scale, const float* shift, float* out,
+                                   int32_t* arg, void* stream);
 int gaddpg_feat_finish_impl(const float* Y, int C, const float* scale, const float* shift, const float* time,
                             float time_offset, int B, float* feat, int ld, void* stream);
 // head_ops.cu

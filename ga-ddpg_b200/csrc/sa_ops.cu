@@ -506,6 +506,28 @@ __global__ void __launch_bounds__(256) pool_bwd_sparse_kernel(const float* __res
     for (int i = tid; i < 2 * C; i += 256) stats[(long long)slot * 2 * C + i] = 0.f;
 }
 
+// Fused max-pool, second half: keys[seg][c] = {max key, min key} written by the epilogue of the last shared-MLP layer
+// (tc_common.cuh: epi_pool32): the per-segment maximum of the raw output for gamma >= 0, the minimum otherwise.  BatchNorm is
+// monotone per channel, so relu(bn(extreme)) is bit-identical to pooling the normalised activations.  Keys are re-zeroed
+// for the next pass.
+__device__ __forceinline__ float key_value(unsigned int hi) {
+  return __uint_as_float((hi & 0x80000000u) ? (hi & 0x7FFFFFFFu) : ~hi);
+}
+__global__ void __launch_bounds__(256) pool_keys_finalize_kernel(unsigned long long* __restrict__ keys, long long total, int C,
+                                                                 const float* __restrict__ gamma, const float* __restrict__ scale,
+                                                                 const float* __restrict__ shift, float* __restrict__ out,
+                                                                 int32_t* __restrict__ arg) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(e % C);
+    const unsigned long long kk = keys[e];
+    const unsigned int hi = (unsigned int)(kk >> 32);
+    const float v = key_value(gamma[c] < 0.f ? ~hi : hi);
+    out[e] = fmaxf(fmaf(v, scale[c], shift[c]), 0.f);
+    if (arg) arg[e] = (int32_t)(0xFFFFFFFFu - (unsigned int)(kk & 0xFFFFFFFFull));
+    keys[e] = 0ull;
+  }
+}
+
 // feat[b][0:C] = relu(y*scale+shift), feat[b][C] = time[b], feat[b][C+1:ld] = 0
 __global__ void feat_finish_kernel(const float* __restrict__ Y, int C, const float* __restrict__ scale,
                                    const float* __restrict__ shift, const float* __restrict__ time, float time_offset,
@@ -694,6 +716,16 @@ int gaddpg_pool_bwd_sparse_impl(const float* dOut, int ldo, const float* out, co
   grid = grid < GADDPG_STAT_SLOTS ? grid : GADDPG_STAT_SLOTS;
   pool_bwd_sparse_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dOut, ldo, out, arg, Y, C, S, mean, rstd, E, mask, stats);
   GADDPG_CHECK_LAUNCH("pool_bwd_sparse_kernel");
+  return GADDPG_OK;
+}
+
+int gaddpg_pool_keys_finalize_impl(unsigned long long* keys, int S, int C, const float* gamma, const float* scale,
+                                   const float* shift, float* out, int32_t* arg, void* stream) {
+  GADDPG_CHECK_ARG(keys && gamma && scale && shift && out && S >= 1 && C >= 1, "pool_keys_finalize: bad argument");
+  const long long total = (long long)S * C;
+  const int grid = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  pool_keys_finalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(keys, total, C, gamma, scale, shift, out, arg);
+  GADDPG_CHECK_LAUNCH("pool_keys_finalize_kernel");
   return GADDPG_OK;
 }
 

@@ -129,6 +129,48 @@ __device__ __forceinline__ float4 load_operand4(const Operand& d, int row, int c
 // ---------------------------------------------------------------------------------------------------------
 constexpr int EPI_LD = 36;  // staging row pitch in floats: 16-byte aligned rows, conflict-free STS.128 / LDS.128
 
+// Fused max-pool, first half (gaddpg_nt_problem.pool_keys): lane = column.  The pooled activation of a column is
+// relu(bn(max y)) when the BatchNorm scale gamma*rstd is non-negative and relu(bn(min y)) otherwise, and the sign of the scale is
+// the sign of gamma (rstd > 0), which is known before the layer runs: each column tracks ONE extreme.  The 32 staged rows
+// are loaded up front (independent LDS), then every distinct segment of the block (rows of a segment are contiguous; a block
+// usually holds one or two) is reduced branch-free and flushed with one 64-bit atomicMax per column.  Key = order-preserving
+// float bits (complemented for a negative gamma) in the high word, ~row in the low word: the maximum key is the extreme value
+// at the lowest row that attains it, independent of the order in which CTAs arrive.
+__device__ __forceinline__ uint32_t ordered_bits(float y) {
+  const uint32_t u = __float_as_uint(y);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ void epi_pool32(const NTProblem& p, const float* stage, int lane, int row_base, int col0, int M, int N) {
+  const int col = col0 + lane;
+  const bool cval = col < N;
+  const int myrow = row_base + lane;
+  const int segv = myrow < M ? p.pool_seg[myrow] : -1;
+  const bool neg = cval && p.pool_gamma[col] < 0.f;
+  const float bias = (p.bias && cval) ? p.bias[col] : 0.f;
+  uint32_t u[32];
+#pragma unroll
+  for (int rr = 0; rr < 32; ++rr) {
+    const uint32_t o = ordered_bits(stage[rr * EPI_LD + lane] + bias);
+    u[rr] = neg ? ~o : o;
+  }
+  int cur = __shfl_sync(0xffffffffu, segv, 0);
+  while (cur >= 0) {  // warp-uniform: one pass per distinct segment of the block (segment ids increase with the row)
+    uint32_t best = 0u;
+    int arow = 0, nxt = -1;
+#pragma unroll
+    for (int rr = 0; rr < 32; ++rr) {
+      const int sg = __shfl_sync(0xffffffffu, segv, rr);
+      const bool better = (sg == cur) && (u[rr] > best);
+      best = better ? u[rr] : best;
+      arow = better ? rr : arow;
+      nxt = (nxt < 0 && sg > cur) ? sg : nxt;
+    }
+    if (cval)
+      atomicMax(p.pool_keys + (long long)cur * N + col, ((unsigned long long)best << 32) | (0xFFFFFFFFu - (uint32_t)(row_base + arow)));
+    cur = nxt;
+  }
+}
+
 template <int EMODE>
 __device__ __forceinline__ void epi_block32(const NTProblem& p, uint32_t taddr, float* stage, int lane, int row_base, int col0,
                                             int M, int N, const float (&wr)[8], bool do_stats, float (&s0)[4], float (&s1)[4]) {
@@ -167,11 +209,54 @@ __device__ __forceinline__ void epi_block32(const NTProblem& p, uint32_t taddr, 
   for (int j = 0; j < 8; ++j)
     *reinterpret_cast<float4*>(stage + lane * EPI_LD + 4 * j) = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
   __syncwarp();
+  if (EMODE == EPI_STORE && p.pool_keys != nullptr) epi_pool32(p, stage, lane, row_base, col0, M, N);
   float4 v[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const float4*>(stage + (4 * i + rsub) * EPI_LD + c4);
   __syncwarp();
   const bool relu = (EMODE == EPI_STORE) && p.relu;
+  // Fast path (warp-uniform): every row and column of the block is valid and, for the store epilogue, there is no bias /
+  // ReLU (the shared-MLP convs have neither) — no per-row predicates, one pointer + constant stride for the stores.  The
+  // epilogue warps are the busiest role of the SA1 forward kernels (ncu: never waiting on the accumulator), so the
+  // instructions dropped here are kernel time.
+  const bool fast = (row_base + 32 <= M) && (col0 + 32 <= N) && (EMODE == EPI_DMASK || (!relu && p.bias == nullptr));
+  if (fast) {
+    float* cp = p.C + (long long)(row_base + rsub) * p.ldc + col;
+    const long long step = 4ll * p.ldc;
+    if (EMODE == EPI_STORE) {
+      if (!p.no_store) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(cp + i * step) = v[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 x = v[i];
+        const float w = wr[i];
+        s0[0] = fmaf(w, x.x, s0[0]); s1[0] = fmaf(w * x.x, x.x, s1[0]);
+        s0[1] = fmaf(w, x.y, s0[1]); s1[1] = fmaf(w * x.y, x.y, s1[1]);
+        s0[2] = fmaf(w, x.z, s0[2]); s1[2] = fmaf(w * x.z, x.z, s1[2]);
+        s0[3] = fmaf(w, x.w, s0[3]); s1[3] = fmaf(w * x.w, x.w, s1[3]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float4 x = v[i];
+        const float4 y = yp[i];
+        const float zx = has_psc ? fmaf(y.x, k0.x, k1.x) : y.x, zy = has_psc ? fmaf(y.y, k0.y, k1.y) : y.y;
+        const float zz = has_psc ? fmaf(y.z, k0.z, k1.z) : y.z, zw = has_psc ? fmaf(y.w, k0.w, k1.w) : y.w;
+        x.x = zx > 0.f ? x.x : 0.f;
+        x.y = zy > 0.f ? x.y : 0.f;
+        x.z = zz > 0.f ? x.z : 0.f;
+        x.w = zw > 0.f ? x.w : 0.f;
+        *reinterpret_cast<float4*>(cp + i * step) = x;
+        s0[0] += x.x; s1[0] = fmaf(x.x, (y.x - k2.x) * k3.x, s1[0]);
+        s0[1] += x.y; s1[1] = fmaf(x.y, (y.y - k2.y) * k3.y, s1[1]);
+        s0[2] += x.z; s1[2] = fmaf(x.z, (y.z - k2.z) * k3.z, s1[2]);
+        s0[3] += x.w; s1[3] = fmaf(x.w, (y.w - k2.w) * k3.w, s1[3]);
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int row = row_base + 4 * i + rsub;
@@ -182,7 +267,7 @@ __device__ __forceinline__ void epi_block32(const NTProblem& p, uint32_t taddr, 
       if (relu) {
         x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
       }
-      if (ok) *reinterpret_cast<float4*>(p.C + (long long)row * p.ldc + col) = x;
+      if (ok && !p.no_store) *reinterpret_cast<float4*>(p.C + (long long)row * p.ldc + col) = x;
       if (!ok) x = zero4;  // TMEM columns >= N / rows >= M may hold anything (0 * NaN would poison the sums)
       const float w = ok ? wr[i] : 0.f;
       s0[0] = fmaf(w, x.x, s0[0]); s1[0] = fmaf(w * x.x, x.x, s1[0]);
@@ -218,6 +303,7 @@ __device__ __forceinline__ void epi_reduce_stats(float (&s)[4]) {
 // the NT epilogue needs 16-byte aligned rows of C (and of the mask source): everything else stays on gemm_rows.cu
 static inline bool tc_epilogue_ok(const NTProblem& p, int emode) {
   if (p.N % 4 != 0 || p.ldc % 4 != 0 || ((uintptr_t)p.C & 15u) != 0) return false;
+  if (p.pool_keys && (emode != EPI_STORE || !p.pool_seg || !p.pool_gamma || p.relu)) return false;
   if (emode == EPI_DMASK) {
     if (p.ldyp % 4 != 0 || ((uintptr_t)p.Yprev & 15u) != 0) return false;
     if (p.psc && ((((uintptr_t)p.psc) | ((uintptr_t)p.psh)) & 15u) != 0) return false;

@@ -65,6 +65,15 @@ class Workspace:
         self.red = _f(device, 2048)
         self.sa1_ws_bytes = 0
         self.sa1_ws = None
+        self._keys = None
+
+    def keys(self, S, C):
+        """Zero-initialised key table of the fused max-pool, (S, C) uint64; the finalize kernel
+        re-zeroes what it reads, so one table per stream serves every pass."""
+        n = S * C
+        if self._keys is None or self._keys.numel() < n:
+            self._keys = torch.zeros(n, dtype=torch.int64, device=self.device)
+        return self._keys
 
     def sa1(self, B, cap):
         jmax = -(-(-(-cap // max(B, 1))) // 256)
@@ -142,12 +151,14 @@ def nt(problems, amode, emode):
 
 
 def nt_problem(A, Bw, ldb, C, ldc, M_max, M_dev, N, K, bias=None, relu=0, stats=None, srw=None, Yprev=None, ldyp=0,
-               pbn=None):
+               pbn=None, pool_keys=None, pool_seg=None, pool_gamma=None, no_store=0):
     p = NTProblem(A=A, Bw=dp(Bw) if torch.is_tensor(Bw) else Bw, ldb=ldb, bias=dp(bias), C=dp(C) if torch.is_tensor(C) else C,
                   ldc=ldc, M_max=M_max, M_dev=M_dev, N=N, K=K, relu=relu, stats=dp(stats), srw=dp(srw),
                   Yprev=dp(Yprev) if torch.is_tensor(Yprev) else Yprev, ldyp=ldyp)
     if pbn is not None:
         p.psc, p.psh, p.pmean, p.prstd = dp(pbn.scale), dp(pbn.shift), dp(pbn.mean), dp(pbn.rstd)
+    if pool_keys is not None:
+        p.pool_keys, p.pool_seg, p.pool_gamma, p.no_store = dp(pool_keys), dp(pool_seg), dp(pool_gamma), no_store
     return p
 
 
@@ -382,11 +393,13 @@ WIDTHS = [(64, 64, 128), (128, 128, 256), (256, 256, 512)]
 # ------------------------------------------------------------------------------------------------
 # encoder forward / backward
 # ------------------------------------------------------------------------------------------------
-def encoder_forward(ws, ef, geom, cloud, skip, Cp, bc, ctx, time=None, time_offset=0.0, train=True, bn_stage=None):
+def encoder_forward(ws, ef, geom, cloud, skip, Cp, bc, ctx, time=None, time_offset=0.0, train=True, bn_stage=None, keep=True):
     """One pass of an encoder over ``cloud`` (B, C, skip+N).  Per-point input channels are cloud rows [0, Cp);
     ``bc`` (B, Cb) are per-sample constant channels appended after them (the action for the value encoder).
     Writes ctx.feat (B, 516) = [z(512) | time+offset | 0 0 0] and keeps the activations backward needs.
-    ``bn_stage`` (BNStage): defer the running-statistics update of this pass (see BNStage)."""
+    ``bn_stage`` (BNStage): defer the running-statistics update of this pass (see BNStage).  ``keep=False``: the pass is
+    never differentiated (target chain, select_action), so the last SA1 / SA2 layer outputs are not written at all —
+    their max-pool is fused into the producing kernel."""
     B, C, Np = cloud.shape
     st = current_stream()
     l1, l2 = geom.lv
@@ -401,16 +414,15 @@ def encoder_forward(ws, ef, geom, cloud, skip, Cp, bc, ctx, time=None, time_offs
                           dp(l1.row_seg), dp(l1.row_src), dp(l1.row_w), l1.cap, l1.M_dev, dp(W0.W), W0.K, dp(ctx.bcbias),
                           dp(s.Y[0]), dp(ws.stats) if train else None, st)
     bn_fwd(ws, 64, B * geom.npoint * l1.ns, W0, s.bn[0], train, bn_stage)
-    _mlp_tail_forward(ws, [L["sa0.1"], L["sa0.2"]], s, 1, l1.cap, l1.M_dev, l1.row_w, B * geom.npoint * l1.ns, train, bn_stage)
-    lib.gaddpg_pool_fwd(dp(s.Y[2]), 128, dp(s.bn[2].scale), dp(s.bn[2].shift), dp(l1.seg_off), 0, l1.S, dp(s.out), dp(s.arg), st)
+    _mlp_tail_forward(ws, [L["sa0.1"], L["sa0.2"]], s, 1, l1.cap, l1.M_dev, l1.row_w, B * geom.npoint * l1.ns, train, bn_stage,
+                      pool=NS(lv=l1, keep=keep))
     # ---- SA2: gather [feats | dxyz | pad] rows, three row-GEMMs, pool
     s2 = ctx.sa[1]
     lib.gaddpg_gather_rows(dp(s.out), 128, dp(l1.new_xyz), geom.npoint, dp(l2.new_xyz), geom.npoint, dp(l2.row_seg),
                            dp(l2.row_src), l2.cap, l2.M_dev, dp(s2.G), s2.G.shape[1], st)
     _mlp_first_forward(ws, L["sa1.0"], s2, l2.cap, l2.M_dev, l2.row_w, B * geom.npoint * l2.ns, train, bn_stage)
-    _mlp_tail_forward(ws, [L["sa1.1"], L["sa1.2"]], s2, 1, l2.cap, l2.M_dev, l2.row_w, B * geom.npoint * l2.ns, train, bn_stage)
-    lib.gaddpg_pool_fwd(dp(s2.Y[2]), 256, dp(s2.bn[2].scale), dp(s2.bn[2].shift), dp(l2.seg_off), 0, l2.S, dp(s2.out),
-                        dp(s2.arg), st)
+    _mlp_tail_forward(ws, [L["sa1.1"], L["sa1.2"]], s2, 1, l2.cap, l2.M_dev, l2.row_w, B * geom.npoint * l2.ns, train, bn_stage,
+                      pool=NS(lv=l2, keep=keep))
     # ---- SA3: GroupAll over the 32 SA2 centroids (absolute xyz)
     s3 = ctx.sa[2]
     M3 = B * geom.npoint
@@ -439,12 +451,37 @@ def _mlp_first_forward(ws, Lp, s, M_max, M_dev, rw, count, train, bn_stage=None)
     bn_fwd(ws, Lp.N, count, Lp, s.bn[0], train, bn_stage)
 
 
-def _mlp_tail_forward(ws, layers, s, first, M_max, M_dev, rw, count, train, bn_stage=None):
+FUSED_POOL = False  # max-pool of SA1 / SA2 inside the epilogue of their last layer: correct and bit-identical, but measured slower
+
+
+def _mlp_tail_forward(ws, layers, s, first, M_max, M_dev, rw, count, train, bn_stage=None, pool=None):
+    """Layers ``first``.. of one SA level.  ``pool`` (lv = geometry level, keep): the level's max-pool follows the last
+    layer; on the tcgen05 kernels it is fused into that layer's epilogue (per-segment max / min keys of the raw output,
+    turned into s.out / s.arg by gaddpg_pool_keys_finalize once the batch statistics exist)."""
     for j, Lp in enumerate(layers):
         l = first + j
-        nt([nt_problem(op_bnrelu(s.Y[l - 1], s.bn[l - 1]), Lp.Wf, Lp.Kp, s.Y[l], Lp.N, M_max, M_dev, Lp.N, Lp.Kp,
-                       stats=ws.stats if train else None, srw=rw)], OP_BNRELU, EPI_STORE)
+        kw = dict(stats=ws.stats if train else None, srw=rw)
+        A = op_bnrelu(s.Y[l - 1], s.bn[l - 1])
+        fused = False
+        if pool is not None and j == len(layers) - 1 and FUSED_POOL:
+            lv = pool.lv
+            prob = nt_problem(A, Lp.Wf, Lp.Kp, s.Y[l], Lp.N, M_max, M_dev, Lp.N, Lp.Kp, pool_keys=ws.keys(lv.S, Lp.N),
+                              pool_seg=lv.row_seg, pool_gamma=Lp.gamma, no_store=0 if pool.keep else 1, **kw)
+            g = NTGroup()
+            g.p[0] = prob
+            fused = lib.gaddpg_gemm_nt_path(ctypes.byref(g), 1, OP_BNRELU, EPI_STORE) in (1, 2)
+        if not fused:
+            prob = nt_problem(A, Lp.Wf, Lp.Kp, s.Y[l], Lp.N, M_max, M_dev, Lp.N, Lp.Kp, **kw)
+        nt([prob], OP_BNRELU, EPI_STORE)
         bn_fwd(ws, Lp.N, count, Lp, s.bn[l], train, bn_stage)
+        if pool is not None and j == len(layers) - 1:
+            lv, st = pool.lv, current_stream()
+            if fused:
+                lib.gaddpg_pool_keys_finalize(dp(ws.keys(lv.S, Lp.N)), lv.S, Lp.N, dp(Lp.gamma), dp(s.bn[l].scale), dp(s.bn[l].shift), dp(s.out),
+                                              dp(s.arg), st)
+            else:
+                lib.gaddpg_pool_fwd(dp(s.Y[l]), Lp.N, dp(s.bn[l].scale), dp(s.bn[l].shift), dp(lv.seg_off), 0, lv.S, dp(s.out),
+                                    dp(s.arg), st)
 
 
 def encoder_backward(ws, ef, ctx, sc, want_dw=True, want_dbc=False, accumulate=0, dfeat=None):

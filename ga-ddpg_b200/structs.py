@@ -25,7 +25,8 @@ class NTProblem(ctypes.Structure):
     _fields_ = [("A", Operand), ("Bw", _P), ("ldb", _I), ("bias", _P), ("C", _P), ("ldc", _I),
                 ("M_max", _I), ("M_dev", _P), ("N", _I), ("K", _I), ("relu", _I),
                 ("stats", _P), ("srw", _P), ("Yprev", _P), ("ldyp", _I),
-                ("psc", _P), ("psh", _P), ("pmean", _P), ("prstd", _P)]
+                ("psc", _P), ("psh", _P), ("pmean", _P), ("prstd", _P),
+                ("pool_keys", _P), ("pool_seg", _P), ("pool_gamma", _P), ("no_store", _I)]
 
 
 class NTGroup(ctypes.Structure):

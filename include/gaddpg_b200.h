@@ -127,6 +127,15 @@ typedef struct gaddpg_nt_problem {
   float* stats; const float* srw;
   const float* Yprev; int ldyp;
   const float* psc; const float* psh; const float* pmean; const float* prstd;
+  /* GADDPG_EPI_STORE on the tcgen05 kernels only — max-pool fused into the last shared-MLP layer (upstream
+   * F.max_pool2d(kernel=[1,nsample]) after build_shared_mlp): when pool_keys != NULL the epilogue also reduces the raw
+   * conv output per (segment, column) to its extreme value and the row that attains it, as one 64-bit key
+   * pool_keys[seg][col] (atomicMax on order-preserving keys: deterministic; ties keep the lowest row).  BatchNorm is
+   * monotone per channel and the sign of its scale is the sign of pool_gamma[col] (the BatchNorm weight), so
+   * relu(bn(max)) (gamma >= 0) or relu(bn(min)) (gamma < 0) IS the pooled activation: gaddpg_pool_keys_finalize turns the
+   * keys into out / arg once the batch statistics are known and re-zeroes them.
+   * pool_seg (M): segment of every row.  no_store: do not write C at all (passes that never run backward). */
+  unsigned long long* pool_keys; const int32_t* pool_seg; const float* pool_gamma; int no_store;
 } gaddpg_nt_problem;
 
 typedef struct gaddpg_nt_group { gaddpg_nt_problem p[GADDPG_MAX_GROUP]; } gaddpg_nt_group;
@@ -210,6 +219,11 @@ GADDPG_API int gaddpg_pool_bwd(const float* dOut, int ld_dout, const float* out,
 GADDPG_API int gaddpg_pool_bwd_sparse(const float* dOut, int ldo, const float* out, const int32_t* arg, const float* Y, int C,
                                       int S, const float* mean, const float* rstd, float* E, uint32_t* mask, int M_max,
                                       float* stats, void* stream);
+/* Second half of the fused max-pool (see gaddpg_nt_problem.pool_keys): out[s][c] = relu(v*scale[c]+shift[c]) with
+ * v = the extreme value held by keys[s][c] (max for gamma[c] >= 0, min otherwise), arg[s][c] = the row attaining it;
+ * every key is reset to 0 (= empty) for the next pass.  keys must be zero-initialised once by the caller. */
+GADDPG_API int gaddpg_pool_keys_finalize(unsigned long long* keys, int S, int C, const float* gamma, const float* scale,
+                                         const float* shift, float* out, int32_t* arg, void* stream);
 /* feat[b] = [relu(Y*scale+shift) (C) | time[b]+time_offset | 0-pad to ld]  (ddpg.py:56-57 appends the time column) */
 GADDPG_API int gaddpg_feat_finish(const float* Y, int C, const float* scale, const float* shift, const float* time,
                                   float time_offset, int B, float* feat, int ld, void* stream);

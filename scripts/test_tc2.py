@@ -158,5 +158,43 @@ if "pool" in which or which == "nt,tn":
         same = bool(torch.equal(res["dense"][i], res["pool"][i]))
         print("BNBWD_POOL vs dense BNBWD: %s bit-identical %s" % (what, same), "OK" if same else "FAIL")
         ok = ok and same
+if "pool" in which or which == "nt,tn":
+    # fused max-pool: per-segment max / min keys from the NT epilogue + gaddpg_pool_keys_finalize against gaddpg_pool_fwd on
+    # the stored layer output (scales of both signs); the pooled values must be bit-identical, arg must point at a row that
+    # attains them; no_store must leave C untouched.  Shapes: SA1 (K=64 -> N=128, resident-weight kernel) and SA2 (K=128 ->
+    # N=256, K-chunked kernel).
+    for (Kin, Nout) in ((64, 128), (128, 256)):
+        lens = torch.randint(1, 65, (900,))
+        Mtrue = int(lens.sum()); Mmax = max(Mtrue + 200, 8192); S = lens.numel()
+        seg_off = torch.zeros(S + 1, dtype=torch.int32); seg_off[1:] = torch.cumsum(lens, 0)
+        row_seg = torch.cat([torch.repeat_interleave(torch.arange(S, dtype=torch.int32), lens), torch.zeros(Mmax - Mtrue, dtype=torch.int32)]).to(dev)
+        seg_off = seg_off.to(dev)
+        Mdev = torch.tensor([Mtrue], dtype=torch.int32, device=dev)
+        X = torch.randn(Mmax, Kin, device=dev); W = torch.randn(Nout, Kin, device=dev) * 0.2; rwp = torch.ones(Mmax, device=dev)
+        bin_, bout = bn(Kin), bn(Nout)
+        bout.scale = bout.scale * torch.where(torch.rand(Nout, device=dev) < 0.4, -1.0, 1.0)   # negative BatchNorm scales too
+        keys = torch.zeros(S * Nout, dtype=torch.int64, device=dev)
+        gam = torch.where(bout.scale < 0, -1.0, 1.0) * (torch.rand(Nout, device=dev) + 0.5)   # the BatchNorm weight: same sign as the scale
+        Yf = torch.full((Mmax, Nout), 7.0, device=dev)
+        nt([nt_problem(op_bnrelu(X, bin_), W, Kin, Yf, Nout, Mmax, Mdev.data_ptr(), Nout, Kin, stats=ws.stats, srw=rwp,
+                       pool_keys=keys, pool_seg=row_seg, pool_gamma=gam)], OP_BNRELU, EPI_STORE)
+        out_f = torch.zeros(S, Nout, device=dev); arg_f = torch.zeros(S, Nout, dtype=torch.int32, device=dev)
+        lib.gaddpg_pool_keys_finalize(dp(keys), S, Nout, dp(gam), dp(bout.scale), dp(bout.shift), dp(out_f), dp(arg_f), 0)
+        out_r = torch.zeros(S, Nout, device=dev); arg_r = torch.zeros(S, Nout, dtype=torch.int32, device=dev)
+        lib.gaddpg_pool_fwd(dp(Yf), Nout, dp(bout.scale), dp(bout.shift), dp(seg_off), 0, S, dp(out_r), dp(arg_r), 0)
+        Yn = torch.full((Mmax, Nout), 7.0, device=dev)
+        nt([nt_problem(op_bnrelu(X, bin_), W, Kin, Yn, Nout, Mmax, Mdev.data_ptr(), Nout, Kin, stats=ws.stats, srw=rwp,
+                       pool_keys=keys, pool_seg=row_seg, pool_gamma=gam, no_store=1)], OP_BNRELU, EPI_STORE)
+        out_n = torch.zeros(S, Nout, device=dev)
+        lib.gaddpg_pool_keys_finalize(dp(keys), S, Nout, dp(gam), dp(bout.scale), dp(bout.shift), dp(out_n), None, 0)
+        torch.cuda.synchronize()
+        at_arg = torch.relu(torch.gather(Yf, 0, arg_f.long()) * bout.scale + bout.shift)
+        seg_ok = bool((torch.gather(row_seg[:, None].expand(-1, Nout), 0, arg_f.long()) == torch.arange(S, device=dev)[:, None]).all())
+        good = (torch.equal(out_f, out_r) and torch.equal(out_n, out_r) and bool((Yn == 7.0).all()) and bool((keys == 0).all())
+                and seg_ok and float((at_arg - out_f).abs().max()) <= 1e-6 * float(out_f.abs().max()))
+        print("fused max-pool K=%d N=%d: out == pool_fwd %s, no_store out %s / C untouched %s, keys re-zeroed %s, arg in segment %s, bn(Y[arg]) - out %.1e"
+              % (Kin, Nout, torch.equal(out_f, out_r), torch.equal(out_n, out_r), bool((Yn == 7.0).all()), bool((keys == 0).all()), seg_ok,
+                 float((at_arg - out_f).abs().max())), "OK" if good else "FAIL")
+        ok = ok and good
 lib.gaddpg_set_tensor_core(3)
 print("ALL OK" if ok else "SOME FAILED")
