@@ -38,8 +38,8 @@ AGENT_KW = dict(extra_latent=3, policy_aux=False, critic_aux=False)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch (mean over the captured launches of that kernel) from the
 # `ncu --set full` capture summarised in profiles/ (same workload: cfg2); keyed like profile()'s kernel families
 NCU_TRAFFIC = {   # profiles/r1_ncu_full_v2.md (SA1 shapes, M = 423 k rows): bytes per launch, by shape label
-    "gemm_nt:tc:": {"nt[64x64,a1,e0]": 171.1e6, "nt[128x64,a1,e0]": 270.3e6, "nt[64x64,a2,e1]": 406.1e6, "nt[64x128,a3,e1]": 425.7e6},
-    "gemm_tn:": {"tn[128x64,p3,q1]": 341.7e6, "tn[64x64,p2,q1]": 328.1e6},
+    "gemm_nt:tc:": {"nt[64x64,a1,e0]": 166.1e6, "nt[128x64,a1,e0]": 264.7e6, "nt[64x64,a2,e1]": 409.0e6, "nt[64x128,a3,e1]": 430.6e6},
+    "gemm_tn:": {"tn[128x64,p3,q1]": 343.4e6, "tn[64x64,p2,q1]": 331.5e6},
 }
 
 
