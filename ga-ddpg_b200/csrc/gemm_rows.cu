@@ -334,6 +334,24 @@ __global__ void __launch_bounds__(256) tn_reduce_kernel(const float* __restrict_
     __syncthreads();
   }
 }
+// same result layout for few splits (the M = B layers: 4-8 row splits, up to 512 x 1024 outputs): one thread per output,
+// splits summed in index order — no shared-memory round trip, fully coalesced.
+__global__ void __launch_bounds__(256) tn_reduce_few_kernel(const float* __restrict__ partial, int splits, int N, int Ntrue, int K,
+                                                            int Ktrue, int rot, float* __restrict__ dst, int ldd, int accumulate,
+                                                            float scale) {
+  const long long total = (long long)Ntrue * Ktrue, stride = (long long)N * K;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(e / Ktrue), k = (int)(e % Ktrue);
+    const float* src = partial + (long long)n * K + k;
+    float s = 0.f;
+#pragma unroll 8
+    for (int sp = 0; sp < splits; ++sp) s += src[sp * stride];
+    int kd = k + rot;
+    if (kd >= Ktrue) kd -= Ktrue;
+    float* d = dst + (long long)n * ldd + kd;
+    *d = (accumulate ? *d : 0.f) + s * scale;
+  }
+}
 __global__ void bias_reduce_kernel(const float* __restrict__ partial, int splits, int N, int Ntrue, float* __restrict__ dst,
                                    int accumulate) {
   int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -574,7 +592,12 @@ int gaddpg_gemm_tn_impl(const TNProblem* p, int pmode, int qmode, float* dW, int
     if (rc) return rc;
     long long tot = (long long)Ntrue * Ktrue;
     int rg = (int)((tot + 31) / 32 < 1184 ? (tot + 31) / 32 : 1184);
-    tn_reduce_kernel<<<rg, 256, 0, st>>>(ws, sp, p->N, Ntrue, p->K, Ktrue, rot, dW, ldd, accumulate, 1.0f);
+    if (sp <= 16) {
+      int fg = (int)((tot + 255) / 256 < 1184 ? (tot + 255) / 256 : 1184);
+      tn_reduce_few_kernel<<<fg, 256, 0, st>>>(ws, sp, p->N, Ntrue, p->K, Ktrue, rot, dW, ldd, accumulate, 1.0f);
+    } else {
+      tn_reduce_kernel<<<rg, 256, 0, st>>>(ws, sp, p->N, Ntrue, p->K, Ktrue, rot, dW, ldd, accumulate, 1.0f);
+    }
     GADDPG_CHECK_LAUNCH("tn_reduce_kernel");
     if (dbias) {
       bias_reduce_kernel<<<ceil_div(Ntrue, 128), 128, 0, st>>>(wsb, sp, p->N, Ntrue, dbias, accumulate);
