@@ -3,6 +3,10 @@
 #pragma once
 #include "common.cuh"
 #include "gemm_rows.cuh"
+#ifndef TCP_ADD
+#define TCP_ADD(slot, v)
+#define TCP_T() 0ll
+#endif
 
 namespace {
 
@@ -204,7 +208,9 @@ __device__ __forceinline__ void epi_block32(const NTProblem& p, uint32_t taddr, 
     }
   }
   float r[32];
+  const long long tq0 = TCP_T();
   tmem_ld32(taddr, r);
+  const long long tq1 = TCP_T();
 #pragma unroll
   for (int j = 0; j < 8; ++j)
     *reinterpret_cast<float4*>(stage + lane * EPI_LD + 4 * j) = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
@@ -214,6 +220,8 @@ __device__ __forceinline__ void epi_block32(const NTProblem& p, uint32_t taddr, 
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const float4*>(stage + (4 * i + rsub) * EPI_LD + c4);
   __syncwarp();
+  const long long tq2 = TCP_T();
+  if ((threadIdx.x & 31) == 0 && (threadIdx.x >> 5) == 9) { TCP_ADD(8, tq1 - tq0); TCP_ADD(9, tq2 - tq1); }
   const bool relu = (EMODE == EPI_STORE) && p.relu;
   // Fast path (warp-uniform): every row and column of the block is valid and, for the store epilogue, there is no bias /
   // ReLU (the shared-MLP convs have neither) — no per-row predicates, one pointer + constant stride for the stores.  The
@@ -255,6 +263,7 @@ __device__ __forceinline__ void epi_block32(const NTProblem& p, uint32_t taddr, 
         s0[3] += x.w; s1[3] = fmaf(x.w, (y.w - k2.w) * k3.w, s1[3]);
       }
     }
+    if ((threadIdx.x & 31) == 0 && (threadIdx.x >> 5) == 9) { TCP_ADD(10, TCP_T() - tq2); TCP_ADD(11, 1); }
     return;
   }
 #pragma unroll

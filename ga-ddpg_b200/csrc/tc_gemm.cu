@@ -19,6 +19,15 @@
 //                          one slot per CTA); shared with tc_gemm_kc.cu (tc_common.cuh: epi_block32)
 // No TMA here by design: every A element passes through a per-element prologue before it may reach the tensor
 // core, so the producer warps ARE the copy engine; W is 16-64 KB and loaded once per CTA.
+#ifdef TC_PROFILE
+__device__ unsigned long long g_tc_prof[148 * 16];
+#define TCP_ADD(slot, v) atomicAdd(&g_tc_prof[blockIdx.x * 16 + (slot)], (unsigned long long)(v))
+#define TCP_T() clock64()
+#else
+#define TCP_ADD(slot, v)
+#define TCP_T() 0ll
+#endif
+
 #include "tc_common.cuh"
 #include "impl.h"
 
@@ -225,7 +234,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
       const int kcol = h * TC_KS + kc;
       ColConsts<AMODE> cc;
       cc.load(cct, kcol);
-      if (i0 == 0) mbar_wait(&a_empty[s], ((uint32_t)(g >> 1) & 1u) ^ 1u);
+      if (i0 == 0) {
+        const long long t0 = TCP_T();
+        mbar_wait(&a_empty[s], ((uint32_t)(g >> 1) & 1u) ^ 1u);
+        if (tid == 0) TCP_ADD(0, TCP_T() - t0);
+      }
       unsigned char* ah = smem + L.a_hi[s];
       unsigned char* al = smem + L.a_lo[s];
 #pragma unroll
@@ -248,6 +261,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
       }
     };
     Regs RA, RB;
+    const long long tp0 = TCP_T();
     if (AMODE == OP_BNBWD_POOL) prefetch_seg(0);
     if (total_units > 0) issue(RA, 0);
 #pragma unroll 1
@@ -257,6 +271,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
       if (u + 2 < total_units) issue(RA, u + 2);
       if (u + 1 < total_units) process(RB, u + 1);
     }
+    if (tid == 0) TCP_ADD(1, TCP_T() - tp0);
   } else if (warp == TC_PW) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
@@ -267,16 +282,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
       mbar_wait(w_full, 0);
       tc_fence_after();
       int it = 0, g = 0;
+      const long long tm0 = TCP_T();
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
         const int b = it & 1;
         const uint32_t bph = (uint32_t)(it >> 1) & 1u;
-        mbar_wait(&acc_empty[b], bph ^ 1u);
+        {
+          const long long t0 = TCP_T();
+          mbar_wait(&acc_empty[b], bph ^ 1u);
+          TCP_ADD(2, TCP_T() - t0);
+        }
         const uint32_t d_tmem = tmem_base + (uint32_t)(b * N);
         uint32_t acc = 0;
 #pragma unroll
         for (int h = 0; h < NH; ++h, ++g) {
           const int s = g & 1;
-          mbar_wait(&a_full[s], (uint32_t)(g >> 1) & 1u);
+          {
+            const long long t0 = TCP_T();
+            mbar_wait(&a_full[s], (uint32_t)(g >> 1) & 1u);
+            TCP_ADD(3, TCP_T() - t0);
+          }
           tc_fence_after();
 #pragma unroll
           for (int kb = 0; kb < (TC_KS >> 5); ++kb) {
@@ -296,6 +320,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
         }
         umma_commit(&acc_full[b]);   // accumulator ready for the epilogue
       }
+      TCP_ADD(4, TCP_T() - tm0);
     }
     __syncwarp();
   } else {
@@ -325,14 +350,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
           wr[i] = (row < M) ? p.srw[row] : 0.f;
         }
       }
-      mbar_wait(&acc_full[b], bph);
+      {
+        const long long t0 = TCP_T();
+        mbar_wait(&acc_full[b], bph);
+        if (warp == TC_PW + 1 && lane == 0) TCP_ADD(5, TCP_T() - t0);
+      }
       tc_fence_after();
+      const long long te0 = TCP_T();
 #pragma unroll
       for (int cb = 0; cb < NCB; ++cb) {
         if (cb * 32 < N)
           epi_block32<EMODE>(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * N + cb * 32), stage, lane, row_base, cb * 32,
                              M, N, wr, do_stats, s0[cb], s1[cb]);
       }
+      if (warp == TC_PW + 1 && lane == 0) { TCP_ADD(6, TCP_T() - te0); TCP_ADD(7, 1); }
       tc_fence_before();
       if (lane == 0) mbar_arrive(&acc_empty[b]);
     }
@@ -426,3 +457,14 @@ int gaddpg_tc_gemm_nt_impl(const NTProblem* p, int amode, int emode, void* strea
   gaddpg_set_error("tc_gemm_nt: unsupported mode pair (%d,%d)", amode, emode);
   return GADDPG_ERR_UNSUPPORTED;
 }
+
+#ifdef TC_PROFILE
+extern "C" __attribute__((visibility("default"))) int gaddpg_debug_tc_prof(unsigned long long* host_out, int reset) {
+  if (host_out) cudaMemcpyFromSymbol(host_out, g_tc_prof, sizeof(unsigned long long) * 148 * 16);
+  if (reset) {
+    static unsigned long long z[148 * 16];
+    cudaMemcpyToSymbol(g_tc_prof, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
