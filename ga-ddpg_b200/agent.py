@@ -26,7 +26,7 @@ import numpy as np
 import torch
 from torch.optim.lr_scheduler import MultiStepLR
 
-from . import engine, nets
+from . import checkpoint, engine, nets
 from .capi import current_stream, lib
 from .config import DEFAULTS, LOSS_KEYS
 from .engine import FEAT_LD, QA_AUX, QA_LD, QA_Q2, dp
@@ -405,6 +405,104 @@ class AgentB200:
     def refresh_all(self):
         for f in (self.ef_p, self.ef_v, self.pf, self.pft) + ((self.cf, self.cft) if self.has_critic else ()):
             f.refresh_derived()
+
+    # ---- checkpoints in the reference's file / dict layout (agent.py:282-431) -------------------------------
+    def _opt_table(self):
+        """(file, key of the optimiser dict, key of the scheduler dict, parameters in torch order, moments callback,
+        Adam-step counter name, scheduler, eps, weight decay) for every optimiser the reference checkpoints."""
+        ex = self._extractor
+        pr, _ = self.pf.adam_ranges(self.policy_aux)
+        rows = [("actor", "opt", "sch", list(self.policy.parameters()), checkpoint.arena_moments(self.pf.arena, pr), "policy",
+                 self._sch.policy, 1e-5, 1e-5)]
+        if self.has_critic:
+            rows.append(("critic", "opt", "sch", list(self.critic.parameters()), checkpoint.arena_moments(self.cf.arena), "critic",
+                         self._sch.critic, 1e-5, 1e-5))
+        rows += [
+            # the whole-extractor optimiser is never stepped (only its scheduler is, agent.py:187-189)
+            ("state_feat", "opt", "sch", list(ex.parameters()), lambda i, p: None, None, self._sch.enc, 1e-8, 0.0),
+            ("state_feat", "encoder_opt", "encoder_sch", list(ex.encoder.parameters()), checkpoint.arena_moments(self.ef_p.arena),
+             "enc", self._sch.enc, 1e-8, 0.0),
+            ("state_feat", "val_encoder_opt", "val_encoder_sch", list(ex.value_encoder.parameters()),
+             checkpoint.arena_moments(self.ef_v.arena), "venc", self._sch.venc, 1e-8, 0.0),
+        ]
+        return rows
+
+    def save_model(self, step, output_dir="", surfix="latest", actor_path=None, critic_path=None, goal_feat_path=None,
+                   state_feat_path=None):
+        """agent.py:282-352: same three files, same dict keys, torch-format ``Adam`` / ``MultiStepLR`` state dicts
+        assembled from the fused arenas, so the reference's ``load_model`` reads them unchanged."""
+        torch.cuda.synchronize(self.device)
+        p = checkpoint.paths(output_dir, self.name, self.env_name, surfix)
+        files = {"actor": actor_path or p["actor"], "critic": critic_path or p["critic"],
+                 "state_feat": state_feat_path or p["state_feat"]}
+        cpu = lambda sd: {k: v.detach().cpu().clone() for k, v in sd.items()}  # noqa: E731
+        out = {"actor": {"net": cpu(self.policy.state_dict())},
+               "state_feat": {"net": cpu(self.state_dicts()["state_feat"]), "step": step}}  # "module."-prefixed (DataParallel)
+        if self.has_critic:
+            out["critic"] = {"net": cpu(self.critic.state_dict())}
+        for f, ok, sk, params, moments, which, sch, eps, wd in self._opt_table():
+            cpu_m = (lambda mo: (lambda i, q: None if mo(i, q) is None else tuple(t.cpu() for t in mo(i, q))))(moments)
+            out[f][ok] = checkpoint.adam_state_dict(params, cpu_m, self.opt_steps[which] if which else 0, sch.lr, eps, wd,
+                                                    initial_lr=sch.sched.base_lrs[0])
+            out[f][sk] = sch.sched.state_dict()
+        for f, d in out.items():
+            checkpoint.save(d, files[f])
+        return files
+
+    def load_model(self, output_dir, surfix="latest", set_init_step=False, reinit_value_feat=False):
+        """agent.py:354-431.  Returns the restored ``update_step`` (0 when there is no feature-extractor file)."""
+        import os
+        p = checkpoint.paths(output_dir, self.name, self.env_name, surfix)
+        table = {}
+        for row in self._opt_table():
+            table.setdefault(row[0], []).append(row)
+        strip = lambda sd: {k[len("module."):] if k.startswith("module.") else k: v for k, v in sd.items()}  # noqa: E731
+
+        def restore(d, rows, tolerant):
+            for _, ok, sk, params, moments, which, sch, eps, wd in rows:
+                try:
+                    step, lr = checkpoint.load_adam_state_dict(d[ok], params, moments)
+                    if sk in d:
+                        sch.sched.load_state_dict(d[sk])
+                    sch.opt.param_groups[0]["lr"] = lr
+                    if which:
+                        self.opt_steps[which] = step
+                except (KeyError, ValueError, RuntimeError):
+                    if not tolerant:
+                        raise
+                    print("loading feature optim has mismatches")  # agent.py:418-419
+
+        def reinit(sch, milestones):
+            # agent.py:380-389 / 401-409: restart at reinit_lr with a fresh gamma=0.5 schedule
+            fresh = _Sched(self.reinit_lr, milestones, 0.5)
+            sch.opt, sch.sched = fresh.opt, fresh.sched
+
+        if os.path.exists(p["actor"]):
+            d = checkpoint.load(p["actor"])
+            self.policy.load_state_dict(d["net"])
+            restore(d, table["actor"], tolerant=False)
+            if getattr(self, "reinit_optim", False) and set_init_step:
+                reinit(self._sch.policy, self.policy_milestones)
+            self.policy_target.load_state_dict(self.policy.state_dict())       # hard_update (utils.py:761-763)
+        if self.has_critic and os.path.exists(p["critic"]):
+            d = checkpoint.load(p["critic"])
+            self.critic.load_state_dict(d["net"])
+            restore(d, table["critic"], tolerant=False)
+            if getattr(self, "reinit_optim", False) and set_init_step:
+                reinit(self._sch.critic, self.value_milestones)
+            self.critic_target.load_state_dict(self.critic.state_dict())
+        step = 0
+        if os.path.exists(p["state_feat"]):
+            d = checkpoint.load(p["state_feat"])
+            self._extractor.load_state_dict(strip(d["net"]))
+            restore(d, table["state_feat"], tolerant=True)
+            self.update_step = step = d["step"]
+            if set_init_step:
+                self.init_step = self.update_step
+        self.refresh_all()
+        self._graphs = {}   # schedule index / learning-rate state may have moved: re-capture lazily
+        torch.cuda.synchronize(self.device)
+        return step
 
 
 class DDPGB200(AgentB200):

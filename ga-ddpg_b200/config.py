@@ -11,7 +11,7 @@ DEFAULTS = dict(
     train_value_feature=True, train_feature=True, use_action_limit=True, sa_channel_concat=True, use_time=True,
     value_model=True, shared_feature=False, policy_update_gap=2, policy_aux=True, critic_aux=True, action_noise=0.01,
     noise_ratio_list=[3.0, 2.5, 2.0, 1.5, 1, 0.5], noise_type="uniform", target_update_interval=3000, channel_num=5,
-    overwrite_feat_milestone=[], env_name="PandaYCBEnv", concat_option="point_wise",
+    overwrite_feat_milestone=[], env_name="PandaYCBEnv", concat_option="point_wise", reinit_optim=False, reinit_lr=1e-4,
     # model spec (state_feature_extractor)
     extra_latent=1, feat_lr=1e-3, feat_milestones=[8000, 16000, 30000, 50000, 70000, 90000], feat_gamma=0.3,
 )

@@ -252,6 +252,58 @@ class OracleAgent:
         self.last = dict(pi=pi.detach(), policy_feat=f.detach())
         return out
 
+    # ---- checkpoints (agent.py:282-431) -----------------------------------------------------------
+    def _paths(self, output_dir, surfix):
+        env = self.cfg.get("env_name", "PandaYCBEnv")
+        mk = lambda part: "{}/{}_{}_{}_{}".format(output_dir, self.name, part, env, surfix)  # noqa: E731
+        return mk("actor"), mk("critic"), mk("state_feat")
+
+    def save_model(self, step, output_dir="", surfix="latest"):
+        """agent.py:282-352: three torch.save files with the reference's dict keys."""
+        import os
+        os.makedirs(output_dir, exist_ok=True)
+        actor, critic, feat = self._paths(output_dir, surfix)
+        torch.save({"net": self.policy.state_dict(), "opt": self.policy_opt.state_dict(),
+                    "sch": self.policy_sched.state_dict()}, actor)
+        if self.has_critic:
+            torch.save({"net": self.critic.state_dict(), "opt": self.critic_opt.state_dict(),
+                        "sch": self.critic_sched.state_dict()}, critic)
+        torch.save({"net": self.state_dicts()["state_feat"], "opt": self.feat_opt.state_dict(),
+                    "encoder_opt": self.enc_opt.state_dict(), "sch": self.feat_sched.state_dict(),
+                    "encoder_sch": self.enc_sched.state_dict(), "val_encoder_opt": self.venc_opt.state_dict(),
+                    "val_encoder_sch": self.venc_sched.state_dict(), "step": step}, feat)
+
+    def load_model(self, output_dir, surfix="latest"):
+        """agent.py:354-431 (default flags: no optimiser re-initialisation); targets are hard-updated from the
+        loaded online networks (utils.py:761-763)."""
+        import os
+        actor, critic, feat = self._paths(output_dir, surfix)
+        ld = lambda f: torch.load(f, weights_only=False)  # noqa: E731
+        if os.path.exists(actor):
+            d = ld(actor)
+            self.policy.load_state_dict(d["net"])
+            self.policy_opt.load_state_dict(d["opt"])
+            self.policy_sched.load_state_dict(d["sch"])
+            self.policy_target.load_state_dict(self.policy.state_dict())
+        if self.has_critic and os.path.exists(critic):
+            d = ld(critic)
+            self.critic.load_state_dict(d["net"])
+            self.critic_opt.load_state_dict(d["opt"])
+            self.critic_sched.load_state_dict(d["sch"])
+            self.critic_target.load_state_dict(self.critic.state_dict())
+        if os.path.exists(feat):
+            d = ld(feat)
+            self.feat.load_state_dict({k[len("module."):] if k.startswith("module.") else k: v for k, v in d["net"].items()})
+            self.feat_opt.load_state_dict(d["opt"])
+            self.feat_sched.load_state_dict(d["sch"])
+            self.enc_opt.load_state_dict(d["encoder_opt"])
+            self.enc_sched.load_state_dict(d["encoder_sch"])
+            self.venc_opt.load_state_dict(d["val_encoder_opt"])
+            self.venc_sched.load_state_dict(d["val_encoder_sch"])
+            self.update_step = d["step"]
+            return self.update_step
+        return 0
+
     def step_scheduler(self):
         """agent.py:179-190 — the value-encoder scheduler is never stepped."""
         if self.has_critic:

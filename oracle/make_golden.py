@@ -102,6 +102,48 @@ def run(policy, write):
         np.savez_compressed(os.path.join(GOLDEN, "%s_b%d_n%d.npz" % (policy.lower(), B, N)), **fx)
 
 
+def checkpoint_roundtrip(policy="DDPG"):
+    """Pin the oracle's save_model / load_model (agent.py:282-431) to the unmodified reference, both directions:
+    reference saves after 2 steps -> oracle loads -> third step identical; oracle saves -> reference loads ->
+    fourth step identical (weights, Adam moments and schedules all travel through the files)."""
+    import tempfile
+
+    ns, ref, _ = refstack.make_reference_agent(policy, seed=SEED)
+    ora = OracleAgent(policy, seed=SEED + 1)          # different weights: everything must come from the files
+    def both(step, r_agent, o_agent):
+        batch = synthetic.make_batch(B, N, step=step)
+        torch.manual_seed(1000 + step)
+        r = r_agent.update_parameters(batch, r_agent.update_step, 0)
+        r_agent.step_scheduler(r_agent.update_step)
+        torch.manual_seed(1000 + step)
+        o = o_agent.update_parameters(batch)
+        o_agent.step_scheduler()
+        return r, o
+    for step in range(2):
+        batch = synthetic.make_batch(B, N, step=step)
+        torch.manual_seed(1000 + step)
+        ref.update_parameters(batch, ref.update_step, 0)
+        ref.step_scheduler(ref.update_step)
+    with tempfile.TemporaryDirectory() as d:
+        ref.save_model(ref.update_step, d, surfix="pin")
+        assert ora.load_model(d, surfix="pin") == ref.update_step
+        # the reference hard-updates its targets on load; do the same on the saver so both sides continue equal
+        ref.load_model(d, surfix="pin")
+        r, o = both(2, ref, ora)
+        for k in LOSS_KEYS:
+            assert r[k] == o[k] or (np.isnan(r[k]) and np.isnan(o[k])), ("ref->oracle", k, r[k], o[k])
+        assert_same_weights(ref_state_dicts(ref), ora.state_dicts(), "ref->oracle checkpoint")
+        ora.save_model(ora.update_step, d, surfix="pin2")
+        ns2, ref2, _ = refstack.make_reference_agent(policy, seed=SEED + 2)
+        assert ref2.load_model(d, surfix="pin2") == ora.update_step
+        ora.load_model(d, surfix="pin2")
+        r, o = both(3, ref2, ora)
+        for k in LOSS_KEYS:
+            assert r[k] == o[k] or (np.isnan(r[k]) and np.isnan(o[k])), ("oracle->ref", k, r[k], o[k])
+        assert_same_weights(ref_state_dicts(ref2), ora.state_dicts(), "oracle->ref checkpoint")
+    print("[make_golden] %s: checkpoint files interchange with the unmodified reference in both directions" % policy)
+
+
 def index_fixture(write):
     """FPS / ball-query outputs of the oracle's C code on the first synthetic batch and on tie-heavy clouds."""
     cloud = torch.from_numpy(synthetic.make_batch(B, N, step=0)["point_state_batch"])
@@ -125,4 +167,5 @@ if __name__ == "__main__":
     run("DDPG", not a.check)
     run("BC", not a.check)
     index_fixture(not a.check)
+    checkpoint_roundtrip("DDPG")
     print("[make_golden] done")
