@@ -177,6 +177,7 @@ def main():
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-replay", action="store_true", help="skip the device-resident replay leg (SURVEY.md §8 row f1)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -251,6 +252,8 @@ def main():
                e2e=dict(value=e2e, unit=UNIT, ms_per_step=ms_e2e / K, h2d_bytes_per_step=agent.h2d_bytes(), d2h_bytes_per_step=64),
                gpu_launches=int(launches_per_2 * K / 2), clocks=clk.result(), graph=bool(agent.use_graph))
 
+    if rank == 0 and n_gpus == 1 and not args.no_replay:
+        out["replay"] = replay_leg(agent, devb, args, run, nb)
     if rank == 0 and not args.no_profile:
         out.update(profile(agent, devb, args))
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
@@ -261,6 +264,65 @@ def main():
         print(json.dumps(out))
     if world:
         world.close()
+
+
+def replay_leg(agent, devb, args, run, nb):
+    """Row f1: the same update fed from the device-resident replay buffer (ReplayMemoryB200.sample = host index draw +
+    one gather launch) instead of pinned host batches, and the gather kernel alone against the HBM roofline
+    (algorithmic bytes = 2 clouds x B rows read once + written once, plus the 128-byte records)."""
+    import numpy as np
+    import torch
+
+    from gaddpg_b200 import replay_memory as rm
+
+    B, N = args.batch, args.points
+    clouds = torch.cat([b[k] for b in devb for k in ("point_state_batch", "next_point_state_batch")])
+    cap, C = clouds.shape[0], clouds.shape[1]
+    mem = rm.ReplayMemoryB200(cap, uniform_num_pts=N, channels=C, device=clouds.device)
+    mem.point_state.copy_(clouds)
+    del clouds
+    rs = np.random.RandomState(0)
+    cat = lambda k: torch.cat([b[k].reshape(B, -1) for b in devb] * 2).cpu().numpy()  # noqa: E731
+    mem.action[:], mem.expert_action[:], mem.goal[:] = cat("action_batch"), cat("expert_action_batch"), cat("goal_batch")
+    for name, key in (("reward", "reward_batch"), ("returns", "return_batch"), ("terminal", "mask_batch"),
+                      ("expert_flags", "expert_flag_batch"), ("perturb_flags", "perturb_flag_batch")):
+        getattr(mem, name)[:] = cat(key)[:, 0]
+    L = 16                                                      # synthetic episodes of 16 transitions
+    mem.timestep[:] = np.arange(cap) % L + 1
+    mem.episode_map[:] = np.minimum((np.arange(cap) // L) * L + L - 1, cap - 1)
+    mem.cur_idx, mem.is_full = 0, True
+    mem._mark(0, cap)
+    np.random.seed(0)
+
+    class Feed:                                                 # run() indexes batches[i % nb]: draw a fresh minibatch each time
+        def __getitem__(self, i):
+            d = mem.sample(B)
+            d["noise_u"] = devb[i]["noise_u"]
+            return d
+
+    run(Feed(), 4, False)
+    ms = run(Feed(), args.steps, True)
+    # the gather alone: CUDA events on its stream, fresh random indices per launch; store (%d MB) + outputs > the 126 MB L2
+    idx = [mem.draw_indices(B) for _ in range(20)]
+    for i in idx[:3]:
+        mem.gather(i)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in idx:
+        mem.gather(i)
+    e1.record()
+    torch.cuda.synchronize()
+    us = 1e3 * e0.elapsed_time(e1) / len(idx)
+    row_bytes = 4 * C * (N + 6)
+    alg = 2 * B * row_bytes * 2 + B * 128 * 3
+    pk = peaks()
+    gbs = alg / (us * 1e-6) / 1e9
+    return dict(value=args.steps / (ms / 1e3), unit=UNIT, ms_per_step=ms / args.steps, store_transitions=cap,
+                gather=dict(us_per_minibatch=us, algorithmic_bytes=alg, achieved=gbs, peak=pk["hbm"], unit="GB/s",
+                            frac=gbs / pk["hbm"], bound="hbm", peak_source=pk["src"], includes="index H2D (1 KB) + cloud gather + record gather"),
+                note="update_parameters(ReplayMemoryB200.sample(B)): minibatch assembled on the GPU from a float32 store in HBM; "
+                     "no cloud bytes cross PCIe")
 
 
 def profile(agent, devb, args):

@@ -236,7 +236,10 @@ class AgentB200:
 
         put_cloud(self.cloud, self.cloud_host, cloud)
         if self.has_critic:
-            if self.overlap:  # only the target chain (side stream) reads it: its copy overlaps the state chain
+            nxt = batch["next_point_state_batch"]
+            # only the target chain (side stream) reads it: its H2D copy overlaps the state chain.  A device-resident
+            # batch (ReplayMemoryB200.sample) was produced on the current stream, so its D2D copy stays there
+            if self.overlap and not (torch.is_tensor(nxt) and nxt.is_cuda):
                 with torch.cuda.stream(self.side_enc.stream):
                     put_cloud(self.next_cloud, self.next_cloud_host, batch["next_point_state_batch"])
             else:

@@ -6,7 +6,7 @@
 #include "common.cuh"
 #include "impl.h"
 
-#define GADDPG_ABI_VERSION 2
+#define GADDPG_ABI_VERSION 3
 
 static thread_local char g_err[512] = "";
 long long g_gaddpg_launches = 0;
@@ -224,6 +224,12 @@ int gaddpg_wprep(const float* W, int N, int K, int rot, float* Wp, int ldp, floa
 }
 int gaddpg_f64_to_f32(const double* src, float* dst, long long n, void* stream) {
   return gaddpg_f64_to_f32_impl(src, dst, n, stream);
+}
+int gaddpg_replay_gather(const float* cloud_store, long long row_floats, const float* rec_store, int rec_width, int ts_col,
+                         const int32_t* episode_map, long long capacity, const int32_t* idx, int B, float* state_out, float* next_out,
+                         float* rec_out, int32_t* inc_out, void* stream) {
+  return gaddpg_replay_gather_impl(cloud_store, row_floats, rec_store, rec_width, ts_col, episode_map, capacity, idx, B, state_out,
+                                   next_out, rec_out, inc_out, stream);
 }
 
 }  // extern "C"

@@ -93,6 +93,9 @@ int gaddpg_absmax_impl(const float* x, long long n, float* out, float* ws, void*
 int gaddpg_clip_coef_impl(const float* g, long long n, float max_norm, float* coef_out, float* norm_out, float* ws, void* stream);
 int gaddpg_wprep_impl(const float* W, int N, int K, int rot, float* Wp, int ldp, float* WT, int ldt, void* stream);
 int gaddpg_f64_to_f32_impl(const double* src, float* dst, long long n, void* stream);
+int gaddpg_replay_gather_impl(const float* cloud_store, long long row_floats, const float* rec_store, int rec_width, int ts_col,
+                              const int32_t* episode_map, long long capacity, const int32_t* idx, int B, float* state_out,
+                              float* next_out, float* rec_out, int32_t* inc_out, void* stream);
 // tc_gemm.cu
 bool gaddpg_tc_gemm_supported(const NTProblem& p, int amode, int emode);
 int gaddpg_tc_gemm_nt_impl(const NTProblem* p, int amode, int emode, void* stream);

@@ -295,6 +295,63 @@ int ilog2_floor(int n) {
   return l;
 }
 
+// FPS for clouds too large for the register-resident kernel (N > 8192: the environment-side down-sampler
+// regularize_pc_point_count, /root/reference/core/utils.py:784-812, sees raw depth clouds).  Same Spec S1 arithmetic and
+// packed-key arg-max; the running min-distance lives in shared memory (4 B/point), xyz is re-read from L2 each round
+// (12 B/point, 240 KB at N = 20 000) and the selected centroids go straight to global memory, so neither N nor m is
+// bounded by the centroid stage.  One CTA of 1024 threads per cloud.
+template <int T>
+__global__ void __launch_bounds__(T) fps_large_kernel(XyzView xyz, int N, int m, int bs, int log2bs, int per,
+                                                      int32_t* __restrict__ fps_idx, float* __restrict__ new_xyz) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int NW = T / 32;
+  unsigned long long* s_slot = reinterpret_cast<unsigned long long*>(smem_raw);
+  float* s_t = reinterpret_cast<float*>(s_slot + 2 * NW);
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* base = xyz.p + (long long)b * xyz.sb;
+  for (int k = tid; k < N; k += T) s_t[k] = 1e10f;
+  int old = 0;
+  float ox = base[0], oy = base[xyz.sc], oz = base[2 * xyz.sc];
+  if (tid == 0) {
+    fps_idx[(long long)b * m] = 0;
+    if (new_xyz) {
+      float* c = new_xyz + (long long)b * m * 3;
+      c[0] = ox, c[1] = oy, c[2] = oz;
+    }
+  }
+  __syncthreads();
+  for (int j = 1; j < m; ++j) {
+    unsigned long long best = 0ull;
+    for (int k = tid; k < N; k += T) {
+      const float* q = base + (long long)k * xyz.sk;
+      float x = __ldg(q), y = __ldg(q + xyz.sc), z = __ldg(q + 2 * xyz.sc);
+      float mag = __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x)));
+      if ((double)mag <= 1e-3) continue;
+      float t = fminf(sqdist3(x, y, z, ox, oy, oz), s_t[k]);
+      s_t[k] = t;
+      unsigned low = 0xFFFFFFFFu - fps_rank(k, bs, log2bs, per);
+      unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) | low;
+      best = key > best ? key : best;
+    }
+    best = warp_max_u64(best);
+    unsigned long long* slot = s_slot + (j & 1) * NW;
+    if (lane == 0) slot[warp] = best;
+    __syncthreads();
+    unsigned long long v = slot[lane & (NW - 1)];
+    v = warp_max_u64(v);
+    old = v ? fps_unrank(0xFFFFFFFFu - (unsigned)(v & 0xFFFFFFFFull), bs, log2bs, per) : 0;
+    const float* q = base + (long long)old * xyz.sk;
+    ox = __ldg(q), oy = __ldg(q + xyz.sc), oz = __ldg(q + 2 * xyz.sc);
+    if (tid == 0) {
+      fps_idx[(long long)b * m + j] = old;
+      if (new_xyz) {
+        float* c = new_xyz + ((long long)b * m + j) * 3;
+        c[0] = ox, c[1] = oy, c[2] = oz;
+      }
+    }
+  }
+}
+
 template <int T, int P>
 int launch_fps(XyzView v, int B, int N, int m, int bs, int32_t* fps_idx, float* new_xyz, int do_bq, float radius,
                int nsample, int32_t* bq_idx, int32_t* bq_cnt, cudaStream_t st) {
@@ -324,15 +381,27 @@ int gaddpg_fps_ballquery_impl(const float* xyz, long long sb, int sk, int sc, in
   GADDPG_CHECK_ARG(xyz && fps_idx, "fps: null pointer");
   GADDPG_CHECK_ARG(B >= 0 && N >= 1 && m >= 1, "fps: bad shape B=%d N=%d m=%d", B, N, m);
   GADDPG_CHECK_ARG(!do_bq || (bq_idx && nsample >= 1), "fps_ballquery: ball query outputs missing");
-  GADDPG_CHECK_ARG(m * 3 <= 8192, "fps: npoint=%d too large for the centroid stage", m);
   if (B == 0) return GADDPG_OK;
-  if (N > 8192) {
-    gaddpg_set_error("fps: N=%d > 8192 points per cloud is not supported by the register-resident kernel", N);
-    return GADDPG_ERR_UNSUPPORTED;
-  }
   XyzView v{xyz, sb, sk, sc};
   cudaStream_t st = (cudaStream_t)stream;
   int bs = gaddpg_opt_n_threads(N);
+  if (N > 8192 || m * 3 > 8192) {
+    if (do_bq) {
+      gaddpg_set_error("fps_ballquery: N=%d / npoint=%d exceed the fused kernel (N <= 8192, npoint <= 2730); call fps alone", N, m);
+      return GADDPG_ERR_UNSUPPORTED;
+    }
+    constexpr int T = 1024;
+    size_t smem = sizeof(float) * (size_t)N + sizeof(unsigned long long) * 2 * (T / 32);
+    if (smem > 200 * 1024) {
+      gaddpg_set_error("fps: N=%d points per cloud exceed the shared-memory distance table (N <= 51072)", N);
+      return GADDPG_ERR_UNSUPPORTED;
+    }
+    if (smem > 48 * 1024)
+      GADDPG_CUDA(cudaFuncSetAttribute(fps_large_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fps_large_kernel<T><<<B, T, smem, st>>>(v, N, m, bs, ilog2_floor(bs), (N + bs - 1) / bs, fps_idx, new_xyz);
+    GADDPG_CHECK_LAUNCH("fps_large_kernel");
+    return GADDPG_OK;
+  }
 #define L(T, P) return launch_fps<T, P>(v, B, N, m, bs, fps_idx, new_xyz, do_bq, radius, nsample, bq_idx, bq_cnt, st)
   if (N <= 128) L(128, 1);
   int p = (N + 511) / 512;

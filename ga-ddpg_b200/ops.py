@@ -144,3 +144,30 @@ def row_table(bq_cnt, bq_idx, nsample, n_src=None):
     lib.gaddpg_row_table(ptr(bq_cnt), ptr(bq_idx), S, nsample, ptr(rt.seg_off), ptr(rt.row_seg), ptr(rt.row_src),
                          ptr(rt.row_w), current_stream())
     return rt
+
+
+def regularize_pc_point_count(pc, npoints, use_farthest_point=False):
+    """Drop-in for ``core.utils.regularize_pc_point_count`` (/root/reference/core/utils.py:784-812), the second FPS call
+    site of the reference (environment-side resampling of a raw cloud to ``uniform_num_pts`` points).
+
+    ``pc`` is an (N, C) numpy array (xyz first).  N > npoints: farthest-point down-sampling on the GPU
+    (``gaddpg_fps`` + ``gaddpg_gather_points``; clouds above 8192 points take the shared-memory-table FPS kernel) or a
+    uniform choice without replacement; N < npoints: over-sampling with replacement.  The random branches use numpy's
+    global state exactly like the reference, so a seeded run reproduces its output."""
+    import numpy as np
+
+    if pc.shape[0] > npoints:
+        if use_farthest_point:
+            t = torch.from_numpy(np.ascontiguousarray(pc)).cuda()[None].float()
+            idx = furthest_point_sample(t[..., :3].contiguous(), npoints)
+            new = gather_operation(t.transpose(1, 2).contiguous(), idx).contiguous()
+            pc = new[0].T.detach().cpu().numpy()
+        else:
+            center_indexes = np.random.choice(range(pc.shape[0]), size=npoints, replace=False)
+            pc = pc[center_indexes, :]
+    else:
+        required = npoints - pc.shape[0]
+        if required > 0:
+            index = np.random.choice(range(pc.shape[0]), size=required)
+            pc = np.concatenate((pc, pc[index, :]), axis=0)
+    return pc

@@ -88,3 +88,30 @@ def make_batch(B, N, step=0, channels=4, dtype=np.float32, seed=1234):
     if not (batch["perturb_flag_batch"] < 1).any():
         batch["perturb_flag_batch"][0] = 0.0
     return batch
+
+
+def make_episode(length, N, seed=0, success=True, expert=True):
+    """One rollout as the list of per-step dicts ``BaseMemory.add_episode`` consumes (replay_memory.py:209-232; keys =
+    ``attr_names`` :33-50 as the environment loop fills them): float64 ``point_state`` (4, N+6), 6-D actions, the
+    sparse terminal reward, 1-based ``timestep``, unit-quaternion + translation ``goal``."""
+    rs = np.random.RandomState(10_000 + seed)
+    centre = np.array([[rs.uniform(-0.05, 0.05), rs.uniform(-0.05, 0.05), rs.uniform(0.15, 0.45)]])
+    half = rs.uniform(0.03, 0.10, size=(1, 3))
+    episode = []
+    for t in range(length):
+        action = rs.uniform(ACTION_LOW, ACTION_HIGH).astype(np.float32)
+        cloud, _, _ = make_cloud(rs, 1, N, 4, centre=centre, half=half, dtype=np.float64)
+        centre = centre - action[None, :3].astype(np.float64)
+        q = rs.normal(size=4)
+        q /= np.linalg.norm(q)
+        pose = np.eye(4, dtype=np.float32)
+        pose[:3, 3] = rs.uniform(-0.3, 0.3, 3)
+        last = t == length - 1
+        episode.append({
+            "action": action, "expert_action": rs.uniform(ACTION_LOW, ACTION_HIGH).astype(np.float32),
+            "pose": rs.normal(size=64).astype(np.float32), "point_state": cloud[0], "target_idx": float(seed % 7),
+            "reward": float(success and last), "terminal": float(last), "timestep": float(t + 1), "state_pose": pose,
+            "collide": 0.0, "grasp": float(last), "perturb_flags": float(rs.rand() < 0.1), "expert_flags": float(expert),
+            "goal": np.concatenate([q, rs.uniform(-0.1, 0.3, 3)]).astype(np.float32), "target_name": "box%d" % (seed % 7),
+        })
+    return episode

@@ -271,6 +271,23 @@ GADDPG_API int gaddpg_dmask_stats(const float* dX, int ldx, const float* Yprev, 
                                   const float* pmean, const float* prstd, float* D, float* stats, void* stream);
 GADDPG_API int gaddpg_f64_to_f32(const double* src, float* dst, long long n, void* stream);
 
+/* ---- device-resident replay buffer -------------------------------------------------------
+ * Replaces the producer of update_parameters' input dict when the buffer lives in HBM: the numpy fancy indexing of
+ * BaseMemory.__getitem__ / post_process_batch (/root/reference/core/replay_memory.py:109-127,251-272) and the
+ * float64->float32 + H2D staging of Agent.prepare_data (/root/reference/core/agent.py:211-240).
+ *   cloud_store[capacity][row_floats]  one stored cloud per row ((C, N+6) flattened, float32 of the reference's float64)
+ *   rec_store[capacity][rec_width]     the small per-transition fields packed as one float32 record (<= 32 columns);
+ *                                      ts_col is the `timestep` column; may be NULL (clouds only)
+ *   episode_map[capacity]              index of the last transition of the episode a slot belongs to (uint32 bits)
+ *   idx[B]                             sampled slots (batch_idx); out-of-range values are clamped into the store
+ * Outputs: state_out[B][row_floats] = cloud_store[idx]; next_out[B][row_floats] = cloud_store[inc] with
+ * inc = min(episode_map[idx], idx + 1); rec_out[B][2*rec_width] = [rec_store[idx] | rec_store[inc]] where the timestep
+ * column of the first half holds the remaining time (timestep[episode_map[idx]] + 1) - timestep[idx]; inc_out[B]
+ * (optional) = inc.  Bit-exact against the reference (byte movement plus one float32 add/sub). */
+GADDPG_API int gaddpg_replay_gather(const float* cloud_store, long long row_floats, const float* rec_store, int rec_width, int ts_col,
+                                    const int32_t* episode_map, long long capacity, const int32_t* idx, int B, float* state_out,
+                                    float* next_out, float* rec_out, int32_t* inc_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

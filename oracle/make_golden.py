@@ -144,6 +144,65 @@ def checkpoint_roundtrip(policy="DDPG"):
     print("[make_golden] %s: checkpoint files interchange with the unmodified reference in both directions" % policy)
 
 
+REPLAY_N, REPLAY_CAP, REPLAY_B = 128, 200, 16
+
+
+def replay_episodes():
+    """The episode stream of the replay fixture: lengths 3..22, ~30 % failures, every 4th episode on-policy (not
+    expert); 200 slots so the ring wraps (buffer_start_idx = 0) before the last samples are drawn."""
+    from gaddpg_b200 import synthetic
+    rs = np.random.RandomState(777)
+    return [synthetic.make_episode(int(rs.randint(3, 23)), REPLAY_N, seed=e, success=bool(rs.rand() > 0.3), expert=e % 4 != 3)
+            for e in range(24)]
+
+
+def replay_fixture(write):
+    """Pin oracle/replay_cpu.py to the UNMODIFIED reference BaseMemory (replay_memory.py): same episodes in, same numpy
+    seed => every key of every sampled minibatch bit-identical, before and after the ring wraps."""
+    import importlib
+
+    from oracle.replay_cpu import OracleMemory
+    ns = refstack.load()
+    ns.config.process_cfg()
+    cfg = ns.config.cfg
+    old = cfg.RL_TRAIN.uniform_num_pts
+    cfg.RL_TRAIN.uniform_num_pts = REPLAY_N
+    try:
+        ref = importlib.import_module("core.replay_memory").BaseMemory(REPLAY_CAP, cfg, "expert")
+    finally:
+        cfg.RL_TRAIN.uniform_num_pts = old
+    ora = OracleMemory(REPLAY_CAP, uniform_num_pts=REPLAY_N, episode_max_len=cfg.RL_MAX_STEP, gamma=cfg.RL_TRAIN.gamma,
+                       buffer_start_idx=cfg.RL_TRAIN.buffer_start_idx, RL=cfg.RL_TRAIN.RL)
+    fx, rounds = {}, 0
+    for e, ep in enumerate(replay_episodes()):
+        ref.add_episode(ep)
+        ora.add_episode(ep)
+        assert ref.cur_idx == ora.cur_idx and ref.is_full == ora.is_full and ref.upper_idx() == ora.upper_idx(), e
+        if ora.upper_idx() <= ora.episode_max_len + 1:
+            continue
+        np.random.seed(500 + e)
+        r = ref.sample(REPLAY_B)
+        np.random.seed(500 + e)
+        o = ora.sample(REPLAY_B)
+        assert set(r.keys()) == set(o.keys()), (sorted(r.keys()), sorted(o.keys()))
+        for k in r:
+            a, b = np.asarray(r[k]), np.asarray(o[k])
+            assert a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a, b), (e, k, a.dtype, b.dtype, a.shape, b.shape)
+        for k in ("batch_idx", "time_batch", "return_batch", "reward_batch", "mask_batch", "expert_flag_batch",
+                  "perturb_flag_batch", "action_batch", "goal_batch", "next_goal_batch", "next_return_batch"):
+            fx["r%d:%s" % (rounds, k)] = np.asarray(o[k])
+        fx["r%d:cloud_digest" % rounds] = np.array([o["point_state_batch"].sum(), np.abs(o["next_point_state_batch"]).sum()])
+        fx["r%d:episode" % rounds] = np.array(e)
+        rounds += 1
+    for name in ("returns", "episode_map", "reward", "timestep", "terminal"):
+        assert np.array_equal(getattr(ref, name), getattr(ora, name)), name
+    assert ora.is_full, "the fixture is meant to wrap the ring"
+    fx["rounds"], fx["returns"], fx["episode_map"] = np.array(rounds), ora.returns, ora.episode_map
+    print("[make_golden] replay: oracle == unmodified BaseMemory over %d sampled minibatches (ring wrapped: %s)" % (rounds, ora.is_full))
+    if write:
+        np.savez_compressed(os.path.join(GOLDEN, "replay_n%d.npz" % REPLAY_N), **fx)
+
+
 def index_fixture(write):
     """FPS / ball-query outputs of the oracle's C code on the first synthetic batch and on tie-heavy clouds."""
     cloud = torch.from_numpy(synthetic.make_batch(B, N, step=0)["point_state_batch"])
@@ -168,4 +227,5 @@ if __name__ == "__main__":
     run("BC", not a.check)
     index_fixture(not a.check)
     checkpoint_roundtrip("DDPG")
+    replay_fixture(not a.check)
     print("[make_golden] done")

@@ -107,6 +107,40 @@ def test_gather_group_and_grads(cuda):
 def test_errors_are_loud(cuda):
     ops = _ops()
     with pytest.raises(RuntimeError):
-        ops.furthest_point_sample(torch.zeros(1, 9000, 3, device=cuda), 4)  # N > 8192 unsupported, no fallback
+        ops.furthest_point_sample(torch.zeros(1, 60000, 3, device=cuda), 4)  # N > 51072 unsupported, no fallback
+    with pytest.raises(RuntimeError):
+        ops.fps_ballquery_xyz(torch.zeros(1, 9000, 3, device=cuda), 32, 0.02, 64)  # fused kernel: N <= 8192
     with pytest.raises((RuntimeError, AssertionError)):
         ops.furthest_point_sample(torch.zeros(1, 10, 3), 4)  # CPU tensor
+
+
+@pytest.mark.parametrize("B,N,m", [(2, 9000, 1024), (1, 20000, 1024), (1, 8193, 33), (3, 4096, 3000), (1, 51072, 16)])
+def test_fps_large_clouds_bit_exact(cuda, B, N, m):
+    """Clouds beyond the register-resident kernel (N > 8192 or npoint > 2730) take fps_large_kernel: same Spec S1
+    arithmetic and tie-break, indices bit-exact against the oracle's literal launch-shape simulation — including exact
+    ties (duplicated points) and invalid (near-origin) points."""
+    U, ops = _U(), _ops()
+    rs = np.random.RandomState(N + m)
+    xyz = rs.uniform(-0.2, 0.4, (B, N, 3)).astype(np.float32)
+    xyz[:, N // 2: N // 2 + N // 8] = xyz[:, : N // 8]                  # exact duplicates -> tie-break by (bitrev, k)
+    xyz[:, rs.choice(N, N // 40, replace=False)] = 0.0                  # |p|^2 <= 1e-3: never selected
+    want = U.fps_raw(torch.from_numpy(xyz), m)
+    got = ops.furthest_point_sample(torch.from_numpy(xyz).to(cuda), m)
+    assert torch.equal(got.cpu(), want)
+
+
+def test_regularize_pc_point_count_matches_oracle(cuda):
+    """core/utils.py:784-812 through the CUDA ops: FPS down-sampling (small and > 8192-point clouds) bit-exact against
+    the oracle restatement; the numpy branches reproduce the same seeded draws."""
+    from gaddpg_b200.ops import regularize_pc_point_count
+    from oracle.utils_cpu import regularize_pc_point_count as oracle_fn
+    from tests.test_regularize_cpu import raw_cloud
+
+    for n, m, fp, seed in ((3000, 1024, True, 0), (9000, 1024, True, 1), (20000, 1024, True, 5), (520, 64, True, 2),
+                           (3000, 1024, False, 3), (700, 1024, False, 4), (1024, 1024, True, 6)):
+        pc = raw_cloud(n, seed)
+        np.random.seed(seed)
+        want = oracle_fn(pc.copy(), m, use_farthest_point=fp)
+        np.random.seed(seed)
+        got = regularize_pc_point_count(pc.copy(), m, use_farthest_point=fp)
+        assert want.dtype == got.dtype and want.shape == got.shape and np.array_equal(want, got), (n, m, fp)
