@@ -177,6 +177,7 @@ def main():
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--ab-h2d", action="store_true", help="also time e2e with the other H2D ordering (experiment)")
     ap.add_argument("--no-replay", action="store_true", help="skip the device-resident replay leg (SURVEY.md §8 row f1)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -241,6 +242,12 @@ def main():
     # ---- e2e: pinned host buffers through the public API (H2D of the batch + D2H of the scalars inside the timed region)
     run(host, 2, False)
     ms_e2e = run(host, K, True)
+    e2e_alt = None
+    if args.ab_h2d:      # A/B of the H2D ordering inside update_parameters (agent.serial_h2d), same process, same clocks
+        agent.serial_h2d = not agent.serial_h2d
+        run(host, 2, False)
+        e2e_alt = dict(serial_h2d=agent.serial_h2d, ms_per_step=run(host, K, True) / K)
+        agent.serial_h2d = not agent.serial_h2d
     clk.stop_flag = True
     clk.join(timeout=2)
     n_gpus = world.size if world else 1
@@ -251,9 +258,21 @@ def main():
                scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", config=workload(args),
                e2e=dict(value=e2e, unit=UNIT, ms_per_step=ms_e2e / K, h2d_bytes_per_step=agent.h2d_bytes(), d2h_bytes_per_step=64),
                gpu_launches=int(launches_per_2 * K / 2), clocks=clk.result(), graph=bool(agent.use_graph))
+    out["e2e"]["serial_h2d"] = bool(agent.serial_h2d)
+    if e2e_alt:
+        out["e2e_ab"] = e2e_alt
 
     if rank == 0 and n_gpus == 1 and not args.no_replay:
         out["replay"] = replay_leg(agent, devb, args, run, nb)
+        # row f2: select_action latency (B = 1, eval-mode policy path; H2D of the cloud + one graph replay + D2H of 80 bytes)
+        cloud1 = host[0]["point_state_batch"][0].numpy()
+        for _ in range(4):
+            agent.select_action([[cloud1, None]], remain_timestep=5)
+        t0 = time.perf_counter()
+        for _ in range(50):
+            agent.select_action([[cloud1, None]], remain_timestep=5)
+        out["select_action"] = dict(ms_per_action=1e3 * (time.perf_counter() - t0) / 50, points=args.points,
+                                    timing="host wall clock over 50 synchronous calls (each ends with a device->host read)")
     if rank == 0 and not args.no_profile:
         out.update(profile(agent, devb, args))
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
@@ -302,15 +321,28 @@ def replay_leg(agent, devb, args, run, nb):
 
     run(Feed(), 4, False)
     ms = run(Feed(), args.steps, True)
-    # the gather alone: CUDA events on its stream, fresh random indices per launch; store (%d MB) + outputs > the 126 MB L2
-    idx = [mem.draw_indices(B) for _ in range(20)]
-    for i in idx[:3]:
-        mem.gather(i)
+    # the gather alone: 20 launches with distinct pre-uploaded random index sets captured in one CUDA graph (no host time
+    # between launches), CUDA events around the replay; store (~200 MB) + outputs (~100 MB) exceed the 126 MB L2
+    from gaddpg_b200.capi import current_stream, lib
+    o = mem._buffers(B)
+    idx = [torch.from_numpy(mem.draw_indices(B).astype(np.int32)).to(o["idx"].device) for _ in range(20)]
+
+    def gathers():
+        for t in idx:
+            lib.gaddpg_replay_gather(mem.point_state.data_ptr(), C * (N + 6), mem.records.data_ptr(), rm.REC_W, rm.C_TIMESTEP,
+                                     mem.episode_map_dev.data_ptr(), cap, t.data_ptr(), B, o["state"].data_ptr(), o["next"].data_ptr(),
+                                     o["rec"].data_ptr(), o["inc"].data_ptr(), current_stream())
+
+    gathers()
+    g = torch.cuda.CUDAGraph()
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g):
+        gathers()
+    g.replay()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
-    for i in idx:
-        mem.gather(i)
+    g.replay()
     e1.record()
     torch.cuda.synchronize()
     us = 1e3 * e0.elapsed_time(e1) / len(idx)
@@ -320,7 +352,7 @@ def replay_leg(agent, devb, args, run, nb):
     gbs = alg / (us * 1e-6) / 1e9
     return dict(value=args.steps / (ms / 1e3), unit=UNIT, ms_per_step=ms / args.steps, store_transitions=cap,
                 gather=dict(us_per_minibatch=us, algorithmic_bytes=alg, achieved=gbs, peak=pk["hbm"], unit="GB/s",
-                            frac=gbs / pk["hbm"], bound="hbm", peak_source=pk["src"], includes="index H2D (1 KB) + cloud gather + record gather"),
+                            frac=gbs / pk["hbm"], bound="hbm", peak_source=pk["src"], includes="cloud gather kernel + record gather kernel (2 launches per minibatch)"),
                 note="update_parameters(ReplayMemoryB200.sample(B)): minibatch assembled on the GPU from a float32 store in HBM; "
                      "no cloud bytes cross PCIe")
 

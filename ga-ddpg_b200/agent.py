@@ -20,6 +20,7 @@ Step structure (ddpg.py:146-185; F = encoder forward, B = backward):
 Each phase is captured once per step parity into a CUDA graph and replayed.
 """
 import math
+import os
 from types import SimpleNamespace as NS
 
 import numpy as np
@@ -141,6 +142,8 @@ class AgentB200:
         # stream-level overlap inside a step (identical arithmetic, see _phase1): a second encoder chain and the
         # weight-gradient products run on side streams; ``overlap = False`` issues everything on one stream
         self.overlap = True
+        self.serial_h2d = os.environ.get("GADDPG_SERIAL_H2D", "1") != "0"
+        self._h2d_state_done = torch.cuda.Event()
         self.side_enc = engine.SideStream(dev)
         self.side_dw = engine.SideStream(dev)
         self.ef_p = engine.EncoderFlat(self._extractor.encoder, dev)
@@ -240,6 +243,11 @@ class AgentB200:
             # only the target chain (side stream) reads it: its H2D copy overlaps the state chain.  A device-resident
             # batch (ReplayMemoryB200.sample) was produced on the current stream, so its D2D copy stays there
             if self.overlap and not (torch.is_tensor(nxt) and nxt.is_cuda):
+                if self.serial_h2d:
+                    # both clouds share one PCIe link: let the state cloud have all of it first (its chain starts after
+                    # half the transfer time instead of all of it), then the next-state cloud
+                    self._h2d_state_done.record()
+                    self.side_enc.stream.wait_event(self._h2d_state_done)
                 with torch.cuda.stream(self.side_enc.stream):
                     put_cloud(self.next_cloud, self.next_cloud_host, batch["next_point_state_batch"])
             else:
@@ -360,33 +368,57 @@ class AgentB200:
         return self._act(cloud, float(remain_timestep), eps)
 
     def _act(self, cloud, remain, eps):
+        """Eval-mode policy path for a (B, C, N+6) cloud batch: geometry, policy encoder (running BatchNorm statistics),
+        policy heads, tanh-mean / sampled action / log-prob / aux.  ~70 launches with fixed shapes and static buffers:
+        the first call of a shape runs eagerly, the second captures a CUDA graph, later calls replay it (one graph launch
+        + one 128-byte read-back per action; rollouts in train_test_offline.test are launch-latency bound otherwise)."""
         dev = self.device
         B, C, Np = cloud.shape
         skip = 6 if Np != 1024 else 0
         key = ("act", B, C, Np)
-        st = getattr(self, "_act_state", None)
-        if st is None or st.key != key:
+        if not hasattr(self, "_act_states"):
+            self._act_states = {}     # one set of static buffers per input shape: a captured graph is bound to them
+        st = self._act_states.get(key)
+        if st is None:
             geom = engine.Geometry(B, Np - skip, dev)
             caps = (geom.lv[0].cap, geom.lv[1].cap)
             st = NS(key=key, geom=geom, ctx=engine.EncoderCtx(B, caps, engine.WIDTHS, dev), pc=engine.policy_ctx(B, self.pf, dev),
-                    time=torch.zeros(B, device=dev), aux=torch.zeros(B, 7, device=dev), act=torch.zeros(B, 6, device=dev),
-                    logp=torch.zeros(B, device=dev), eps=torch.zeros(B, 6, device=dev))
-            self._act_state = st
-        st.time.fill_(remain)
-        st.eps.copy_(torch.randn(B, 6) if eps is None else torch.as_tensor(eps, dtype=torch.float32).view(B, 6))
-        st.geom.build(cloud, skip)
-        feat = engine.encoder_forward(self.ws, self.ef_p, st.geom, cloud, skip, self.Cp_policy, None, st.ctx, time=st.time,
-                                      train=False, keep=False)
-        raw = engine.policy_forward(self.pf, feat, st.pc, B)
-        s = current_stream()
-        lib.gaddpg_policy_head_fwd(dp(raw), self.pf.NHp, B, dp(st.pc.pi), s)
-        lib.gaddpg_policy_sample(dp(raw), self.pf.NHp, 6 + self.pf.E, dp(st.eps), B, dp(st.act), dp(st.logp), s)
-        if self.policy_aux:
-            lib.gaddpg_quat_head(raw.data_ptr() + 4 * 6, self.pf.NHp, B, dp(st.aux), s)
-            aux = st.aux.cpu().numpy()[0]
-        else:
-            aux = raw[:, 6:6 + self.pf.E].cpu().numpy()[0]
-        return st.pc.pi.cpu().numpy()[0], st.logp.cpu().numpy()[0], st.act.cpu().numpy()[0], aux
+                    cloud=torch.zeros(B, C, Np, device=dev), time=torch.zeros(B, device=dev), eps=torch.zeros(B, 6, device=dev),
+                    # [pi(6) | sampled action(6) | aux(7) | log-prob(1)] per sample, one D2H
+                    res=torch.zeros(B, 20, device=dev), res_host=torch.zeros(B, 20).pin_memory(),
+                    in_host=torch.zeros(B, 7).pin_memory(), in_dev=torch.zeros(B, 7, device=dev))
+            self._act_states[key] = st
+        st.cloud.copy_(cloud, non_blocking=True)
+        st.in_host[:, :6] = torch.randn(B, 6) if eps is None else torch.as_tensor(eps, dtype=torch.float32).view(B, 6)
+        st.in_host[:, 6] = remain
+        st.in_dev.copy_(st.in_host, non_blocking=True)
+
+        def fn():
+            s = current_stream()
+            st.eps.copy_(st.in_dev[:, :6])
+            st.time.copy_(st.in_dev[:, 6])
+            st.geom.build(st.cloud, skip)
+            feat = engine.encoder_forward(self.ws, self.ef_p, st.geom, st.cloud, skip, self.Cp_policy, None, st.ctx, time=st.time,
+                                          train=False, keep=False)
+            raw = engine.policy_forward(self.pf, feat, st.pc, B)
+            pi, act, aux, logp = st.res[:, 0:6], st.res[:, 6:12], st.res[:, 12:19], st.res[:, 19]
+            lib.gaddpg_policy_head_fwd(dp(raw), self.pf.NHp, B, dp(st.pc.pi), s)
+            lib.gaddpg_policy_sample(dp(raw), self.pf.NHp, 6 + self.pf.E, dp(st.eps), B, dp(st.ctx_act), dp(st.ctx_logp), s)
+            if self.policy_aux:
+                lib.gaddpg_quat_head(raw.data_ptr() + 4 * 6, self.pf.NHp, B, dp(st.ctx_aux), s)
+            else:
+                st.ctx_aux.zero_()
+                st.ctx_aux[:, : self.pf.E].copy_(raw[:, 6:6 + self.pf.E])
+            pi.copy_(st.pc.pi), act.copy_(st.ctx_act), aux.copy_(st.ctx_aux), logp.copy_(st.ctx_logp)
+
+        if not hasattr(st, "ctx_act"):
+            st.ctx_act, st.ctx_logp, st.ctx_aux = torch.zeros(B, 6, device=dev), torch.zeros(B, device=dev), torch.zeros(B, 7, device=dev)
+        self._run(key, fn)
+        st.res_host.copy_(st.res, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        r = st.res_host.numpy()
+        E = 7 if self.policy_aux else self.pf.E
+        return r[0, 0:6].copy(), r[0, 19].copy(), r[0, 6:12].copy(), r[0, 12:12 + E].copy()
 
     # ---- weights (ddpg.py:22-34, bc.py:15-25) -------------------------------------------------------------
     def state_dicts(self):

@@ -203,6 +203,36 @@ def replay_fixture(write):
         np.savez_compressed(os.path.join(GOLDEN, "replay_n%d.npz" % REPLAY_N), **fx)
 
 
+def pin_at_step(step0, steps=2, policy="DDPG", empty_goal_mask=False):
+    """Schedule-dependent behaviour the 4-step fixtures never reach, pinned to the unmodified reference by jumping
+    ``update_step``: the Q2 hard target copy at multiples of target_update_interval = 3000 (agent.py:204-209,
+    utils.py:750-770) and the mix / TD3-noise ratios past the first mix milestone (4000).  ``empty_goal_mask``: a batch
+    without a single positive return -> the goal-auxiliary losses are NaN on both sides (loss.py:17-23)."""
+    ns, ref, _ = refstack.make_reference_agent(policy, seed=SEED)
+    ora = OracleAgent(policy, seed=SEED)
+    ref.update_step = ora.update_step = step0
+    for step in range(steps):
+        batch = synthetic.make_batch(B, N, step=step)
+        if empty_goal_mask:
+            batch["return_batch"][:] = 0.0
+        torch.manual_seed(1000 + step)
+        r = ref.update_parameters(batch, ref.update_step, 0)
+        torch.manual_seed(1000 + step)
+        o = ora.update_parameters(batch)
+        for k in LOSS_KEYS:
+            assert r[k] == o[k] or (np.isnan(r[k]) and np.isnan(o[k])), (policy, step0, step, k, r[k], o[k])
+        if empty_goal_mask:
+            assert np.isnan(o["policy_grasp_aux_loss"]) and np.isnan(o["critic_grasp_aux_loss"])
+            return
+    assert ref.update_step == ora.update_step == step0 + steps
+    a, b = ref_state_dicts(ref), ora.state_dicts()
+    for k in a:
+        for n in a[k]:
+            x, y = a[k][n], b[k][n]
+            assert torch.equal(x, y) or (torch.isnan(x) == torch.isnan(y)).all(), (k, n)
+    print("[make_golden] %s: oracle == unmodified reference for steps %d..%d" % (policy, step0, step0 + steps - 1))
+
+
 def index_fixture(write):
     """FPS / ball-query outputs of the oracle's C code on the first synthetic batch and on tie-heavy clouds."""
     cloud = torch.from_numpy(synthetic.make_batch(B, N, step=0)["point_state_batch"])
@@ -228,4 +258,7 @@ if __name__ == "__main__":
     index_fixture(not a.check)
     checkpoint_roundtrip("DDPG")
     replay_fixture(not a.check)
+    pin_at_step(2999)
+    pin_at_step(4001)
+    pin_at_step(1, empty_goal_mask=True)
     print("[make_golden] done")

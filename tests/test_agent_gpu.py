@@ -207,9 +207,20 @@ def test_select_action_matches_oracle(cuda):
         cloud = synthetic.make_batch(1, n_pts, step=99)["point_state_batch"][0]
         eps = np.random.RandomState(3).randn(1, 6).astype(np.float32)
         want = ora.select_action(cloud, 7, eps=torch.from_numpy(eps))
-        got = mine.select_action([[cloud, None]], remain_timestep=7, eps=eps)
-        for w, g, name in zip(want, got, ("mean", "logp", "sample", "aux")):
-            assert np.allclose(np.asarray(g), np.asarray(w), rtol=1e-4, atol=1e-5), (n_pts, name, g, w)
+        # call 1 runs eagerly, call 2 captures the CUDA graph, calls 3+ replay it: all must return the same arrays
+        outs = [mine.select_action([[cloud, None]], remain_timestep=7, eps=eps) for _ in range(4)]
+        for got in outs:
+            for w, g, name in zip(want, got, ("mean", "logp", "sample", "aux")):
+                assert np.allclose(np.asarray(g), np.asarray(w), rtol=1e-4, atol=1e-5), (n_pts, name, g, w)
+        for got in outs[1:]:
+            assert all(np.array_equal(np.asarray(a), np.asarray(b)) for a, b in zip(outs[0], got))
+        # the replayed graph reads fresh inputs (cloud, noise, remaining time) from its static buffers
+        cloud2 = synthetic.make_batch(1, n_pts, step=100)["point_state_batch"][0]
+        eps2 = np.random.RandomState(4).randn(1, 6).astype(np.float32)
+        want2 = ora.select_action(cloud2, 3, eps=torch.from_numpy(eps2))
+        got2 = mine.select_action([[cloud2, None]], remain_timestep=3, eps=eps2)
+        for w, g, name in zip(want2, got2, ("mean", "logp", "sample", "aux")):
+            assert np.allclose(np.asarray(g), np.asarray(w), rtol=1e-4, atol=1e-5), (n_pts, "replay", name, g, w)
 
 
 def test_bc_and_no_aux_configs(cuda):

@@ -64,3 +64,16 @@ def test_oracle_matches_unmodified_reference_when_present():
     from oracle import make_golden
 
     make_golden.run("BC", write=False)
+
+
+@pytest.mark.parametrize("step0,empty", [(2999, False), (4001, False), (1, True)])
+def test_oracle_schedule_points_match_reference_when_present(step0, empty):
+    """The Q2 hard target copy at step 3000, the mix / noise ratios past milestone 4000 and the NaN of an empty goal
+    mask, against the unmodified reference (the 4-step fixtures never reach them)."""
+    from oracle import refstack
+
+    if not refstack.available():
+        pytest.skip("/root/reference not present (GPU box)")
+    from oracle import make_golden
+
+    make_golden.pin_at_step(step0, empty_goal_mask=empty)

@@ -53,12 +53,12 @@ def test_next_index_and_time_edge_cases(cuda):
     from gaddpg_b200.replay_memory import ReplayMemoryB200
     from oracle.replay_cpu import OracleMemory
 
-    cap = 42
+    cap = 43
     ora, mem = OracleMemory(cap, uniform_num_pts=128), ReplayMemoryB200(cap, uniform_num_pts=128)
     for e, n in enumerate((5, 7, 30)):
         ep = synthetic.make_episode(n, 128, seed=e)
         ora.add_episode(ep), mem.add_episode(ep)
-    assert mem.is_full and ora.is_full and mem.cur_idx == ora.cur_idx == 0
+    assert not mem.is_full and not ora.is_full and mem.cur_idx == ora.cur_idx == 42
     idx = np.array([0, 4, 5, 11, 12, 41, 41, 0, 40])
     d, w = mem.gather(idx), ora.gather(idx)
     _same(d, w, "edge")
@@ -66,6 +66,16 @@ def test_next_index_and_time_edge_cases(cuda):
     assert d["time_batch"].cpu().tolist() == [5, 1, 7, 1, 30, 1, 1, 5, 2]
     with pytest.raises(IndexError):
         mem.gather(np.array([cap]))
+    # sic (replay_memory.py:223-232): an episode that ends exactly on the last slot wraps cur_idx to buffer_start_idx
+    # BEFORE the returns / episode map are written, so they stay 0 for that episode — reproduced, not fixed
+    ora2, mem2 = OracleMemory(42, uniform_num_pts=128), ReplayMemoryB200(42, uniform_num_pts=128)
+    for e, n in enumerate((5, 7, 30)):
+        ep = synthetic.make_episode(n, 128, seed=e)
+        ora2.add_episode(ep), mem2.add_episode(ep)
+    assert mem2.cur_idx == ora2.cur_idx == 0 and list(mem2.episode_map[12:]) == [0] * 30 == list(ora2.episode_map[12:])
+    d2, w2 = mem2.gather(idx), ora2.gather(idx)
+    _same(d2, w2, "exact wrap")
+    assert d2["increment_idx"].cpu().tolist() == [1, 4, 6, 11, 0, 0, 0, 1, 0]
     assert mem.gather(np.zeros(0, dtype=np.int64))["point_state_batch"].shape == (0, 4, 134)
     bc = ReplayMemoryB200(50, uniform_num_pts=128, RL=False)
     bc.add_episode(synthetic.make_episode(6, 128, seed=9, success=False))
