@@ -177,7 +177,6 @@ def main():
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--ab-h2d", action="store_true", help="also time e2e with the other H2D ordering (experiment)")
     ap.add_argument("--no-replay", action="store_true", help="skip the device-resident replay leg (SURVEY.md §8 row f1)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -242,12 +241,6 @@ def main():
     # ---- e2e: pinned host buffers through the public API (H2D of the batch + D2H of the scalars inside the timed region)
     run(host, 2, False)
     ms_e2e = run(host, K, True)
-    e2e_alt = None
-    if args.ab_h2d:      # A/B of the H2D ordering inside update_parameters (agent.serial_h2d), same process, same clocks
-        agent.serial_h2d = not agent.serial_h2d
-        run(host, 2, False)
-        e2e_alt = dict(serial_h2d=agent.serial_h2d, ms_per_step=run(host, K, True) / K)
-        agent.serial_h2d = not agent.serial_h2d
     clk.stop_flag = True
     clk.join(timeout=2)
     n_gpus = world.size if world else 1
@@ -258,9 +251,6 @@ def main():
                scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", config=workload(args),
                e2e=dict(value=e2e, unit=UNIT, ms_per_step=ms_e2e / K, h2d_bytes_per_step=agent.h2d_bytes(), d2h_bytes_per_step=64),
                gpu_launches=int(launches_per_2 * K / 2), clocks=clk.result(), graph=bool(agent.use_graph))
-    out["e2e"]["serial_h2d"] = bool(agent.serial_h2d)
-    if e2e_alt:
-        out["e2e_ab"] = e2e_alt
 
     if rank == 0 and n_gpus == 1 and not args.no_replay:
         out["replay"] = replay_leg(agent, devb, args, run, nb)

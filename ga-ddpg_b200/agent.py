@@ -142,8 +142,6 @@ class AgentB200:
         # stream-level overlap inside a step (identical arithmetic, see _phase1): a second encoder chain and the
         # weight-gradient products run on side streams; ``overlap = False`` issues everything on one stream
         self.overlap = True
-        self.serial_h2d = os.environ.get("GADDPG_SERIAL_H2D", "1") != "0"
-        self._h2d_state_done = torch.cuda.Event()
         self.side_enc = engine.SideStream(dev)
         self.side_dw = engine.SideStream(dev)
         self.ef_p = engine.EncoderFlat(self._extractor.encoder, dev)
@@ -221,10 +219,28 @@ class AgentB200:
         return self._bc_buf[slot]
 
     # ---- data staging (agent.py:211-240 prepare_data) ------------------------------------------------------
-    def prepare_data(self, batch, noise_u=None):
-        """Stage one replay minibatch (the dict BaseMemory.sample returns, replay_memory.py:166-176) into pinned
-        host buffers and issue the H2D copies.  float64 clouds are converted on the host like
-        torch.cuda.FloatTensor(ndarray) does in the reference."""
+    def prepare_data(self, batch, noise_u=None, after_clouds=None):
+        """Stage one replay minibatch (the dict BaseMemory.sample returns, replay_memory.py:166-176) into the device
+        input buffers.  Host batches go through pinned buffers (float64 clouds are converted on the host like
+        torch.cuda.FloatTensor(ndarray) does in the reference); a lazy ``ReplayBatch`` of the device-resident replay is
+        gathered straight into the buffers by one CUDA launch pair.  ``after_clouds`` is called as soon as the cloud
+        transfers are issued (the agents launch the xyz-only geometry kernels there, so the GPU is busy while the host
+        stages the small per-sample fields)."""
+        from .replay_memory import ReplayBatch
+
+        lazy = isinstance(batch, ReplayBatch) and not batch.materialised
+        if lazy:
+            mem = batch.memory
+            B, (C, Np) = len(batch.batch_idx), mem.row
+            if self._shape != (B, C, Np):
+                self._alloc(B, C, Np)
+            mem.gather_into(batch.batch_idx, self.cloud, self.next_cloud if self.has_critic else None, self.vec, self._vec_off)
+            if after_clouds is not None:
+                after_clouds()
+            if self.has_critic:
+                self.v.noise_u.copy_(torch.rand(B, 6, device=self.device) if noise_u is None
+                                     else torch.as_tensor(noise_u, dtype=torch.float32).view(B, 6), non_blocking=True)
+            return
         cloud = batch["point_state_batch"]
         B, C, Np = cloud.shape
         if self._shape != (B, C, Np):
@@ -241,17 +257,14 @@ class AgentB200:
         if self.has_critic:
             nxt = batch["next_point_state_batch"]
             # only the target chain (side stream) reads it: its H2D copy overlaps the state chain.  A device-resident
-            # batch (ReplayMemoryB200.sample) was produced on the current stream, so its D2D copy stays there
+            # batch was produced on the current stream, so its D2D copy stays there
             if self.overlap and not (torch.is_tensor(nxt) and nxt.is_cuda):
-                if self.serial_h2d:
-                    # both clouds share one PCIe link: let the state cloud have all of it first (its chain starts after
-                    # half the transfer time instead of all of it), then the next-state cloud
-                    self._h2d_state_done.record()
-                    self.side_enc.stream.wait_event(self._h2d_state_done)
                 with torch.cuda.stream(self.side_enc.stream):
-                    put_cloud(self.next_cloud, self.next_cloud_host, batch["next_point_state_batch"])
+                    put_cloud(self.next_cloud, self.next_cloud_host, nxt)
             else:
-                put_cloud(self.next_cloud, self.next_cloud_host, batch["next_point_state_batch"])
+                put_cloud(self.next_cloud, self.next_cloud_host, nxt)
+        if after_clouds is not None:
+            after_clouds()
         on_device = torch.is_tensor(cloud) and cloud.is_cuda
         tgt = self.v if on_device else self.vh   # device-resident batch: D2D straight into the kernel inputs
 
@@ -269,6 +282,20 @@ class AgentB200:
             put(tgt.noise_u, torch.rand(B, 6, device=self.device if on_device else "cpu") if noise_u is None else noise_u)
         if not on_device:
             self.vec.copy_(self.vec_host, non_blocking=True)
+
+    # ---- geometry (FPS, ball query, row tables) of the minibatch's clouds: needs xyz only ------------------------
+    def _geometry(self):
+        """Launched right after the cloud transfers are issued.  State cloud on the main stream, next-state cloud on the
+        target chain's stream (which already carries its H2D copy, or is forked off the main stream for device batches)."""
+        if self.has_critic:
+            if self.overlap:
+                side = self.side_enc
+                side.fork()
+                with torch.cuda.stream(side.stream):
+                    self._run(("gn",), lambda: self.geom_n.build(self.next_cloud, self.skip))
+            else:
+                self._run(("gn",), lambda: self.geom_n.build(self.next_cloud, self.skip))
+        self._run(("gs",), lambda: self.geom_s.build(self.cloud, self.skip))
 
     def h2d_bytes(self):
         n = self.cloud_host.numel() * (2 if self.has_critic else 1) + self.vec_host.numel()
@@ -564,7 +591,6 @@ class DDPGB200(AgentB200):
     def _phase1_state(self):
         B, ws, v = self.B, self.ws, self.v
         self.out.zero_()
-        self.geom_s.build(self.cloud, self.skip)
         f1 = engine.encoder_forward(ws, self.ef_v, self.geom_s, self.cloud, self.skip, self.Cp_value, self._bc(v.action, 0), self.ctx_v1,
                                     time=v.time, time_offset=0.0, train=True, bn_stage=self.bnst[1])              # F1
         engine.encoder_forward(ws, self.ef_p, self.geom_s, self.cloud, self.skip, self.Cp_policy, None, self.ctx_p,
@@ -573,7 +599,6 @@ class DDPGB200(AgentB200):
 
     def _phase1_target(self, ws):
         B, v, s = self.B, self.v, current_stream()
-        self.geom_n.build(self.next_cloud, self.skip)
         f2 = engine.encoder_forward(ws, self.ef_p, self.geom_n, self.next_cloud, self.skip, self.Cp_policy, None, self.ctx_n,
                                     time=v.time, time_offset=-1.0, train=True, bn_stage=self.bnst[2], keep=False)  # F2
         rawt = engine.policy_forward(self.pft, f2, self.pct, B)
@@ -664,7 +689,9 @@ class DDPGB200(AgentB200):
     def update_parameters(self, batch_data, updates=None, k=None, test=False, noise_u=None, staged=False):
         """ddpg.py:146-185.  ``staged=True``: the batch is already in the device buffers (bench/value path)."""
         if not staged:
-            self.prepare_data(batch_data, noise_u)
+            self.prepare_data(batch_data, noise_u, after_clouds=self._geometry)
+        else:
+            self._geometry()
         even = (self.update_step % self.policy_update_gap) == 0
         hard = (self.update_step % self.target_update_interval) == 0
         sig = (self._mix_idx(),)
@@ -692,7 +719,6 @@ class BCB200(AgentB200):
     def _phase(self):
         B, ws, v, s = self.B, self.ws, self.v, current_stream()
         self.out.zero_()
-        self.geom_s.build(self.cloud, self.skip)
         f = engine.encoder_forward(ws, self.ef_p, self.geom_s, self.cloud, self.skip, self.Cp_policy, None, self.ctx_p,
                                    time=v.time, time_offset=0.0, train=True)
         raw = engine.policy_forward(self.pf, f, self.pc, B)
@@ -720,7 +746,9 @@ class BCB200(AgentB200):
     def update_parameters(self, batch_data, updates=None, k=None, noise_u=None, staged=False):
         """bc.py:40-56."""
         if not staged:
-            self.prepare_data(batch_data)
+            self.prepare_data(batch_data, after_clouds=self._geometry)
+        else:
+            self._geometry()
         self._set_dyn(("policy",) + (("enc",) if self.train_feature else ()))
         self._run(("bc",), self._phase)
         self._allreduce([self.ef_p.arena, self.pf.arena])

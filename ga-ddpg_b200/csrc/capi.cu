@@ -227,9 +227,9 @@ int gaddpg_f64_to_f32(const double* src, float* dst, long long n, void* stream) 
 }
 int gaddpg_replay_gather(const float* cloud_store, long long row_floats, const float* rec_store, int rec_width, int ts_col,
                          const int32_t* episode_map, long long capacity, const int32_t* idx, int B, float* state_out, float* next_out,
-                         float* rec_out, int32_t* inc_out, void* stream) {
+                         float* rec_out, int32_t* inc_out, const int32_t* soa_map, float* soa_out, void* stream) {
   return gaddpg_replay_gather_impl(cloud_store, row_floats, rec_store, rec_width, ts_col, episode_map, capacity, idx, B, state_out,
-                                   next_out, rec_out, inc_out, stream);
+                                   next_out, rec_out, inc_out, soa_map, soa_out, stream);
 }
 
 }  // extern "C"

@@ -95,7 +95,7 @@ int gaddpg_wprep_impl(const float* W, int N, int K, int rot, float* Wp, int ldp,
 int gaddpg_f64_to_f32_impl(const double* src, float* dst, long long n, void* stream);
 int gaddpg_replay_gather_impl(const float* cloud_store, long long row_floats, const float* rec_store, int rec_width, int ts_col,
                               const int32_t* episode_map, long long capacity, const int32_t* idx, int B, float* state_out,
-                              float* next_out, float* rec_out, int32_t* inc_out, void* stream);
+                              float* next_out, float* rec_out, int32_t* inc_out, const int32_t* soa_map, float* soa_out, void* stream);
 // tc_gemm.cu
 bool gaddpg_tc_gemm_supported(const NTProblem& p, int amode, int emode);
 int gaddpg_tc_gemm_nt_impl(const NTProblem* p, int amode, int emode, void* stream);

@@ -68,9 +68,12 @@ __global__ void __launch_bounds__(256) replay_gather_cloud_scalar_kernel(const f
 
 // One warp per sample: lane c moves record column c (rec_width <= 32).  rec_out[b] = [record(idx) | record(inc)], with
 // the timestep column of the first half replaced by the remaining time (timestep[episode_end] + 1) - timestep[idx].
+// soa_map (optional, 2*W ints: base[c], stride[c]; base < 0 = skip) additionally scatters the current record field-major
+// into soa_out — the layout Agent.prepare_data's per-field device vectors have, so no per-field copies are needed.
 __global__ void __launch_bounds__(256) replay_gather_records_kernel(const float* __restrict__ rec, int W, int ts_col,
                                                                     const int32_t* __restrict__ episode_map, long long capacity,
-                                                                    const int32_t* __restrict__ idx, int B, float* __restrict__ rec_out) {
+                                                                    const int32_t* __restrict__ idx, int B, float* __restrict__ rec_out,
+                                                                    const int32_t* __restrict__ soa_map, float* __restrict__ soa_out) {
   const int b = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (b >= B) return;
   long long i = idx[b];
@@ -85,8 +88,14 @@ __global__ void __launch_bounds__(256) replay_gather_records_kernel(const float*
       float t_end = __ldg(rec + end * W + ts_col);
       cur = __fsub_rn(__fadd_rn(t_end, 1.0f), cur);  // float32(timestep[episode_map[idx]]) + 1 - time_batch
     }
-    rec_out[(long long)b * 2 * W + lane] = cur;
-    rec_out[(long long)b * 2 * W + W + lane] = nxt;
+    if (rec_out) {
+      rec_out[(long long)b * 2 * W + lane] = cur;
+      rec_out[(long long)b * 2 * W + W + lane] = nxt;
+    }
+    if (soa_map) {  // field-major copy of the current record: column c of sample b -> soa_out[base[c] + b * stride[c]]
+      int base = soa_map[lane], stride = soa_map[W + lane];
+      if (base >= 0) soa_out[base + (long long)b * stride] = cur;
+    }
   }
 }
 
@@ -94,11 +103,13 @@ __global__ void __launch_bounds__(256) replay_gather_records_kernel(const float*
 
 int gaddpg_replay_gather_impl(const float* cloud_store, long long row_floats, const float* rec_store, int rec_width, int ts_col,
                               const int32_t* episode_map, long long capacity, const int32_t* idx, int B, float* state_out,
-                              float* next_out, float* rec_out, int32_t* inc_out, void* stream) {
+                              float* next_out, float* rec_out, int32_t* inc_out, const int32_t* soa_map, float* soa_out,
+                              void* stream) {
   GADDPG_CHECK_ARG(cloud_store && episode_map && idx && state_out && next_out, "replay_gather: null pointer");
   GADDPG_CHECK_ARG(B >= 0 && capacity >= 1 && row_floats >= 1, "replay_gather: bad size");
-  GADDPG_CHECK_ARG(!rec_store || (rec_out && rec_width >= 1 && rec_width <= 32 && ts_col >= 0 && ts_col < rec_width),
-                   "replay_gather: record table needs rec_out, 1 <= rec_width <= 32 and a timestep column");
+  GADDPG_CHECK_ARG(!rec_store || ((rec_out || soa_map) && rec_width >= 1 && rec_width <= 32 && ts_col >= 0 && ts_col < rec_width),
+                   "replay_gather: record table needs rec_out or soa_map, 1 <= rec_width <= 32 and a timestep column");
+  GADDPG_CHECK_ARG(!soa_map || (rec_store && soa_out), "replay_gather: soa_map needs rec_store and soa_out");
   if (B == 0) return GADDPG_OK;
   GADDPG_CHECK_ARG(2 * (long long)B <= 65535, "replay_gather: batch too large for one launch (2B <= 65535)");
   cudaStream_t s = (cudaStream_t)stream;
@@ -118,7 +129,8 @@ int gaddpg_replay_gather_impl(const float* cloud_store, long long row_floats, co
     GADDPG_CHECK_LAUNCH("replay_gather_cloud_scalar_kernel");
   }
   if (rec_store) {
-    replay_gather_records_kernel<<<(B + 7) / 8, 256, 0, s>>>(rec_store, rec_width, ts_col, episode_map, capacity, idx, B, rec_out);
+    replay_gather_records_kernel<<<(B + 7) / 8, 256, 0, s>>>(rec_store, rec_width, ts_col, episode_map, capacity, idx, B, rec_out,
+                                                             soa_map, soa_out);
     GADDPG_CHECK_LAUNCH("replay_gather_records_kernel");
   }
   return GADDPG_OK;

@@ -34,6 +34,51 @@ ATTR_NAMES = ["action", "pose", "point_state", "target_idx", "reward", "terminal
               "image_state", "collide", "grasp", "perturb_flags", "goal", "expert_flags", "expert_action"]
 
 
+class ReplayBatch(dict):
+    """What ``ReplayMemoryB200.sample`` returns: the reference's minibatch dict, assembled lazily.
+
+    Handed straight to ``DDPGB200/BCB200.update_parameters`` it is never materialised: ``prepare_data`` asks the memory to
+    gather the sampled rows directly into the agent's input buffers (one launch pair, no intermediate copy, no
+    per-field copies).  Any dict access (``batch["point_state_batch"]``, ``keys()``, ``items()`` ...) materialises the
+    full dict of device tensors first, so code written against ``BaseMemory.sample`` keeps working."""
+
+    def __init__(self, memory, batch_idx):
+        super().__init__()
+        self.memory, self.batch_idx, self.materialised = memory, np.asarray(batch_idx), False
+
+    def materialise(self):
+        if not self.materialised:
+            self.materialised = True
+            dict.update(self, self.memory.gather(self.batch_idx))
+        return self
+
+    def __getitem__(self, k):
+        if not dict.__contains__(self, k):      # keys the caller attached itself do not force the gather
+            self.materialise()
+        return dict.__getitem__(self, k)
+
+    def __contains__(self, k):
+        return dict.__contains__(self.materialise(), k)
+
+    def __iter__(self):
+        return dict.__iter__(self.materialise())
+
+    def __len__(self):
+        return dict.__len__(self.materialise())
+
+    def get(self, k, default=None):
+        return dict.get(self.materialise(), k, default)
+
+    def keys(self):
+        return dict.keys(self.materialise())
+
+    def values(self):
+        return dict.values(self.materialise())
+
+    def items(self):
+        return dict.items(self.materialise())
+
+
 class ReplayMemoryB200:
     def __init__(self, buffer_size, args=None, name="expert", device=None, uniform_num_pts=None, episode_max_len=None,
                  gamma=None, buffer_start_idx=None, RL=None, channels=4, save_data_name="data_buffer.npz"):
@@ -185,15 +230,12 @@ class ReplayMemoryB200:
             raise IndexError("replay index out of range [0, %d)" % self.buffer_size)
         self._flush()
         o = self._buffers(B)
-        o["copied"].synchronize()          # the previous minibatch's index upload must have left the pinned buffer
-        o["idx_host"].numpy()[:] = batch_idx
-        o["idx"].copy_(o["idx_host"], non_blocking=True)
-        o["copied"].record()
+        self._upload_indices(o, batch_idx)
         row_floats = self.row[0] * self.row[1]
         if B:
             lib.gaddpg_replay_gather(self.point_state.data_ptr(), row_floats, self.records.data_ptr(), REC_W, C_TIMESTEP,
                                      self.episode_map_dev.data_ptr(), self.buffer_size, o["idx"].data_ptr(), B, o["state"].data_ptr(),
-                                     o["next"].data_ptr(), o["rec"].data_ptr(), o["inc"].data_ptr(), current_stream())
+                                     o["next"].data_ptr(), o["rec"].data_ptr(), o["inc"].data_ptr(), None, None, current_stream())
         r, n = o["rec"][:, :REC_W], o["rec"][:, REC_W:]
         data = {
             "point_state_batch": o["state"], "next_point_state_batch": o["next"],
@@ -211,7 +253,46 @@ class ReplayMemoryB200:
         return data
 
     def sample(self, batch_size):
-        return self.gather(self.draw_indices(batch_size))
+        return ReplayBatch(self, self.draw_indices(batch_size))
+
+    def _upload_indices(self, o, batch_idx):
+        o["copied"].synchronize()          # the previous minibatch's index upload must have left the pinned buffer
+        o["idx_host"].numpy()[:] = batch_idx
+        o["idx"].copy_(o["idx_host"], non_blocking=True)
+        o["copied"].record()
+
+    def gather_into(self, batch_idx, cloud, next_cloud, vec, vec_layout):
+        """Gather a minibatch straight into an agent's input buffers: ``cloud`` / ``next_cloud`` (B, C, N+6) and the
+        field-major vector ``vec`` whose layout is ``vec_layout`` = {field: (offset, width)} with the agent's field
+        names (action, expert_action, goal, reward, ret, done, time, expert_flag, perturb_flag)."""
+        batch_idx = np.asarray(batch_idx)
+        B = int(batch_idx.shape[0])
+        if tuple(cloud.shape) != (B,) + self.row or (next_cloud is not None and tuple(next_cloud.shape) != (B,) + self.row):
+            raise ValueError("agent cloud buffers %s do not match the stored rows %s" % (tuple(cloud.shape), (B,) + self.row))
+        if B and (batch_idx.min() < 0 or batch_idx.max() >= self.buffer_size):
+            raise IndexError("replay index out of range [0, %d)" % self.buffer_size)
+        self._flush()
+        o = self._buffers(B)
+        key = tuple(sorted(vec_layout.items()))
+        if o.get("soa_key") != key:
+            cols = dict(action=(C_ACTION, 6), expert_action=(C_EXPERT_ACTION, 6), goal=(C_GOAL, 7), reward=(C_REWARD, 1),
+                        ret=(C_RETURN, 1), done=(C_TERMINAL, 1), time=(C_TIMESTEP, 1), expert_flag=(C_EXPERT, 1),
+                        perturb_flag=(C_PERTURB, 1))
+            m = np.full((2, REC_W), -1, dtype=np.int32)
+            for name, (c0, w) in cols.items():
+                if name in vec_layout:
+                    off, width = vec_layout[name]
+                    assert width == w, (name, width, w)
+                    m[0, c0:c0 + w] = off + np.arange(w)
+                    m[1, c0:c0 + w] = w
+            o["soa_map"], o["soa_key"] = torch.from_numpy(m).to(self.device), key
+        self._upload_indices(o, batch_idx)
+        if B:
+            nxt = next_cloud if next_cloud is not None else o["next"]
+            lib.gaddpg_replay_gather(self.point_state.data_ptr(), self.row[0] * self.row[1], self.records.data_ptr(), REC_W, C_TIMESTEP,
+                                     self.episode_map_dev.data_ptr(), self.buffer_size, o["idx"].data_ptr(), B, cloud.data_ptr(),
+                                     nxt.data_ptr(), None, o["inc"].data_ptr(), o["soa_map"].data_ptr(), vec.data_ptr(),
+                                     current_stream())
 
     # ---- persistence (replay_memory.py:274-357) ---------------------------------------------------------------
     def save(self, save_dir="."):

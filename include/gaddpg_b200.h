@@ -283,10 +283,13 @@ GADDPG_API int gaddpg_f64_to_f32(const double* src, float* dst, long long n, voi
  * Outputs: state_out[B][row_floats] = cloud_store[idx]; next_out[B][row_floats] = cloud_store[inc] with
  * inc = min(episode_map[idx], idx + 1); rec_out[B][2*rec_width] = [rec_store[idx] | rec_store[inc]] where the timestep
  * column of the first half holds the remaining time (timestep[episode_map[idx]] + 1) - timestep[idx]; inc_out[B]
- * (optional) = inc.  Bit-exact against the reference (byte movement plus one float32 add/sub). */
+ * (optional) = inc.  soa_map (optional; 2*rec_width device ints base[c], stride[c], base < 0 = skip) additionally
+ * scatters column c of the CURRENT record of sample b to soa_out[base[c] + b*stride[c]] — the field-major vectors
+ * Agent.prepare_data keeps on the device — so a minibatch lands in the update's input buffers with no per-field copies
+ * (rec_out may then be NULL).  Bit-exact against the reference (byte movement plus one float32 add/sub). */
 GADDPG_API int gaddpg_replay_gather(const float* cloud_store, long long row_floats, const float* rec_store, int rec_width, int ts_col,
                                     const int32_t* episode_map, long long capacity, const int32_t* idx, int B, float* state_out,
-                                    float* next_out, float* rec_out, int32_t* inc_out, void* stream);
+                                    float* next_out, float* rec_out, int32_t* inc_out, const int32_t* soa_map, float* soa_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -102,14 +102,32 @@ def test_c_abi_gather_paths(cuda):
         so, no = torch.zeros(B, row).cuda(), torch.zeros(B, row).cuda()
         inc = torch.zeros(B, dtype=torch.int32).cuda()
         lib.gaddpg_replay_gather(store.data_ptr(), row, None, 0, 0, emap.data_ptr(), cap, idx.data_ptr(), B, so.data_ptr(),
-                                 no.data_ptr(), None, inc.data_ptr(), current_stream())
+                                 no.data_ptr(), None, inc.data_ptr(), None, None, current_stream())
         cl = idx.clamp(0, cap - 1).long()
         want_inc = torch.minimum(emap[cl].long(), cl + 1)
         assert inc.cpu().tolist() == want_inc.cpu().tolist() == [1, 7, 9, 63, 63, 6, 6, 1, 63]
         assert torch.equal(so, store[cl]) and torch.equal(no, store[want_inc])
+    # field-major scatter of the current record (soa_map): column c of sample b -> soa_out[base[c] + b * stride[c]]
+    cap, B, W = 32, 5, 32
+    store = torch.zeros(cap, 4).cuda()
+    rec = torch.arange(cap * W, dtype=torch.float32).view(cap, W).cuda()
+    emap = torch.full((cap,), cap - 1, dtype=torch.int32).cuda()
+    idx = torch.tensor([3, 0, 31, 7, 7], dtype=torch.int32).cuda()
+    m = torch.full((2, W), -1, dtype=torch.int32)
+    m[0, 0:6], m[1, 0:6] = torch.arange(6, dtype=torch.int32), 6               # a 6-wide field at offset 0
+    m[0, 20], m[1, 20] = 40, 1                                                 # a scalar field at offset 40
+    out = torch.full((64,), -7.0).cuda()
+    so, no = torch.zeros(B, 4).cuda(), torch.zeros(B, 4).cuda()
+    lib.gaddpg_replay_gather(store.data_ptr(), 4, rec.data_ptr(), W, 22, emap.data_ptr(), cap, idx.data_ptr(), B, so.data_ptr(),
+                             no.data_ptr(), None, None, m.cuda().data_ptr(), out.data_ptr(), current_stream())
+    want = torch.full((64,), -7.0)
+    for b, i in enumerate(idx.cpu().tolist()):
+        want[b * 6: b * 6 + 6] = rec[i, 0:6].cpu()
+        want[40 + b] = rec[i, 20].cpu()
+    assert torch.equal(out.cpu(), want)
     raw = lib.load().gaddpg_replay_gather
     z = ctypes.c_void_p(0)
-    assert raw(z, 8, z, 0, 0, z, 4, z, 1, z, z, z, z, z) == -1     # GADDPG_ERR_ARG: null pointers
+    assert raw(z, 8, z, 0, 0, z, 4, z, 1, z, z, z, z, z, z, z) == -1     # GADDPG_ERR_ARG: null pointers
     assert b"replay_gather" in lib.load().gaddpg_last_error()
 
 
@@ -125,18 +143,28 @@ def test_update_from_device_replay_equals_update_from_host_batch(cuda):
     for e in range(12):
         ep = synthetic.make_episode(8 + e, N, seed=100 + e, success=e % 3 != 0)
         ora.add_episode(ep), mem.add_episode(ep)
-    a, b = ag.make_agent("DDPG", seed=123456), ag.make_agent("DDPG", seed=123456)
+    from gaddpg_b200.replay_memory import ReplayBatch
+
+    a, b, c = (ag.make_agent("DDPG", seed=123456) for _ in range(3))
     rs = np.random.RandomState(1)
-    for step in range(3):
+    for step in range(4):       # eager, graph capture, graph replay x2
         np.random.seed(step)
         host = ora.sample(B)
         np.random.seed(step)
-        dev = mem.sample(B)
+        lazy = mem.sample(B)                   # never materialised: gathered straight into the agent's input buffers
+        assert isinstance(lazy, ReplayBatch) and not lazy.materialised
         u = rs.rand(B, 6).astype(np.float32)
         ra = a.update_parameters(host, a.update_step, 0, noise_u=u)
-        rb = b.update_parameters(dev, b.update_step, 0, noise_u=torch.from_numpy(u).cuda())
+        rb = b.update_parameters(lazy, b.update_step, 0, noise_u=torch.from_numpy(u).cuda())
+        assert not lazy.materialised
+        np.random.seed(step)
+        full = mem.sample(B).materialise()     # the dict-of-device-tensors path (what code written for BaseMemory sees)
+        assert "point_state_batch" in full and full.materialised
+        rc = c.update_parameters(full, c.update_step, 0, noise_u=u)
         for k in ra:
-            assert ra[k] == rb[k] or (np.isnan(ra[k]) and np.isnan(rb[k])), (step, k, ra[k], rb[k])
+            assert ra[k] == rb[k] == rc[k] or (np.isnan(ra[k]) and np.isnan(rb[k]) and np.isnan(rc[k])), (step, k, ra[k], rb[k], rc[k])
+    # the lazy path filled the same input buffers the host path filled
+    assert torch.equal(a.cloud, b.cloud) and torch.equal(a.next_cloud, b.next_cloud) and torch.equal(a.vec, b.vec)
 
 
 def test_full_size_gather_roundtrip(cuda):
