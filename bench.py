@@ -321,7 +321,7 @@ def replay_leg(agent, devb, args, run, nb):
         for t in idx:
             lib.gaddpg_replay_gather(mem.point_state.data_ptr(), C * (N + 6), mem.records.data_ptr(), rm.REC_W, rm.C_TIMESTEP,
                                      mem.episode_map_dev.data_ptr(), cap, t.data_ptr(), B, o["state"].data_ptr(), o["next"].data_ptr(),
-                                     o["rec"].data_ptr(), o["inc"].data_ptr(), current_stream())
+                                     o["rec"].data_ptr(), o["inc"].data_ptr(), None, None, current_stream())
 
     gathers()
     g = torch.cuda.CUDAGraph()
