@@ -142,6 +142,10 @@ class AgentB200:
         # stream-level overlap inside a step (identical arithmetic, see _phase1): a second encoder chain and the
         # weight-gradient products run on side streams; ``overlap = False`` issues everything on one stream
         self.overlap = True
+        # geometry is launched before the small-field staging for device-resident batches (+1 % steps/s: the GPU no longer
+        # idles behind ~100 us of host work); for host batches that ordering measured 0.17 ms SLOWER per step (5.59 vs
+        # 5.42 ms, A/B in one process), so they keep transfers -> staging -> geometry
+        self.early_geometry_host = False
         self.side_enc = engine.SideStream(dev)
         self.side_dw = engine.SideStream(dev)
         self.ef_p = engine.EncoderFlat(self._extractor.encoder, dev)
@@ -263,9 +267,10 @@ class AgentB200:
                     put_cloud(self.next_cloud, self.next_cloud_host, nxt)
             else:
                 put_cloud(self.next_cloud, self.next_cloud_host, nxt)
-        if after_clouds is not None:
-            after_clouds()
         on_device = torch.is_tensor(cloud) and cloud.is_cuda
+        early = after_clouds is not None and (on_device or self.early_geometry_host)
+        if early:
+            after_clouds()
         tgt = self.v if on_device else self.vh   # device-resident batch: D2D straight into the kernel inputs
 
         def put(dst, key_or_val):
@@ -282,6 +287,8 @@ class AgentB200:
             put(tgt.noise_u, torch.rand(B, 6, device=self.device if on_device else "cpu") if noise_u is None else noise_u)
         if not on_device:
             self.vec.copy_(self.vec_host, non_blocking=True)
+        if after_clouds is not None and not early:
+            after_clouds()
 
     # ---- geometry (FPS, ball query, row tables) of the minibatch's clouds: needs xyz only ------------------------
     def _geometry(self):
