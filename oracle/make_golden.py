@@ -233,6 +233,51 @@ def pin_at_step(step0, steps=2, policy="DDPG", empty_goal_mask=False):
     print("[make_golden] %s: oracle == unmodified reference for steps %d..%d" % (policy, step0, step0 + steps - 1))
 
 
+def replay_save_load_pin():
+    """BaseMemory.save / load (replay_memory.py:274-356) interchange .npz files with the oracle in both directions; the
+    minibatches sampled after loading are bit-identical (load re-derives the returns and drops the last stored slot)."""
+    import importlib
+    import tempfile
+
+    from oracle.replay_cpu import OracleMemory
+    ns = refstack.load()
+    ns.config.process_cfg()
+    cfg = ns.config.cfg
+    BaseMemory = importlib.import_module("core.replay_memory").BaseMemory
+
+    def ref_mem():
+        old = cfg.RL_TRAIN.uniform_num_pts
+        cfg.RL_TRAIN.uniform_num_pts = REPLAY_N
+        try:
+            return BaseMemory(REPLAY_CAP, cfg, "expert")
+        finally:
+            cfg.RL_TRAIN.uniform_num_pts = old
+
+    def same(a, b, what):
+        np.random.seed(3)
+        x = a.sample(REPLAY_B)
+        np.random.seed(3)
+        y = b.sample(REPLAY_B)
+        assert a.cur_idx == b.cur_idx and a.is_full == b.is_full and a.total_env_step == b.total_env_step, what
+        for k in x:
+            assert np.array_equal(np.asarray(x[k]), np.asarray(y[k])), (what, k)
+
+    ref, ora = ref_mem(), OracleMemory(REPLAY_CAP, uniform_num_pts=REPLAY_N)
+    for ep in replay_episodes()[:10]:
+        ref.add_episode(ep), ora.add_episode(ep)
+    with tempfile.TemporaryDirectory() as d:
+        ref.save(d)
+        ora2, ref2 = OracleMemory(REPLAY_CAP, uniform_num_pts=REPLAY_N), ref_mem()
+        ora2.load(d, ref.save_data_name), ref2.load(d)
+        same(ref2, ora2, "reference file -> both")
+    with tempfile.TemporaryDirectory() as d:
+        ora.save(d, ref.save_data_name)
+        ora3, ref3 = OracleMemory(REPLAY_CAP, uniform_num_pts=REPLAY_N), ref_mem()
+        ora3.load(d, ref.save_data_name), ref3.load(d)
+        same(ref3, ora3, "oracle file -> both")
+    print("[make_golden] replay: save/load files interchange with the unmodified BaseMemory in both directions")
+
+
 def index_fixture(write):
     """FPS / ball-query outputs of the oracle's C code on the first synthetic batch and on tie-heavy clouds."""
     cloud = torch.from_numpy(synthetic.make_batch(B, N, step=0)["point_state_batch"])
@@ -258,6 +303,7 @@ if __name__ == "__main__":
     index_fixture(not a.check)
     checkpoint_roundtrip("DDPG")
     replay_fixture(not a.check)
+    replay_save_load_pin()
     pin_at_step(2999)
     pin_at_step(4001)
     pin_at_step(1, empty_goal_mask=True)

@@ -96,6 +96,29 @@ class OracleMemory:
                 cost_to_go = out[cur - i - 1]
         self.returns = out
 
+    def save(self, save_dir=".", save_data_name="data_buffer.npz"):            # :336-356
+        import os
+        os.makedirs(save_dir, exist_ok=True)
+        d = {name: getattr(self, name) for name in ATTR_NAMES + ["episode_map", "is_full", "cur_idx", "total_env_step", "target_idx"]}
+        np.savez(os.path.join(save_dir, save_data_name), **d)
+
+    def load(self, data_dir, save_data_name="data_buffer.npz"):                # :274-334 (use_image = False)
+        import os
+        path = os.path.join(data_dir, save_data_name)
+        if not os.path.exists(path):
+            return
+        data = np.load(path, allow_pickle=True, mmap_mode="r")
+        n = np.amax(data["episode_map"])           # sic: the slice [:n] leaves the last stored transition out
+        for name in ATTR_NAMES + ["episode_map", "target_idx"]:
+            if name == "image_state" or name not in data:
+                continue
+            getattr(self, name)[:n] = data[name][:n]
+        self.cur_idx = n
+        self.total_env_step = int(data["total_env_step"])
+        self.is_full = bool(data["is_full"]) and self.cur_idx >= self.buffer_size - 1
+        self.cur_idx = self.upper_idx()
+        self.recompute_return_with_gamma()
+
     def draw_indices(self, batch_size):                                        # :169-172
         batch_idx = np.random.randint(self.episode_max_len, self.upper_idx(), batch_size)
         np.random.shuffle(batch_idx)

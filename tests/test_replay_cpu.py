@@ -87,3 +87,13 @@ def test_oracle_replay_matches_unmodified_reference_when_present():
     from oracle import make_golden
 
     make_golden.replay_fixture(write=False)
+
+
+def test_oracle_replay_save_load_matches_reference_when_present():
+    from oracle import refstack
+
+    if not refstack.available():
+        pytest.skip("/root/reference not present (GPU box)")
+    from oracle import make_golden
+
+    make_golden.replay_save_load_pin()

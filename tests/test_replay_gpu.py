@@ -187,3 +187,29 @@ def test_full_size_gather_roundtrip(cuda):
     assert torch.equal(d["point_state_batch"], mem.point_state[bi.cuda()])
     assert torch.equal(idx, torch.minimum((bi // 16) * 16 + 15, bi + 1))
     assert torch.equal(d["time_batch"].cpu(), (16 + 1 - (bi % 16 + 1)).float())
+
+
+def test_save_load_interchange_with_reference_format(cuda, tmp_path):
+    """replay_memory.py:274-356: the .npz the reference writes (oracle.save is pinned to it) loads into the device store
+    and vice versa; minibatches sampled after loading are bit-identical (load re-derives the returns and, like the
+    reference, leaves the last stored slot out)."""
+    from gaddpg_b200.replay_memory import ReplayMemoryB200
+    from oracle.make_golden import REPLAY_CAP, REPLAY_N, replay_episodes
+    from oracle.replay_cpu import OracleMemory
+
+    ora, mem = OracleMemory(REPLAY_CAP, uniform_num_pts=REPLAY_N), ReplayMemoryB200(REPLAY_CAP, uniform_num_pts=REPLAY_N)
+    for ep in replay_episodes()[:10]:
+        ora.add_episode(ep), mem.add_episode(ep)
+    d1, d2 = tmp_path / "from_oracle", tmp_path / "from_device"
+    ora.save(str(d1), mem.save_data_name)
+    mem.save(str(d2))
+    for src in (d1, d2):
+        o2, m2 = OracleMemory(REPLAY_CAP, uniform_num_pts=REPLAY_N), ReplayMemoryB200(REPLAY_CAP, uniform_num_pts=REPLAY_N)
+        o2.load(str(src), mem.save_data_name), m2.load(str(src))
+        assert o2.cur_idx == m2.cur_idx and o2.is_full == m2.is_full and o2.total_env_step == m2.total_env_step
+        assert np.array_equal(o2.returns, m2.returns) and np.array_equal(o2.episode_map, m2.episode_map)
+        np.random.seed(3)
+        want = o2.sample(16)
+        np.random.seed(3)
+        got = m2.sample(16)
+        _same(got, want, str(src))
