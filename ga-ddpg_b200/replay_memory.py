@@ -34,6 +34,24 @@ ATTR_NAMES = ["action", "pose", "point_state", "target_idx", "reward", "terminal
               "image_state", "collide", "grasp", "perturb_flags", "goal", "expert_flags", "expert_action"]
 
 
+def replay_config(args=None, uniform_num_pts=None, episode_max_len=None, gamma=None, buffer_start_idx=None, RL=None,
+                  save_data_name=None):
+    """The fields ``BaseMemory.__init__`` takes from the reference's cfg (replay_memory.py:28-32: every ``RL_TRAIN`` key
+    becomes an attribute, plus ``RL_MAX_STEP`` and ``RL_SAVE_DATA_NAME``); explicit keyword arguments win, and without a
+    cfg the defaults of experiments/config.py apply.  Unsupported switches fail loudly instead of being ignored."""
+    tr = getattr(args, "RL_TRAIN", None) if args is not None else None
+    has = lambda key: tr is not None and key in tr  # noqa: E731
+    pick = lambda v, key, default: v if v is not None else (tr[key] if has(key) else default)  # noqa: E731
+    if has("use_image") and tr["use_image"]:
+        raise NotImplementedError("ReplayMemoryB200: use_image = True (image observations) is outside the point-cloud update path")
+    if has("self_supervision") and tr["self_supervision"]:
+        raise NotImplementedError("ReplayMemoryB200: self_supervision (set_onpolicy_goal) is not built")
+    return dict(uniform_num_pts=int(pick(uniform_num_pts, "uniform_num_pts", 1024)), gamma=float(pick(gamma, "gamma", 0.95)),
+                buffer_start_idx=int(pick(buffer_start_idx, "buffer_start_idx", 0)), RL=bool(pick(RL, "RL", True)),
+                episode_max_len=int(episode_max_len if episode_max_len is not None else getattr(args, "RL_MAX_STEP", 20)),
+                save_data_name=save_data_name if save_data_name is not None else getattr(args, "RL_SAVE_DATA_NAME", "data_buffer.npz"))
+
+
 class ReplayBatch(dict):
     """What ``ReplayMemoryB200.sample`` returns: the reference's minibatch dict, assembled lazily.
 
@@ -81,21 +99,17 @@ class ReplayBatch(dict):
 
 class ReplayMemoryB200:
     def __init__(self, buffer_size, args=None, name="expert", device=None, uniform_num_pts=None, episode_max_len=None,
-                 gamma=None, buffer_start_idx=None, RL=None, channels=4, save_data_name="data_buffer.npz"):
+                 gamma=None, buffer_start_idx=None, RL=None, channels=4, save_data_name=None):
         """``args`` may be the reference's cfg (RL_TRAIN / RL_MAX_STEP / RL_SAVE_DATA_NAME, replay_memory.py:20-32);
         explicit keyword arguments win over it."""
         if not torch.cuda.is_available():
             raise RuntimeError("ReplayMemoryB200 keeps the replay in GPU memory: no CUDA device, no CPU fallback")
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
         self.cur_idx, self.total_env_step, self.is_full, self.name = 0, 0, False, name
-        tr = getattr(args, "RL_TRAIN", None) if args is not None else None
-        pick = lambda v, key, default: v if v is not None else (tr[key] if tr is not None and key in tr else default)  # noqa: E731
-        self.uniform_num_pts = pick(uniform_num_pts, "uniform_num_pts", 1024)
-        self.gamma = pick(gamma, "gamma", 0.95)
-        self.buffer_start_idx = pick(buffer_start_idx, "buffer_start_idx", 0)
-        self.RL = pick(RL, "RL", True)
-        self.episode_max_len = episode_max_len if episode_max_len is not None else getattr(args, "RL_MAX_STEP", 20)
-        self.save_data_name = getattr(args, "RL_SAVE_DATA_NAME", save_data_name)
+        c = replay_config(args, uniform_num_pts=uniform_num_pts, episode_max_len=episode_max_len, gamma=gamma,
+                          buffer_start_idx=buffer_start_idx, RL=RL, save_data_name=save_data_name)
+        for k, v in c.items():
+            setattr(self, k, v)
         self.buffer_size, self.channels = int(buffer_size), channels
         self.attr_names = ATTR_NAMES[:]
         self.init_buffer()
@@ -154,7 +168,7 @@ class ReplayMemoryB200:
         self._dirty = None
 
     # ---- writers (replay_memory.py:178-232) -----------------------------------------------------------------
-    def push(self, step_dict):
+    def push(self, step_dict, _pending=None):
         store_idx = self.cur_idx % self.buffer_size
         ps = np.asarray(step_dict["point_state"])
         if ps.shape[1] < 100 or ps.sum() == 0:
@@ -166,7 +180,11 @@ class ReplayMemoryB200:
                 continue
             getattr(self, name)[store_idx] = step_dict[name]
         # float64 -> float32 here (the reference converts the same values at sample time, agent.py:221-222)
-        self.point_state[store_idx].copy_(torch.from_numpy(np.ascontiguousarray(ps, dtype=np.float32)), non_blocking=False)
+        ps32 = np.ascontiguousarray(ps, dtype=np.float32)
+        if _pending is None:
+            self.point_state[store_idx].copy_(torch.from_numpy(ps32), non_blocking=False)
+        else:
+            _pending.append((store_idx, ps32))       # add_episode uploads runs of consecutive slots with one copy each
         self._mark(store_idx, store_idx + 1)
         if self.cur_idx >= self.buffer_size - 1:
             self.is_full = True
@@ -179,8 +197,16 @@ class ReplayMemoryB200:
         n = len(episode)
         if (not self.RL) and episode[-1]["reward"] < 0.5 and not explore:
             return
+        pending = []
         for transition in episode:
-            self.push(transition)
+            self.push(transition, pending)
+        i = 0
+        while i < len(pending):                      # one H2D per run of consecutive slots (two when the ring wraps)
+            j = i
+            while j + 1 < len(pending) and pending[j + 1][0] == pending[j][0] + 1:
+                j += 1
+            self.point_state[pending[i][0]: pending[j][0] + 1].copy_(torch.from_numpy(np.stack([c for _, c in pending[i: j + 1]])))
+            i = j + 1
         if self.cur_idx - n >= 0 and n > 0:
             cost_to_go = 0
             for i in range(n):

@@ -97,3 +97,31 @@ def test_oracle_replay_save_load_matches_reference_when_present():
     from oracle import make_golden
 
     make_golden.replay_save_load_pin()
+
+
+def test_replay_config_from_reference_cfg():
+    """ReplayMemoryB200 takes the reference's constructor arguments (buffer_size, cfg): the cfg fields BaseMemory reads
+    resolve to the same values (checked against the unmodified experiments/config.py when present)."""
+    from types import SimpleNamespace
+
+    from gaddpg_b200.replay_memory import replay_config
+
+    assert replay_config(None) == dict(uniform_num_pts=1024, gamma=0.95, buffer_start_idx=0, RL=True, episode_max_len=20,
+                                       save_data_name="data_buffer.npz")
+    cfg = SimpleNamespace(RL_TRAIN=dict(uniform_num_pts=512, gamma=0.9, buffer_start_idx=3, RL=False), RL_MAX_STEP=30,
+                          RL_SAVE_DATA_NAME="x.npz")
+    assert replay_config(cfg) == dict(uniform_num_pts=512, gamma=0.9, buffer_start_idx=3, RL=False, episode_max_len=30, save_data_name="x.npz")
+    assert replay_config(cfg, gamma=0.5, episode_max_len=7)["gamma"] == 0.5 and replay_config(cfg, episode_max_len=7)["episode_max_len"] == 7
+    with pytest.raises(NotImplementedError):
+        replay_config(SimpleNamespace(RL_TRAIN=dict(use_image=True)))
+    with pytest.raises(NotImplementedError):
+        replay_config(SimpleNamespace(RL_TRAIN=dict(self_supervision=True)))
+    from oracle import refstack
+
+    if refstack.available():
+        ns = refstack.load()
+        ns.config.process_cfg()
+        c, ref = replay_config(ns.config.cfg), ns.config.cfg
+        assert c["uniform_num_pts"] == ref.RL_TRAIN.uniform_num_pts and c["gamma"] == ref.RL_TRAIN.gamma
+        assert c["episode_max_len"] == ref.RL_MAX_STEP and c["save_data_name"] == ref.RL_SAVE_DATA_NAME
+        assert c["buffer_start_idx"] == ref.RL_TRAIN.buffer_start_idx and c["RL"] == ref.RL_TRAIN.RL
