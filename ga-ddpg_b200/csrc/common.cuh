@@ -77,3 +77,20 @@ __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v)
   }
   return v;
 }
+
+// Fixed-order sum of n values: s = ((v0 + v1) + v2) + ... exactly like the plain loop, but U loads are issued before the
+// first add so the loop is not one exposed memory latency per term (the partial-sum reductions read L2-resident slots).
+template <int U, typename F>
+__device__ __forceinline__ float ordered_sum(int n, F load) {
+  float s = 0.f;
+  int i = 0;
+  for (; i + U <= n; i += U) {
+    float v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = load(i + u);
+#pragma unroll
+    for (int u = 0; u < U; ++u) s += v[u];
+  }
+  for (; i < n; ++i) s += load(i);
+  return s;
+}

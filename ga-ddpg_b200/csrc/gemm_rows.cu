@@ -320,7 +320,8 @@ __global__ void __launch_bounds__(256) tn_reduce_kernel(const float* __restrict_
       n = (int)(e / Ktrue);
       k = (int)(e % Ktrue);
       const float* src = partial + (long long)n * K + k;
-      for (int sp = g; sp < splits; sp += 8) s += src[(long long)sp * N * K];
+      const long long stride = (long long)N * K;
+      s = ordered_sum<4>((splits - g + 7) / 8, [&](int i) { return src[(long long)(g + 8 * i) * stride]; });
     }
     red[g][ox] = s;
     __syncthreads();
@@ -356,8 +357,7 @@ __global__ void bias_reduce_kernel(const float* __restrict__ partial, int splits
                                    int accumulate) {
   int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= Ntrue) return;
-  float s = 0.f;
-  for (int sp = 0; sp < splits; ++sp) s += partial[(long long)sp * N + n];
+  const float s = ordered_sum<8>(splits, [&](int sp) { return partial[(long long)sp * N + n]; });
   dst[n] = (accumulate ? dst[n] : 0.f) + s;
 }
 

@@ -146,6 +146,9 @@ __global__ void sa1_bcbias_kernel(const float* __restrict__ bc, int Cb, int B, c
 // Backward of the same layer, same item decomposition: dY1 = BN-backward of (D1, Y1) on the fly (never stored),
 // dW1[n][k] += dY1[r][n] * in[r][k] in 2x16 register accumulators per lane, and -- when the layer has broadcast
 // channels -- the per-sample column sums of dY1 as one [64] partial per item (fixed-order sum in sa1_dbc_kernel).
+#ifndef SA1_BWD_ROWS
+#define SA1_BWD_ROWS 8
+#endif
 __global__ void __launch_bounds__(256, 2) sa1_l1_bwd_kernel(const float* __restrict__ cloud, long long cloud_sb, int cloud_sc,
                                                             int skip, int Cp, const float* __restrict__ ctr, int npoint,
                                                             const int32_t* __restrict__ seg_off,
@@ -185,16 +188,18 @@ __global__ void __launch_bounds__(256, 2) sa1_l1_bwd_kernel(const float* __restr
       sa1_stage_row(cloud, cloud_sb, cloud_sc, skip, Cp, ctr, row_seg, row_src, row_w, b, base + lane, lane < nrows,
                     myIn + lane * SA1_LDI, myRw + lane);
       __syncwarp();
-      for (int r4 = 0; r4 < nrows; r4 += 4) {
-        float2 d[4], y[4];
+      // SA1_BWD_ROWS rows of D and Y (2 x 8-byte loads per row and lane) are requested before the first one is consumed:
+      // the kernel is bound by the latency of these streams, not by the 40 FMAs per row
+      for (int r4 = 0; r4 < nrows; r4 += SA1_BWD_ROWS) {
+        float2 d[SA1_BWD_ROWS], y[SA1_BWD_ROWS];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < SA1_BWD_ROWS; ++u) {
           const bool ok = r4 + u < nrows;
           d[u] = ok ? *reinterpret_cast<const float2*>(D + (long long)(base + r4 + u) * SA1_CO + 2 * lane) : make_float2(0.f, 0.f);
           y[u] = ok ? *reinterpret_cast<const float2*>(Y + (long long)(base + r4 + u) * SA1_CO + 2 * lane) : make_float2(0.f, 0.f);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < SA1_BWD_ROWS; ++u) {
           if (r4 + u < nrows) {
             const float w = myRw[r4 + u];
             const float dy0 = gn.x * (d[u].x - w * (m1n.x + (y[u].x - mun.x) * rsn.x * m2n.x));
@@ -248,8 +253,7 @@ __global__ void sa1_dw_reduce_kernel(const float* __restrict__ partial, int nblk
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= SA1_CO * K1) return;
   int n = e / K1, k = e % K1;
-  float s = 0.f;
-  for (int b = 0; b < nblk; ++b) s += partial[((long long)b * SA1_CO + n) * SA1_KMAX + k];
+  const float s = ordered_sum<8>(nblk, [&](int b) { return partial[((long long)b * SA1_CO + n) * SA1_KMAX + k]; });
   float* d = dW + n * ldw + k;
   *d = (accumulate ? *d : 0.f) + s;
 }
@@ -260,8 +264,7 @@ __global__ void __launch_bounds__(64) sa1_dbc_kernel(const float* __restrict__ c
                                                      float* __restrict__ dbc) {
   __shared__ float s[SA1_CO];
   const int b = blockIdx.x, n = threadIdx.x;
-  float a = 0.f;
-  for (int j = 0; j < jmax; ++j) a += colsum_part[((long long)b * jmax + j) * SA1_CO + n];
+  const float a = ordered_sum<4>(jmax, [&](int j) { return colsum_part[((long long)b * jmax + j) * SA1_CO + n]; });
   s[n] = a;
   if (colsum) colsum[(long long)b * SA1_CO + n] = a;
   __syncthreads();
@@ -366,7 +369,21 @@ __global__ void pool_fwd_kernel(const float* __restrict__ Y, int C, const float*
     const float sc = scale[c], sh = shift[c];
     float best = -1.f;
     int bi = r0;
-    for (int r = r0; r < r1; ++r) {
+    int r = r0;
+    for (; r + 8 <= r1; r += 8) {  // 8 row loads in flight per thread (the walk is a latency chain otherwise); same visiting order
+      float y[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) y[u] = Y[(long long)(r + u) * C + c];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        float v = fmaxf(fmaf(y[u], sc, sh), 0.f);
+        if (v > best) {
+          best = v;
+          bi = r + u;
+        }
+      }
+    }
+    for (; r < r1; ++r) {
       float v = fmaxf(fmaf(Y[(long long)r * C + c], sc, sh), 0.f);
       if (v > best) {
         best = v;
