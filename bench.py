@@ -342,7 +342,9 @@ def replay_leg(agent, devb, args, run, nb):
     gbs = alg / (us * 1e-6) / 1e9
     return dict(value=args.steps / (ms / 1e3), unit=UNIT, ms_per_step=ms / args.steps, store_transitions=cap,
                 gather=dict(us_per_minibatch=us, algorithmic_bytes=alg, achieved=gbs, peak=pk["hbm"], unit="GB/s",
-                            frac=gbs / pk["hbm"], bound="hbm", peak_source=pk["src"], includes="cloud gather kernel + record gather kernel (2 launches per minibatch)"),
+                            frac=gbs / pk["hbm"], bound="hbm", peak_source=pk["src"], includes="cloud gather kernel + record gather kernel (2 launches per minibatch)",
+                            traffic=49.0e6, traffic_source="ncu --set full, profiles/r1_ncu_full_v3.md: 43.2 MB read + 5.8 MB written per "
+                            "launch at this size; the gathered clouds stay in L2 for the kernels that consume them next"),
                 note="update_parameters(ReplayMemoryB200.sample(B)): minibatch assembled on the GPU from a float32 store in HBM; "
                      "no cloud bytes cross PCIe")
 

@@ -253,7 +253,7 @@ __global__ void sa1_dw_reduce_kernel(const float* __restrict__ partial, int nblk
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= SA1_CO * K1) return;
   int n = e / K1, k = e % K1;
-  const float s = ordered_sum<8>(nblk, [&](int b) { return partial[((long long)b * SA1_CO + n) * SA1_KMAX + k]; });
+  const float s = ordered_sum<32>(nblk, [&](int b) { return partial[((long long)b * SA1_CO + n) * SA1_KMAX + k]; });
   float* d = dW + n * ldw + k;
   *d = (accumulate ? *d : 0.f) + s;
 }
@@ -282,15 +282,15 @@ __global__ void sa1_dwbc_kernel(const float* __restrict__ colsum, const float* _
   int n = e / Cb, c = e % Cb;
   float s = 0.f;
   int b = 0;
-  for (; b + 8 <= B; b += 8) {  // 16 loads in flight, then the FMAs in sample order (same result as the plain loop)
-    float x[8], y[8];
+  for (; b + 16 <= B; b += 16) {  // 32 loads in flight, then the FMAs in sample order (same result as the plain loop)
+    float x[16], y[16];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < 16; ++u) {
       x[u] = colsum[(long long)(b + u) * SA1_CO + n];
       y[u] = bc[(long long)(b + u) * Cb + c];
     }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) s = fmaf(x[u], y[u], s);
+    for (int u = 0; u < 16; ++u) s = fmaf(x[u], y[u], s);
   }
   for (; b < B; ++b) s = fmaf(colsum[(long long)b * SA1_CO + n], bc[(long long)b * Cb + c], s);
   float* d = dW + n * ldw + koff + c;
