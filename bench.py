@@ -392,7 +392,7 @@ def profile(agent, devb, args):
                                                     gbs=r["bytes"] / (r["ms"] * 1e-3) / 1e9, tflops=r["flops"] / (r["ms"] * 1e-3) / 1e12)
     # The dominant KERNEL: every gemm_nt path is exactly one kernel per call, so its event time is that kernel's time.  A
     # gemm_tn call is a composite of 2-3 kernels (tc_tn_kernel split + fixed-order tn_reduce [+ bias_reduce]); in the ncu
-    # launch list (profiles/r1_launches_v2_summary.md) tc_tn_kernel alone is 16 % of the GPU time against 20 % for
+    # launch list (profiles/r1_launches_v3_summary.md) tc_tn_kernel alone is 16.6 % of the GPU time against 21.1 % for
     # tc_gemm_nt_kernel, so the composite is reported beside the roofline ("roofline_tn_composite"), not as "the kernel".
     dom = max((f for f in fam if f != "gemm_tn:"), key=lambda f: fam[f]["ms"])
     d = fam[dom]
