@@ -1,7 +1,7 @@
 """Diagnostic (GPU box): forward accuracy of the fp32 CPU oracle and of the CUDA encoder against a float64 evaluation of the
 same network on the same inputs (value encoder, DDPG init weights, B/N from env)."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import copy
 import numpy as np, torch
 from gaddpg_b200 import agent as ag, synthetic, engine

@@ -1,7 +1,7 @@
 """Diagnostic (GPU box): after ONE DDPG step from identical weights, compare gradients and parameter deltas
 per tensor between the fused agent and the CPU oracle."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from gaddpg_b200 import agent as ag, synthetic
 from oracle.ddpg_cpu import OracleAgent

@@ -1,6 +1,6 @@
 """Diagnostic (GPU box): even step (actor-critic branch) from synchronised state: compare gradients per tensor."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from gaddpg_b200 import agent as ag, synthetic
 from oracle.ddpg_cpu import OracleAgent

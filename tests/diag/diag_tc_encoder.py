@@ -1,6 +1,6 @@
 """Diagnostic (GPU box): encoder backward with the tcgen05 path vs the FFMA path vs the CPU oracle, per tensor."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from gaddpg_b200 import engine, synthetic
 from gaddpg_b200.capi import lib

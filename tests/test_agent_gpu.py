@@ -125,7 +125,7 @@ def test_steps_from_synchronised_state(cuda, policy, over):
         rep = _param_report(mine, ora)
         # heads: well-conditioned gradients -> far below one lr-unit (3e-4) on odd steps; on even steps the actor
         # gradient passes through ReLU/max-pool kinks of the value encoder where two fp32 evaluations can route a few
-        # elements differently (scripts/diag_step2.py, DESIGN.md "Parity"), so allow 2 lr-units there
+        # elements differently (tests/diag/diag_step2.py, DESIGN.md "Parity"), so allow 2 lr-units there
         even = (step % 2 == 1) and policy == "DDPG"
         assert rep["policy"] < (6e-4 if even else 3e-5) and rep.get("critic", 0) < 3e-5, (step, rep)
         assert rep["policy_target"] < 1e-6 and rep.get("critic_target", 0) < 1e-6, (step, rep)

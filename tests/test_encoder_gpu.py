@@ -99,7 +99,7 @@ def test_encoder_forward_backward_matches_oracle(cuda, B, N, with_action, tc):
     vals = sorted(errs.values())
     # typical tensor: rounding level; worst tensor: a few ReLU / max-pool kink flips.  The 3xTF32 path carries ~3x the
     # forward rounding error of FFMA (1e-5 instead of 5e-6 at z), so it flips a few more elements — every flip moves one
-    # full gradient element, which shows as 1e-3..5e-2 on the tensors below it (scripts/diag_tc_encoder.py)
+    # full gradient element, which shows as 1e-3..5e-2 on the tensors below it (tests/diag/diag_tc_encoder.py)
     assert vals[len(vals) // 2] < (2e-3 if tc else 2e-4), errs
     assert vals[-1] < (1e-1 if tc else 2e-2), errs
     for k in ("1.0.bias", "1.3.bias"):
