@@ -29,8 +29,10 @@ FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # 148 SMs x 128 FFMA lanes x 
 
 
 def workload(args):
-    return dict(workload="cfg2: offline TD3/DDPG update, B=%d per GPU, N=%d points x 6 channels (extra_latent=3), aux heads off"
-                % (args.batch, args.points), B=args.batch, N=args.points, channels=6, policy_update_gap=2,
+    name = "cfg3" if getattr(args, "aux", False) else "cfg2"
+    return dict(workload="%s: offline TD3/DDPG update, B=%d per GPU, N=%d points x 6 channels (extra_latent=3), aux heads %s"
+                % (name, args.batch, args.points, "on (goal-aux + grasp-aux losses)" if name == "cfg3" else "off"),
+                B=args.batch, N=args.points, channels=6, policy_update_gap=2,
                 l2="per-step working set (activations of 5 encoder passes, ~GBs) >> 126 MB L2 and 4 distinct batches are cycled: no flush needed")
 
 
@@ -178,7 +180,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-replay", action="store_true", help="skip the device-resident replay leg (SURVEY.md §8 row f1)")
+    ap.add_argument("--aux", action="store_true", help="BASELINE config 3: both auxiliary losses on (use with --batch 512); "
+                    "the default run is config 2, the one the metric is quoted on")
     args = ap.parse_args()
+    if args.aux:
+        AGENT_KW.update(policy_aux=True, critic_aux=True)
+    global UNIT
+    UNIT = "update steps/s (%d-sample minibatch per GPU)" % args.batch
     if args.impl == "reference":
         return run_reference(args)
 
