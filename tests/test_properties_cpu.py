@@ -9,7 +9,7 @@ from oracle.pointnet2_ops_cpu import pointnet2_utils as U
 from tests.fps_closed_form import fps_closed_form
 
 
-@settings(max_examples=40, deadline=None)
+@settings(max_examples=40, deadline=None, derandomize=True)
 @given(n=st.integers(2, 700), m=st.integers(1, 40), seed=st.integers(0, 10_000), grid=st.sampled_from([0, 4, 16]),
        zero_frac=st.sampled_from([0.0, 0.1, 0.9]))
 def test_fps_closed_form_equals_simulation(n, m, seed, grid, zero_frac):
@@ -27,7 +27,7 @@ def test_fps_closed_form_equals_simulation(n, m, seed, grid, zero_frac):
     assert all(valid[i] or i == 0 for i in want)          # an invalid point is only ever emitted as the index-0 filler
 
 
-@settings(max_examples=30, deadline=None)
+@settings(max_examples=30, deadline=None, derandomize=True)
 @given(n=st.integers(1, 300), m=st.integers(1, 20), ns=st.sampled_from([1, 4, 64]), r=st.sampled_from([0.02, 0.1, 0.5]),
        seed=st.integers(0, 10_000))
 def test_ball_query_invariants(n, m, ns, r, seed):
