@@ -134,7 +134,6 @@ class ReplayMemoryB200:
         self.pose = np.zeros((n, 64), dtype=np.float32)
         self.state_pose = np.zeros((n, 4, 4), dtype=np.float32)
         self.image_state = np.zeros((n, 1), dtype=np.uint16)
-        self._stage = None
         self._dirty = None     # [lo, hi) of host record / episode-map rows not yet mirrored to the device
         self._out = {}
 
@@ -155,6 +154,12 @@ class ReplayMemoryB200:
 
     def _mark(self, lo, hi):
         self._dirty = (lo, hi) if self._dirty is None else (min(lo, self._dirty[0]), max(hi, self._dirty[1]))
+
+    def mark_dirty(self, lo=0, hi=None):
+        """Call after editing the host-side arrays (``returns``, ``episode_map``, ``reward`` ...) in place for slots
+        [lo, hi): the next ``sample`` mirrors them to the device record table.  ``push`` / ``add_episode`` / ``load`` /
+        ``recompute_return_with_gamma`` do this themselves."""
+        self._mark(lo, self.buffer_size if hi is None else hi)
 
     def _flush(self):
         """Mirror the host-side records / episode map of the slots touched since the last sample to the device."""
