@@ -100,6 +100,22 @@ def save(obj, path):
     torch.save(obj, path)
 
 
-def load(path, map_location="cpu"):
-    """torch.load as agent.py:374 does; ``weights_only=False`` because the scheduler dict holds a Counter."""
-    return torch.load(path, map_location=map_location, weights_only=False)
+def load(path, map_location="cpu", trusted=None):
+    """Read one checkpoint file.  The reference calls plain ``torch.load`` (agent.py:374), i.e. full pickle; here the
+    default is torch's restricted unpickler (tensors, containers, numbers) plus ``collections.Counter`` — the only extra
+    type a ``MultiStepLR.state_dict()`` holds — which reads every file the reference or this package writes.  Files that
+    need arbitrary pickle (e.g. written by very old torch versions) load only with ``trusted=True`` or
+    ``GADDPG_TRUSTED_CHECKPOINTS=1``: unpickling executes code, so only do that for files you produced yourself."""
+    import collections
+    import pickle
+
+    if trusted is None:
+        trusted = os.environ.get("GADDPG_TRUSTED_CHECKPOINTS", "0") == "1"
+    if trusted:
+        return torch.load(path, map_location=map_location, weights_only=False)
+    try:
+        with torch.serialization.safe_globals([collections.Counter]):
+            return torch.load(path, map_location=map_location, weights_only=True)
+    except pickle.UnpicklingError as e:
+        raise RuntimeError("%s needs full pickle to load (%s); pass trusted=True / set GADDPG_TRUSTED_CHECKPOINTS=1 if you "
+                           "trust its origin" % (path, str(e).splitlines()[0])) from e

@@ -114,3 +114,29 @@ def test_oracle_checkpoints_interchange_with_reference_when_present():
     from oracle import make_golden
 
     make_golden.checkpoint_roundtrip("DDPG")
+
+
+def test_checkpoint_load_is_restricted_by_default(tmp_path):
+    """Files in the reference's layout (tensors, numbers, the scheduler's Counter) load with the restricted unpickler;
+    a file that needs arbitrary pickle is refused unless the caller declares it trusted."""
+    import collections
+
+    from torch.optim.lr_scheduler import MultiStepLR
+
+    mod, arena = _toy()
+    opt = _adam_steps(mod, arena, 1)
+    sch = MultiStepLR(opt, milestones=[5, 9], gamma=0.5)
+    good = str(tmp_path / "good")
+    checkpoint.save({"net": mod.state_dict(), "opt": opt.state_dict(), "sch": sch.state_dict(), "step": 3}, good)
+    d = checkpoint.load(good)
+    assert d["step"] == 3 and isinstance(d["sch"]["milestones"], collections.Counter) and torch.equal(d["net"]["0.weight"], mod[0].weight)
+
+    class Evil:
+        def __reduce__(self):
+            return (print, ("arbitrary code ran",))
+
+    bad = str(tmp_path / "bad")
+    torch.save({"net": Evil()}, bad)
+    with pytest.raises(RuntimeError, match="trusted"):
+        checkpoint.load(bad)
+    assert "net" in checkpoint.load(bad, trusted=True)
