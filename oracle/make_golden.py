@@ -278,6 +278,27 @@ def replay_save_load_pin():
     print("[make_golden] replay: save/load files interchange with the unmodified BaseMemory in both directions")
 
 
+def pin_variant(extra_latent=3, channels=6, steps=2, **overrides):
+    """The benchmark's channel variant (BASELINE "x6-ch": ``extra_latent: 3`` => 6-channel clouds, value encoder
+    hard-sliced to 10 of 12 channels, networks.py:206-207,238) and the aux-off switch of cfg2, against the unmodified
+    reference: same seeds and batches => identical scalars and weights."""
+    ns, ref, _ = refstack.make_reference_agent("DDPG", extra_latent=extra_latent, seed=SEED, overrides=overrides)
+    ora = OracleAgent("DDPG", seed=SEED, extra_latent=extra_latent, **overrides)
+    assert_same_weights(ref_state_dicts(ref), ora.state_dicts(), "variant init")
+    for step in range(steps):
+        batch = synthetic.make_batch(B, N, step=step, channels=channels)
+        torch.manual_seed(1000 + step)
+        r = ref.update_parameters(batch, ref.update_step, 0)
+        ref.step_scheduler(ref.update_step)
+        torch.manual_seed(1000 + step)
+        o = ora.update_parameters(batch)
+        ora.step_scheduler()
+        for k in LOSS_KEYS:
+            assert r[k] == o[k] or (np.isnan(r[k]) and np.isnan(o[k])), (extra_latent, overrides, step, k, r[k], o[k])
+    assert_same_weights(ref_state_dicts(ref), ora.state_dicts(), "variant after %d steps" % steps)
+    print("[make_golden] DDPG extra_latent=%d %s: oracle == unmodified reference over %d steps" % (extra_latent, overrides, steps))
+
+
 def index_fixture(write):
     """FPS / ball-query outputs of the oracle's C code on the first synthetic batch and on tie-heavy clouds."""
     cloud = torch.from_numpy(synthetic.make_batch(B, N, step=0)["point_state_batch"])
@@ -304,6 +325,8 @@ if __name__ == "__main__":
     checkpoint_roundtrip("DDPG")
     replay_fixture(not a.check)
     replay_save_load_pin()
+    pin_variant(3, 6, policy_aux=False, critic_aux=False)
+    pin_variant(3, 6)
     pin_at_step(2999)
     pin_at_step(4001)
     pin_at_step(1, empty_goal_mask=True)

@@ -77,3 +77,16 @@ def test_oracle_schedule_points_match_reference_when_present(step0, empty):
     from oracle import make_golden
 
     make_golden.pin_at_step(step0, empty_goal_mask=empty)
+
+
+@pytest.mark.parametrize("over", [dict(policy_aux=False, critic_aux=False), {}])
+def test_oracle_six_channel_variant_matches_reference_when_present(over):
+    """The configuration bench.py measures (cfg2: ``extra_latent: 3`` => 6-channel clouds, aux heads off) and its aux-on
+    sibling (cfg3), against the unmodified reference."""
+    from oracle import refstack
+
+    if not refstack.available():
+        pytest.skip("/root/reference not present (GPU box)")
+    from oracle import make_golden
+
+    make_golden.pin_variant(3, 6, **over)
