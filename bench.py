@@ -109,61 +109,65 @@ def make_batches(B, N, nb, pinned=True):
     return out
 
 
-def run_reference(args):
-    """The reference algorithm's CPU implementation of the step (oracle port of core/ddpg.py + networks + pointnet2_ops,
-    pinned to the unmodified reference by oracle/make_golden.py), all host threads, a bounded sub-batch per step."""
+REF_MAX_TIMED, REF_MAX_WARMUP = 4, 1   # a real B=256 CPU step takes ~10 s on the box's 16 cores: cap the reference arm
+
+
+def _oracle_steps(args, warmup, steps):
+    """Real full-size steps of the oracle port (pinned bit-exactly to the unmodified reference, oracle/make_golden.py): the
+    SAME minibatch size, cloud size and channel count as the GPU arm — nothing is scaled.  -> (seconds, cores, torch)"""
     import torch
 
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
     from gaddpg_b200 import synthetic
     from oracle.ddpg_cpu import OracleAgent
 
     cores = os.cpu_count()
     torch.set_num_threads(cores)
-    Bs = args.ref_batch
     agent = OracleAgent("DDPG", seed=123456, **AGENT_KW)
-    batches = [synthetic.make_batch(Bs, args.points, step=i, channels=6) for i in range(2)]
-    for i in range(args.warmup):
+    batches = [synthetic.make_batch(args.ref_batch, args.points, step=i, channels=6) for i in range(2)]
+    for i in range(warmup):                       # update_step 1 (odd): no actor-critic branch
         agent.update_parameters(batches[i % 2])
         agent.step_scheduler()
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        agent.update_parameters(batches[i % 2])
+    for i in range(steps):                        # alternating even / odd update steps, starting with an even one
+        agent.update_parameters(batches[(i + warmup) % 2])
         agent.step_scheduler()
-    dt = time.perf_counter() - t0
-    value = args.steps / dt * (Bs / float(args.batch))
-    sample = "each step = one full DDPG update on a %d-sample sub-batch of the %d-sample minibatch (N=%d, 6 ch); value scaled by %d/%d" % (
-        Bs, args.batch, args.points, Bs, args.batch)
-    print(json.dumps(dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                          ms_per_step=1e3 * dt / args.steps * (args.batch / float(Bs)), higher_is_better=True, scaling="weak",
-                          vs_baseline=None, dtype="f32", data="synthetic", config=workload(args), impl="reference",
-                          cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port", sample=sample,
-                                            torch=torch.__version__),
+    return time.perf_counter() - t0, cores, torch.__version__
+
+
+def run_reference(args):
+    """The reference algorithm's CPU implementation of the step (oracle port of core/ddpg.py + networks + pointnet2_ops,
+    pinned to the unmodified reference by oracle/make_golden.py) on all host threads at the REAL workload size.  A full
+    B=256 step costs ~10 s of CPU, so the arm times at most REF_MAX_TIMED steps after at most REF_MAX_WARMUP warm-up
+    steps whatever --steps / --warmup say, and prints the counts it actually ran."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    warmup, steps = min(args.warmup, REF_MAX_WARMUP), max(1, min(args.steps, REF_MAX_TIMED))
+    dt, cores, tver = _oracle_steps(args, warmup, steps)
+    scale = args.ref_batch / float(args.batch)
+    value = steps / dt * scale
+    cfg = workload(args)
+    extrap = args.ref_batch != args.batch
+    if extrap:  # only on explicit request (--ref-batch): say so and do not pose as the same configuration
+        cfg.update(B=args.ref_batch, extrapolated=True)
+    sample = "%d real DDPG update steps (alternating even / odd) on a %d-sample minibatch (N=%d, 6 ch) after %d warm-up; %.1f s of CPU work%s" % (
+        steps, args.ref_batch, args.points, warmup, dt, "; value scaled by %d/%d (EXTRAPOLATED)" % (args.ref_batch, args.batch) if extrap else "; nothing scaled")
+    print(json.dumps(dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=steps, warmup=warmup,
+                          requested=dict(steps=args.steps, warmup=args.warmup), ms_per_step=1e3 * dt / steps,
+                          higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", config=cfg,
+                          impl="reference", extrapolated=extrap,
+                          cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port", sample=sample, torch=tver),
                           e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
 
 
 def cpu_baseline(args):
-    import torch
-
-    from gaddpg_b200 import synthetic
-    from oracle.ddpg_cpu import OracleAgent
-
-    cores = os.cpu_count()
-    torch.set_num_threads(cores)
-    Bs = args.ref_batch
-    agent = OracleAgent("DDPG", seed=123456, **AGENT_KW)
-    batches = [synthetic.make_batch(Bs, args.points, step=i, channels=6) for i in range(2)]
-    agent.update_parameters(batches[0])  # warm-up (odd step)
-    t0 = time.perf_counter()
+    """1 warm-up + 2 timed (one even, one odd) REAL B=256 steps of the oracle port: ~30 s on the box's host cores."""
     n = args.cpu_steps
-    for i in range(n):  # alternating even / odd steps
-        agent.update_parameters(batches[(i + 1) % 2])
-    dt = time.perf_counter() - t0
-    return dict(value=n / dt * (Bs / float(args.batch)), unit=UNIT, cores=cores, kind="port", torch=torch.__version__,
-                sample="oracle port, %d timed DDPG steps (alternating even / odd) on a %d-sample sub-batch (N=%d, 6 ch) after 1 warm-up; "
-                       "scaled by %d/%d to the 256-sample unit; %.1f s of CPU work" % (n, Bs, args.points, Bs, args.batch, dt))
+    dt, cores, tver = _oracle_steps(args, 1, n)
+    extrap = args.ref_batch != args.batch
+    return dict(value=n / dt * (args.ref_batch / float(args.batch)), unit=UNIT, cores=cores, kind="port", torch=tver, extrapolated=extrap,
+                sample="oracle port, %d timed real DDPG steps (alternating even / odd) on a %d-sample minibatch (N=%d, 6 ch) after 1 warm-up; "
+                       "%.1f s of CPU work%s" % (n, args.ref_batch, args.points, dt, "; scaled by %d/%d (EXTRAPOLATED)" % (args.ref_batch, args.batch) if extrap else "; nothing scaled"))
 
 
 def main():
@@ -174,17 +178,20 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--points", type=int, default=4096)
-    ap.add_argument("--ref-batch", type=int, default=32)
-    ap.add_argument("--cpu-steps", type=int, default=10, help="timed CPU-baseline steps (about 1.3 s each on 16 cores)")
+    ap.add_argument("--ref-batch", type=int, default=0, help="minibatch of the CPU arm (default: --batch, i.e. the real workload)")
+    ap.add_argument("--cpu-steps", type=int, default=2, help="timed CPU-baseline steps (about 10 s each at B=256 on 16 cores)")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the e2e_f64 and dense-worst-case legs")
     ap.add_argument("--no-replay", action="store_true", help="skip the device-resident replay leg (SURVEY.md §8 row f1)")
     ap.add_argument("--aux", action="store_true", help="BASELINE config 3: both auxiliary losses on (use with --batch 512); "
                     "the default run is config 2, the one the metric is quoted on")
     args = ap.parse_args()
     if args.aux:
         AGENT_KW.update(policy_aux=True, critic_aux=True)
+    if args.ref_batch <= 0:
+        args.ref_batch = args.batch
     global UNIT
     UNIT = "update steps/s (%d-sample minibatch per GPU)" % args.batch
     if args.impl == "reference":
@@ -260,8 +267,49 @@ def main():
                e2e=dict(value=e2e, unit=UNIT, ms_per_step=ms_e2e / K, h2d_bytes_per_step=agent.h2d_bytes(), d2h_bytes_per_step=64),
                gpu_launches=int(launches_per_2 * K / 2), clocks=clk.result(), graph=bool(agent.use_graph))
 
+    if not args.no_extra:
+        # ---- e2e_f64: the dict the reference's BaseMemory.sample returns (replay_memory.py:166-176,376): float64 ndarray
+        # clouds, ndarray fields — the host f64->f32 conversion of 2 x B x C x (N+6) x 8 bytes is inside the timed region
+        import numpy as np
+
+        from gaddpg_b200 import synthetic
+
+        host64 = []
+        for i in range(nb):
+            b = synthetic.make_batch(args.batch, args.points, step=i, channels=6, dtype=np.float64)
+            b["noise_u"] = host[i]["noise_u"]
+            host64.append(b)
+        run(host64, 2, False)
+        k64 = max(4, K // 2)
+        ms64 = run(host64, k64, True)
+        out["e2e_f64"] = dict(value=n_gpus * k64 / (ms64 / 1e3), unit=UNIT, ms_per_step=ms64 / k64, steps=k64,
+                              host_bytes_converted_per_step=2 * host64[0]["point_state_batch"].nbytes,
+                              h2d_bytes_per_step=agent.h2d_bytes(), d2h_bytes_per_step=64,
+                              note="update_parameters(dict of float64 ndarrays, exactly what BaseMemory.sample returns); the reference "
+                                   "pays the same conversion in torch.cuda.FloatTensor(v) (agent.py:221-222)")
+        del host64
+        # ---- dense worst case: clouds that defeat duplicate folding (every SA1 ball holds >= 64 distinct points, all 32 SA2
+        # centroids lie within one radius): M1 = B*32*64, M2 = B*32*32 live rows — the upper bound of the data-dependent cost
+        dense = []
+        for i in range(2):
+            b = synthetic.make_batch(args.batch, args.points, step=100 + i, channels=6, compact=True)
+            t = {k: torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32)).to(dev) for k, v in b.items()
+                 if k not in ("grasp_sample_batch", "batch_idx")}
+            t["noise_u"] = devb[i]["noise_u"]
+            dense.append(t)
+        dense = dense * 2
+        run(dense, 4, False)
+        msd = run(dense, K, True)
+        out["dense_worst_case"] = dict(value=n_gpus * K / (msd / 1e3), unit=UNIT, ms_per_step=msd / K,
+                                       live_rows={"sa1": int(agent.geom_s.lv[0].seg_off[-1]), "sa2": int(agent.geom_s.lv[1].seg_off[-1])},
+                                       dense_rows={"sa1": agent.B * 32 * 64, "sa2": agent.B * 32 * 32},
+                                       note="2 cm-cube objects: no duplicate rows to fold at SA1, all 32 x 32 centroid pairs live at SA2")
+        del dense
+        run(devb, 2, False)   # back to the metric's clouds for the legs below
+    if not args.no_replay:
+        # every rank runs its own device-resident store (the N>1 number is the honest end-to-end figure for a device store)
+        out["replay"] = replay_leg(agent, devb, args, run, nb, n_gpus, rank == 0 and n_gpus == 1)
     if rank == 0 and n_gpus == 1 and not args.no_replay:
-        out["replay"] = replay_leg(agent, devb, args, run, nb)
         # row f2: select_action latency (B = 1, eval-mode policy path; H2D of the cloud + one graph replay + D2H of 80 bytes)
         cloud1 = host[0]["point_state_batch"][0].numpy()
         for _ in range(4):
@@ -283,7 +331,7 @@ def main():
         world.close()
 
 
-def replay_leg(agent, devb, args, run, nb):
+def replay_leg(agent, devb, args, run, nb, n_gpus=1, gather_bench=True):
     """Row f1: the same update fed from the device-resident replay buffer (ReplayMemoryB200.sample = host index draw +
     one gather launch) instead of pinned host batches, and the gather kernel alone against the HBM roofline
     (algorithmic bytes = 2 clouds x B rows read once + written once, plus the 128-byte records)."""
@@ -319,6 +367,9 @@ def replay_leg(agent, devb, args, run, nb):
 
     run(Feed(), 4, False)
     ms = run(Feed(), args.steps, True)
+    if not gather_bench:
+        return dict(value=n_gpus * args.steps / (ms / 1e3), unit=UNIT, ms_per_step=ms / args.steps, store_transitions=cap,
+                    note="every rank feeds update_parameters from its own ReplayMemoryB200 store in HBM (max over ranks, aggregate)")
     # the gather alone: 20 launches with distinct pre-uploaded random index sets captured in one CUDA graph (no host time
     # between launches), CUDA events around the replay; store (~200 MB) + outputs (~100 MB) exceed the 126 MB L2
     from gaddpg_b200.capi import current_stream, lib

@@ -46,11 +46,14 @@ def make_cloud(rs, B, N, channels=4, centre=None, half=None, zero_frac=0.005, dt
     return cloud.astype(dtype), centre, half
 
 
-def make_batch(B, N, step=0, channels=4, dtype=np.float32, seed=1234):
-    """One replay minibatch dict (keys = what Agent.prepare_data consumes, agent.py:211-240)."""
+def make_batch(B, N, step=0, channels=4, dtype=np.float32, seed=1234, compact=False):
+    """One replay minibatch dict (keys = what Agent.prepare_data consumes, agent.py:211-240).  ``compact``: 2 cm-cube
+    objects — every SA1 ball (r = 0.02) then holds >= 64 distinct points and all 32 SA2 centroids lie within one SA2
+    radius (0.04) of each other, i.e. the ball-query groups have no duplicate slots to fold (the dense worst case)."""
     rs = np.random.RandomState(seed + step)
     action = rs.uniform(ACTION_LOW, ACTION_HIGH, size=(B, 6)).astype(np.float32)
-    cloud, centre, half = make_cloud(rs, B, N, channels, dtype=dtype)
+    cloud, centre, half = make_cloud(rs, B, N, channels, dtype=dtype, half=np.full((B, 3), 0.01) if compact else None,
+                                     zero_frac=0.0 if compact else 0.005)
     next_cloud, _, _ = make_cloud(rs, B, N, channels, centre=centre - action[:, :3].astype(np.float64), half=half, dtype=dtype)
     ret = (rs.rand(B) < 0.6).astype(np.float32) * rs.uniform(0.2, 1.0, B).astype(np.float32)
     if not (ret > 0).any():
