@@ -33,6 +33,7 @@ from .config import DEFAULTS, LOSS_KEYS
 from .engine import FEAT_LD, QA_AUX, QA_LD, QA_Q2, dp
 from .networks import PointNetFeatureB200
 
+RING = 2   # host staging slots (see AgentB200._begin_step)
 O_CRITIC, O_CRITIC_AUX, O_NGOAL_C, O_BC, O_POLICY_AUX, O_NGOAL_A, O_AC, O_PPARAM, O_CGRAD, O_CPARAM, O_CLIP, O_GNORM = range(12)
 
 
@@ -50,6 +51,47 @@ class _Sched:
     @property
     def lr(self):
         return self.opt.param_groups[0]["lr"]
+
+
+def _on_device(fn):
+    """Run a public entry point with the agent's device current: every launch goes to ``torch.cuda.current_stream()`` of
+    the CURRENT device, so an agent built with ``device="cuda:1"`` must not depend on what the caller left selected."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *a, **k):
+        if torch.cuda.current_device() == self.device.index:
+            return fn(self, *a, **k)
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **k)
+
+    return wrapped
+
+
+class PendingResult:
+    """Handle returned by ``update_parameters(..., defer=True)``: the 11 scalars of a step whose kernels may still be
+    running.  ``result()`` waits for that step only — the caller can enqueue the next step first (feed.FeedLoop)."""
+
+    def __init__(self, agent, slot, event):
+        self.agent, self.slot, self.event, self._r = agent, slot, event, None
+
+    def result(self):
+        if self._r is None:
+            self.event.synchronize()
+            self._r = self.agent._scalars(self.agent.out_host[self.slot])
+        return self._r
+
+
+def _sched_args(entry, opt_key, sch_key, lr, milestones, gamma, eps=1e-8, wd=0.0):
+    """Learning-rate schedule / Adam constants of one optimiser of the reference's net_dict (utils.py:211-234) when the
+    caller built them (model-spec ``opt_kwargs`` / ``scheduler_kwargs``), else the configured defaults."""
+    opt, sch = (entry or {}).get(opt_key), (entry or {}).get(sch_key)
+    if opt is not None and getattr(opt, "param_groups", None):
+        g = opt.param_groups[0]
+        lr, eps, wd = g.get("initial_lr", g["lr"]), g.get("eps", eps), g.get("weight_decay", wd)
+    if sch is not None and hasattr(sch, "milestones"):
+        milestones, gamma = sorted(sch.milestones.elements()), sch.gamma
+    return float(lr), list(milestones), float(gamma), float(eps), float(wd)
 
 
 def _cfg_get(cfg, k):
@@ -119,8 +161,10 @@ class AgentB200:
         return self
 
     def setup_feature_extractor(self, net_dict, eval=False):
-        """agent.py:149-164.  Accepts the reference's net_dict (net possibly wrapped in nn.DataParallel); optimisers
-        in it are not used — Adam runs fused on the arenas — but their schedulers keep driving the learning rates."""
+        """agent.py:149-164.  Accepts the reference's net_dict (net possibly wrapped in nn.DataParallel).  The torch
+        optimisers in it are not stepped — Adam runs fused on the arenas — but their hyper-parameters (lr, eps,
+        weight_decay) and their schedulers' milestones / gamma are read from it when present (model-spec ``opt_kwargs`` /
+        ``scheduler_kwargs``, utils.py:211-234); otherwise the configured defaults apply."""
         if self._pending_seeded_build:
             self._make_heads()
             self._pending_seeded_build = False
@@ -131,13 +175,22 @@ class AgentB200:
         assert isinstance(self._extractor, PointNetFeatureB200), "model_spec must select class: PointNetFeatureB200"
         self.goal_feature_extractor = net_dict.get("goal_feature_extractor", {}).get("net")
         c = self
+        fm = c.overwrite_feat_milestone or c.feat_milestones
+        e_lr, e_ms, e_g, e_eps, e_wd = _sched_args(sfe, "encoder_opt", "encoder_scheduler", c.feat_lr, fm, c.feat_gamma)
+        v_lr, v_ms, v_g, v_eps, v_wd = _sched_args(sfe, "val_encoder_opt", "val_encoder_scheduler", c.feat_lr, fm, c.feat_gamma)
+        self._adam_hp = dict(enc=(e_eps, e_wd), venc=(v_eps, v_wd), policy=(1e-5, 1e-5), critic=(1e-5, 1e-5))  # utils.py:969,993
         self._sch = NS(
             policy=_Sched(c.lr, c.policy_milestones, c.lr_gamma),
             critic=_Sched(c.value_lr, c.value_milestones, c.value_lr_gamma) if self.has_critic else None,
-            enc=_Sched(c.feat_lr, c.overwrite_feat_milestone or c.feat_milestones, c.feat_gamma),
-            venc=_Sched(c.feat_lr, c.overwrite_feat_milestone or c.feat_milestones, c.feat_gamma),  # never stepped
+            enc=_Sched(e_lr, e_ms, e_g),
+            venc=_Sched(v_lr, v_ms, v_g),  # never stepped (agent.py:179-190)
         )
         dev = self.device
+        engine._init_once(dev)
+        with torch.cuda.device(dev):
+            self._setup_device_state(dev)
+
+    def _setup_device_state(self, dev):
         self.ws = engine.Workspace(dev)
         # stream-level overlap inside a step (identical arithmetic, see _phase1): a second encoder chain and the
         # weight-gradient products run on side streams; ``overlap = False`` issues everything on one stream
@@ -148,35 +201,62 @@ class AgentB200:
         self.early_geometry_host = False
         self.side_enc = engine.SideStream(dev)
         self.side_dw = engine.SideStream(dev)
-        self.ef_p = engine.EncoderFlat(self._extractor.encoder, dev)
-        self.ef_v = engine.EncoderFlat(self._extractor.value_encoder, dev)
+        # one contiguous gradient range per optimiser phase: [policy encoder | policy] and [value encoder | critic]
+        ex = self._extractor
+        self.gpool_a = nets.GradPool(nets.GradPool.capacity_for(ex.encoder, self.policy), dev)
+        self.gpool_c = nets.GradPool(nets.GradPool.capacity_for(ex.value_encoder, self.critic), dev) if self.has_critic else None
+        self.ef_p = engine.EncoderFlat(self._extractor.encoder, dev, grad_pool=self.gpool_a)
+        self.ef_v = engine.EncoderFlat(self._extractor.value_encoder, dev, grad_pool=self.gpool_c)
         self._extractor._flats[("policy", str(dev))] = self.ef_p
         self._extractor._flats[("value", str(dev))] = self.ef_v
         # per-pass staging of the BatchNorm running statistics (F1, F3: value encoder | F2, F4: policy encoder)
         self.bnst = {1: engine.BNStage(self.ef_v, dev), 2: engine.BNStage(self.ef_p, dev), 3: engine.BNStage(self.ef_v, dev),
                      4: engine.BNStage(self.ef_p, dev)}
-        self.pf = engine.PolicyFlat(self.policy, dev)
+        self.pf = engine.PolicyFlat(self.policy, dev, grad_pool=self.gpool_a)
         self.pft = engine.PolicyFlat(self.policy_target, dev, with_opt=False)
         if self.has_critic:
-            self.cf = engine.CriticFlat(self.critic, dev)
+            self.cf = engine.CriticFlat(self.critic, dev, grad_pool=self.gpool_c)
             self.cft = engine.CriticFlat(self.critic_target, dev, with_opt=False)
             self.tau_soft, self.tau_hard = self.cft.tau_vectors(self.tau)
-        self.Cp_policy = min(self._extractor.policy_input_dim, 3 + self.extra_latent)
-        self.Cb_value = self._extractor.critic_input_dim - min(3 + self.extra_latent, self._extractor.critic_input_dim)
-        self.Cp_value = self._extractor.critic_input_dim - self.Cb_value
+        self._set_channels(3 + self.extra_latent)
         self.opt_steps = dict(policy=0, critic=0, enc=0, venc=0)
+        # host staging is a ring of RING slots (pinned): a slot is rewritten only after the step that read it has finished
+        # on the GPU, so ``update_parameters(..., defer=True)`` may run one step ahead of the device (feed.FeedLoop)
         self.dyn = torch.zeros(4, 2, dtype=torch.float32, device=dev)
-        self.dyn_host = torch.zeros(4, 2, dtype=torch.float32).pin_memory()
+        self.dyn_host = [torch.zeros(4, 2, dtype=torch.float32).pin_memory() for _ in range(RING)]
         self.out = torch.zeros(16, dtype=torch.float32, device=dev)
-        self.out_host = torch.zeros(16, dtype=torch.float32).pin_memory()
+        self.out_host = [torch.zeros(16, dtype=torch.float32).pin_memory() for _ in range(RING)]
+        self._slot_done = [torch.cuda.Event() for _ in range(RING)]
+        self._slot = 0
+        self._pending = [None] * RING
+        self._pending_reduce = []
+        self.step_start_events = self.step_end_events = None    # feed.FeedLoop installs lists here to measure the GPU idle gap between steps
+        self.split_reduce = True         # sharded runs: all-reduce everything but SA1's gradients behind the SA1 backward
         self._shape = None
         self._graphs = {}
         self.use_graph = True
         self._built = True
+        self.policy.sample = self.policy_sample   # reference call style: agent.policy.sample(feat) (networks.py:353-371)
+
+    def _set_channels(self, C):
+        """Per-point / broadcast channel split of the two encoders for clouds with ``C`` channels — the same rule as the
+        plug-in path (networks.PointNetFeatureB200.split_input, reference networks.py:232-242): the policy encoder takes
+        the first policy_input_dim cloud channels, the value encoder min(C, critic_input_dim) cloud channels followed by
+        the first critic_input_dim - that many action channels."""
+        ex = self._extractor
+        if C < ex.policy_input_dim:
+            raise ValueError("clouds have %d channels, the policy encoder needs %d" % (C, ex.policy_input_dim))
+        self.Cp_policy = ex.policy_input_dim
+        self.Cp_value = min(C, ex.critic_input_dim)
+        self.Cb_value = ex.critic_input_dim - self.Cp_value
+        if self.Cb_value > 6:
+            raise ValueError("value encoder would need %d action channels (critic_input_dim %d, cloud channels %d)"
+                             % (self.Cb_value, ex.critic_input_dim, C))
 
     # ---- buffers sized for one (B, C, N) ------------------------------------------------------------------
     def _alloc(self, B, C, Np):
         dev = self.device
+        self._set_channels(C)
         skip = 6 if Np != 1024 else 0
         N = Np - skip
         self._shape = (B, C, Np)
@@ -191,12 +271,13 @@ class AgentB200:
             self._vec_off[n] = (total, w)
             total += seg(B * w)
         self.vec = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.vec_host = torch.zeros(total, dtype=torch.float32).pin_memory()
-        self.cloud_host = torch.zeros(B, C, Np, dtype=torch.float32).pin_memory()
-        self.next_cloud_host = torch.zeros(B, C, Np, dtype=torch.float32).pin_memory()
+        self.vec_host = [torch.zeros(total, dtype=torch.float32).pin_memory() for _ in range(RING)]
+        self._cloud_shape = (B, C, Np)
+        self._cloud_host = [None] * RING        # pinned cloud staging: allocated on first use (host-fed batches only)
+        self._next_cloud_host = [None] * RING
         self.v = NS(**{n: self.vec[o: o + B * w].view(B, w) if w > 1 else self.vec[o: o + B] for n, (o, w) in self._vec_off.items()})
-        self.vh = NS(**{n: self.vec_host[o: o + B * w].view(B, w) if w > 1 else self.vec_host[o: o + B]
-                        for n, (o, w) in self._vec_off.items()})
+        self.vh = [NS(**{n: vh[o: o + B * w].view(B, w) if w > 1 else vh[o: o + B] for n, (o, w) in self._vec_off.items()})
+                   for vh in self.vec_host]
         self.geom_s = engine.Geometry(B, N, dev)
         self.geom_n = engine.Geometry(B, N, dev)
         caps = (self.geom_s.lv[0].cap, self.geom_s.lv[1].cap)
@@ -223,6 +304,7 @@ class AgentB200:
         return self._bc_buf[slot]
 
     # ---- data staging (agent.py:211-240 prepare_data) ------------------------------------------------------
+    @_on_device
     def prepare_data(self, batch, noise_u=None, after_clouds=None):
         """Stage one replay minibatch (the dict BaseMemory.sample returns, replay_memory.py:166-176) into the device
         input buffers.  Host batches go through pinned buffers (float64 clouds are converted on the host like
@@ -239,6 +321,7 @@ class AgentB200:
             if self._shape != (B, C, Np):
                 self._alloc(B, C, Np)
             mem.gather_into(batch.batch_idx, self.cloud, self.next_cloud if self.has_critic else None, self.vec, self._vec_off)
+            mem._lazy.pop(id(batch), None)   # consumed: a later write to the buffer need not snapshot it
             if after_clouds is not None:
                 after_clouds()
             if self.has_critic:
@@ -250,28 +333,32 @@ class AgentB200:
         if self._shape != (B, C, Np):
             self._alloc(B, C, Np)
 
-        def put_cloud(dst, stage, src):
+        slot = self._slot
+
+        def put_cloud(dst, ring, src):
             if torch.is_tensor(src) and src.dtype == torch.float32 and (src.is_cuda or src.is_pinned()):
                 dst.copy_(src, non_blocking=True)       # already pinned fp32 (or device resident): straight DMA
             else:
-                stage.copy_(torch.as_tensor(src))        # float64 ndarray of the reference's replay buffer: convert on host
-                dst.copy_(stage, non_blocking=True)
+                if ring[slot] is None:
+                    ring[slot] = torch.zeros(self._cloud_shape, dtype=torch.float32).pin_memory()
+                ring[slot].copy_(torch.as_tensor(src))   # float64 ndarray of the reference's replay buffer: convert on host
+                dst.copy_(ring[slot], non_blocking=True)
 
-        put_cloud(self.cloud, self.cloud_host, cloud)
+        put_cloud(self.cloud, self._cloud_host, cloud)
         if self.has_critic:
             nxt = batch["next_point_state_batch"]
             # only the target chain (side stream) reads it: its H2D copy overlaps the state chain.  A device-resident
             # batch was produced on the current stream, so its D2D copy stays there
             if self.overlap and not (torch.is_tensor(nxt) and nxt.is_cuda):
                 with torch.cuda.stream(self.side_enc.stream):
-                    put_cloud(self.next_cloud, self.next_cloud_host, nxt)
+                    put_cloud(self.next_cloud, self._next_cloud_host, nxt)
             else:
-                put_cloud(self.next_cloud, self.next_cloud_host, nxt)
+                put_cloud(self.next_cloud, self._next_cloud_host, nxt)
         on_device = torch.is_tensor(cloud) and cloud.is_cuda
         early = after_clouds is not None and (on_device or self.early_geometry_host)
         if early:
             after_clouds()
-        tgt = self.v if on_device else self.vh   # device-resident batch: D2D straight into the kernel inputs
+        tgt = self.v if on_device else self.vh[slot]   # device-resident batch: D2D straight into the kernel inputs
 
         def put(dst, key_or_val):
             src = batch[key_or_val] if isinstance(key_or_val, str) else key_or_val
@@ -286,7 +373,7 @@ class AgentB200:
             # torch.rand_like in get_noise_delta (utils.py:575) unless the caller injects the uniform draw
             put(tgt.noise_u, torch.rand(B, 6, device=self.device if on_device else "cpu") if noise_u is None else noise_u)
         if not on_device:
-            self.vec.copy_(self.vec_host, non_blocking=True)
+            self.vec.copy_(self.vec_host[slot], non_blocking=True)
         if after_clouds is not None and not early:
             after_clouds()
 
@@ -305,7 +392,8 @@ class AgentB200:
         self._run(("gs",), lambda: self.geom_s.build(self.cloud, self.skip))
 
     def h2d_bytes(self):
-        n = self.cloud_host.numel() * (2 if self.has_critic else 1) + self.vec_host.numel()
+        B, C, Np = self._cloud_shape
+        n = B * C * Np * (2 if self.has_critic else 1) + self.vec_host[0].numel()
         return 4 * n
 
     # ---- schedules ---------------------------------------------------------------------------------------
@@ -342,22 +430,55 @@ class AgentB200:
             if n in names:
                 self.opt_steps[n] += 1
             t = max(self.opt_steps[n], 1)
-            self.dyn_host[i, 0] = lrs[n] / (1.0 - 0.9 ** t)
-            self.dyn_host[i, 1] = math.sqrt(1.0 - 0.999 ** t)
-        self.dyn.copy_(self.dyn_host, non_blocking=True)
+            self.dyn_host[self._slot][i, 0] = lrs[n] / (1.0 - 0.9 ** t)
+            self.dyn_host[self._slot][i, 1] = math.sqrt(1.0 - 0.999 ** t)
+        self.dyn.copy_(self.dyn_host[self._slot], non_blocking=True)
 
     # ---- fused optimiser helpers ---------------------------------------------------------------------------
-    def _adam(self, arena, off, n, which, eps, wd, clip=None, write_back=0):
+    def _adam(self, arena, off, n, which, clip=None, write_back=0):
         i = ("policy", "critic", "enc", "venc").index(which)
+        eps, wd = self._adam_hp[which]
         gs = 1.0  # sharded runs average the gradients right after the all-reduce (see _allreduce)
         lib.gaddpg_adam_step(arena.p.data_ptr() + 4 * off, arena.g.data_ptr() + 4 * off, arena.m.data_ptr() + 4 * off,
                              arena.v.data_ptr() + 4 * off, n, 0.0, 0.9, 0.999, eps, wd, 0, self.dyn.data_ptr() + 8 * i, gs,
                              clip, write_back, None, 0.0, current_stream())
 
-    def _allreduce(self, arenas):
-        if self.world is not None and self.world.size > 1:
-            for a in arenas:
-                self.world.all_reduce_mean(a.g)  # DDP semantics: per-rank mean losses averaged over ranks
+    # ---- gradient all-reduce (sharded runs): ONE contiguous range per optimiser phase (nets.GradPool) ----------------
+    # DDP semantics: per-rank mean losses averaged over ranks.  The pool is laid out [encoder: SA1 | SA2 SA3 FC | heads];
+    # with ``split_reduce`` everything behind the SA1 block — 99 % of the bytes, complete once the SA2 backward is done —
+    # is reduced asynchronously on the collective's own stream while the SA1 backward (the longest part of a backward
+    # pass) still runs, and only SA1's ~13 k gradients are reduced after it; otherwise one blocking call per phase.
+    def _sharded(self):
+        return self.world is not None and self.world.size > 1
+
+    def _reduce_early(self, pool, ef):
+        if self._sharded() and self.split_reduce:
+            self._pending_reduce = [self.world.all_reduce_mean(pool.used[ef.sa1_end:], async_op=True)]
+
+    def _reduce_late(self, pool, ef):
+        if not self._sharded():
+            return
+        if self.split_reduce:
+            self._pending_reduce.append(self.world.all_reduce_mean(pool.used[: ef.sa1_end], async_op=True))
+            for h in self._pending_reduce:
+                self.world.wait(h)      # stream-side wait: the host does not block
+            self._pending_reduce = []
+        else:
+            self.world.all_reduce_mean(pool.used)
+
+    def _begin_step(self):
+        """Pick the host staging slot of this step; wait (host side) until the step that last used it has finished on the
+        GPU, so its pinned buffers may be overwritten."""
+        self._slot = (self._slot + 1) % RING
+        old = self._pending[self._slot]
+        if old is not None:
+            old.result()                 # a deferred result nobody read yet: keep its scalars before the slot is reused
+            self._pending[self._slot] = None
+        self._slot_done[self._slot].synchronize()
+        if self.step_start_events is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.step_start_events.append(e)
 
     def _run(self, key, fn):
         """Run ``fn`` eagerly the first time for a key, then capture and replay it as a CUDA graph."""
@@ -381,10 +502,21 @@ class AgentB200:
         g.replay()
 
     # ---- statistics / result ----------------------------------------------------------------------------
-    def _finish(self):
-        self.out_host.copy_(self.out, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        o = self.out_host
+    def _finish(self, defer=False):
+        slot = self._slot
+        self.out_host[slot].copy_(self.out, non_blocking=True)
+        self._slot_done[slot].record()
+        if self.step_end_events is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.step_end_events.append(e)
+        if defer:
+            self._pending[slot] = PendingResult(self, slot, self._slot_done[slot])
+            return self._pending[slot]
+        self._slot_done[slot].synchronize()
+        return self._scalars(self.out_host[slot])
+
+    def _scalars(self, o):
         r = {k: 0.0 for k in LOSS_KEYS}
         r.update(bc_loss=float(o[O_BC]), policy_grasp_aux_loss=float(o[O_POLICY_AUX]), policy_param=float(o[O_PPARAM]))
         if self.has_critic:
@@ -396,22 +528,78 @@ class AgentB200:
 
     # ---- inference (agent.py:82-125) ----------------------------------------------------------------------
     @torch.no_grad()
+    @_on_device
     def select_action(self, state, actions=None, goal_state=None, vis=False, remain_timestep=0, grasp_set=None,
                       gt_goal_rollout=False, repeat=False, eps=None):
         cloud = torch.as_tensor(np.asarray(state[0][0], dtype=np.float32))[None].to(self.device).contiguous()
-        return self._act(cloud, float(remain_timestep), eps)
+        pi, logp, act, aux = self._act(cloud, float(remain_timestep), eps)
+        return pi[0], logp[0], act[0], aux[0]
 
-    def _act(self, cloud, remain, eps):
-        """Eval-mode policy path for a (B, C, N+6) cloud batch: geometry, policy encoder (running BatchNorm statistics),
-        policy heads, tanh-mean / sampled action / log-prob / aux.  ~70 launches with fixed shapes and static buffers:
-        the first call of a shape runs eagerly, the second captures a CUDA graph, later calls replay it (one graph launch
-        + one 128-byte read-back per action; rollouts in train_test_offline.test are launch-latency bound otherwise)."""
-        dev = self.device
+    @torch.no_grad()
+    @_on_device
+    def select_action_batch(self, point_state_batch, remain_timestep=0, eps=None):
+        """Batched inference — what the reference's deployment script does by hand for a set of simulated view points
+        (test_realworld_ros_final.py:1257-1261: ``extract_feature(img, point_state_batch, value=False, time_batch=time)``
+        followed by ``policy.sample``): eval-mode policy path for a (B, C, N[+6]) batch of clouds and per-sample (or one
+        scalar) remaining time steps.  Returns (tanh-mean action (B,6), log-prob (B,), sampled action (B,6), aux (B,E))."""
+        cloud = point_state_batch if torch.is_tensor(point_state_batch) else torch.as_tensor(np.asarray(point_state_batch, dtype=np.float32))
+        cloud = cloud.to(self.device, dtype=torch.float32).contiguous()
+        assert cloud.dim() == 3, "point_state_batch must be (B, C, N)"
+        return self._act(cloud, remain_timestep, eps)
+
+    @torch.no_grad()
+    @_on_device
+    def extract_feature(self, image_batch, point_state_batch, action_batch=None, goal_batch=None, traj_point_state=None,
+                        time_batch=None, vis=False, value=False, repeat=False, train=False):
+        """ddpg.py:36-59 / bc.py:27-38 as an inference entry point (the update itself never calls this): eval-mode
+        BatchNorm unless ``train``; ``value=True`` runs the value encoder on cloud (+) action.  Returns a NEW device tensor
+        (B, 513) = [z | time] like the reference (use_time)."""
+        cloud = point_state_batch if torch.is_tensor(point_state_batch) else torch.as_tensor(np.asarray(point_state_batch, dtype=np.float32))
+        cloud = cloud.to(self.device, dtype=torch.float32).contiguous()
         B, C, Np = cloud.shape
+        skip = 6 if Np != 1024 else 0
+        st = self._act_state(B, C, Np)
+        t = torch.zeros(B, device=self.device) if time_batch is None else torch.as_tensor(time_batch, dtype=torch.float32).to(self.device).view(B)
+        st.geom.build(cloud, skip)
+        if value:
+            assert action_batch is not None, "value features need the action (channel-wise concat, utils.py:291-297)"
+            Cp = min(C, self._extractor.critic_input_dim)
+            a = torch.as_tensor(action_batch, dtype=torch.float32).to(self.device).view(B, -1)[:, : self._extractor.critic_input_dim - Cp].contiguous()
+            feat = engine.encoder_forward(self.ws, self.ef_v, st.geom, cloud, skip, Cp, a if a.shape[1] else None, st.ctx,
+                                          time=t, train=train, keep=False)
+        else:
+            feat = engine.encoder_forward(self.ws, self.ef_p, st.geom, cloud, skip, self.Cp_policy, None, st.ctx, time=t, train=train,
+                                          keep=False)
+        return feat[:, :513].clone()
+
+    @torch.no_grad()
+    @_on_device
+    def policy_sample(self, feat, eps=None):
+        """GaussianPolicy.sample (networks.py:353-371) on a (B, 513) device feature tensor through the CUDA heads:
+        (tanh-mean action, log-prob, sampled action, aux) as device tensors.  Also bound as ``agent.policy.sample``."""
+        B = feat.shape[0]
+        f = torch.zeros(B, FEAT_LD, device=self.device)
+        f[:, :513] = feat
+        pc = engine.policy_ctx(B, self.pf, self.device)
+        raw = engine.policy_forward(self.pf, f, pc, B)
+        s = current_stream()
+        act, logp, aux = torch.zeros(B, 6, device=self.device), torch.zeros(B, device=self.device), torch.zeros(B, 7, device=self.device)
+        e = torch.randn(B, 6, device=self.device) if eps is None else torch.as_tensor(eps, dtype=torch.float32).to(self.device).view(B, 6)
+        lib.gaddpg_policy_head_fwd(dp(raw), self.pf.NHp, B, dp(pc.pi), s)
+        lib.gaddpg_policy_sample(dp(raw), self.pf.NHp, 6 + self.pf.E, dp(e.contiguous()), B, dp(act), dp(logp), s)
+        if self.policy_aux:
+            lib.gaddpg_quat_head(raw.data_ptr() + 4 * 6, self.pf.NHp, B, dp(aux), s)
+        else:
+            aux[:, : self.pf.E].copy_(raw[:, 6:6 + self.pf.E])
+        return pc.pi, logp.view(B, 1), act, aux[:, : (7 if self.policy_aux else self.pf.E)]
+
+    def _act_state(self, B, C, Np):
+        """Static buffers of the inference path for one input shape (a captured graph is bound to them)."""
+        dev = self.device
         skip = 6 if Np != 1024 else 0
         key = ("act", B, C, Np)
         if not hasattr(self, "_act_states"):
-            self._act_states = {}     # one set of static buffers per input shape: a captured graph is bound to them
+            self._act_states = {}
         st = self._act_states.get(key)
         if st is None:
             geom = engine.Geometry(B, Np - skip, dev)
@@ -420,11 +608,23 @@ class AgentB200:
                     cloud=torch.zeros(B, C, Np, device=dev), time=torch.zeros(B, device=dev), eps=torch.zeros(B, 6, device=dev),
                     # [pi(6) | sampled action(6) | aux(7) | log-prob(1)] per sample, one D2H
                     res=torch.zeros(B, 20, device=dev), res_host=torch.zeros(B, 20).pin_memory(),
-                    in_host=torch.zeros(B, 7).pin_memory(), in_dev=torch.zeros(B, 7, device=dev))
+                    in_host=torch.zeros(B, 7).pin_memory(), in_dev=torch.zeros(B, 7, device=dev),
+                    ctx_act=torch.zeros(B, 6, device=dev), ctx_logp=torch.zeros(B, device=dev), ctx_aux=torch.zeros(B, 7, device=dev))
             self._act_states[key] = st
+        return st
+
+    def _act(self, cloud, remain, eps):
+        """Eval-mode policy path for a (B, C, N+6) cloud batch: geometry, policy encoder (running BatchNorm statistics),
+        policy heads, tanh-mean / sampled action / log-prob / aux.  ~70 launches with fixed shapes and static buffers:
+        the first call of a shape runs eagerly, the second captures a CUDA graph, later calls replay it (one graph launch
+        + one 128-byte read-back per action; rollouts in train_test_offline.test are launch-latency bound otherwise)."""
+        B, C, Np = cloud.shape
+        skip = 6 if Np != 1024 else 0
+        st = self._act_state(B, C, Np)
+        key = st.key
         st.cloud.copy_(cloud, non_blocking=True)
         st.in_host[:, :6] = torch.randn(B, 6) if eps is None else torch.as_tensor(eps, dtype=torch.float32).view(B, 6)
-        st.in_host[:, 6] = remain
+        st.in_host[:, 6] = torch.as_tensor(remain, dtype=torch.float32)   # scalar or (B,)
         st.in_dev.copy_(st.in_host, non_blocking=True)
 
         def fn():
@@ -445,14 +645,12 @@ class AgentB200:
                 st.ctx_aux[:, : self.pf.E].copy_(raw[:, 6:6 + self.pf.E])
             pi.copy_(st.pc.pi), act.copy_(st.ctx_act), aux.copy_(st.ctx_aux), logp.copy_(st.ctx_logp)
 
-        if not hasattr(st, "ctx_act"):
-            st.ctx_act, st.ctx_logp, st.ctx_aux = torch.zeros(B, 6, device=dev), torch.zeros(B, device=dev), torch.zeros(B, 7, device=dev)
         self._run(key, fn)
         st.res_host.copy_(st.res, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         r = st.res_host.numpy()
         E = 7 if self.policy_aux else self.pf.E
-        return r[0, 0:6].copy(), r[0, 19].copy(), r[0, 6:12].copy(), r[0, 12:12 + E].copy()
+        return r[:, 0:6].copy(), r[:, 19].copy(), r[:, 6:12].copy(), r[:, 12:12 + E].copy()
 
     # ---- weights (ddpg.py:22-34, bc.py:15-25) -------------------------------------------------------------
     def state_dicts(self):
@@ -462,6 +660,7 @@ class AgentB200:
             d["critic"], d["critic_target"] = self.critic.state_dict(), self.critic_target.state_dict()
         return d
 
+    @_on_device
     def load_state_dicts(self, d):
         self.policy.load_state_dict(d["policy"])
         self.policy_target.load_state_dict(d["policy_target"])
@@ -471,6 +670,7 @@ class AgentB200:
             self.critic_target.load_state_dict(d["critic_target"])
         self.refresh_all()
 
+    @_on_device
     def refresh_all(self):
         for f in (self.ef_p, self.ef_v, self.pf, self.pft) + ((self.cf, self.cft) if self.has_critic else ()):
             f.refresh_derived()
@@ -490,12 +690,13 @@ class AgentB200:
             # the whole-extractor optimiser is never stepped (only its scheduler is, agent.py:187-189)
             ("state_feat", "opt", "sch", list(ex.parameters()), lambda i, p: None, None, self._sch.enc, 1e-8, 0.0),
             ("state_feat", "encoder_opt", "encoder_sch", list(ex.encoder.parameters()), checkpoint.arena_moments(self.ef_p.arena),
-             "enc", self._sch.enc, 1e-8, 0.0),
+             "enc", self._sch.enc) + self._adam_hp["enc"],
             ("state_feat", "val_encoder_opt", "val_encoder_sch", list(ex.value_encoder.parameters()),
-             checkpoint.arena_moments(self.ef_v.arena), "venc", self._sch.venc, 1e-8, 0.0),
+             checkpoint.arena_moments(self.ef_v.arena), "venc", self._sch.venc) + self._adam_hp["venc"],
         ]
         return rows
 
+    @_on_device
     def save_model(self, step, output_dir="", surfix="latest", actor_path=None, critic_path=None, goal_feat_path=None,
                    state_feat_path=None):
         """agent.py:282-352: same three files, same dict keys, torch-format ``Adam`` / ``MultiStepLR`` state dicts
@@ -518,6 +719,7 @@ class AgentB200:
             checkpoint.save(d, files[f])
         return files
 
+    @_on_device
     def load_model(self, output_dir, surfix="latest", set_init_step=False, reinit_value_feat=False):
         """agent.py:354-431.  Returns the restored ``update_step`` (0 when there is no feature-extractor file)."""
         import os
@@ -616,16 +818,28 @@ class DDPGB200(AgentB200):
         qat = engine.critic_forward(self.cft, f3, self.cct, B, nb=2)
         lib.gaddpg_td3_target(dp(qat), QA_LD, QA_Q2, dp(v.reward), dp(v.done), float(self.gamma), B, dp(self.y), s)
 
-    def _phase1_critic(self):
+    def _phase1_critic(self, part="all"):
+        """``part``: "all", or "a" (losses, critic backward, value-encoder backward down to SA2) / "b" (SA1 backward) when
+        the sharded run reduces the upper gradients in between (_reduce_early)."""
         B, ws, v, s = self.B, self.ws, self.v, current_stream()
-        for k in (1, 3, 2, 4):
-            self.bnst[k].apply()
         qa, f1 = self.cc1.qa, self.ctx_v1.feat
-        lib.gaddpg_critic_loss(dp(qa), QA_LD, QA_Q2, QA_AUX, dp(self.y), dp(v.perturb_flag), dp(v.ret), dp(v.goal),
-                               1 if self.critic_aux else 0, B, 1.0, dp(self.cc1.dqa), self.out.data_ptr() + 4 * O_CRITIC, s)
-        with engine.side_dw(self.side_dw if self.overlap else None):
-            engine.critic_backward(ws, self.cf, f1, self.cc1, B, self.cf.nb, self.ctx_v1, self.sc, accumulate=0)     # B1
-            engine.encoder_backward(ws, self.ef_v, self.ctx_v1, self.sc, want_dw=True, want_dbc=False, accumulate=0)
+        dw = self.side_dw if self.overlap else None
+        if part != "b":
+            for k in (1, 3, 2, 4):
+                self.bnst[k].apply()
+            lib.gaddpg_critic_loss(dp(qa), QA_LD, QA_Q2, QA_AUX, dp(self.y), dp(v.perturb_flag), dp(v.ret), dp(v.goal),
+                                   1 if self.critic_aux else 0, B, 1.0, dp(self.cc1.dqa), self.out.data_ptr() + 4 * O_CRITIC, s)
+        if part == "all":
+            with engine.side_dw(dw):
+                engine.critic_backward(ws, self.cf, f1, self.cc1, B, self.cf.nb, self.ctx_v1, self.sc, accumulate=0)     # B1
+                engine.encoder_backward(ws, self.ef_v, self.ctx_v1, self.sc, want_dw=True, want_dbc=False, accumulate=0)
+        elif part == "a":
+            with engine.side_dw(dw):
+                engine.critic_backward(ws, self.cf, f1, self.cc1, B, self.cf.nb, self.ctx_v1, self.sc, accumulate=0)
+                engine.encoder_backward(ws, self.ef_v, self.ctx_v1, self.sc, want_dw=True, want_dbc=False, accumulate=0, part="upper")
+        else:
+            with engine.side_dw(dw):
+                engine.encoder_backward(ws, self.ef_v, self.ctx_v1, self.sc, want_dw=True, want_dbc=False, accumulate=0, part="sa1")
 
     def _phase1(self, sig):
         if self.overlap:
@@ -638,17 +852,26 @@ class DDPGB200(AgentB200):
         else:
             self._run(("p1s",) + sig, self._phase1_state)
             self._run(("p1t",) + sig, lambda: self._phase1_target(self.ws))
-        self._run(("p1c",) + sig, self._phase1_critic)
+        if self._sharded() and self.split_reduce:
+            self._run(("p1ca",) + sig, lambda: self._phase1_critic("a"))
+            self._reduce_early(self.gpool_c, self.ef_v)
+            self._run(("p1cb",) + sig, lambda: self._phase1_critic("b"))
+        else:
+            self._run(("p1c",) + sig, self._phase1_critic)
 
     # -- phase 2: critic/value-encoder step, then the actor side -----------------------------------------------
-    def _phase2(self, even):
+    def _phase2(self, even, part="all"):
         B, ws, v, s = self.B, self.ws, self.v, current_stream()
         dw = self.side_dw if self.overlap else None
+        if part == "b":
+            with engine.side_dw(dw):
+                engine.encoder_backward(ws, self.ef_p, self.ctx_p, self.sc, want_dw=True, want_dbc=False, accumulate=0, part="sa1")
+            return
         cA = self.cf.arena
         lib.gaddpg_clip_coef(dp(cA.g), cA.n, float(self.clip_grad), self.out.data_ptr() + 4 * O_CLIP,
                              self.out.data_ptr() + 4 * O_GNORM, dp(ws.red), s)
-        self._adam(self.ef_v.arena, 0, self.ef_v.arena.n, "venc", 1e-8, 0.0)
-        self._adam(cA, 0, cA.n, "critic", 1e-5, 1e-5, clip=self.out.data_ptr() + 4 * O_CLIP, write_back=1)
+        self._adam(self.ef_v.arena, 0, self.ef_v.arena.n, "venc")
+        self._adam(cA, 0, cA.n, "critic", clip=self.out.data_ptr() + 4 * O_CLIP, write_back=1)
         self.ef_v.refresh_derived()
         self.cf.refresh_derived()
         f4 = self.ctx_p.feat                                                                                     # F4: phase 1
@@ -673,16 +896,17 @@ class DDPGB200(AgentB200):
                               dp(self.pc.draw), self.pf.NHp, self.out.data_ptr() + 4 * O_BC, s)
         with engine.side_dw(dw):
             engine.policy_backward(ws, self.pf, f4, self.pc, B, n_grad, self.ctx_p, self.sc, accumulate=0)          # B2
-            engine.encoder_backward(ws, self.ef_p, self.ctx_p, self.sc, want_dw=True, want_dbc=False, accumulate=0)
+            engine.encoder_backward(ws, self.ef_p, self.ctx_p, self.sc, want_dw=True, want_dbc=False, accumulate=0,
+                                    part="upper" if part == "a" else "all")
 
     # -- phase 3: actor step, targets, statistics --------------------------------------------------------------
     def _phase3(self, hard):
         ws, s = self.ws, current_stream()
         ranges, _ = self.pf.adam_ranges(self.policy_aux)
         for off, n in ranges:
-            self._adam(self.pf.arena, off, n, "policy", 1e-5, 1e-5)
+            self._adam(self.pf.arena, off, n, "policy")
         if self.train_feature:
-            self._adam(self.ef_p.arena, 0, self.ef_p.arena.n, "enc", 1e-8, 0.0)
+            self._adam(self.ef_p.arena, 0, self.ef_p.arena.n, "enc")
         lib.gaddpg_polyak(dp(self.pft.arena.p), dp(self.pf.arena.p), self.pf.arena.n, float(self.tau), s)
         lib.gaddpg_polyak_vec(dp(self.cft.arena.p), dp(self.cf.arena.p), dp(self.tau_soft), self.cf.arena.n, s)
         if hard:
@@ -693,8 +917,11 @@ class DDPGB200(AgentB200):
         lib.gaddpg_absmax(dp(self.cf.arena.g), self.cf.arena.n, self.out.data_ptr() + 4 * O_CGRAD, dp(ws.red), s)
         lib.gaddpg_absmax(dp(self.cf.arena.p), self.cf.arena.n, self.out.data_ptr() + 4 * O_CPARAM, dp(ws.red), s)
 
-    def update_parameters(self, batch_data, updates=None, k=None, test=False, noise_u=None, staged=False):
-        """ddpg.py:146-185.  ``staged=True``: the batch is already in the device buffers (bench/value path)."""
+    @_on_device
+    def update_parameters(self, batch_data, updates=None, k=None, test=False, noise_u=None, staged=False, defer=False):
+        """ddpg.py:146-185.  ``staged=True``: the batch is already in the device buffers (bench/value path).
+        ``defer=True``: return a ``PendingResult`` instead of waiting for the step's scalars."""
+        self._begin_step()
         if not staged:
             self.prepare_data(batch_data, noise_u, after_clouds=self._geometry)
         else:
@@ -704,12 +931,17 @@ class DDPGB200(AgentB200):
         sig = (self._mix_idx(),)
         self._set_dyn(("critic", "venc", "policy") + (("enc",) if self.train_feature else ()))
         self._phase1(sig)
-        self._allreduce([self.ef_v.arena, self.cf.arena])
-        self._run(("p2", even) + sig, lambda: self._phase2(even))
-        self._allreduce([self.ef_p.arena, self.pf.arena])
+        self._reduce_late(self.gpool_c, self.ef_v)
+        if self._sharded() and self.split_reduce:
+            self._run(("p2a", even) + sig, lambda: self._phase2(even, "a"))
+            self._reduce_early(self.gpool_a, self.ef_p)
+            self._run(("p2b", even) + sig, lambda: self._phase2(even, "b"))
+        else:
+            self._run(("p2", even) + sig, lambda: self._phase2(even))
+        self._reduce_late(self.gpool_a, self.ef_p)
         self._run(("p3", hard) + sig, lambda: self._phase3(hard))
         self.update_step += 1
-        return self._finish()
+        return self._finish(defer)
 
 
 class BCB200(AgentB200):
@@ -742,26 +974,28 @@ class BCB200(AgentB200):
         ws, s = self.ws, current_stream()
         ranges, _ = self.pf.adam_ranges(self.policy_aux)
         for off, n in ranges:
-            self._adam(self.pf.arena, off, n, "policy", 1e-5, 1e-5)
+            self._adam(self.pf.arena, off, n, "policy")
         if self.train_feature:
-            self._adam(self.ef_p.arena, 0, self.ef_p.arena.n, "enc", 1e-8, 0.0)
+            self._adam(self.ef_p.arena, 0, self.ef_p.arena.n, "enc")
         lib.gaddpg_polyak(dp(self.pft.arena.p), dp(self.pf.arena.p), self.pf.arena.n, float(self.tau), s)
         for f in (self.pf, self.ef_p, self.pft):
             f.refresh_derived()
         lib.gaddpg_absmax(dp(self.pf.arena.p), self.pf.arena.n, self.out.data_ptr() + 4 * O_PPARAM, dp(ws.red), s)
 
-    def update_parameters(self, batch_data, updates=None, k=None, noise_u=None, staged=False):
+    @_on_device
+    def update_parameters(self, batch_data, updates=None, k=None, noise_u=None, staged=False, defer=False):
         """bc.py:40-56."""
+        self._begin_step()
         if not staged:
             self.prepare_data(batch_data, after_clouds=self._geometry)
         else:
             self._geometry()
         self._set_dyn(("policy",) + (("enc",) if self.train_feature else ()))
         self._run(("bc",), self._phase)
-        self._allreduce([self.ef_p.arena, self.pf.arena])
+        self._reduce_late(self.gpool_a, self.ef_p)   # BC is one short backward: a single blocking call
         self._run(("bcopt",), self._phase_opt)
         self.update_step += 1
-        return self._finish()
+        return self._finish(defer)
 
 
 def make_agent(policy="DDPG", seed=123456, device=None, world=None, **overrides):

@@ -119,3 +119,23 @@ def load(path, map_location="cpu", trusted=None):
     except pickle.UnpicklingError as e:
         raise RuntimeError("%s needs full pickle to load (%s); pass trusted=True / set GADDPG_TRUSTED_CHECKPOINTS=1 if you "
                            "trust its origin" % (path, str(e).splitlines()[0])) from e
+
+
+def migrate_model(in_model, out_model, surfix="latest", grasp_model=None, env_name="PandaYCBEnv"):
+    """/root/reference/core/utils.py:319-334: copy a (BC or DDPG) checkpoint's files to DDPG names in another directory
+    — how a behaviour-cloning run is turned into the initialisation of a DDPG run.  Same file set and the same fallback
+    (``BC_*`` if present, else ``DDPG_*``, sticky once switched, like the reference's loop); returns the copies made."""
+    import shutil
+
+    in_policy, out_policy, done = "BC", "DDPG", []
+    os.makedirs(out_model, exist_ok=True)
+    for part in ("actor", "state_feat", "goal_feat", "critic"):
+        name = "{}_{}_{}".format(part, env_name, surfix)
+        if not os.path.exists("{}/{}_{}".format(in_model, in_policy, name)):
+            in_policy = "DDPG"
+        src, dst = "{}/{}_{}".format(in_model, in_policy, name), "{}/{}_{}".format(out_model, out_policy, name)
+        if os.path.exists(src):
+            if os.path.abspath(src) != os.path.abspath(dst):
+                shutil.copyfile(src, dst)
+            done.append((src, dst))
+    return done

@@ -305,7 +305,15 @@ __global__ void policy_sample_kernel(const float* __restrict__ raw, int ldr, int
   logp[b] = lp;
 }
 
-bool g_consts_ready = false;
+// __constant__ symbols exist once per device: remember which devices were initialised (a second agent on
+// another GPU of the same process must not run with zeroed action scale / control points)
+bool g_consts_ready[64] = {};
+
+int cur_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return (d >= 0 && d < 64) ? d : 0;
+}
 
 }  // namespace
 
@@ -314,11 +322,11 @@ int gaddpg_heads_init_impl(const float* act_scale, const float* act_bias, const 
   GADDPG_CUDA(cudaMemcpyToSymbol(c_act_scale, act_scale, 6 * sizeof(float)));
   GADDPG_CUDA(cudaMemcpyToSymbol(c_act_bias, act_bias, 6 * sizeof(float)));
   GADDPG_CUDA(cudaMemcpyToSymbol(c_cp_rotz, cp_rotz, 18 * sizeof(float)));
-  g_consts_ready = true;
+  g_consts_ready[cur_device()] = true;
   return GADDPG_OK;
 }
 
-#define NEED_CONSTS(name) GADDPG_CHECK_ARG(g_consts_ready, name ": call gaddpg_heads_init first")
+#define NEED_CONSTS(name) GADDPG_CHECK_ARG(g_consts_ready[cur_device()], name ": call gaddpg_heads_init on this device first")
 
 int gaddpg_policy_head_fwd_impl(const float* raw, int ldr, int B, float* pi, void* stream) {
   NEED_CONSTS("policy_head_fwd");

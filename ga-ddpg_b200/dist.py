@@ -30,15 +30,28 @@ class World:
                 kw["device_id"] = torch.device("cuda", self.local_rank)
             dist.init_process_group(backend=backend, rank=self.rank, world_size=self.size, **kw)
 
-    def all_reduce_mean(self, t):
+    def all_reduce_mean(self, t, async_op=False):
+        """Mean over ranks, in place.  ``async_op=True`` returns a handle for ``wait``: the collective runs on the process
+        group's own stream (it starts once the work already enqueued on the current stream is done) and the current
+        stream only blocks where ``wait`` is called — what the agents use to hide the reduce behind the SA1 backward."""
         if self.size == 1:
-            return t
+            return None if async_op else t
         if self.backend == "nccl":
-            dist.all_reduce(t, op=dist.ReduceOp.AVG)
-        else:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
-            t.mul_(1.0 / self.size)
+            w = dist.all_reduce(t, op=dist.ReduceOp.AVG, async_op=async_op)
+            return (w, None) if async_op else t
+        w = dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=async_op)   # gloo has no AVG
+        if async_op:
+            return (w, t)
+        t.mul_(1.0 / self.size)
         return t
+
+    def wait(self, handle):
+        if handle is None:
+            return
+        w, scale_me = handle
+        w.wait()
+        if scale_me is not None:
+            scale_me.mul_(1.0 / self.size)
 
     def all_reduce_max(self, t):
         if self.size > 1:

@@ -27,13 +27,16 @@ from .structs import (EPI_DMASK, EPI_STORE, OP_BNBWD, OP_BNBWD_POOL, OP_BNRELU, 
                       TNProblem, check_sizes, dp, op_bnbwd, op_bnbwd_pool, op_bnrelu, op_plain)
 
 BN_EPS, BN_MOMENTUM = 1e-5, 0.1
-_checked = False
+_checked = set()   # device indices whose __constant__ tables (action scale / bias, control points) are uploaded
 
 
-def _init_once():
-    global _checked
-    if not _checked:
-        check_sizes()
+def _init_once(device=None):
+    """Per DEVICE: the constant tables live in each GPU's constant bank, and cudaMemcpyToSymbol targets the current one."""
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    if idx not in _checked:
+        if not _checked:
+            check_sizes()
         scale = ((nets.ACTION_HIGH - nets.ACTION_LOW) / 2.0).astype(np.float32)
         bias = ((nets.ACTION_HIGH + nets.ACTION_LOW) / 2.0).astype(np.float32)
         cp = np.array([[0, 0, 0], [0, 0, 0], [0.053, -0.0, 0.075], [-0.053, 0, 0.075], [0.053, -0.0, 0.105],
@@ -41,8 +44,9 @@ def _init_once():
         a = np.pi / 2  # utils.py:826-829: float64 matmul with rotZ(pi/2)[:3,:3], then cast to float32
         rz = np.array([[np.cos(a), -np.sin(a), 0.0], [np.sin(a), np.cos(a), 0.0], [0.0, 0.0, 1.0]])
         cpz = np.ascontiguousarray(np.matmul(cp, rz).astype(np.float32))
-        lib.gaddpg_heads_init(scale.ctypes.data, bias.ctypes.data, cpz.ctypes.data)
-        _checked = True
+        with torch.cuda.device(idx):
+            lib.gaddpg_heads_init(scale.ctypes.data, bias.ctypes.data, cpz.ctypes.data)
+        _checked.add(idx)
 
 
 def _f(device, *shape):
@@ -57,7 +61,7 @@ class Workspace:
     """Scratch shared by all passes on one device (stream-ordered reuse)."""
 
     def __init__(self, device):
-        _init_once()
+        _init_once(device)
         self.device = device
         self.stats = _f(device, STAT_SLOTS * 2 * 1024)
         self.tn_bytes = int(lib.gaddpg_gemm_tn_workspace_bytes())
@@ -260,7 +264,7 @@ class Geometry:
 class EncoderFlat:
     """Arena + per-layer views of an ``nets.make_encoder_params`` module tree."""
 
-    def __init__(self, enc, device):
+    def __init__(self, enc, device, grad_pool=None):
         sa_mods, fc = enc[0], enc[1]
         order, bufs = [], []
         self.bn_modules = []
@@ -276,7 +280,10 @@ class EncoderFlat:
             order += [("fc%d.W" % j, lin.weight, False), ("fc%d.b" % j, lin.bias, False), ("fc%d.gamma" % j, bn.weight, False),
                       ("fc%d.beta" % j, bn.bias, False)]
             bufs.append(("fc%d" % j, bn))
-        self.arena = nets.Arena(order, device)
+        self.arena = nets.Arena(order, device, grad_pool=grad_pool)
+        # the SA1 layers come first in the arena: their gradients are the LAST to be produced by a backward pass, so
+        # [sa1_end, n) can be all-reduced while the SA1 backward still runs (agent._reduce_early / _reduce_late)
+        self.sa1_end = self.arena.offsets["sa1.0.W"]
         # running statistics: float arena (no optimiser state) + int64 counters
         border = []
         for name, bn in bufs:
@@ -484,16 +491,20 @@ def _mlp_tail_forward(ws, layers, s, first, M_max, M_dev, rw, count, train, bn_s
                                     dp(s.arg), st)
 
 
-def encoder_backward(ws, ef, ctx, sc, want_dw=True, want_dbc=False, accumulate=0, dfeat=None):
+def encoder_backward(ws, ef, ctx, sc, want_dw=True, want_dbc=False, accumulate=0, dfeat=None, part="all"):
     """Backward of ``encoder_forward``.  Entry: either ``dfeat`` (B, >=512) is given (gradient w.r.t. ctx.feat;
     masked here), or the caller already produced sc.Dfc[1] and its BN sums in ws.stats through an EPI_DMASK
     epilogue (the fused path).  Writes parameter gradients into the arena (``want_dw``) and, for the broadcast
-    channels, sc.dbc (B, Cb) (``want_dbc``)."""
+    channels, sc.dbc (B, Cb) (``want_dbc``).  ``part``: "upper" stops after SA2 (FC head, SA3, SA2 and the scatter into
+    SA1's pooled gradient: every parameter gradient except SA1's is complete), "sa1" runs the rest — the sharded agent
+    all-reduces the upper gradients while the SA1 backward runs."""
     B = ctx.B
     st = current_stream()
     geom = ctx.geom
     l1, l2 = geom.lv
     L = ef.layers
+    if part == "sa1":
+        return _encoder_backward_sa1(ws, ef, ctx, sc, want_dw, want_dbc, accumulate)
     f = ctx.fc
     F0, F1 = L["fc0"], L["fc1"]
     if dfeat is not None:
@@ -524,6 +535,17 @@ def encoder_backward(ws, ef, ctx, sc, want_dw=True, want_dbc=False, accumulate=0
                  l2.M_dev, l2.row_w, B * geom.npoint * l2.ns, want_dw, accumulate, True)
     lib.gaddpg_scatter_rows(dp(sc.dG[1]), sc.dG[1].shape[1], 128, B, geom.npoint, geom.npoint, dp(l2.seg_off), dp(l2.row_src),
                             dp(sc.dout[0]), st)
+    if part == "upper":
+        return None
+    return _encoder_backward_sa1(ws, ef, ctx, sc, want_dw, want_dbc, accumulate)
+
+
+def _encoder_backward_sa1(ws, ef, ctx, sc, want_dw, want_dbc, accumulate):
+    B = ctx.B
+    st = current_stream()
+    geom = ctx.geom
+    l1, l2 = geom.lv
+    L = ef.layers
     # ---- SA1: layers 2,1 generic; layer 0 custom
     s = ctx.sa[0]
     W0 = L["sa0.0"]
@@ -594,14 +616,14 @@ def _jobs_tensor(jobs, device):
 class PolicyFlat:
     """GaussianPolicy (networks.py:303-351): 513 -> 256 -> 256 -> [mean(6) | extra_pred(E) | log_std(6)]."""
 
-    def __init__(self, mod, device, with_opt=True):
+    def __init__(self, mod, device, with_opt=True, grad_pool=None):
         self.mod, self.E = mod, mod.extra_pred_dim
         E = self.E
         order = [("l1.W", mod.linear1.weight, False), ("l1.b", mod.linear1.bias, False),
                  ("l2.W", mod.linear2.weight, False), ("l2.b", mod.linear2.bias, False),
                  ("h.W", mod.mean.weight, False), ("h.W.e", mod.extra_pred.weight, True), ("h.W.s", mod.log_std_linear.weight, True),
                  ("h.b", mod.mean.bias, False), ("h.b.e", mod.extra_pred.bias, True), ("h.b.s", mod.log_std_linear.bias, True)]
-        self.arena = A = nets.Arena(order, device, with_opt=with_opt)
+        self.arena = A = nets.Arena(order, device, with_opt=with_opt, grad_pool=grad_pool)
         self.NH = 6 + E + 6
         self.NHp = _pad4(self.NH)
         self.Kin = mod.linear1.weight.shape[1]
@@ -671,7 +693,7 @@ class CriticFlat:
     """QNetwork (networks.py:253-300, num_actions=0): twin Q (linear1-3, linear4-6) + aux branch (linear7, 8,
     extra_pred) when extra_pred_dim > 0.  First layers are stacked into one (256*nb, 513) matrix."""
 
-    def __init__(self, mod, device, with_opt=True):
+    def __init__(self, mod, device, with_opt=True, grad_pool=None):
         self.mod, self.E = mod, mod.extra_pred_dim
         self.nb = 3 if self.E > 0 else 2
         l1 = [mod.linear1, mod.linear4] + ([mod.linear7] if self.E else [])
@@ -690,7 +712,7 @@ class CriticFlat:
         for i, m in enumerate(l3):
             order.append(("l3.W.%d" % i, m.weight, False))
             order.append(("l3.b.%d" % i, m.bias, False))
-        self.arena = A = nets.Arena(order, device, with_opt=with_opt)
+        self.arena = A = nets.Arena(order, device, with_opt=with_opt, grad_pool=grad_pool)
         self.Kin = mod.linear1.weight.shape[1]
         o, nb = A.offsets, self.nb
         Kp = _pad4(self.Kin)

@@ -102,15 +102,41 @@ class GaussianPolicyParams(nn.Module):
         self.apply(_xavier)
 
 
+class GradPool:
+    """One contiguous fp32 buffer that the gradient regions of SEVERAL arenas are carved from, in construction order, so
+    that everything one optimiser phase reduces across GPUs is a single range (value encoder + critic | policy encoder +
+    policy): one NCCL all-reduce per phase instead of one per network."""
+
+    def __init__(self, capacity, device):
+        self.buf = torch.zeros(capacity, dtype=torch.float32, device=device)
+        self.off = 0
+
+    def take(self, n):
+        assert self.off + n <= self.buf.numel(), "GradPool too small"
+        t = self.buf[self.off: self.off + n]
+        self.off += n
+        return t
+
+    @property
+    def used(self):
+        return self.buf[: self.off]
+
+    @staticmethod
+    def capacity_for(*modules):
+        """Upper bound of the arena sizes of ``modules`` (every tensor padded to ALIGN, plus the arena tail)."""
+        return sum(sum((p.numel() + ALIGN) for p in m.parameters()) + ALIGN for m in modules)
+
+
 class Arena:
-    """One contiguous fp32 buffer [params | grads | m | v] (+ optional Polyak target copy elsewhere).
+    """One contiguous fp32 buffer [params | grads | m | v] (+ optional Polyak target copy elsewhere); with ``grad_pool`` the
+    gradient region lives in that shared pool instead ([params | m | v] here).
 
     ``order`` is a list of (name, tensor) in the order they should be laid out; tensors that must be adjacent
     for stacked GEMMs (e.g. linear1/4/7 of the critic) are simply listed next to each other with ``pack=True``
     rows so no alignment gap is inserted between them.
     """
 
-    def __init__(self, order, device, with_opt=True):
+    def __init__(self, order, device, with_opt=True, grad_pool=None):
         self.offsets, self.sizes = {}, {}
         off = 0
         for name, t, pack in order:
@@ -119,12 +145,17 @@ class Arena:
             self.offsets[name], self.sizes[name] = off, t.numel()
             off += t.numel()
         self.n = (off + ALIGN - 1) // ALIGN * ALIGN
-        k = 4 if with_opt else 1
+        pooled = with_opt and grad_pool is not None
+        k = (3 if pooled else 4) if with_opt else 1
         self.buf = torch.zeros(k * self.n, dtype=torch.float32, device=device)
         self.p = self.buf[: self.n]
-        self.g = self.buf[self.n: 2 * self.n] if with_opt else None
-        self.m = self.buf[2 * self.n: 3 * self.n] if with_opt else None
-        self.v = self.buf[3 * self.n:] if with_opt else None
+        if pooled:
+            self.g = grad_pool.take(self.n)
+            self.m, self.v = self.buf[self.n: 2 * self.n], self.buf[2 * self.n:]
+        else:
+            self.g = self.buf[self.n: 2 * self.n] if with_opt else None
+            self.m = self.buf[2 * self.n: 3 * self.n] if with_opt else None
+            self.v = self.buf[3 * self.n:] if with_opt else None
         for name, t, _ in order:
             view = self.view(name, t.shape)
             view.copy_(t.detach().to(device))

@@ -17,6 +17,7 @@ minibatches.  A 180 GB B200 holds 10.9 M transitions of the default 1030-column 
 Default configuration only (``use_image = False``, ``self_supervision = False``; experiments/config.py:105,113).
 """
 import os
+import weakref
 
 import numpy as np
 import torch
@@ -63,11 +64,18 @@ class ReplayBatch(dict):
     def __init__(self, memory, batch_idx):
         super().__init__()
         self.memory, self.batch_idx, self.materialised = memory, np.asarray(batch_idx), False
+        reg = getattr(memory, "_lazy", None)
+        if reg is not None:
+            reg[id(self)] = weakref.ref(self)     # a write to the buffer snapshots this batch first (BaseMemory.sample copies at sample time)
 
-    def materialise(self):
+    def materialise(self, snapshot=False):
         if not self.materialised:
             self.materialised = True
-            dict.update(self, self.memory.gather(self.batch_idx))
+            getattr(self.memory, "_lazy", {}).pop(id(self), None)
+            d = self.memory.gather(self.batch_idx)
+            if snapshot:   # the per-batch-size output buffers are reused by the next gather: keep private copies
+                d = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in d.items()}
+            dict.update(self, d)
         return self
 
     def __getitem__(self, k):
@@ -134,8 +142,9 @@ class ReplayMemoryB200:
         self.pose = np.zeros((n, 64), dtype=np.float32)
         self.state_pose = np.zeros((n, 4, 4), dtype=np.float32)
         self.image_state = np.zeros((n, 1), dtype=np.uint16)
-        self._dirty = None     # [lo, hi) of host record / episode-map rows not yet mirrored to the device
+        self._dirty = []       # disjoint [lo, hi) ranges of host record / episode-map rows not yet mirrored to the device
         self._out = {}
+        self._lazy = {}                  # id -> weakref of ReplayBatch objects handed out by sample() and not gathered yet
 
     def upper_idx(self):
         return max(self.cur_idx, 1) if not self.is_full else self.buffer_size
@@ -153,27 +162,49 @@ class ReplayMemoryB200:
         self.cur_idx, self.is_full = 0, False
 
     def _mark(self, lo, hi):
-        self._dirty = (lo, hi) if self._dirty is None else (min(lo, self._dirty[0]), max(hi, self._dirty[1]))
+        """Add [lo, hi) to the dirty set, kept as a few disjoint ranges (a ring that wraps dirties its tail and its head,
+        not the whole table)."""
+        r = sorted(self._dirty + [(int(lo), int(hi))])
+        out = [r[0]]
+        for a, b in r[1:]:
+            if a <= out[-1][1]:
+                out[-1] = (out[-1][0], max(out[-1][1], b))
+            else:
+                out.append((a, b))
+        while len(out) > 4:      # bound the bookkeeping: fuse the two closest ranges
+            k = min(range(len(out) - 1), key=lambda i: out[i + 1][0] - out[i][1])
+            out[k: k + 2] = [(out[k][0], out[k + 1][1])]
+        self._dirty = out
+
+    def _settle(self):
+        """Called before the buffer is written: minibatches that were sampled but not consumed yet are gathered NOW, so
+        they keep the contents they had at sample time (replay_memory.py:166-176 copies in ``sample``)."""
+        if self._lazy:
+            for ref in list(self._lazy.values()):
+                b = ref()
+                if b is not None:
+                    b.materialise(snapshot=True)
+            self._lazy.clear()
 
     def mark_dirty(self, lo=0, hi=None):
         """Call after editing the host-side arrays (``returns``, ``episode_map``, ``reward`` ...) in place for slots
         [lo, hi): the next ``sample`` mirrors them to the device record table.  ``push`` / ``add_episode`` / ``load`` /
         ``recompute_return_with_gamma`` do this themselves."""
+        self._settle()
         self._mark(lo, self.buffer_size if hi is None else hi)
 
     def _flush(self):
         """Mirror the host-side records / episode map of the slots touched since the last sample to the device."""
-        if self._dirty is None:
-            return
-        lo, hi = self._dirty
-        self._emap_host.numpy()[lo:hi] = self.episode_map[lo:hi].astype(np.int64).astype(np.int32)  # keep the uint32 bits
-        # blocking copies: the host arrays are live (the next push writes into them), the ranges are small
-        self.records[lo:hi].copy_(self._rec_host[lo:hi])
-        self.episode_map_dev[lo:hi].copy_(self._emap_host[lo:hi])
-        self._dirty = None
+        for lo, hi in self._dirty:
+            self._emap_host.numpy()[lo:hi] = self.episode_map[lo:hi].astype(np.int64).astype(np.int32)  # keep the uint32 bits
+            # blocking copies: the host arrays are live (the next push writes into them), the ranges are small
+            self.records[lo:hi].copy_(self._rec_host[lo:hi])
+            self.episode_map_dev[lo:hi].copy_(self._emap_host[lo:hi])
+        self._dirty = []
 
     # ---- writers (replay_memory.py:178-232) -----------------------------------------------------------------
     def push(self, step_dict, _pending=None):
+        self._settle()
         store_idx = self.cur_idx % self.buffer_size
         ps = np.asarray(step_dict["point_state"])
         if ps.shape[1] < 100 or ps.sum() == 0:
@@ -221,6 +252,7 @@ class ReplayMemoryB200:
             self._mark(self.cur_idx - n, self.cur_idx)
 
     def recompute_return_with_gamma(self):
+        self._settle()
         ends = np.sort(np.unique(self.episode_map))
         out = self.returns.copy()
         for k in range(len(ends) - 1):
@@ -261,9 +293,11 @@ class ReplayMemoryB200:
             raise IndexError("replay index out of range [0, %d)" % self.buffer_size)
         self._flush()
         o = self._buffers(B)
-        self._upload_indices(o, batch_idx)
+        with torch.cuda.device(self.device):
+            self._upload_indices(o, batch_idx)
         row_floats = self.row[0] * self.row[1]
         if B:
+          with torch.cuda.device(self.device):
             lib.gaddpg_replay_gather(self.point_state.data_ptr(), row_floats, self.records.data_ptr(), REC_W, C_TIMESTEP,
                                      self.episode_map_dev.data_ptr(), self.buffer_size, o["idx"].data_ptr(), B, o["state"].data_ptr(),
                                      o["next"].data_ptr(), o["rec"].data_ptr(), o["inc"].data_ptr(), None, None, current_stream())
@@ -317,8 +351,10 @@ class ReplayMemoryB200:
                     m[0, c0:c0 + w] = off + np.arange(w)
                     m[1, c0:c0 + w] = w
             o["soa_map"], o["soa_key"] = torch.from_numpy(m).to(self.device), key
-        self._upload_indices(o, batch_idx)
+        with torch.cuda.device(self.device):
+            self._upload_indices(o, batch_idx)
         if B:
+          with torch.cuda.device(self.device):
             nxt = next_cloud if next_cloud is not None else o["next"]
             lib.gaddpg_replay_gather(self.point_state.data_ptr(), self.row[0] * self.row[1], self.records.data_ptr(), REC_W, C_TIMESTEP,
                                      self.episode_map_dev.data_ptr(), self.buffer_size, o["idx"].data_ptr(), B, cloud.data_ptr(),
@@ -334,11 +370,14 @@ class ReplayMemoryB200:
         d.update(episode_map=self.episode_map, is_full=self.is_full, cur_idx=self.cur_idx, total_env_step=self.total_env_step)
         np.savez(os.path.join(save_dir, self.save_data_name), **d)
 
-    def load(self, data_dir, buffer_size=100000, **kwargs):
+    def load(self, data_dir, buffer_size=100000, trusted=False, **kwargs):
+        """replay_memory.py:316-357.  The file holds numeric arrays only, so pickled objects are refused unless the caller
+        vouches for the file (``trusted=True``: the reference itself loads with ``allow_pickle=True``)."""
         path = os.path.join(data_dir, self.save_data_name)
         if not os.path.exists(path):
             return
-        data = np.load(path, allow_pickle=True, mmap_mode="r")
+        self._settle()
+        data = np.load(path, allow_pickle=bool(trusted), mmap_mode="r")
         n = int(np.amax(data["episode_map"]))
         for name in self.attr_names + ["episode_map"]:
             if name == "image_state" or name not in data:

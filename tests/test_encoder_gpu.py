@@ -107,6 +107,30 @@ def test_encoder_forward_backward_matches_oracle(cuda, B, N, with_action, tc):
         assert float(pm.grad.abs().max()) < 1e-4 * float(R.abs().max()) * B
     if with_action:
         assert _rel(dbc, act_o.grad) < (5e-2 if tc else 2e-2)
+    # ---- float64 referee for the kink-tolerant bounds above: over all gradient elements the CUDA backward is as close to
+    # the float64 gradient as the fp32 oracle's autograd is (tests/f64ref.py)
+    import copy
+
+    from tests.f64ref import f64_ops, referee_l2
+
+    o64 = copy.deepcopy(ora).double()
+    o64.zero_grad()
+    for m_ in o64.modules():   # the forward above already updated the running statistics once; irrelevant in train mode
+        if isinstance(m_, (torch.nn.BatchNorm1d, torch.nn.BatchNorm2d)):
+            m_.reset_running_stats()
+    act64 = action.double().clone().requires_grad_(True) if with_action else None
+    with f64_ops():
+        z64 = _oracle_forward(o64, cloud.double(), act64)
+        (z64 * R.double()).sum().backward()
+    assert _rel(feat[:, :512], z64) < 1e-4
+    keys = [k for k, _ in ora.named_parameters() if not k.endswith(("1.0.bias", "1.3.bias"))]
+    po, pm, p64 = dict(ora.named_parameters()), dict(mine.named_parameters()), dict(o64.named_parameters())
+    ec, eo = referee_l2("encoder parameter gradients (tc=%d)" % tc, [pm[k].grad.cpu().numpy() for k in keys],
+                        [po[k].grad.numpy() for k in keys], [p64[k].grad.numpy() for k in keys], k=5.0, floor=2e-5)
+    print("encoder grads vs float64 (relative L2): cuda %.2e, oracle32 %.2e" % (ec, eo))
+    if with_action:
+        ec, eo = referee_l2("d/d(action) (tc=%d)" % tc, [dbc.cpu().numpy()], [act_o.grad.numpy()], [act64.grad.numpy()], k=5.0, floor=2e-5)
+        print("d/d(action) vs float64 (relative L2): cuda %.2e, oracle32 %.2e" % (ec, eo))
 
     # ---- eval mode (running statistics), as select_action uses it
     ora.eval()
@@ -140,3 +164,44 @@ def test_duplicate_folding_matches_dense_semantics(cuda):
     ctx = engine.EncoderCtx(B, (geom.lv[0].cap, geom.lv[1].cap), engine.WIDTHS, cuda)
     feat = engine.encoder_forward(ws, ef, geom, cloud.to(cuda), 6, 4, None, ctx, train=True)
     assert _rel(feat[:, :512], z_o) < 1e-4
+
+
+@pytest.mark.parametrize("B,N", [(24, 8192), (512, 2048), (1024, 1024)])
+def test_encoder_forward_cfg5_corners(cuda, B, N):
+    """BASELINE config 5's corners (N up to 8192 points, B up to 1024): value-encoder forward (cloud + action channels,
+    train-mode BatchNorm) on the production kernels — the 8192-point FPS variant (xyz staged in 96 KB of shared memory),
+    row counts up to ~1.7 M at SA1 — against the CPU oracle: features within 1e-4, running statistics within 1e-4,
+    FPS / ball-query indices of the whole batch bit-exact."""
+    import os
+
+    from gaddpg_b200 import engine, synthetic
+    from oracle.pointnet2_ops_cpu import pointnet2_utils as U
+
+    torch.set_num_threads(os.cpu_count())
+    ora, mine, ef = _build(10, 21, cuda)
+    batch = synthetic.make_batch(B, N, step=3)
+    cloud = torch.from_numpy(batch["point_state_batch"])
+    action = torch.from_numpy(batch["action_batch"])
+    ora.train()
+    with torch.no_grad():
+        z_o = _oracle_forward(ora, cloud, action)
+    ws = engine.Workspace(cuda)
+    cl = cloud.to(cuda)
+    geom = engine.Geometry(B, N, cuda).build(cl, 6)
+    ctx = engine.EncoderCtx(B, (geom.lv[0].cap, geom.lv[1].cap), engine.WIDTHS, cuda)
+    feat = engine.encoder_forward(ws, ef, geom, cl, 6, 4, action.to(cuda).contiguous(), ctx, train=True)
+    torch.cuda.synchronize()
+    assert _rel(feat[:, :512], z_o) < 1e-4, (B, N)
+    sd_o, sd_m = ora.state_dict(), mine.state_dict()
+    for k in sd_o:
+        if "running" in k:
+            assert _rel(sd_m[k], sd_o[k]) < 1e-4, k
+    xyz = cloud[:, :3, 6:].transpose(1, 2).contiguous()
+    fps = U.fps_raw(xyz, 32)
+    assert torch.equal(geom.lv[0].fps_idx.cpu(), fps), "FPS indices"
+    ctr = torch.gather(xyz, 1, fps.long().unsqueeze(-1).expand(-1, -1, 3)).contiguous()
+    assert torch.equal(geom.lv[0].bq_idx.cpu(), U.ball_query_raw(0.02, 64, xyz, ctr)), "SA1 ball-query indices"
+    fps2 = U.fps_raw(ctr, 32)
+    assert torch.equal(geom.lv[1].fps_idx.cpu(), fps2), "SA2 FPS indices"
+    c2 = torch.gather(ctr, 1, fps2.long().unsqueeze(-1).expand(-1, -1, 3)).contiguous()
+    assert torch.equal(geom.lv[1].bq_idx.cpu(), U.ball_query_raw(0.04, 128, ctr, c2)), "SA2 ball-query indices"

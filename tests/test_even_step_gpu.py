@@ -1,0 +1,196 @@
+"""GPU: the even (actor-critic) DDPG step — F5, ``actor_critic_loss``, the dX-only backward through the value encoder to
+d(pi), the accumulated critic gradients, B2 — held to the oracle with a FLOAT64 REFEREE wherever two fp32 evaluations
+cannot be expected to agree to 1e-4.
+
+Three instruments (tests/f64ref.py):
+  * the plain 1e-4 comparison with the fp32 oracle (north_star's bar) — used for everything computed from identical
+    weights through well-conditioned arithmetic;
+  * ``hybrid_actor_eval``: the oracle's actor half evaluated on the CUDA agent's OWN post-critic-update weights, so that
+    ``actor_critic_loss`` is compared at 1e-4 from identical weights (the in-step Adam update legitimately leaves the two
+    sides ~lr apart in noise-gradient directions, which is what the old 3e-3 tolerance papered over);
+  * ``referee``: |cuda - f64| <= k |oracle32 - f64| + floor for gradients (ReLU / max-pool kinks: the fp32 oracle itself
+    is ~1e-2 away from the float64 gradient d(ac)/d(pi)) and for post-step parameters.
+"""
+import gc
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+CHAOTIC = ("actor_critic_loss", "critic_grad", "policy_param", "critic_param")
+
+
+def _close(a, b, rtol=1e-4, atol=1e-6):
+    return (np.isnan(a) and np.isnan(b)) or abs(a - b) <= atol + rtol * abs(b)
+
+
+def _clone_state(sd):
+    return {n: {k: v.detach().cpu().clone() for k, v in d.items()} for n, d in sd.items()}
+
+
+def _snap_clipped_b1(ora):
+    """Record the oracle's critic gradients right after clip_grad_norm_ (ddpg.py:141), i.e. before B2 accumulates the
+    actor-loss gradients onto them (agent.py:242-259 reads critic_grad after B2)."""
+    box = {}
+    orig = ora.critic_opt.step
+
+    def step(*a, **k):
+        box["g"] = {n: p.grad.detach().clone() for n, p in ora.critic.named_parameters() if p.grad is not None}
+        return orig(*a, **k)
+
+    ora.critic_opt.step = step
+    return box, (lambda: setattr(ora.critic_opt, "step", orig))
+
+
+def _actor_half_checks(name, mine, m, pre, batch, step_no, over, box, with_f64, report):
+    """``mine`` just ran an EVEN step from the synchronised state ``pre``; ``m`` = its scalars."""
+    from tests.f64ref import hybrid_actor_eval, referee
+
+    post = _clone_state(mine.state_dicts())
+    h32 = hybrid_actor_eval(pre, post, batch, step_no, over, torch.float32)
+    # actor_critic_loss from IDENTICAL weights: north_star's 1e-4
+    assert _close(m["actor_critic_loss"], h32["ac"], rtol=1e-4), (name, "actor_critic_loss", m["actor_critic_loss"], h32["ac"])
+    assert float((mine.pc.pi.cpu() - h32["pi"]).abs().max() / h32["pi"].abs().max()) < 1e-4
+    q = torch.stack([h32["q1"].view(-1), h32["q2"].view(-1)], 1)
+    qm = torch.stack([mine.cc5.qa[:, 0], mine.cc5.qa[:, 4]], 1).cpu()
+    assert float((qm - q).abs().max() / q.abs().max()) < 1e-4, (name, "Q(s, pi(s)) from identical weights")
+    # accumulated critic gradient statistic: clipped B1 gradients (identical pre-step weights on both sides) + actor part
+    exp_cg = max(float((box["g"][k] + (h32["critic"][k] if h32["critic"].get(k) is not None else 0)).abs().max()) for k in box["g"])
+    if not with_f64:
+        assert _close(m["critic_grad"], exp_cg, rtol=1e-3), (name, "critic_grad", m["critic_grad"], exp_cg)
+        return
+    h64 = hybrid_actor_eval(pre, post, batch, step_no, over, torch.float64)
+    report["ac"] = referee(name + ":actor_critic_loss", m["actor_critic_loss"], h32["ac"], h64["ac"])
+    report["dpi"] = referee(name + ":d(ac)/d(pi)", mine.dpi_ac.cpu().numpy(), h32["dpi"].numpy(), h64["dpi"].numpy())
+    exp_cg64 = max(float((box["g"][k].double() + (h64["critic"][k] if h64["critic"].get(k) is not None else 0)).abs().max()) for k in box["g"])
+    report["critic_grad"] = referee(name + ":critic_grad", m["critic_grad"], exp_cg, exp_cg64, rel_floor=2e-5)
+    worst = (0.0, 0.0, None)
+    for which, mod in (("policy", mine.policy), ("encoder", mine._extractor.encoder)):
+        for k, p in mod.named_parameters():
+            g32, g64 = h32[which].get(k), h64[which].get(k)
+            if g32 is None:
+                continue
+            ec, eo = referee("%s:grad %s.%s" % (name, which, k), p.grad.detach().cpu().numpy(), g32.numpy(), g64.numpy(), rel_floor=2e-5)
+            if ec > worst[0]:
+                worst = (ec, eo, which + "." + k)
+    report["worst_grad"] = worst
+
+
+@pytest.mark.parametrize("over", [dict(), dict(policy_aux=False, critic_aux=False, extra_latent=3)])
+def test_even_step_small_with_f64_referee(cuda, over):
+    """B = 8, N = 512, four teacher-forced steps (odd, even, odd, even).  Every returned scalar is within 1e-4 of the fp32
+    oracle, or — for the four quantities downstream of the in-step Adam update / of a max over gradient elements — no
+    further from the float64 twin of the same step than 4x the fp32 oracle itself; post-step parameters likewise, tensor
+    by tensor (this replaces the blanket 2.5e-3 bound: only tensors where the ORACLE is that far from float64 get it)."""
+    from gaddpg_b200 import agent as ag, synthetic
+    from gaddpg_b200.config import LOSS_KEYS
+    from oracle.ddpg_cpu import OracleAgent
+    from tests.f64ref import f64_twin, referee
+    from tests.test_agent_gpu import _sync_from_oracle
+
+    B, N = 8, 512
+    ch = 6 if over.get("extra_latent") == 3 else 4
+    ora = OracleAgent("DDPG", seed=123456, **over)
+    mine = ag.make_agent("DDPG", seed=123456, **over)
+    rs = np.random.RandomState(9)
+    for step in range(4):
+        _sync_from_oracle(mine, ora)
+        pre = _clone_state(ora.state_dicts())
+        twin = f64_twin(ora)
+        batch = synthetic.make_batch(B, N, step=step, channels=ch)
+        u = rs.rand(B, 6).astype(np.float32)
+        box, undo = _snap_clipped_b1(ora)
+        step_no = ora.update_step
+        o = ora.update_parameters(batch, noise_u=u)
+        undo()
+        ora.step_scheduler()
+        r = twin.update_parameters(batch, noise_u=u)
+        m = mine.update_parameters(batch, mine.update_step, 0, noise_u=u)
+        mine.step_scheduler(mine.update_step)
+        even = step_no % 2 == 0
+        for k in LOSS_KEYS:
+            if _close(m[k], o[k], rtol=1e-4):
+                continue
+            assert k in CHAOTIC, (step, k, m[k], o[k])          # everything else: 1e-4, no excuses
+            referee("step %d %s" % (step, k), m[k], o[k], r[k], k=4.0, rel_floor=2e-5)
+        # post-step parameters, tensor by tensor, against the float64 twin
+        sm, so, sr = mine.state_dicts(), ora.state_dicts(), twin.state_dicts()
+        loose = []
+        for net in so:
+            for k in so[net]:
+                if "num_batches_tracked" in k:
+                    assert int(sm[net][k]) == int(so[net][k])
+                    continue
+                a, b, c = sm[net][k].detach().cpu().double(), so[net][k].double(), sr[net][k].double()
+                if float((a - b).abs().max()) <= 1e-6 + 1e-4 * float(b.abs().max()) and "running" in k:
+                    continue
+                ec, eo = referee("step %d param %s.%s" % (step, net, k), a.numpy(), b.numpy(), c.numpy(), k=4.0, rel_floor=1e-5, abs_floor=2e-7)
+                if float((a - b).abs().max()) > 2.5e-4:
+                    loose.append((net, k, float((a - b).abs().max())))
+        # tensors that end up more than a quarter learning-rate unit apart: only where the oracle is as far from float64
+        # (the referee above held); the genuinely gradient-free ones are the Linear biases in front of BatchNorm1d
+        print("step %d: tensors > 2.5e-4 apart: %s" % (step, loose))
+        if even:
+            rep = {}
+            _actor_half_checks("small step %d" % step, mine, m, pre, batch, step_no, over, box, True, rep)
+            print("even step %d referee (cuda err, oracle32 err) relative to scale: %s" % (step, rep))
+
+
+@pytest.mark.parametrize("name,B,over", [
+    ("cfg2", 256, dict(extra_latent=3, policy_aux=False, critic_aux=False)),   # BASELINE config 2 (the bench workload)
+    ("cfg3", 512, dict()),                                                       # BASELINE config 3: goal-aux + grasp-aux losses on
+])
+def test_full_size_even_step_matches_oracle(cuda, name, B, over):
+    """BASELINE.json's full-size configurations, teacher-forced SECOND step (update_step 2: the policy_update_gap branch,
+    ddpg.py:170-177): F5 through the value encoder at M ~ 423 k rows, ``actor_critic_loss``, the dX-only backward with the
+    per-sample action-channel gradient (sa1_dbc), the accumulated critic gradients and B2 on the production kernels
+    (tcgen05 SA1/SA2/SA3, sparse pool backward, multi-stream schedule)."""
+    from gaddpg_b200 import agent as ag, synthetic
+    from gaddpg_b200.config import LOSS_KEYS
+    from oracle.ddpg_cpu import OracleAgent
+    from tests.f64ref import f64_twin, referee
+    from tests.test_agent_gpu import _sync_from_oracle
+
+    N = 4096
+    torch.set_num_threads(os.cpu_count())
+    ch = 6 if over.get("extra_latent") == 3 else 4
+    ora = OracleAgent("DDPG", seed=123456, **over)
+    mine = ag.make_agent("DDPG", seed=123456, **over)
+    rs = np.random.RandomState(5)
+    ora.update_parameters(synthetic.make_batch(B, N, step=0, channels=ch), noise_u=rs.rand(B, 6).astype(np.float32))  # step 1 (odd)
+    ora.step_scheduler()
+    _sync_from_oracle(mine, ora)
+    assert mine.update_step == 2
+    pre = _clone_state(ora.state_dicts())
+    # float64 referee at B = 256 only: the float64 autograd graph of a B = 512 step needs > 30 GB of host memory
+    with_f64 = B <= 256
+    twin = f64_twin(ora) if with_f64 else None
+    batch = synthetic.make_batch(B, N, step=1, channels=ch)
+    u = rs.rand(B, 6).astype(np.float32)
+    box, undo = _snap_clipped_b1(ora)
+    o = ora.update_parameters(batch, noise_u=u)
+    undo()
+    m = mine.update_parameters(batch, mine.update_step, 0, noise_u=u)
+    r = twin.update_parameters(batch, noise_u=u) if with_f64 else None
+    del twin
+    gc.collect()
+    assert o["actor_critic_loss"] != 0.0 and m["actor_critic_loss"] != 0.0
+    for k in LOSS_KEYS:
+        if _close(m[k], o[k], rtol=1e-4):
+            continue
+        assert k in CHAOTIC, (name, k, m[k], o[k])     # everything else: 1e-4 from identical weights, no excuses
+        if with_f64:
+            referee("%s %s" % (name, k), m[k], o[k], r[k], k=4.0, rel_floor=2e-5)
+    rel = lambda a, b: float((a.cpu().double() - b.double()).abs().max() / (b.double().abs().max() + 1e-30))  # noqa: E731
+    assert rel(mine.y, ora.last["y"]) < 1e-4
+    assert rel(mine.cc1.qa[:, 0], ora.last["q1"].view(-1)) < 1e-4 and rel(mine.cc1.qa[:, 4], ora.last["q2"].view(-1)) < 1e-4
+    rep = {}
+    _actor_half_checks(name, mine, m, pre, batch, 2, over, box, with_f64, rep)
+    print("%s even step: referee (cuda err, oracle32 err) relative to scale: %s" % (name, rep))
+    if not with_f64:
+        # max |param| after Adam: each side moved its largest element by at most one learning-rate unit (3e-4)
+        for k in ("policy_param", "critic_param"):
+            assert abs(m[k] - o[k]) <= 2 * 3e-4, (name, k, m[k], o[k])

@@ -71,6 +71,25 @@ def test_plugin_forward_backward_like_reference_extractor(cuda):
     (v_m * R.to(cuda)).sum().backward()
     assert _rel(a_m.grad, a_o.grad) < 0.25
     _grads_close(ora.value_encoder.named_parameters(), net.module.value_encoder.named_parameters())
+    # float64 referee for the two kink-tolerant bounds above (B = 8: BatchNorm1d over 8 samples amplifies every flip):
+    # the autograd plugin's gradients are as close to the float64 gradients as the fp32 oracle's are
+    import copy
+
+    from tests.f64ref import f64_ops, referee_l2
+
+    o64 = copy.deepcopy(ora).double()
+    o64.zero_grad()
+    a64 = action.double().clone().requires_grad_(True)
+    with f64_ops():
+        v64 = o64(torch.cat((cloud.double(), a64.unsqueeze(2).expand(-1, -1, cloud.shape[2])), 1), value=True)
+        (v64 * R.double()).sum().backward()
+    ec, eo = referee_l2("plugin d/d(action)", [a_m.grad.cpu().numpy()], [a_o.grad.numpy()], [a64.grad.numpy()], k=5.0, floor=2e-5)
+    print("plugin d/d(action) vs float64 (relative L2): cuda %.2e, oracle32 %.2e" % (ec, eo))
+    keys = [k for k, _ in ora.value_encoder.named_parameters() if not k.endswith(("1.0.bias", "1.3.bias"))]
+    po, pm, p64 = dict(ora.value_encoder.named_parameters()), dict(net.module.value_encoder.named_parameters()), dict(o64.value_encoder.named_parameters())
+    ec, eo = referee_l2("plugin value-encoder gradients", [pm[k].grad.cpu().numpy() for k in keys], [po[k].grad.numpy() for k in keys],
+                        [p64[k].grad.numpy() for k in keys], k=5.0, floor=2e-5)
+    print("plugin value-encoder grads vs float64 (relative L2): cuda %.2e, oracle32 %.2e" % (ec, eo))
 
     # a torch optimiser may step the parameters between calls (the reference's Adam instances do): views stay valid
     opt = torch.optim.Adam(net.module.encoder.parameters(), lr=1e-3)

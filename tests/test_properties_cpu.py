@@ -71,3 +71,29 @@ def test_replay_batch_is_lazy_and_dict_compatible():
     b2 = ReplayBatch(mem, [0])
     assert sorted(b2) == ["point_state_batch", "reward_batch"] and mem.calls == 2    # iteration materialises once
     assert isinstance(b2, dict)
+
+
+def test_lazy_batches_are_snapshotted_before_a_write():
+    """BaseMemory.sample copies at sample time (replay_memory.py:166-176); a lazy ReplayBatch must therefore
+    be gathered before the buffer is written, and the dirty bookkeeping keeps a wrapped ring as two ranges."""
+    from gaddpg_b200.replay_memory import ReplayBatch, ReplayMemoryB200
+
+    class M(_StubMemory):
+        _settle = ReplayMemoryB200._settle
+        _mark = ReplayMemoryB200._mark
+
+        def __init__(self):
+            super().__init__()
+            self._lazy, self._dirty = {}, []
+
+    mem = M()
+    b = ReplayBatch(mem, [5, 6])
+    assert len(mem._lazy) == 1 and mem.calls == 0
+    mem._settle()                                  # what push / add_episode / load / mark_dirty call first
+    assert mem.calls == 1 and b.materialised and not mem._lazy
+    assert b["point_state_batch"] == "cloud[5, 6]" and mem.calls == 1
+    mem._mark(90, 100), mem._mark(0, 4), mem._mark(3, 7)      # ring wrapped: tail + head, not [0, 100)
+    assert mem._dirty == [(0, 7), (90, 100)]
+    for k in range(10, 80, 10):
+        mem._mark(k, k + 1)
+    assert len(mem._dirty) <= 4 and mem._dirty[0][0] == 0 and mem._dirty[-1][1] == 100
