@@ -10,8 +10,16 @@ pytestmark = pytest.mark.gpu
 def _fill(mem, N, episodes=12):
     from gaddpg_b200 import synthetic
 
-    for e in range(episodes):
-        mem.add_episode(synthetic.make_episode(14, N, seed=e))
+    for e in range(episodes):   # mixed expert / on-policy, successful / failed rollouts: no empty loss masks (NaN, a16)
+        mem.add_episode(synthetic.make_episode(14, N, seed=e, success=e % 4 != 0, expert=e % 3 != 0))
+
+
+def _same(a, b):
+    """Loss-dict lists equal bit for bit (NaN == NaN: an empty mask gives NaN on both sides, like the reference)."""
+    assert len(a) == len(b)
+    for i, (x, y) in enumerate(zip(a, b)):
+        for k in x:
+            assert x[k] == y[k] or (np.isnan(x[k]) and np.isnan(y[k])), (i, k, x[k], y[k])
 
 
 def test_pipelined_feed_loop_keeps_the_gpu_busy_and_changes_nothing(cuda):
@@ -35,7 +43,7 @@ def test_pipelined_feed_loop_keeps_the_gpu_busy_and_changes_nothing(cuda):
         loop._starts.clear(), loop._ends.clear()
         res[pipelined] = loop.train_iter(K, pipelined=pipelined)
         gaps[pipelined] = np.array(loop.gaps_us())
-    assert res[True] == res[False]
+    _same(res[True], res[False])
     med_sync, med_pipe = float(np.median(gaps[False])), float(np.median(gaps[True]))
     print("GPU idle gap between steps: synchronous %.0f us, pipelined %.0f us (median of %d)" % (med_sync, med_pipe, len(gaps[True])))
     assert med_pipe < 40.0, gaps[True]
@@ -53,13 +61,12 @@ def test_host_memory_prefetch_thread_matches_synchronous_loop(cuda):
     out = {}
     for pipelined in (False, True):
         mem = OracleMemory(256, uniform_num_pts=N)
-        for e in range(12):
-            mem.add_episode(synthetic.make_episode(14, N, seed=e))
+        _fill(mem, N)
         agent = ag.make_agent("DDPG", seed=123456)
         torch.manual_seed(5)
         np.random.seed(3)
         out[pipelined] = FeedLoop(agent, mem, B).train_iter(8, pipelined=pipelined)
-    assert out[True] == out[False]
+    _same(out[True], out[False])
 
 
 def test_batched_select_action_and_extract_feature(cuda):
