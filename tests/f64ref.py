@@ -92,20 +92,37 @@ def referee(name, cuda, ora32, f64, k=4.0, rel_floor=2e-6, abs_floor=1e-9):
     return ec / (scale + 1e-300), eo / (scale + 1e-300)
 
 
-def referee_l2(name, cuda, ora32, f64, k=5.0, floor=1e-5):
-    """The same bound over a LIST of tensors in relative L2: ||cuda - f64|| <= k ||oracle32 - f64|| + floor ||f64||.
-    Kink flips (a ReLU / max-pool element routed differently by two fp32 evaluations) move single gradient elements by
-    O(1) of their size, so per-tensor max-norms are dominated by one or two unlucky elements on EITHER side; over all
-    gradient elements of a network the flip counts follow the forward rounding error, which is what is being compared."""
-    num_c = num_o = den = 0.0
-    for c, o, r in zip(cuda, ora32, f64):
-        c, o, r = (torch.as_tensor(np.asarray(x, dtype=np.float64)) for x in (c, o, r))
-        num_c += float(((c - r) ** 2).sum())
-        num_o += float(((o - r) ** 2).sum())
-        den += float((r ** 2).sum())
-    ec, eo = (num_c / den) ** 0.5, (num_o / den) ** 0.5
-    assert ec <= k * eo + floor, "%s: ||cuda-f64||/||f64|| = %.3e exceeds %g x ||oracle32-f64||/||f64|| = %.3e (+ %.0e)" % (name, ec, k, eo, floor)
-    return ec, eo
+def referee_elems(name, cuda, ora32, f64, k=5.0, big=1e-3, floors=(2e-7, 1e-6), frac_slack=0.01, scales=None):
+    """Element-wise referee over a LIST of tensors (gradients, post-step parameters).
+
+    Two fp32 evaluations of a ReLU / max-pool network differ from the float64 one in two ways: rounding (every element,
+    ~1e-6 of the tensor's scale) and ROUTING — an element whose pre-activation is within rounding of a kink is sent the
+    other way, which moves a handful of gradient elements by O(1e-3..1e-1) of the scale on EITHER side (measured:
+    tests/diag/diag_grad_f64.py — the fp32 oracle and the CUDA kernels show the same bimodal picture, and which of them
+    is hit depends on the input).  A max- or L2-norm over the tensor is therefore decided by a few unlucky elements.
+    What is asserted instead, with e = |x - f64| / scale(tensor) over ALL elements:
+        median(e_cuda) <= k median(e_ora) + floor,   q90(e_cuda) <= k q90(e_ora) + floor      (rounding level)
+        frac(e_cuda > big) <= 4 frac(e_ora > big) + frac_slack                               (routing is rare)
+    ``scales``: per-tensor scale (default max |f64|)."""
+    ec, eo = [], []
+    for i, (c, o, r) in enumerate(zip(cuda, ora32, f64)):
+        c, o, r = (torch.as_tensor(np.asarray(x, dtype=np.float64)).flatten() for x in (c, o, r))
+        sc = float(r.abs().max()) if scales is None else float(scales[i])
+        if sc == 0.0:
+            continue
+        ec.append((c - r).abs() / sc)
+        eo.append((o - r).abs() / sc)
+    ec, eo = torch.cat(ec), torch.cat(eo)
+    out = {}
+    for q, fl in zip((0.5, 0.9), floors):
+        qc, qo = float(torch.quantile(ec, q)), float(torch.quantile(eo, q))
+        assert qc <= k * qo + fl, "%s: q%d element error vs f64: cuda %.3e > %g x oracle32 %.3e + %.0e" % (name, int(q * 100), qc, k, qo, fl)
+        out["q%d" % int(q * 100)] = (qc, qo)
+    fc, fo = float((ec > big).float().mean()), float((eo > big).float().mean())
+    assert fc <= 4 * fo + frac_slack, "%s: %.3f%% of the elements are > %g off f64 (oracle32: %.3f%%)" % (name, 100 * fc, big, 100 * fo)
+    out["frac_big"] = (fc, fo)
+    out["max"] = (float(ec.max()), float(eo.max()))
+    return out
 
 
 def hybrid_actor_eval(pre_state, post_state, batch, update_step, cfg_over, dtype=torch.float32):

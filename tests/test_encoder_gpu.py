@@ -111,7 +111,7 @@ def test_encoder_forward_backward_matches_oracle(cuda, B, N, with_action, tc):
     # the float64 gradient as the fp32 oracle's autograd is (tests/f64ref.py)
     import copy
 
-    from tests.f64ref import f64_ops, referee_l2
+    from tests.f64ref import f64_ops, referee_elems
 
     o64 = copy.deepcopy(ora).double()
     o64.zero_grad()
@@ -125,12 +125,13 @@ def test_encoder_forward_backward_matches_oracle(cuda, B, N, with_action, tc):
     assert _rel(feat[:, :512], z64) < 1e-4
     keys = [k for k, _ in ora.named_parameters() if not k.endswith(("1.0.bias", "1.3.bias"))]
     po, pm, p64 = dict(ora.named_parameters()), dict(mine.named_parameters()), dict(o64.named_parameters())
-    ec, eo = referee_l2("encoder parameter gradients (tc=%d)" % tc, [pm[k].grad.cpu().numpy() for k in keys],
-                        [po[k].grad.numpy() for k in keys], [p64[k].grad.numpy() for k in keys], k=5.0, floor=2e-5)
-    print("encoder grads vs float64 (relative L2): cuda %.2e, oracle32 %.2e" % (ec, eo))
-    if with_action:
-        ec, eo = referee_l2("d/d(action) (tc=%d)" % tc, [dbc.cpu().numpy()], [act_o.grad.numpy()], [act64.grad.numpy()], k=5.0, floor=2e-5)
-        print("d/d(action) vs float64 (relative L2): cuda %.2e, oracle32 %.2e" % (ec, eo))
+    rep = referee_elems("encoder parameter gradients (tc=%d)" % tc, [pm[k].grad.cpu().numpy() for k in keys],
+                        [po[k].grad.numpy() for k in keys], [p64[k].grad.numpy() for k in keys])
+    print("encoder grads vs float64, element errors / tensor scale (cuda, oracle32):", rep)
+    if with_action:   # 6 x B numbers: every one of them sums over all points, so routing flips show in all — quantiles only
+        rep = referee_elems("d/d(action) (tc=%d)" % tc, [dbc.cpu().numpy()], [act_o.grad.numpy()], [act64.grad.numpy()],
+                            floors=(2e-5, 1e-4), big=5e-2, frac_slack=0.05)
+        print("d/d(action) vs float64 (cuda, oracle32):", rep)
 
     # ---- eval mode (running statistics), as select_action uses it
     ora.eval()

@@ -47,7 +47,7 @@ def _snap_clipped_b1(ora):
 
 def _actor_half_checks(name, mine, m, pre, batch, step_no, over, box, with_f64, report):
     """``mine`` just ran an EVEN step from the synchronised state ``pre``; ``m`` = its scalars."""
-    from tests.f64ref import hybrid_actor_eval, referee
+    from tests.f64ref import hybrid_actor_eval, referee, referee_elems
 
     post = _clone_state(mine.state_dicts())
     h32 = hybrid_actor_eval(pre, post, batch, step_no, over, torch.float32)
@@ -63,20 +63,17 @@ def _actor_half_checks(name, mine, m, pre, batch, step_no, over, box, with_f64, 
         assert _close(m["critic_grad"], exp_cg, rtol=1e-3), (name, "critic_grad", m["critic_grad"], exp_cg)
         return
     h64 = hybrid_actor_eval(pre, post, batch, step_no, over, torch.float64)
-    report["ac"] = referee(name + ":actor_critic_loss", m["actor_critic_loss"], h32["ac"], h64["ac"])
-    report["dpi"] = referee(name + ":d(ac)/d(pi)", mine.dpi_ac.cpu().numpy(), h32["dpi"].numpy(), h64["dpi"].numpy())
+    report["ac"] = referee(name + ":actor_critic_loss", m["actor_critic_loss"], h32["ac"], h64["ac"], rel_floor=2e-5)
+    # d(ac)/d(pi): B x 6 numbers, each a sum over every point of the cloud -> routing flips (f64ref.referee_elems) reach all
+    report["dpi"] = referee_elems(name + ":d(ac)/d(pi)", [mine.dpi_ac.cpu().numpy()], [h32["dpi"].numpy()], [h64["dpi"].numpy()],
+                                  floors=(2e-5, 1e-4), big=5e-2, frac_slack=0.05)
     exp_cg64 = max(float((box["g"][k].double() + (h64["critic"][k] if h64["critic"].get(k) is not None else 0)).abs().max()) for k in box["g"])
-    report["critic_grad"] = referee(name + ":critic_grad", m["critic_grad"], exp_cg, exp_cg64, rel_floor=2e-5)
-    worst = (0.0, 0.0, None)
+    report["critic_grad"] = referee(name + ":critic_grad", m["critic_grad"], exp_cg, exp_cg64, k=10.0, rel_floor=1e-4)
     for which, mod in (("policy", mine.policy), ("encoder", mine._extractor.encoder)):
-        for k, p in mod.named_parameters():
-            g32, g64 = h32[which].get(k), h64[which].get(k)
-            if g32 is None:
-                continue
-            ec, eo = referee("%s:grad %s.%s" % (name, which, k), p.grad.detach().cpu().numpy(), g32.numpy(), g64.numpy(), rel_floor=2e-5)
-            if ec > worst[0]:
-                worst = (ec, eo, which + "." + k)
-    report["worst_grad"] = worst
+        keys = [k for k, _ in mod.named_parameters() if h32[which].get(k) is not None and not k.endswith(("1.0.bias", "1.3.bias"))]
+        pm = dict(mod.named_parameters())
+        report["grad_" + which] = referee_elems("%s:actor-loss gradients of the %s" % (name, which), [pm[k].grad.detach().cpu().numpy() for k in keys],
+                                                [h32[which][k].numpy() for k in keys], [h64[which][k].numpy() for k in keys])
 
 
 @pytest.mark.parametrize("over", [dict(), dict(policy_aux=False, critic_aux=False, extra_latent=3)])
@@ -88,7 +85,7 @@ def test_even_step_small_with_f64_referee(cuda, over):
     from gaddpg_b200 import agent as ag, synthetic
     from gaddpg_b200.config import LOSS_KEYS
     from oracle.ddpg_cpu import OracleAgent
-    from tests.f64ref import f64_twin, referee
+    from tests.f64ref import f64_twin, referee, referee_elems
     from tests.test_agent_gpu import _sync_from_oracle
 
     B, N = 8, 512
@@ -115,24 +112,33 @@ def test_even_step_small_with_f64_referee(cuda, over):
             if _close(m[k], o[k], rtol=1e-4):
                 continue
             assert k in CHAOTIC, (step, k, m[k], o[k])          # everything else: 1e-4, no excuses
-            referee("step %d %s" % (step, k), m[k], o[k], r[k], k=4.0, rel_floor=2e-5)
-        # post-step parameters, tensor by tensor, against the float64 twin
+            referee("step %d %s" % (step, k), m[k], o[k], r[k], k=10.0, rel_floor=1e-4)
+        # post-step parameters against the float64 twin, in LEARNING-RATE UNITS (Adam's first steps move every weight by
+        # ~lr * g / (|g| + eps): a weight whose gradient is rounding noise lands anywhere within +-lr on any fp32 side)
         sm, so, sr = mine.state_dicts(), ora.state_dicts(), twin.state_dicts()
-        loose = []
-        for net in so:
+        lr_of = {"policy": 3e-4, "critic": 3e-4, "state_feat": 1e-3}
+        for net in ("policy", "critic", "state_feat"):
+            keys = [k for k in so[net] if "running" not in k and "num_batches" not in k]
             for k in so[net]:
                 if "num_batches_tracked" in k:
                     assert int(sm[net][k]) == int(so[net][k])
-                    continue
-                a, b, c = sm[net][k].detach().cpu().double(), so[net][k].double(), sr[net][k].double()
-                if float((a - b).abs().max()) <= 1e-6 + 1e-4 * float(b.abs().max()) and "running" in k:
-                    continue
-                ec, eo = referee("step %d param %s.%s" % (step, net, k), a.numpy(), b.numpy(), c.numpy(), k=4.0, rel_floor=1e-5, abs_floor=2e-7)
-                if float((a - b).abs().max()) > 2.5e-4:
-                    loose.append((net, k, float((a - b).abs().max())))
-        # tensors that end up more than a quarter learning-rate unit apart: only where the oracle is as far from float64
-        # (the referee above held); the genuinely gradient-free ones are the Linear biases in front of BatchNorm1d
-        print("step %d: tensors > 2.5e-4 apart: %s" % (step, loose))
+            null = [k for k in keys if k.endswith(("1.0.bias", "1.3.bias"))]     # Linear biases in front of BatchNorm1d
+            live = [k for k in keys if k not in null]
+            A = lambda d, ks: [d[net][k].detach().cpu().double().numpy() for k in ks]  # noqa: E731
+            rep = referee_elems("step %d %s parameters (lr units)" % (step, net), A(sm, live), A(so, live), A(sr, live), k=5.0, big=0.25,
+                                floors=(1e-4, 1e-3), frac_slack=0.002, scales=[lr_of[net]] * len(live))
+            worst = max(float(np.abs(a - b).max()) for a, b in zip(A(sm, live), A(so, live)))
+            assert worst <= 2.0 * lr_of[net] * 1.01, (step, net, worst)                       # the mechanistic bound: one lr per side
+            for k_ in null:   # exactly-zero true gradient: pure rounding noise through Adam on both sides — only the 2 lr bound
+                assert float((sm[net][k_].detach().cpu() - so[net][k_]).abs().max()) <= 2.5e-3, (step, net, k_)
+            print("step %d %-10s param error / lr vs f64 (cuda, oracle32): %s; max |cuda - oracle32| = %.2e" % (step, net, rep, worst))
+        for net in ("policy_target", "critic_target"):
+            for k in so[net]:
+                assert float((sm[net][k].detach().cpu() - so[net][k]).abs().max()) < 1e-6, (step, net, k)
+        for k in so["state_feat"]:
+            if "running" in k:
+                a, b = sm["state_feat"][k].detach().cpu().double(), so["state_feat"][k].double()
+                assert float((a - b).abs().max()) <= 1e-6 + 1e-4 * float(b.abs().max()), (step, k)
         if even:
             rep = {}
             _actor_half_checks("small step %d" % step, mine, m, pre, batch, step_no, over, box, True, rep)
@@ -183,7 +189,7 @@ def test_full_size_even_step_matches_oracle(cuda, name, B, over):
             continue
         assert k in CHAOTIC, (name, k, m[k], o[k])     # everything else: 1e-4 from identical weights, no excuses
         if with_f64:
-            referee("%s %s" % (name, k), m[k], o[k], r[k], k=4.0, rel_floor=2e-5)
+            referee("%s %s" % (name, k), m[k], o[k], r[k], k=10.0, rel_floor=1e-4)
     rel = lambda a, b: float((a.cpu().double() - b.double()).abs().max() / (b.double().abs().max() + 1e-30))  # noqa: E731
     assert rel(mine.y, ora.last["y"]) < 1e-4
     assert rel(mine.cc1.qa[:, 0], ora.last["q1"].view(-1)) < 1e-4 and rel(mine.cc1.qa[:, 4], ora.last["q2"].view(-1)) < 1e-4

@@ -75,7 +75,7 @@ def test_plugin_forward_backward_like_reference_extractor(cuda):
     # the autograd plugin's gradients are as close to the float64 gradients as the fp32 oracle's are
     import copy
 
-    from tests.f64ref import f64_ops, referee_l2
+    from tests.f64ref import f64_ops, referee_elems
 
     o64 = copy.deepcopy(ora).double()
     o64.zero_grad()
@@ -83,13 +83,14 @@ def test_plugin_forward_backward_like_reference_extractor(cuda):
     with f64_ops():
         v64 = o64(torch.cat((cloud.double(), a64.unsqueeze(2).expand(-1, -1, cloud.shape[2])), 1), value=True)
         (v64 * R.double()).sum().backward()
-    ec, eo = referee_l2("plugin d/d(action)", [a_m.grad.cpu().numpy()], [a_o.grad.numpy()], [a64.grad.numpy()], k=5.0, floor=2e-5)
-    print("plugin d/d(action) vs float64 (relative L2): cuda %.2e, oracle32 %.2e" % (ec, eo))
+    rep = referee_elems("plugin d/d(action)", [a_m.grad.cpu().numpy()], [a_o.grad.numpy()], [a64.grad.numpy()],
+                        floors=(2e-5, 1e-4), big=5e-2, frac_slack=0.05)
+    print("plugin d/d(action) vs float64 (cuda, oracle32):", rep)
     keys = [k for k, _ in ora.value_encoder.named_parameters() if not k.endswith(("1.0.bias", "1.3.bias"))]
     po, pm, p64 = dict(ora.value_encoder.named_parameters()), dict(net.module.value_encoder.named_parameters()), dict(o64.value_encoder.named_parameters())
-    ec, eo = referee_l2("plugin value-encoder gradients", [pm[k].grad.cpu().numpy() for k in keys], [po[k].grad.numpy() for k in keys],
-                        [p64[k].grad.numpy() for k in keys], k=5.0, floor=2e-5)
-    print("plugin value-encoder grads vs float64 (relative L2): cuda %.2e, oracle32 %.2e" % (ec, eo))
+    rep = referee_elems("plugin value-encoder gradients", [pm[k].grad.cpu().numpy() for k in keys], [po[k].grad.numpy() for k in keys],
+                        [p64[k].grad.numpy() for k in keys])
+    print("plugin value-encoder grads vs float64 (cuda, oracle32):", rep)
 
     # a torch optimiser may step the parameters between calls (the reference's Adam instances do): views stay valid
     opt = torch.optim.Adam(net.module.encoder.parameters(), lr=1e-3)
