@@ -72,7 +72,7 @@ class _Lib:
         lib = self.load()
         fn = getattr(lib, name)
         if self.protos[name][0] != "int" or name in ("gaddpg_version", "gaddpg_opt_n_threads", "gaddpg_launch_count", "gaddpg_get_tensor_core",
-                                                   "gaddpg_gemm_nt_path"):
+                                                   "gaddpg_gemm_nt_path", "gaddpg_sa1_fused_grid"):
             return fn
 
         def checked(*a):

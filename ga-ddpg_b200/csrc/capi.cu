@@ -128,6 +128,25 @@ int gaddpg_sa1_l1_bwd(const float* cloud, long long cloud_stride_b, int cloud_st
                                 row_w, M_max, M_dev, D, Y, g, m1, m2, mean, rstd, W, ldw, dW, accumulate, dbc, ws,
                                 (size_t)ws_bytes, stream);
 }
+long long gaddpg_sa1f_wsplit_floats(void) { return gaddpg_sa1f_wsplit_floats_impl(); }
+int gaddpg_sa1_fused_grid(int M_max) { return gaddpg_sa1_fused_grid_impl(M_max); }
+int gaddpg_sa1f_wprep(const float* W0, int ld0, int K1, const float* W1, const float* W2, float* wsplit, void* stream) {
+  return gaddpg_sa1f_wprep_impl(W0, ld0, K1, W1, W2, wsplit, stream);
+}
+int gaddpg_sa1_fused_fwd(int phase, const float* cloud, long long cloud_stride_b, int cloud_stride_c, int skip, int Cp, const float* bc,
+                         int Cb, const float* ctr, int npoint, const int32_t* seg_off, const int32_t* row_seg, const int32_t* row_src,
+                         const float* row_w, int M_max, const int* M_dev, const float* wsplit, const float* sc0, const float* sh0,
+                         const float* sc1, const float* sh1, const float* gamma2, float* stats, float* Ykeep, float* ext, int32_t* arg,
+                         float* part_ext, int32_t* part_arg, int32_t* seg_part, void* stream) {
+  return gaddpg_sa1_fused_fwd_impl(phase, cloud, cloud_stride_b, cloud_stride_c, skip, Cp, bc, Cb, ctr, npoint, seg_off, row_seg, row_src,
+                                   row_w, M_max, M_dev, wsplit, sc0, sh0, sc1, sh1, gamma2, stats, Ykeep, ext, arg, part_ext, part_arg,
+                                   seg_part, stream);
+}
+int gaddpg_sa1_pool_finalize(const float* ext, const int32_t* arg, const float* part_ext, const int32_t* part_arg, int32_t* seg_part,
+                             const float* gamma, const float* scale, const float* shift, int S, float* out, int32_t* arg_out,
+                             void* stream) {
+  return gaddpg_sa1_pool_finalize_impl(ext, arg, part_ext, part_arg, seg_part, gamma, scale, shift, S, out, arg_out, stream);
+}
 int gaddpg_gather_rows(const float* feats, int C, const float* xyz, int n_src, const float* ctr, int npoint,
                        const int32_t* row_seg, const int32_t* row_src, int M_max, const int* M_dev, float* G, int ldg,
                        void* stream) {

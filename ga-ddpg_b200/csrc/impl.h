@@ -63,6 +63,18 @@ int gaddpg_pool_keys_finalize_impl(unsigned long long* keys, int S, int C, const
                                    int32_t* arg, void* stream);
 int gaddpg_feat_finish_impl(const float* Y, int C, const float* scale, const float* shift, const float* time,
                             float time_offset, int B, float* feat, int ld, void* stream);
+// sa1_fused.cu
+long long gaddpg_sa1f_wsplit_floats_impl();
+int gaddpg_sa1_fused_grid_impl(int M_max);
+int gaddpg_sa1f_wprep_impl(const float* W0, int ld0, int K1, const float* W1, const float* W2, float* wsplit, void* stream);
+int gaddpg_sa1_fused_fwd_impl(int phase, const float* cloud, long long cloud_sb, int cloud_sc, int skip, int Cp, const float* bc, int Cb,
+                              const float* ctr, int npoint, const int32_t* seg_off, const int32_t* row_seg, const int32_t* row_src,
+                              const float* row_w, int M_max, const int* M_dev, const float* wsplit, const float* sc0, const float* sh0,
+                              const float* sc1, const float* sh1, const float* gamma2, float* stats, float* Ykeep, float* ext,
+                              int32_t* arg, float* part_ext, int32_t* part_arg, int32_t* seg_part, void* stream);
+int gaddpg_sa1_pool_finalize_impl(const float* ext, const int32_t* arg, const float* part_ext, const int32_t* part_arg, int32_t* seg_part,
+                                  const float* gamma, const float* scale, const float* shift, int S, float* out, int32_t* arg_out,
+                                  void* stream);
 // head_ops.cu
 int gaddpg_heads_init_impl(const float* act_scale, const float* act_bias, const float* cp_rotz);
 int gaddpg_policy_head_fwd_impl(const float* raw, int ldr, int B, float* pi, void* stream);

@@ -1,0 +1,705 @@
+// sa1_fused.cu — SA1 shared MLP as ONE TMA-fed, recompute-instead-of-store tcgen05 chain (sm_100a only).
+//
+// Replaces, for the first set-abstraction level (~423 k compact rows at B = 256), what upstream QueryAndGroup + build_shared_mlp
+// (Conv2d 1x1 + train-mode BatchNorm2d + ReLU, three times) + F.max_pool2d do on a materialised (B, C, 32, 64) tensor
+// (/root/reference/core/networks.py:66-71), and what this library did before with five launches
+// that round-tripped every pre-BatchNorm activation through HBM (sa1_l1_fwd -> Y0, gemm_nt -> Y1, gemm_nt -> Y2, pool_fwd).
+//
+// Train-mode BatchNorm makes every layer a grid-wide dependency (layer l+1 needs the batch statistics of layer l), so the
+// chain runs as THREE PHASES — three launches of the same kernel template — and each phase RECOMPUTES the layers below it
+// from the L2-resident cloud instead of reading them back:
+//   phase 1   gather -> conv0                                    -> statistics of Y0                 [keep: Y0 stored]
+//   phase 2   gather -> conv0 -> BN0+ReLU -> conv1               -> statistics of Y1                 [keep: Y1 stored]
+//   phase 3   gather -> conv0 -> BN0+ReLU -> conv1 -> BN1+ReLU -> conv2 -> statistics of Y2 and the per-(ball, channel)
+//             extreme of Y2 (max for gamma >= 0, min otherwise: BN+ReLU is monotone per channel)   [keep: Y2 stored]
+// Forward-only passes (target chain F2/F3, select_action) therefore move NO activation through HBM: algorithmic traffic is
+// the row table (12 B/row), the pooled extremes and the slots.  Passes that are differentiated ("keep") store the three
+// pre-BN outputs for the backward kernels through TMA (cp.async.bulk.tensor stores from a swizzled staging tile) but never
+// read them back in the forward.
+//
+// One CTA per SM, 128-row tiles, a contiguous tile range per CTA (segments = ball groups are contiguous in the row table, so
+// a group is reduced inside one CTA's registers; only the <= 147 groups straddling a CTA boundary are merged by the finalize
+// kernel — no atomics, deterministic).  Warp roles (17 warps):
+//   P   warps 0-3    thread = row: row-table + scattered cloud reads (3+Cp channels, L2), centroid subtraction, broadcast
+//                    (action) channels, hi/lo split, swizzled STS of the [128 x 16] layer-0 operand
+//   MMA warp 4       one thread: TMA loads of the pre-split weights (cp.async.bulk.tensor, SWIZZLE_64B/128B, once per CTA),
+//                    tcgen05.mma kind::tf32 x3 (3xTF32) for conv0 (K=16), conv1 (K=64), conv2 (K=64, N=128) into TMEM
+//   E0  warps 5-8    thread = row: tcgen05.ld of conv0's accumulator, BN0+ReLU, split, STS into the conv1 operand buffer
+//                    (phase 1: statistics of Y0 instead)
+//   E1  warps 9-12   same for conv1's accumulator -> conv2 operand buffer (phase 2: statistics of Y1)
+//   E2  warps 13-16  conv2's accumulator -> swizzled staging tile -> thread = column: one pass over the rows that yields
+//                    the column's statistics AND its running per-segment extreme (flushed when the segment changes)
+// The conv1 and conv2 operands share ONE 64 KB buffer (conv2's operand is produced from conv1's finished accumulator), which
+// is what lets all three weight matrices (hi + lo, 104 KB), the operands and the staging tile fit in 227 KB.
+#include <cuda.h>
+
+#include "tc_common.cuh"
+#include "impl.h"
+
+namespace {
+
+constexpr int F_BM = 128;   // rows per tile (UMMA M)
+constexpr int F_K0 = 16;    // layer-0 K, padded (3 + per-point channels + broadcast channels <= 16)
+constexpr int F_C = 64;     // widths of conv0 / conv1 outputs (networks.py:70: mlp = [in, 64, 64, 128])
+constexpr int F_C3 = 128;   // width of conv2's output
+constexpr int F_WARPS = 17;
+constexpr int F_THREADS = F_WARPS * 32;
+constexpr int W_P = 0, W_MMA = 4, W_E0 = 5, W_E1 = 9, W_E2 = 13;
+
+struct FLayout {
+  uint32_t w0h, w0l, w1h, w1l, w2h, w2l, a0h, a0l, abh, abl, stage, consts, meta, bars, red, total;
+};
+__host__ __device__ inline FLayout f_layout(int phase) {
+  FLayout L;
+  uint32_t off = 0;
+  L.w0h = off; off += F_C * F_K0 * 4;
+  L.w0l = off; off += F_C * F_K0 * 4;
+  L.w1h = off; off += (phase >= 2) ? F_C * F_C * 4 : 0;
+  L.w1l = off; off += (phase >= 2) ? F_C * F_C * 4 : 0;
+  L.w2h = off; off += (phase >= 3) ? F_C3 * F_C * 4 : 0;
+  L.w2l = off; off += (phase >= 3) ? F_C3 * F_C * 4 : 0;
+  L.a0h = off; off += F_BM * F_K0 * 4;
+  L.a0l = off; off += F_BM * F_K0 * 4;
+  L.abh = off; off += (phase >= 2) ? F_BM * F_C * 4 : 0;
+  L.abl = off; off += (phase >= 2) ? F_BM * F_C * 4 : 0;
+  L.stage = off; off += 32768;          // phases 1/2: 4 x [2 col blocks][32 rows x 128 B]; phase 3: [4 col blocks][64 rows x 128 B]
+  L.consts = off; off += 2048;          // sc0, sh0, sc1, sh1 [64 each], sign(gamma2) [128]
+  L.meta = off; off += 1024;            // E2: segment id and multiplicity of the tile's 128 rows
+  L.red = off; off += 2 * 4 * F_C * 4;  // phases 1/2: cross-warp combine of the column sums [2][4 warps][64]
+  L.bars = off; off += 256;
+  L.total = off;
+  return L;
+}
+
+struct Sa1FParams {
+  const float* cloud; long long cloud_sb; int cloud_sc; int skip; int Cp;
+  const float* bc; int Cb;
+  const float* ctr; int npoint;
+  const int32_t* seg_off; const int32_t* row_seg; const int32_t* row_src; const float* row_w;
+  int M_max; const int* M_dev;
+  const float* sc0; const float* sh0; const float* sc1; const float* sh1; const float* gamma2;
+  float* stats;
+  float* ext; int32_t* arg; float* part_ext; int32_t* part_arg; int32_t* seg_part;
+  int keep;
+};
+
+// ---- PTX: TMA + transaction barriers ------------------------------------------------------------------
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst_smem),
+               "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src_smem, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tm)),
+               "r"(src_smem), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// K-major SWIZZLE_64B descriptor (layer-0 operands: rows of 16 floats = 64 B; 8-row atoms of 512 B)
+__device__ __forceinline__ uint64_t make_desc64(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
+}
+__device__ __forceinline__ uint32_t sw64_off(int r, int chunk) {  // 16-byte chunk 0..3 of row r
+  return (uint32_t)(r * 64 + ((chunk ^ ((r >> 1) & 3)) << 4));
+}
+__device__ __forceinline__ uint32_t idesc_tf32(int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(F_BM >> 4) << 24);
+}
+
+// relu(y * sc + sh) of 4 consecutive columns, split and stored into the K-major SWIZZLE_128B operand buffer
+__device__ __forceinline__ void bnrelu_split_store(unsigned char* hi, unsigned char* lo, int row, int col, const float* r4,
+                                                   const float* sc, const float* sh) {
+  const float4 s = *reinterpret_cast<const float4*>(sc + col), t = *reinterpret_cast<const float4*>(sh + col);
+  float4 v;
+  v.x = fmaxf(fmaf(r4[0], s.x, t.x), 0.f);
+  v.y = fmaxf(fmaf(r4[1], s.y, t.y), 0.f);
+  v.z = fmaxf(fmaf(r4[2], s.z, t.z), 0.f);
+  v.w = fmaxf(fmaf(r4[3], s.w, t.w), 0.f);
+  split_store(hi, lo, sw128_off(row, col, F_BM), v);
+}
+
+// Phases 1/2, thread = row with the 64 pre-BN outputs of its row in registers: weighted column sums of the warp's 32 rows
+// through a swizzled [2 col blocks][32 rows x 128 B] staging tile (the TMA store box of the keep mode), lane = column pair.
+__device__ __forceinline__ void stats64_tile(const float* r, float w, unsigned char* st, int lane, bool keep, const CUtensorMap* tmY,
+                                             int grow0, float (&S0)[2], float (&S1)[2]) {
+  if (keep && lane == 0) tma_wait_read0();   // the previous tile's store must have read the staging tile
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+    *reinterpret_cast<float4*>(st + (j >> 3) * 4096 + lane * 128 + (((j & 7) ^ (lane & 7)) << 4)) =
+        make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+  if (keep) fence_proxy_async();   // writers: make the generic-proxy stores visible to the TMA (async proxy) before the sync
+  __syncwarp();
+  if (keep && lane == 0) {
+    tma_store_2d(tmY, smem_u32(st), 0, grow0);
+    tma_store_2d(tmY, smem_u32(st + 4096), 32, grow0);
+    tma_commit();
+  }
+  const int cb = lane >> 4, col = (2 * lane) & 31, chunk = col >> 2;
+  float t00 = 0.f, t01 = 0.f, t10 = 0.f, t11 = 0.f;
+#pragma unroll 8
+  for (int rr = 0; rr < 32; ++rr) {
+    const float2 y = *reinterpret_cast<const float2*>(st + cb * 4096 + rr * 128 + ((chunk ^ (rr & 7)) << 4) + (col & 3) * 4);
+    const float wr = __shfl_sync(0xffffffffu, w, rr);
+    t00 = fmaf(wr, y.x, t00);
+    t01 = fmaf(wr * y.x, y.x, t01);
+    t10 = fmaf(wr, y.y, t10);
+    t11 = fmaf(wr * y.y, y.y, t11);
+  }
+  S0[0] += t00; S1[0] += t01; S0[1] += t10; S1[1] += t11;
+}
+
+template <int PHASE>
+__global__ void __launch_bounds__(F_THREADS, 1)
+sa1_fused_kernel(const Sa1FParams p, const __grid_constant__ CUtensorMap tW0h, const __grid_constant__ CUtensorMap tW0l,
+                 const __grid_constant__ CUtensorMap tW1h, const __grid_constant__ CUtensorMap tW1l,
+                 const __grid_constant__ CUtensorMap tW2h, const __grid_constant__ CUtensorMap tW2l,
+                 const __grid_constant__ CUtensorMap tY) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const FLayout L = f_layout(PHASE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
+  uint64_t* w_full = bars + 0;
+  uint64_t* a0_full = bars + 1;
+  uint64_t* a0_empty = bars + 2;
+  uint64_t* acc0_full = bars + 3;    // [2]
+  uint64_t* acc0_empty = bars + 5;   // [2]
+  uint64_t* ab1_full = bars + 7;
+  uint64_t* ab_free = bars + 8;
+  uint64_t* acc1_full = bars + 9;    // [2]
+  uint64_t* acc1_empty = bars + 11;  // [2]
+  uint64_t* ab2_full = bars + 13;
+  uint64_t* acc2_full = bars + 14;   // [2]
+  uint64_t* acc2_empty = bars + 16;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int M = p.M_dev ? *p.M_dev : p.M_max;
+  M = M < p.M_max ? M : p.M_max;
+  const int ntiles = (M + F_BM - 1) / F_BM;
+  const int tpc = (ntiles + (int)gridDim.x - 1) / (int)gridDim.x;   // contiguous tile range per CTA
+  const int tile0 = (int)blockIdx.x * tpc;
+  int my_tiles = ntiles - tile0;
+  my_tiles = my_tiles < 0 ? 0 : (my_tiles > tpc ? tpc : my_tiles);
+  constexpr uint32_t TMEM_COLS = PHASE == 1 ? 128 : PHASE == 2 ? 256 : 512;
+  constexpr uint32_t ACC0 = 0, ACC1 = 128, ACC2 = 256;
+
+  if (tid == 0) {
+    mbar_init(w_full, 1);
+    mbar_init(a0_full, 128);
+    mbar_init(a0_empty, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc0_full[s], 1);
+      mbar_init(&acc0_empty[s], 4);
+      mbar_init(&acc1_full[s], 1);
+      mbar_init(&acc1_empty[s], 4);
+      mbar_init(&acc2_full[s], 1);
+      mbar_init(&acc2_empty[s], 4);
+    }
+    mbar_init(ab1_full, 128);
+    mbar_init(ab_free, 1);
+    mbar_init(ab2_full, 128);
+    fence_barrier_init();
+  }
+  if (warp == W_MMA) tmem_alloc(tmem_slot, TMEM_COLS);
+  {
+    float* cs = reinterpret_cast<float*>(smem + L.consts);
+    if (PHASE >= 2)
+      for (int i = tid; i < F_C; i += F_THREADS) {
+        cs[i] = p.sc0[i];
+        cs[64 + i] = p.sh0[i];
+      }
+    if (PHASE >= 3)
+      for (int i = tid; i < F_C; i += F_THREADS) {
+        cs[128 + i] = p.sc1[i];
+        cs[192 + i] = p.sh1[i];
+      }
+    if (PHASE >= 3)
+      for (int i = tid; i < F_C3; i += F_THREADS) cs[256 + i] = p.gamma2[i] < 0.f ? -1.f : 1.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t sbase = smem_u32(smem);
+
+  if (warp < W_MMA) {
+    // ===================== P: gather + layer-0 operand =====================
+    const int r = tid;  // tile row
+    const int K1 = 3 + p.Cp + p.Cb;
+    auto gather = [&](int it, float (&in)[F_K0]) {
+#pragma unroll
+      for (int k = 0; k < F_K0; ++k) in[k] = 0.f;
+      const int row = (tile0 + it) * F_BM + r;
+      if (it < my_tiles && row < M) {
+        const int seg = p.row_seg[row], src = p.row_src[row];
+        const int b = seg / p.npoint;
+        const float* pc = p.cloud + (long long)b * p.cloud_sb + p.skip + src;
+#pragma unroll
+        for (int k = 0; k < F_K0 - 3; ++k)
+          if (k < p.Cp) in[3 + k] = pc[(long long)k * p.cloud_sc];
+        in[0] = in[3] - p.ctr[(long long)seg * 3 + 0];
+        in[1] = in[4] - p.ctr[(long long)seg * 3 + 1];
+        in[2] = in[5] - p.ctr[(long long)seg * 3 + 2];
+#pragma unroll
+        for (int k = 3; k < F_K0; ++k) {
+          const int j = k - 3 - p.Cp;
+          if (j >= 0 && k < K1) in[k] = p.bc[(long long)b * p.Cb + j];
+        }
+      }
+    };
+    float cur[F_K0], nxt[F_K0];
+    gather(0, cur);
+    for (int it = 0; it < my_tiles; ++it) {
+      gather(it + 1, nxt);   // the next tile's scattered loads are in flight while this one is written
+      mbar_wait(a0_empty, ((uint32_t)it & 1u) ^ 1u);
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        split_store(smem + L.a0h, smem + L.a0l, sw64_off(r, c), make_float4(cur[4 * c], cur[4 * c + 1], cur[4 * c + 2], cur[4 * c + 3]));
+      fence_proxy_async();
+      mbar_arrive(a0_full);
+#pragma unroll
+      for (int k = 0; k < F_K0; ++k) cur[k] = nxt[k];
+    }
+  } else if (warp == W_MMA) {
+    // ===================== MMA issuer (+ TMA weight loads) =====================
+    if (lane == 0) {
+      constexpr uint32_t WBYTES = 2 * F_C * F_K0 * 4 + (PHASE >= 2 ? 2 * F_C * F_C * 4 : 0) + (PHASE >= 3 ? 2 * F_C3 * F_C * 4 : 0);
+      mbar_expect_tx(w_full, WBYTES);
+      tma_load_2d(sbase + L.w0h, &tW0h, 0, 0, w_full);
+      tma_load_2d(sbase + L.w0l, &tW0l, 0, 0, w_full);
+      if (PHASE >= 2) {
+        for (int kb = 0; kb < 2; ++kb) {
+          tma_load_2d(sbase + L.w1h + kb * F_C * 128, &tW1h, kb * 32, 0, w_full);
+          tma_load_2d(sbase + L.w1l + kb * F_C * 128, &tW1l, kb * 32, 0, w_full);
+        }
+      }
+      if (PHASE >= 3) {
+        for (int kb = 0; kb < 2; ++kb) {
+          tma_load_2d(sbase + L.w2h + kb * F_C3 * 128, &tW2h, kb * 32, 0, w_full);
+          tma_load_2d(sbase + L.w2l + kb * F_C3 * 128, &tW2l, kb * 32, 0, w_full);
+        }
+      }
+      mbar_wait(w_full, 0);
+      tc_fence_after();
+      const uint32_t id64 = idesc_tf32(F_C), id128 = idesc_tf32(F_C3);
+      auto mma0 = [&](int j) {
+        const int b = j & 1;
+        mbar_wait(a0_full, (uint32_t)j & 1u);
+        mbar_wait(&acc0_empty[b], (((uint32_t)j >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d = tmem_base + ACC0 + (uint32_t)b * F_C;
+        uint32_t acc = 0;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          const uint64_t ah = make_desc64(sbase + L.a0h + ks * 32), al = make_desc64(sbase + L.a0l + ks * 32);
+          const uint64_t bh = make_desc64(sbase + L.w0h + ks * 32), bl = make_desc64(sbase + L.w0l + ks * 32);
+          umma_tf32(d, al, bh, id64, acc);
+          umma_tf32(d, ah, bl, id64, 1u);
+          umma_tf32(d, ah, bh, id64, 1u);
+          acc = 1u;
+        }
+        umma_commit(a0_empty);
+        umma_commit(&acc0_full[b]);
+      };
+      auto mma_k64 = [&](uint32_t d, uint32_t wh, uint32_t wl, int nrows_w, uint32_t idesc) {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t aoff = (uint32_t)(kb * F_BM * 128 + ks * 32), boff = (uint32_t)(kb * nrows_w * 128 + ks * 32);
+            const uint64_t ah = make_desc(sbase + L.abh + aoff), al = make_desc(sbase + L.abl + aoff);
+            const uint64_t bh = make_desc(sbase + wh + boff), bl = make_desc(sbase + wl + boff);
+            umma_tf32(d, al, bh, idesc, acc);
+            umma_tf32(d, ah, bl, idesc, 1u);
+            umma_tf32(d, ah, bh, idesc, 1u);
+            acc = 1u;
+          }
+        }
+      };
+      if (my_tiles > 0) mma0(0);
+      for (int it = 0; it < my_tiles; ++it) {
+        if (it + 1 < my_tiles) mma0(it + 1);   // conv0 of the next tile first: E0 can run ahead of conv1/conv2 of this one
+        if (PHASE >= 2) {
+          const int b = it & 1;
+          mbar_wait(ab1_full, (uint32_t)it & 1u);
+          mbar_wait(&acc1_empty[b], (((uint32_t)it >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          mma_k64(tmem_base + ACC1 + (uint32_t)b * F_C, L.w1h, L.w1l, F_C, id64);
+          umma_commit(&acc1_full[b]);
+          if (PHASE == 2) umma_commit(ab_free);
+        }
+        if (PHASE >= 3) {
+          const int b = it & 1;
+          mbar_wait(ab2_full, (uint32_t)it & 1u);
+          mbar_wait(&acc2_empty[b], (((uint32_t)it >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          mma_k64(tmem_base + ACC2 + (uint32_t)b * F_C3, L.w2h, L.w2l, F_C3, id128);
+          umma_commit(&acc2_full[b]);
+          umma_commit(ab_free);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp < W_E1) {
+    // ===================== E0: conv0 accumulator =====================
+    const int q = warp & 3, row = q * 32 + lane;
+    const float* cs = reinterpret_cast<const float*>(smem + L.consts);
+    unsigned char* st = smem + L.stage + (warp - W_E0) * 8192;
+    float S0[2] = {0.f, 0.f}, S1[2] = {0.f, 0.f};
+    for (int it = 0; it < my_tiles; ++it) {
+      const int b = it & 1;
+      const int grow = (tile0 + it) * F_BM + row;
+      float w = 0.f;
+      if (PHASE == 1 && grow < M) w = p.row_w[grow];
+      mbar_wait(&acc0_full[b], ((uint32_t)it >> 1) & 1u);
+      tc_fence_after();
+      float r[F_C];
+      const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + ACC0 + (uint32_t)b * F_C;
+      tmem_ld32(ta, r);
+      tmem_ld32(ta + 32, r + 32);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc0_empty[b]);
+      if (PHASE == 1) {
+        stats64_tile(r, w, st, lane, p.keep != 0, &tY, (tile0 + it) * F_BM + q * 32, S0, S1);
+      } else {
+        mbar_wait(ab_free, ((uint32_t)it & 1u) ^ 1u);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) bnrelu_split_store(smem + L.abh, smem + L.abl, row, 4 * j, r + 4 * j, cs, cs + 64);
+        fence_proxy_async();
+        mbar_arrive(ab1_full);
+      }
+    }
+    if (PHASE == 1) {
+      if (p.keep && lane == 0) tma_wait_all0();
+      float* red = reinterpret_cast<float*>(smem + L.red);
+      const int w4 = warp - W_E0;
+      red[w4 * 64 + 2 * lane] = S0[0];
+      red[w4 * 64 + 2 * lane + 1] = S0[1];
+      red[256 + w4 * 64 + 2 * lane] = S1[0];
+      red[256 + w4 * 64 + 2 * lane + 1] = S1[1];
+    }
+  } else if (warp < W_E2) {
+    // ===================== E1: conv1 accumulator =====================
+    if (PHASE >= 2) {
+      const int q = warp & 3, row = q * 32 + lane;
+      const float* cs = reinterpret_cast<const float*>(smem + L.consts);
+      unsigned char* st = smem + L.stage + (warp - W_E1) * 8192;
+      float S0[2] = {0.f, 0.f}, S1[2] = {0.f, 0.f};
+      for (int it = 0; it < my_tiles; ++it) {
+        const int b = it & 1;
+        const int grow = (tile0 + it) * F_BM + row;
+        float w = 0.f;
+        if (PHASE == 2 && grow < M) w = p.row_w[grow];
+        mbar_wait(&acc1_full[b], ((uint32_t)it >> 1) & 1u);
+        tc_fence_after();
+        float r[F_C];
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + ACC1 + (uint32_t)b * F_C;
+        tmem_ld32(ta, r);
+        tmem_ld32(ta + 32, r + 32);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc1_empty[b]);
+        if (PHASE == 2) {
+          stats64_tile(r, w, st, lane, p.keep != 0, &tY, (tile0 + it) * F_BM + q * 32, S0, S1);
+        } else {
+          // conv1 of this tile has completed (acc1_full), so the shared operand buffer may be overwritten with conv2's operand
+#pragma unroll
+          for (int j = 0; j < 16; ++j) bnrelu_split_store(smem + L.abh, smem + L.abl, row, 4 * j, r + 4 * j, cs + 128, cs + 192);
+          fence_proxy_async();
+          mbar_arrive(ab2_full);
+        }
+      }
+      if (PHASE == 2) {
+        if (p.keep && lane == 0) tma_wait_all0();
+        float* red = reinterpret_cast<float*>(smem + L.red);
+        const int w4 = warp - W_E1;
+        red[w4 * 64 + 2 * lane] = S0[0];
+        red[w4 * 64 + 2 * lane + 1] = S0[1];
+        red[256 + w4 * 64 + 2 * lane] = S1[0];
+        red[256 + w4 * 64 + 2 * lane + 1] = S1[1];
+      }
+    }
+  } else {
+    // ===================== E2: conv2 accumulator -> statistics + per-segment extremes =====================
+    if (PHASE >= 3) {
+      const int q = warp & 3;             // TMEM lane quarter = 32-row group of the tile this warp may read
+      const int c = tid - W_E2 * 32;      // column owned in the row loop
+      const float* cs = reinterpret_cast<const float*>(smem + L.consts);
+      const bool neg = cs[256 + c] < 0.f;
+      int32_t* mseg = reinterpret_cast<int32_t*>(smem + L.meta);
+      float* mw = reinterpret_cast<float*>(smem + L.meta + 512);
+      unsigned char* st = smem + L.stage;
+      const int cta_row0 = tile0 * F_BM;
+      float S0 = 0.f, S1 = 0.f;
+      int cur = -1, barg = 0;
+      float best = 0.f;
+      bool first_flush = true;
+      auto flush = [&]() {
+        if (cur < 0) return;
+        const float v = neg ? -best : best;
+        if (first_flush && p.seg_off[cur] < cta_row0) {   // this segment began in the previous CTA's range: partial result
+          p.part_ext[(long long)blockIdx.x * F_C3 + c] = v;
+          p.part_arg[(long long)blockIdx.x * F_C3 + c] = barg;
+          if (c == 0) p.seg_part[cur] = (int)blockIdx.x;
+        } else {
+          p.ext[(long long)cur * F_C3 + c] = v;
+          p.arg[(long long)cur * F_C3 + c] = barg;
+        }
+        first_flush = false;
+      };
+      for (int it = 0; it < my_tiles; ++it) {
+        const int b = it & 1;
+        const int trow0 = (tile0 + it) * F_BM;
+        named_bar(1, 128);   // every E2 thread is done with the previous tile's meta / staging
+        {
+          const int grow = trow0 + c;
+          mseg[c] = grow < M ? p.row_seg[grow] : -1;
+          mw[c] = grow < M ? p.row_w[grow] : 0.f;
+        }
+        mbar_wait(&acc2_full[b], ((uint32_t)it >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + ACC2 + (uint32_t)b * F_C3;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          if ((q >> 1) == half) {   // this warp's 32 rows belong to this 64-row half: TMEM -> swizzled staging
+            const int lr = (q & 1) * 32 + lane;
+#pragma unroll 1
+            for (int cb = 0; cb < 4; ++cb) {
+              float r[32];
+              tmem_ld32(ta + cb * 32, r);
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4*>(st + cb * 8192 + lr * 128 + ((j ^ (lr & 7)) << 4)) = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+            }
+            if (p.keep) fence_proxy_async();
+          }
+          named_bar(2, 128);
+          if (p.keep && c == 0) {
+#pragma unroll
+            for (int cb = 0; cb < 4; ++cb) tma_store_2d(&tY, smem_u32(st + cb * 8192), cb * 32, trow0 + half * 64);
+            tma_commit();
+          }
+          float t0 = 0.f, t1 = 0.f;
+          const unsigned char* colp = st + (c >> 5) * 8192 + (c & 3) * 4;
+          const int chunk = (c & 31) >> 2;
+          int nr = M - (trow0 + half * 64);
+          nr = nr > 64 ? 64 : nr;
+#pragma unroll 4
+          for (int rr = 0; rr < nr; ++rr) {
+            const int tr = half * 64 + rr;
+            const float v = *reinterpret_cast<const float*>(colp + rr * 128 + ((chunk ^ (rr & 7)) << 4));
+            const int sg = mseg[tr];
+            const float w = mw[tr];
+            t0 = fmaf(w, v, t0);
+            t1 = fmaf(w * v, v, t1);
+            const float key = neg ? -v : v;
+            if (sg != cur) {   // warp-uniform: all columns walk the same rows
+              flush();
+              cur = sg;
+              best = key;
+              barg = trow0 + tr;
+            } else if (key > best) {
+              best = key;
+              barg = trow0 + tr;
+            }
+          }
+          S0 += t0;
+          S1 += t1;
+          if (p.keep && c == 0) tma_wait_read0();
+          named_bar(3, 128);   // the staging tile is free for the other half / the next tile
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc2_empty[b]);
+      }
+      flush();
+      if (p.keep && c == 0) tma_wait_all0();
+      p.stats[(long long)blockIdx.x * 2 * F_C3 + c] = S0;
+      p.stats[(long long)blockIdx.x * 2 * F_C3 + F_C3 + c] = S1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (PHASE <= 2) {   // one slot per CTA: the four row-group warps folded in a fixed order
+    const float* red = reinterpret_cast<const float*>(smem + L.red);
+    if (tid < 2 * F_C) {
+      const int h = tid >> 6, cc = tid & 63;
+      p.stats[(long long)blockIdx.x * 2 * F_C + tid] = my_tiles > 0 ? red[h * 256 + cc] + red[h * 256 + 64 + cc] + red[h * 256 + 128 + cc] + red[h * 256 + 192 + cc] : 0.f;
+    }
+  } else if (my_tiles == 0) {
+    for (int i = tid; i < 2 * F_C3; i += F_THREADS) p.stats[(long long)blockIdx.x * 2 * F_C3 + i] = 0.f;
+  }
+  {
+    constexpr int CW = PHASE <= 2 ? 2 * F_C : 2 * F_C3;
+    for (int slot = blockIdx.x + gridDim.x; slot < GADDPG_STAT_SLOTS; slot += gridDim.x)
+      for (int i = tid; i < CW; i += F_THREADS) p.stats[(long long)slot * CW + i] = 0.f;
+  }
+  if (warp == W_MMA) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// out = relu(bn(extreme)) + arg-max row per (segment, channel); merges the segments that straddle two CTAs' tile ranges
+__global__ void __launch_bounds__(128) sa1_pool_finalize_kernel(const float* __restrict__ ext, const int32_t* __restrict__ arg,
+                                                                const float* __restrict__ part_ext,
+                                                                const int32_t* __restrict__ part_arg, int32_t* __restrict__ seg_part,
+                                                                const float* __restrict__ gamma, const float* __restrict__ scale,
+                                                                const float* __restrict__ shift, int S, float* __restrict__ out,
+                                                                int32_t* __restrict__ arg_out) {
+  const int c = threadIdx.x;
+  const bool neg = gamma[c] < 0.f;
+  const float sc = scale[c], sh = shift[c];
+  for (int s = blockIdx.x; s < S; s += gridDim.x) {
+    float v = ext[(long long)s * F_C3 + c];
+    int a = arg[(long long)s * F_C3 + c];
+    const int sp = seg_part[s];
+    if (sp >= 0) {   // the tail of this segment was reduced by CTA sp: higher rows, so a tie keeps the head's row
+      const float pv = part_ext[(long long)sp * F_C3 + c];
+      if ((neg ? -pv : pv) > (neg ? -v : v)) {
+        v = pv;
+        a = part_arg[(long long)sp * F_C3 + c];
+      }
+    }
+    out[(long long)s * F_C3 + c] = fmaxf(fmaf(v, sc, sh), 0.f);
+    if (arg_out) arg_out[(long long)s * F_C3 + c] = a;
+    __syncthreads();
+    if (c == 0 && sp >= 0) seg_part[s] = -1;
+  }
+}
+
+// pre-split (hi = tf32 bits, lo = x - hi) weight images for the TMA loads, once per optimiser step
+__global__ void sa1f_wprep_kernel(const float* __restrict__ W0, int ld0, int K1, const float* __restrict__ W1, const float* __restrict__ W2,
+                                  float* __restrict__ out) {
+  const int n0 = F_C * F_K0, n1 = F_C * F_C, n2 = F_C3 * F_C;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n0 + n1 + n2; i += gridDim.x * blockDim.x) {
+    float x;
+    float* dst;
+    if (i < n0) {
+      const int n = i / F_K0, k = i % F_K0;
+      x = k < K1 ? W0[(long long)n * ld0 + k] : 0.f;
+      dst = out + i;
+    } else if (i < n0 + n1) {
+      x = W1[i - n0];
+      dst = out + 2 * n0 + (i - n0);
+    } else {
+      x = W2[i - n0 - n1];
+      dst = out + 2 * n0 + 2 * n1 + (i - n0 - n1);
+    }
+    const float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+    const int half = i < n0 ? n0 : (i < n0 + n1 ? n1 : n2);
+    dst[0] = h;
+    dst[half] = x - h;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+// row-major [rows][cols] float32 matrix, box = [box_rows][box_cols] with box_cols * 4 == swizzle span
+bool make_map(CUtensorMap* tm, const float* base, int rows, int cols, int box_rows, int box_cols, CUtensorMapSwizzle sw) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+int gaddpg_sa1f_wprep_impl(const float* W0, int ld0, int K1, const float* W1, const float* W2, float* wsplit, void* stream) {
+  GADDPG_CHECK_ARG(W0 && W1 && W2 && wsplit && K1 >= 4 && K1 <= F_K0 && ld0 >= K1, "sa1f_wprep: bad argument (K1=%d)", K1);
+  sa1f_wprep_kernel<<<24, 256, 0, (cudaStream_t)stream>>>(W0, ld0, K1, W1, W2, wsplit);
+  GADDPG_CHECK_LAUNCH("sa1f_wprep_kernel");
+  return GADDPG_OK;
+}
+
+long long gaddpg_sa1f_wsplit_floats_impl() { return 2ll * (F_C * F_K0 + F_C * F_C + F_C3 * F_C); }
+
+int gaddpg_sa1_fused_fwd_impl(int phase, const float* cloud, long long cloud_sb, int cloud_sc, int skip, int Cp, const float* bc, int Cb,
+                              const float* ctr, int npoint, const int32_t* seg_off, const int32_t* row_seg, const int32_t* row_src,
+                              const float* row_w, int M_max, const int* M_dev, const float* wsplit, const float* sc0, const float* sh0,
+                              const float* sc1, const float* sh1, const float* gamma2, float* stats, float* Ykeep, float* ext,
+                              int32_t* arg, float* part_ext, int32_t* part_arg, int32_t* seg_part, void* stream) {
+  GADDPG_CHECK_ARG(phase >= 1 && phase <= 3, "sa1_fused_fwd: phase must be 1, 2 or 3");
+  GADDPG_CHECK_ARG(cloud && ctr && seg_off && row_seg && row_src && row_w && wsplit && stats && M_max >= 0 && npoint >= 1,
+                   "sa1_fused_fwd: null pointer");
+  GADDPG_CHECK_ARG(Cp >= 3 && Cb >= 0 && 3 + Cp + Cb <= F_K0 && (Cb == 0 || bc), "sa1_fused_fwd: 3 + %d + %d input channels exceed %d", Cp, Cb, F_K0);
+  GADDPG_CHECK_ARG(phase < 2 || (sc0 && sh0), "sa1_fused_fwd: phase %d needs the BatchNorm constants of layer 0", phase);
+  GADDPG_CHECK_ARG(phase < 3 || (sc1 && sh1 && gamma2 && ext && arg && part_ext && part_arg && seg_part), "sa1_fused_fwd: phase 3 arguments");
+  if (M_max == 0) return GADDPG_OK;
+  const int n0 = F_C * F_K0, n1 = F_C * F_C, n2 = F_C3 * F_C;
+  const float *w0h = wsplit, *w0l = wsplit + n0, *w1h = wsplit + 2 * n0, *w1l = w1h + n1, *w2h = w1h + 2 * n1, *w2l = w2h + n2;
+  CUtensorMap m0h, m0l, m1h, m1l, m2h, m2l, mY;
+  bool ok = make_map(&m0h, w0h, F_C, F_K0, F_C, F_K0, CU_TENSOR_MAP_SWIZZLE_64B) && make_map(&m0l, w0l, F_C, F_K0, F_C, F_K0, CU_TENSOR_MAP_SWIZZLE_64B) &&
+            make_map(&m1h, w1h, F_C, F_C, F_C, 32, CU_TENSOR_MAP_SWIZZLE_128B) && make_map(&m1l, w1l, F_C, F_C, F_C, 32, CU_TENSOR_MAP_SWIZZLE_128B) &&
+            make_map(&m2h, w2h, F_C3, F_C, F_C3, 32, CU_TENSOR_MAP_SWIZZLE_128B) && make_map(&m2l, w2l, F_C3, F_C, F_C3, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+  const int CY = phase == 3 ? F_C3 : F_C;
+  if (Ykeep) {
+    GADDPG_CHECK_ARG(((uintptr_t)Ykeep & 15u) == 0, "sa1_fused_fwd: Ykeep must be 16-byte aligned");
+    ok = ok && make_map(&mY, Ykeep, M_max, CY, phase == 3 ? 64 : 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+  } else {
+    mY = m1h;   // unused
+  }
+  if (!ok) {
+    gaddpg_set_error("sa1_fused_fwd: cuTensorMapEncodeTiled failed or is unavailable");
+    return GADDPG_ERR_CUDA;
+  }
+  Sa1FParams p;
+  p.cloud = cloud; p.cloud_sb = cloud_sb; p.cloud_sc = cloud_sc; p.skip = skip; p.Cp = Cp; p.bc = bc; p.Cb = Cb; p.ctr = ctr;
+  p.npoint = npoint; p.seg_off = seg_off; p.row_seg = row_seg; p.row_src = row_src; p.row_w = row_w; p.M_max = M_max; p.M_dev = M_dev;
+  p.sc0 = sc0; p.sh0 = sh0; p.sc1 = sc1; p.sh1 = sh1; p.gamma2 = gamma2; p.stats = stats; p.ext = ext; p.arg = arg;
+  p.part_ext = part_ext; p.part_arg = part_arg; p.seg_part = seg_part; p.keep = Ykeep ? 1 : 0;
+  const int tiles = ceil_div(M_max, F_BM);
+  const int grid = tiles < gaddpg_sm_count() ? tiles : gaddpg_sm_count();
+  const size_t smem = f_layout(phase).total + 1024;
+  cudaStream_t st = (cudaStream_t)stream;
+#define F_LAUNCH(PH)                                                                                             \
+  {                                                                                                              \
+    auto kern = sa1_fused_kernel<PH>;                                                                            \
+    GADDPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
+    kern<<<grid, F_THREADS, smem, st>>>(p, m0h, m0l, m1h, m1l, m2h, m2l, mY);                                    \
+    GADDPG_CHECK_LAUNCH("sa1_fused_kernel");                                                                     \
+  }
+  if (phase == 1) F_LAUNCH(1) else if (phase == 2) F_LAUNCH(2) else F_LAUNCH(3)
+#undef F_LAUNCH
+  return GADDPG_OK;
+}
+
+int gaddpg_sa1_fused_grid_impl(int M_max) {
+  const int tiles = ceil_div(M_max, F_BM);
+  return tiles < gaddpg_sm_count() ? tiles : gaddpg_sm_count();
+}
+
+int gaddpg_sa1_pool_finalize_impl(const float* ext, const int32_t* arg, const float* part_ext, const int32_t* part_arg, int32_t* seg_part,
+                                  const float* gamma, const float* scale, const float* shift, int S, float* out, int32_t* arg_out,
+                                  void* stream) {
+  GADDPG_CHECK_ARG(ext && arg && part_ext && part_arg && seg_part && gamma && scale && shift && out && S >= 1, "sa1_pool_finalize: bad argument");
+  const int grid = S < 4 * gaddpg_sm_count() ? S : 4 * gaddpg_sm_count();
+  sa1_pool_finalize_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(ext, arg, part_ext, part_arg, seg_part, gamma, scale, shift, S, out, arg_out);
+  GADDPG_CHECK_LAUNCH("sa1_pool_finalize_kernel");
+  return GADDPG_OK;
+}

@@ -70,6 +70,7 @@ class Workspace:
         self.sa1_ws_bytes = 0
         self.sa1_ws = None
         self._keys = None
+        self._sa1f = None
 
     def keys(self, S, C):
         """Zero-initialised key table of the fused max-pool, (S, C) uint64; the finalize kernel
@@ -78,6 +79,18 @@ class Workspace:
         if self._keys is None or self._keys.numel() < n:
             self._keys = torch.zeros(n, dtype=torch.int64, device=self.device)
         return self._keys
+
+    def sa1f(self, S, cap):
+        """Scratch of the fused SA1 chain (gaddpg_sa1_fused_fwd): raw per-(group, channel) extremes + rows, the partial
+        results of groups that straddle two CTAs' tile ranges, and the group -> partial map (all -1 between calls)."""
+        grid = int(lib.gaddpg_sa1_fused_grid(cap))
+        b = self._sa1f
+        if b is None or b.S < S or b.grid < grid:
+            i32 = dict(dtype=torch.int32, device=self.device)
+            b = NS(S=S, grid=grid, ext=_f(self.device, S, 128), arg=torch.zeros(S, 128, **i32), part_ext=_f(self.device, grid, 128),
+                   part_arg=torch.zeros(grid, 128, **i32), seg_part=torch.full((S,), -1, **i32))
+            self._sa1f = b
+        return b
 
     def sa1(self, B, cap):
         jmax = -(-(-(-cap // max(B, 1))) // 256)
@@ -341,10 +354,19 @@ class EncoderFlat:
             L.WT = self.derived[wt_off: wt_off + L.Kp * L.N].view(L.Kp, L.N)
             jobs.append([L.W.data_ptr(), L.N, L.K, L.rot, L.Wf.data_ptr() if need_wp else 0, L.Kp, L.WT.data_ptr(), L.N])
         self.jobs = torch.tensor(jobs, dtype=torch.int64, device=device)
+        # hi/lo TF32 split of the three SA1 conv weights, fetched by TMA in the fused SA1 chain (csrc/sa1_fused.cu)
+        L0 = self.layers["sa0.0"]
+        self.sa1f_ok = (L0.K <= 16 and (self.layers["sa0.0"].N, self.layers["sa0.1"].N, self.layers["sa0.2"].N) == (64, 64, 128)
+                        and self.layers["sa0.1"].K == 64 and self.layers["sa0.2"].K == 64)
+        self.sa1f_w = _f(device, int(lib.gaddpg_sa1f_wsplit_floats())) if self.sa1f_ok else None
         self.refresh_derived()
 
     def refresh_derived(self):
-        lib.gaddpg_wprep_batched(dp(self.jobs), self.jobs.shape[0], current_stream())
+        st = current_stream()
+        lib.gaddpg_wprep_batched(dp(self.jobs), self.jobs.shape[0], st)
+        if self.sa1f_ok:
+            L = self.layers
+            lib.gaddpg_sa1f_wprep(dp(L["sa0.0"].W), L["sa0.0"].K, L["sa0.0"].K, dp(L["sa0.1"].W), dp(L["sa0.2"].W), dp(self.sa1f_w), st)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -417,12 +439,70 @@ def encoder_forward(ws, ef, geom, cloud, skip, Cp, bc, ctx, time=None, time_offs
     s = ctx.sa[0]
     W0 = L["sa0.0"]
     assert W0.K == 3 + Cp + Cb, (W0.K, Cp, Cb)
+    if FUSED_SA1 and ef.sa1f_ok and (FUSED_SA1_KEEP or not keep) and lib.gaddpg_get_tensor_core() >= 3:
+        _sa1_fused_forward(ws, ef, geom, cloud, skip, Cp, bc, Cb, ctx, train, bn_stage, keep)
+    else:
+        _sa1_unfused_forward(ws, ef, geom, cloud, skip, Cp, bc, Cb, ctx, train, bn_stage, keep)
+    _encoder_forward_upper(ws, ef, geom, ctx, time, time_offset, train, bn_stage, keep)
+    return ctx.feat
+
+
+FUSED_SA1 = True        # SA1 shared MLP + max-pool as the TMA-fed recompute chain of csrc/sa1_fused.cu (three phases)
+FUSED_SA1_KEEP = True   # ... also for passes that are differentiated (the pre-BN outputs are stored by TMA, never re-read)
+
+
+def _sa1_fused_forward(ws, ef, geom, cloud, skip, Cp, bc, Cb, ctx, train, bn_stage, keep):
+    """SA1 through gaddpg_sa1_fused_fwd: phase k writes the batch statistics of conv k-1 (finalised in between), phase 3
+    also the per-(ball, channel) extremes; forward-only passes never write an activation.  Eval mode (running statistics)
+    needs phase 3 only."""
+    B, C, Np = cloud.shape
+    st = current_stream()
+    l1 = geom.lv[0]
+    s, L = ctx.sa[0], ef.layers
+    lay = [L["sa0.0"], L["sa0.1"], L["sa0.2"]]
+    count = B * geom.npoint * l1.ns
+    b = ws.sa1f(l1.S, l1.cap)
+
+    def phase(k):
+        lib.gaddpg_sa1_fused_fwd(k, dp(cloud), C * Np, Np, skip, Cp, dp(bc), Cb, dp(l1.new_xyz), geom.npoint, dp(l1.seg_off),
+                                 dp(l1.row_seg), dp(l1.row_src), dp(l1.row_w), l1.cap, l1.M_dev, dp(ef.sa1f_w),
+                                 dp(s.bn[0].scale), dp(s.bn[0].shift), dp(s.bn[1].scale), dp(s.bn[1].shift), dp(lay[2].gamma),
+                                 dp(ws.stats), dp(s.Y[k - 1]) if keep else None, dp(b.ext), dp(b.arg), dp(b.part_ext),
+                                 dp(b.part_arg), dp(b.seg_part), st)
+
+    if train:
+        for k in (1, 2, 3):
+            phase(k)
+            bn_fwd(ws, lay[k - 1].N, count, lay[k - 1], s.bn[k - 1], True, bn_stage)
+    else:
+        for k in (1, 2, 3):
+            bn_fwd(ws, lay[k - 1].N, count, lay[k - 1], s.bn[k - 1], False, None)
+        phase(3)
+    lib.gaddpg_sa1_pool_finalize(dp(b.ext), dp(b.arg), dp(b.part_ext), dp(b.part_arg), dp(b.seg_part), dp(lay[2].gamma),
+                                 dp(s.bn[2].scale), dp(s.bn[2].shift), l1.S, dp(s.out), dp(s.arg), st)
+
+
+def _sa1_unfused_forward(ws, ef, geom, cloud, skip, Cp, bc, Cb, ctx, train, bn_stage, keep):
+    B, C, Np = cloud.shape
+    st = current_stream()
+    l1 = geom.lv[0]
+    s, L = ctx.sa[0], ef.layers
+    W0 = L["sa0.0"]
     lib.gaddpg_sa1_l1_fwd(dp(cloud), C * Np, Np, skip, Cp, dp(bc), Cb, B, dp(l1.new_xyz), geom.npoint, dp(l1.seg_off),
                           dp(l1.row_seg), dp(l1.row_src), dp(l1.row_w), l1.cap, l1.M_dev, dp(W0.W), W0.K, dp(ctx.bcbias),
                           dp(s.Y[0]), dp(ws.stats) if train else None, st)
     bn_fwd(ws, 64, B * geom.npoint * l1.ns, W0, s.bn[0], train, bn_stage)
     _mlp_tail_forward(ws, [L["sa0.1"], L["sa0.2"]], s, 1, l1.cap, l1.M_dev, l1.row_w, B * geom.npoint * l1.ns, train, bn_stage,
                       pool=NS(lv=l1, keep=keep))
+
+
+def _encoder_forward_upper(ws, ef, geom, ctx, time, time_offset, train, bn_stage, keep):
+    """SA2, SA3 and the FC head of encoder_forward."""
+    B = ctx.B
+    st = current_stream()
+    l1, l2 = geom.lv
+    L = ef.layers
+    s = ctx.sa[0]
     # ---- SA2: gather [feats | dxyz | pad] rows, three row-GEMMs, pool
     s2 = ctx.sa[1]
     lib.gaddpg_gather_rows(dp(s.out), 128, dp(l1.new_xyz), geom.npoint, dp(l2.new_xyz), geom.npoint, dp(l2.row_seg),

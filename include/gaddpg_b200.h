@@ -198,6 +198,29 @@ GADDPG_API int gaddpg_sa1_l1_bwd(const float* cloud, long long cloud_stride_b, i
                                  const float* Y, const float* g, const float* m1, const float* m2, const float* mean,
                                  const float* rstd, const float* W, int ldw, float* dW, int accumulate, float* dbc, float* ws,
                                  long long ws_bytes, void* stream);
+/* ---- SA1 shared MLP as one TMA-fed, recompute-instead-of-store tcgen05 chain (csrc/sa1_fused.cu) -------------------------
+ * Replaces QueryAndGroup + build_shared_mlp (3 x [Conv2d 1x1, train-mode BatchNorm2d, ReLU]) + F.max_pool2d of the first
+ * set-abstraction module (/root/reference/core/networks.py:66-71) for the compact row list.  Three phases = three calls; phase
+ * k recomputes layers < k from the cloud and writes the batch-statistic slots of layer k-1's output (finalise each with
+ * gaddpg_bn_finalize_fwd before the next phase).  Phase 3 also writes, per (ball group s, channel c), the extreme of the last
+ * pre-BN output (max for gamma2[c] >= 0, else min) and its row; gaddpg_sa1_pool_finalize turns them into
+ * out = relu(bn(extreme)) / arg.  Ykeep: NULL for forward-only passes (no activation touches HBM) or the (M_max, 64 | 64 | 128)
+ * buffer that receives this phase's pre-BN output for the backward kernels (TMA stores).
+ * wsplit: gaddpg_sa1f_wsplit_floats() floats written by gaddpg_sa1f_wprep (hi/lo TF32 split of the three conv weights; redo
+ * after every optimiser step).  part_ext/part_arg: (gaddpg_sa1_fused_grid(M_max), 128); seg_part: (S) int32, all -1 on entry
+ * (the finalize call restores that).  Input channels: [dxyz(3) | cloud rows 0..Cp-1 | bc (B,Cb) broadcast], 3+Cp+Cb <= 16. */
+GADDPG_API long long gaddpg_sa1f_wsplit_floats(void);
+GADDPG_API int gaddpg_sa1_fused_grid(int M_max);
+GADDPG_API int gaddpg_sa1f_wprep(const float* W0, int ld0, int K1, const float* W1, const float* W2, float* wsplit, void* stream);
+GADDPG_API int gaddpg_sa1_fused_fwd(int phase, const float* cloud, long long cloud_stride_b, int cloud_stride_c, int skip, int Cp,
+                                    const float* bc, int Cb, const float* ctr, int npoint, const int32_t* seg_off,
+                                    const int32_t* row_seg, const int32_t* row_src, const float* row_w, int M_max, const int* M_dev,
+                                    const float* wsplit, const float* sc0, const float* sh0, const float* sc1, const float* sh1,
+                                    const float* gamma2, float* stats, float* Ykeep, float* ext, int32_t* arg, float* part_ext,
+                                    int32_t* part_arg, int32_t* seg_part, void* stream);
+GADDPG_API int gaddpg_sa1_pool_finalize(const float* ext, const int32_t* arg, const float* part_ext, const int32_t* part_arg,
+                                        int32_t* seg_part, const float* gamma, const float* scale, const float* shift, int S,
+                                        float* out, int32_t* arg_out, void* stream);
 /* G[r] = [feats[src] (C) | xyz[src]-ctr[seg] (3) | 0-pad]; row tables NULL: identity rows, absolute xyz (GroupAll) */
 GADDPG_API int gaddpg_gather_rows(const float* feats, int C, const float* xyz, int n_src, const float* ctr, int npoint,
                                   const int32_t* row_seg, const int32_t* row_src, int M_max, const int* M_dev, float* G, int ldg,
