@@ -229,6 +229,7 @@ class AgentB200:
         self._slot_done = [torch.cuda.Event() for _ in range(RING)]
         self._slot = 0
         self._pending = [None] * RING
+        self._optjobs = {}
         self._pending_reduce = []
         self.step_start_events = self.step_end_events = None    # feed.FeedLoop installs lists here to measure the GPU idle gap between steps
         self.split_reduce = True         # sharded runs: all-reduce everything but SA1's gradients behind the SA1 backward
@@ -442,6 +443,41 @@ class AgentB200:
         lib.gaddpg_adam_step(arena.p.data_ptr() + 4 * off, arena.g.data_ptr() + 4 * off, arena.m.data_ptr() + 4 * off,
                              arena.v.data_ptr() + 4 * off, n, 0.0, 0.9, 0.999, eps, wd, 0, self.dyn.data_ptr() + 8 * i, gs,
                              clip, write_back, None, 0.0, current_stream())
+
+    def _opt_jobs(self, which):
+        """Job tables of gaddpg_optim_multi, built once (every pointer in them is static)."""
+        t = self._optjobs.get(which)
+        if t is not None:
+            return t
+        t = engine.OptJobs(self.device)
+        dyn = lambda name: self.dyn.data_ptr() + 8 * ("policy", "critic", "enc", "venc").index(name)  # noqa: E731
+        out = lambda slot: self.out.data_ptr() + 4 * slot  # noqa: E731
+        if which == "p2":
+            A = self.ef_v.arena
+            t.adam(A, 0, A.n, dyn("venc"), *self._adam_hp["venc"])
+            A = self.cf.arena
+            t.adam(A, 0, A.n, dyn("critic"), *self._adam_hp["critic"], clip=out(O_CLIP), write_back=1)
+        else:   # "p3", "p3h" (DDPG) and "bc"
+            A, T = self.pf.arena, self.pft.arena
+            ranges, _ = self.pf.adam_ranges(self.policy_aux)
+            pos = 0
+            for off, n in ranges:       # Adam ranges start on 16-byte aligned arena segments; the gaps in between only see Polyak
+                if off > pos:
+                    t.polyak(A.p, T.p, pos, off - pos, tau=float(self.tau), absmax_p=out(O_PPARAM))
+                t.adam(A, off, n, dyn("policy"), *self._adam_hp["policy"], target=T.p, tau=float(self.tau), absmax_p=out(O_PPARAM))
+                pos = off + n
+            if pos < A.n:
+                t.polyak(A.p, T.p, pos, A.n - pos, tau=float(self.tau), absmax_p=out(O_PPARAM))
+            if self.train_feature:
+                E = self.ef_p.arena
+                t.adam(E, 0, E.n, dyn("enc"), *self._adam_hp["enc"])
+            if self.has_critic:
+                C = self.cf.arena
+                tv = (self.tau_soft + self.tau_hard) if which == "p3h" else self.tau_soft   # disjoint supports (Q1 | Q2)
+                self._tau_keep = getattr(self, "_tau_keep", []) + [tv]
+                t.polyak(C.p, self.cft.arena.p, 0, C.n, tau_vec=tv, grads=C.g, absmax_p=out(O_CPARAM), absmax_g=out(O_CGRAD))
+        self._optjobs[which] = t
+        return t
 
     # ---- gradient all-reduce (sharded runs): ONE contiguous range per optimiser phase (nets.GradPool) ----------------
     # DDP semantics: per-rank mean losses averaged over ranks.  The pool is laid out [encoder: SA1 | SA2 SA3 FC | heads];
@@ -870,10 +906,8 @@ class DDPGB200(AgentB200):
         cA = self.cf.arena
         lib.gaddpg_clip_coef(dp(cA.g), cA.n, float(self.clip_grad), self.out.data_ptr() + 4 * O_CLIP,
                              self.out.data_ptr() + 4 * O_GNORM, dp(ws.red), s)
-        self._adam(self.ef_v.arena, 0, self.ef_v.arena.n, "venc")
-        self._adam(cA, 0, cA.n, "critic", clip=self.out.data_ptr() + 4 * O_CLIP, write_back=1)
-        self.ef_v.refresh_derived()
-        self.cf.refresh_derived()
+        self._opt_jobs("p2").launch()               # Adam(value encoder) + Adam(critic, clipped, gradient written back): one launch
+        engine.refresh_many((self.ef_v, self.cf))   # derived weight layouts of both: one launch
         f4 = self.ctx_p.feat                                                                                     # F4: phase 1
         raw = engine.policy_forward(self.pf, f4, self.pc, B)
         lib.gaddpg_policy_head_fwd(dp(raw), self.pf.NHp, B, dp(self.pc.pi), s)
@@ -901,21 +935,10 @@ class DDPGB200(AgentB200):
 
     # -- phase 3: actor step, targets, statistics --------------------------------------------------------------
     def _phase3(self, hard):
-        ws, s = self.ws, current_stream()
-        ranges, _ = self.pf.adam_ranges(self.policy_aux)
-        for off, n in ranges:
-            self._adam(self.pf.arena, off, n, "policy")
-        if self.train_feature:
-            self._adam(self.ef_p.arena, 0, self.ef_p.arena.n, "enc")
-        lib.gaddpg_polyak(dp(self.pft.arena.p), dp(self.pf.arena.p), self.pf.arena.n, float(self.tau), s)
-        lib.gaddpg_polyak_vec(dp(self.cft.arena.p), dp(self.cf.arena.p), dp(self.tau_soft), self.cf.arena.n, s)
-        if hard:
-            lib.gaddpg_polyak_vec(dp(self.cft.arena.p), dp(self.cf.arena.p), dp(self.tau_hard), self.cf.arena.n, s)
-        for f in (self.pf, self.ef_p, self.pft, self.cft):
-            f.refresh_derived()
-        lib.gaddpg_absmax(dp(self.pf.arena.p), self.pf.arena.n, self.out.data_ptr() + 4 * O_PPARAM, dp(ws.red), s)
-        lib.gaddpg_absmax(dp(self.cf.arena.g), self.cf.arena.n, self.out.data_ptr() + 4 * O_CGRAD, dp(ws.red), s)
-        lib.gaddpg_absmax(dp(self.cf.arena.p), self.cf.arena.n, self.out.data_ptr() + 4 * O_CPARAM, dp(ws.red), s)
+        """Adam(policy) [+ Polyak of the policy target + max |param|], Adam(policy encoder), half-soft / half-hard update of the
+        critic target + max |critic param| + max |critic grad|: ONE launch; the derived weight layouts: one more."""
+        self._opt_jobs("p3h" if hard else "p3").launch()
+        engine.refresh_many((self.pf, self.ef_p, self.pft, self.cft))
 
     @_on_device
     def update_parameters(self, batch_data, updates=None, k=None, test=False, noise_u=None, staged=False, defer=False):
@@ -971,16 +994,8 @@ class BCB200(AgentB200):
             engine.encoder_backward(ws, self.ef_p, self.ctx_p, self.sc, want_dw=True, want_dbc=False, accumulate=0)
 
     def _phase_opt(self):
-        ws, s = self.ws, current_stream()
-        ranges, _ = self.pf.adam_ranges(self.policy_aux)
-        for off, n in ranges:
-            self._adam(self.pf.arena, off, n, "policy")
-        if self.train_feature:
-            self._adam(self.ef_p.arena, 0, self.ef_p.arena.n, "enc")
-        lib.gaddpg_polyak(dp(self.pft.arena.p), dp(self.pf.arena.p), self.pf.arena.n, float(self.tau), s)
-        for f in (self.pf, self.ef_p, self.pft):
-            f.refresh_derived()
-        lib.gaddpg_absmax(dp(self.pf.arena.p), self.pf.arena.n, self.out.data_ptr() + 4 * O_PPARAM, dp(ws.red), s)
+        self._opt_jobs("bc").launch()
+        engine.refresh_many((self.pf, self.ef_p, self.pft))
 
     @_on_device
     def update_parameters(self, batch_data, updates=None, k=None, noise_u=None, staged=False, defer=False):

@@ -219,6 +219,9 @@ int gaddpg_adam_step(float* p, float* g, float* m, float* v, long long n, double
   return gaddpg_adam_step_impl(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, dyn, grad_scale, clip, write_back_grad,
                                target, tau, stream);
 }
+int gaddpg_optim_multi(const void* jobs_dev, int njobs, int total_chunks, void* stream) {
+  return gaddpg_optim_multi_impl(jobs_dev, njobs, total_chunks, stream);
+}
 int gaddpg_wprep_batched(const long long* jobs_dev, int njobs, void* stream) {
   return gaddpg_wprep_batched_impl(jobs_dev, njobs, stream);
 }

@@ -96,6 +96,7 @@ int gaddpg_policy_sample_impl(const float* raw, int ldr, int off_logstd, const f
 int gaddpg_adam_step_impl(float* p, float* g, float* m, float* v, long long n, double lr, double beta1, double beta2, double eps,
                           double weight_decay, long long step, const float* dyn, double grad_scale, const float* clip,
                           int write_back_grad, float* target, double tau, void* stream);
+int gaddpg_optim_multi_impl(const void* jobs_dev, int njobs, int total_chunks, void* stream);
 int gaddpg_wprep_batched_impl(const long long* jobs_dev, int njobs, void* stream);
 int gaddpg_dmask_stats_impl(const float* dX, int ldx, const float* Yprev, int C, int M, const float* psc, const float* psh,
                             const float* pmean, const float* prstd, float* D, float* stats, void* stream);

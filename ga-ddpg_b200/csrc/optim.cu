@@ -72,6 +72,120 @@ __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float*
   }
 }
 
+// ---- one launch for a whole optimiser phase -----------------------------------------------------------------------------
+// A job table (device memory, written once) lists element ranges with what happens to them: Adam (optionally followed by the
+// Polyak update of a target copy and the abs-max of the updated parameters), Polyak only (scalar or per-element tau) or abs-max
+// only.  Chunks of OPT_CHUNK elements of all jobs form one grid-stride space, so the five Adam launches, three two-stage
+// abs-max reductions and two or three Polyak launches of a DDPG step (agent.py:192-209,242-259) are two launches.  Same
+// arithmetic per element as adam_kernel / polyak_kernel / polyak_vec_kernel.  abs-max is exact and order-independent:
+// non-negative floats compare like their bit patterns, so one atomicMax per block is deterministic.
+constexpr int OPT_CHUNK = 4096;
+struct OptJob {
+  float* p; float* g; float* m; float* v; float* target; const float* tau_vec; const float* dyn; const float* clip;
+  float* absmax_p; float* absmax_g;
+  long long n, chunk0;
+  float eps, weight_decay, tau;
+  int kind, write_back, pad;   // kind 0: Adam; 1: Polyak (source = p); 2: statistics only
+};
+static_assert(sizeof(OptJob) == 120, "OptJob layout is mirrored in agent.py");
+
+__global__ void __launch_bounds__(256) optim_multi_kernel(const OptJob* __restrict__ jobs, int njobs, int total_chunks) {
+  __shared__ float red[2][8];
+  for (int cid = blockIdx.x; cid < total_chunks; cid += gridDim.x) {   // block-uniform
+    int j = 0;
+    while (j + 1 < njobs && jobs[j + 1].chunk0 <= cid) ++j;
+    const OptJob J = jobs[j];
+    const long long e0 = (long long)(cid - J.chunk0) * OPT_CHUNK;
+    long long e1 = e0 + OPT_CHUNK;
+    e1 = e1 < J.n ? e1 : J.n;
+    float mxp = 0.f, mxg = 0.f;
+    if (J.kind == 0) {
+      AdamArgs a;
+      a.lr_over_bc1 = J.dyn[0];
+      a.bc2_sqrt = J.dyn[1];
+      a.beta1 = 0.9f;
+      a.beta2 = 0.999f;
+      a.one_minus_beta1 = (float)(1.0 - 0.9);
+      a.one_minus_beta2 = (float)(1.0 - 0.999);
+      a.eps = J.eps;
+      a.weight_decay = J.weight_decay;
+      a.grad_scale = 1.f;
+      const float clip = J.clip ? *J.clip : 1.f;
+      const float omt = (float)(1.0 - (double)J.tau);
+      for (long long i = e0 + threadIdx.x * 4; i < e1; i += 256 * 4) {   // job starts are 16-byte aligned; the last <= 3 elements go scalar
+        if (i + 4 > e1) {
+          for (long long k = i; k < e1; ++k) {
+            float P = J.p[k], G = J.g[k], Mm = J.m[k], V = J.v[k];
+            adam_one(P, G, Mm, V, a, clip);
+            J.p[k] = P;
+            J.m[k] = Mm;
+            J.v[k] = V;
+            if (J.write_back) J.g[k] = G;
+            if (J.target) J.target[k] = J.target[k] * omt + P * J.tau;
+            mxp = fmaxf(mxp, fabsf(P));
+            mxg = fmaxf(mxg, fabsf(G));
+          }
+          break;
+        }
+        float4 P = *reinterpret_cast<float4*>(J.p + i), G = *reinterpret_cast<float4*>(J.g + i), Mm = *reinterpret_cast<float4*>(J.m + i),
+               V = *reinterpret_cast<float4*>(J.v + i);
+        adam_one(P.x, G.x, Mm.x, V.x, a, clip);
+        adam_one(P.y, G.y, Mm.y, V.y, a, clip);
+        adam_one(P.z, G.z, Mm.z, V.z, a, clip);
+        adam_one(P.w, G.w, Mm.w, V.w, a, clip);
+        *reinterpret_cast<float4*>(J.p + i) = P;
+        *reinterpret_cast<float4*>(J.m + i) = Mm;
+        *reinterpret_cast<float4*>(J.v + i) = V;
+        if (J.write_back) *reinterpret_cast<float4*>(J.g + i) = G;
+        if (J.target) {
+          float4 T = *reinterpret_cast<float4*>(J.target + i);
+          T.x = T.x * omt + P.x * J.tau;
+          T.y = T.y * omt + P.y * J.tau;
+          T.z = T.z * omt + P.z * J.tau;
+          T.w = T.w * omt + P.w * J.tau;
+          *reinterpret_cast<float4*>(J.target + i) = T;
+        }
+        mxp = fmaxf(fmaxf(mxp, fmaxf(fabsf(P.x), fabsf(P.y))), fmaxf(fabsf(P.z), fabsf(P.w)));
+        mxg = fmaxf(fmaxf(mxg, fmaxf(fabsf(G.x), fabsf(G.y))), fmaxf(fabsf(G.z), fabsf(G.w)));
+      }
+    } else {
+      const float omt = (float)(1.0 - (double)J.tau);
+      for (long long i = e0 + threadIdx.x; i < e1; i += 256) {
+        const float P = J.p[i];
+        if (J.kind == 1) {
+          if (J.tau_vec) {
+            const float tau = J.tau_vec[i];
+            if (tau != 0.f) J.target[i] = J.target[i] * (1.0f - tau) + P * tau;
+          } else {
+            J.target[i] = J.target[i] * omt + P * J.tau;
+          }
+        }
+        mxp = fmaxf(mxp, fabsf(P));
+        if (J.absmax_g) mxg = fmaxf(mxg, fabsf(J.g[i]));
+      }
+    }
+    if (J.absmax_p || J.absmax_g) {   // block-uniform
+      mxp = warp_max(mxp);
+      mxg = warp_max(mxg);
+      __syncthreads();
+      if ((threadIdx.x & 31) == 0) {
+        red[0][threadIdx.x >> 5] = mxp;
+        red[1][threadIdx.x >> 5] = mxg;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        float a = red[0][0], b = red[1][0];
+        for (int w = 1; w < 8; ++w) {
+          a = fmaxf(a, red[0][w]);
+          b = fmaxf(b, red[1][w]);
+        }
+        if (J.absmax_p) atomicMax(reinterpret_cast<unsigned int*>(J.absmax_p), __float_as_uint(a));
+        if (J.absmax_g) atomicMax(reinterpret_cast<unsigned int*>(J.absmax_g), __float_as_uint(b));
+      }
+    }
+  }
+}
+
 // target = target*(1-tau) + source*tau   (utils.py:750-754)
 __global__ void polyak_kernel(float* __restrict__ t, const float* __restrict__ s, long long n, float tau, float one_minus_tau) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -173,6 +287,16 @@ __global__ void __launch_bounds__(256) wprep_batched_kernel(const long long* __r
   const int ldp = (int)J[5];
   float* WT = reinterpret_cast<float*>(J[6]);
   const int ldt = (int)J[7];
+  if (rot < 0) {   // hi/lo TF32 split job (fused SA1 chain): Wp = hi[N][ldp], WT = lo[N][ldp], columns >= K zero
+    for (int e = blockIdx.x * 256 + threadIdx.x; e < N * ldp; e += gridDim.x * 256) {
+      const int n = e / ldp, k = e % ldp;
+      const float x = k < K ? W[(long long)n * K + k] : 0.f;
+      const float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+      Wp[e] = h;
+      WT[e] = x - h;
+    }
+    return;
+  }
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int nmax = (WT && ldt > N) ? ldt : N;
   const int tiles_n = (nmax + 31) >> 5, tiles_k = (ldp + 31) >> 5;
@@ -242,6 +366,14 @@ int gaddpg_adam_step_impl(float* p, float* g, float* m, float* v, long long n, d
   a.one_minus_tau = (float)(1.0 - tau);
   adam_kernel<<<stream_grid(n / 4 + 1), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, a, target);
   GADDPG_CHECK_LAUNCH("adam_kernel");
+  return GADDPG_OK;
+}
+
+int gaddpg_optim_multi_impl(const void* jobs_dev, int njobs, int total_chunks, void* stream) {
+  GADDPG_CHECK_ARG(jobs_dev && njobs >= 1 && njobs <= 64 && total_chunks >= 1, "optim_multi: bad argument");
+  const int cap = gaddpg_sm_count() * 8;
+  optim_multi_kernel<<<total_chunks < cap ? total_chunks : cap, 256, 0, (cudaStream_t)stream>>>((const OptJob*)jobs_dev, njobs, total_chunks);
+  GADDPG_CHECK_LAUNCH("optim_multi_kernel");
   return GADDPG_OK;
 }
 

@@ -47,8 +47,9 @@ constexpr int F_THREADS = F_WARPS * 32;
 constexpr int W_P = 0, W_MMA = 4, W_E0 = 5, W_E1 = 9, W_E2 = 13;
 
 struct FLayout {
-  uint32_t w0h, w0l, w1h, w1l, w2h, w2l, a0h, a0l, abh, abl, stage, consts, meta, bars, red, total;
+  uint32_t w0h, w0l, w1h, w1l, w2h, w2l, a0h[2], a0l[2], abh, abl, stage, consts, meta, bars, red, total;
 };
+__host__ __device__ constexpr int f_na0(int phase) { return phase == 3 ? 1 : 2; }   // layer-0 operand stages (smem is full in phase 3)
 __host__ __device__ inline FLayout f_layout(int phase) {
   FLayout L;
   uint32_t off = 0;
@@ -58,13 +59,15 @@ __host__ __device__ inline FLayout f_layout(int phase) {
   L.w1l = off; off += (phase >= 2) ? F_C * F_C * 4 : 0;
   L.w2h = off; off += (phase >= 3) ? F_C3 * F_C * 4 : 0;
   L.w2l = off; off += (phase >= 3) ? F_C3 * F_C * 4 : 0;
-  L.a0h = off; off += F_BM * F_K0 * 4;
-  L.a0l = off; off += F_BM * F_K0 * 4;
+  for (int i = 0; i < 2; ++i) {
+    L.a0h[i] = off; off += (i < f_na0(phase)) ? F_BM * F_K0 * 4 : 0;
+    L.a0l[i] = off; off += (i < f_na0(phase)) ? F_BM * F_K0 * 4 : 0;
+  }
   L.abh = off; off += (phase >= 2) ? F_BM * F_C * 4 : 0;
   L.abl = off; off += (phase >= 2) ? F_BM * F_C * 4 : 0;
   L.stage = off; off += 32768;          // phases 1/2: 4 x [2 col blocks][32 rows x 128 B]; phase 3: [4 col blocks][64 rows x 128 B]
   L.consts = off; off += 2048;          // sc0, sh0, sc1, sh1 [64 each], sign(gamma2) [128]
-  L.meta = off; off += 1024;            // E2: segment id and multiplicity of the tile's 128 rows
+  L.meta = off; off += 4 * 1024;        // E2: per-warp copy of the segment id and multiplicity of the tile's 128 rows
   L.red = off; off += 2 * 4 * F_C * 4;  // phases 1/2: cross-warp combine of the column sums [2][4 warps][64]
   L.bars = off; off += 256;
   L.total = off;
@@ -167,18 +170,19 @@ sa1_fused_kernel(const Sa1FParams p, const __grid_constant__ CUtensorMap tW0h, c
   const FLayout L = f_layout(PHASE);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint64_t* w_full = bars + 0;
-  uint64_t* a0_full = bars + 1;
-  uint64_t* a0_empty = bars + 2;
-  uint64_t* acc0_full = bars + 3;    // [2]
-  uint64_t* acc0_empty = bars + 5;   // [2]
-  uint64_t* ab1_full = bars + 7;
-  uint64_t* ab_free = bars + 8;
-  uint64_t* acc1_full = bars + 9;    // [2]
-  uint64_t* acc1_empty = bars + 11;  // [2]
-  uint64_t* ab2_full = bars + 13;
-  uint64_t* acc2_full = bars + 14;   // [2]
-  uint64_t* acc2_empty = bars + 16;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* a0_full = bars + 1;      // [2]
+  uint64_t* a0_empty = bars + 3;     // [2]
+  uint64_t* acc0_full = bars + 5;    // [2]
+  uint64_t* acc0_empty = bars + 7;   // [2]
+  uint64_t* ab1_full = bars + 9;
+  uint64_t* ab_free = bars + 10;
+  uint64_t* acc1_full = bars + 11;   // [2]
+  uint64_t* acc1_empty = bars + 13;  // [2]
+  uint64_t* ab2_full = bars + 15;
+  uint64_t* acc2_full = bars + 16;   // [2]
+  uint64_t* acc2_empty = bars + 18;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  constexpr int NA0 = f_na0(PHASE);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int M = p.M_dev ? *p.M_dev : p.M_max;
@@ -193,9 +197,9 @@ sa1_fused_kernel(const Sa1FParams p, const __grid_constant__ CUtensorMap tW0h, c
 
   if (tid == 0) {
     mbar_init(w_full, 1);
-    mbar_init(a0_full, 128);
-    mbar_init(a0_empty, 1);
     for (int s = 0; s < 2; ++s) {
+      mbar_init(&a0_full[s], 128);
+      mbar_init(&a0_empty[s], 1);
       mbar_init(&acc0_full[s], 1);
       mbar_init(&acc0_empty[s], 4);
       mbar_init(&acc1_full[s], 1);
@@ -232,22 +236,35 @@ sa1_fused_kernel(const Sa1FParams p, const __grid_constant__ CUtensorMap tW0h, c
 
   if (warp < W_MMA) {
     // ===================== P: gather + layer-0 operand =====================
+    // Three-deep software pipeline (the row -> (segment, source point) -> cloud reads are two dependent L2 round trips per
+    // tile and only 128 threads issue them): indices of tile it+3, data of tiles it+1 and it+2 are in flight while tile it
+    // is split and stored.
     const int r = tid;  // tile row
     const int K1 = 3 + p.Cp + p.Cb;
-    auto gather = [&](int it, float (&in)[F_K0]) {
-#pragma unroll
-      for (int k = 0; k < F_K0; ++k) in[k] = 0.f;
+    struct Idx { int seg, src; };
+    auto load_idx = [&](int it) {
+      Idx x;
+      x.seg = -1;
+      x.src = 0;
       const int row = (tile0 + it) * F_BM + r;
       if (it < my_tiles && row < M) {
-        const int seg = p.row_seg[row], src = p.row_src[row];
-        const int b = seg / p.npoint;
-        const float* pc = p.cloud + (long long)b * p.cloud_sb + p.skip + src;
+        x.seg = p.row_seg[row];
+        x.src = p.row_src[row];
+      }
+      return x;
+    };
+    auto load_data = [&](const Idx& x, float (&in)[F_K0]) {
+#pragma unroll
+      for (int k = 0; k < F_K0; ++k) in[k] = 0.f;
+      if (x.seg >= 0) {
+        const int b = x.seg / p.npoint;
+        const float* pc = p.cloud + (long long)b * p.cloud_sb + p.skip + x.src;
 #pragma unroll
         for (int k = 0; k < F_K0 - 3; ++k)
           if (k < p.Cp) in[3 + k] = pc[(long long)k * p.cloud_sc];
-        in[0] = in[3] - p.ctr[(long long)seg * 3 + 0];
-        in[1] = in[4] - p.ctr[(long long)seg * 3 + 1];
-        in[2] = in[5] - p.ctr[(long long)seg * 3 + 2];
+        in[0] = p.ctr[(long long)x.seg * 3 + 0];   // centroid: subtracted when the tile is stored
+        in[1] = p.ctr[(long long)x.seg * 3 + 1];
+        in[2] = p.ctr[(long long)x.seg * 3 + 2];
 #pragma unroll
         for (int k = 3; k < F_K0; ++k) {
           const int j = k - 3 - p.Cp;
@@ -255,18 +272,33 @@ sa1_fused_kernel(const Sa1FParams p, const __grid_constant__ CUtensorMap tW0h, c
         }
       }
     };
-    float cur[F_K0], nxt[F_K0];
-    gather(0, cur);
+    float d0[F_K0], d1[F_K0], d2[F_K0];
+    Idx i1 = load_idx(1), i2 = load_idx(2);
+    {
+      Idx i0 = load_idx(0);
+      load_data(i0, d0);
+    }
+    load_data(i1, d1);
     for (int it = 0; it < my_tiles; ++it) {
-      gather(it + 1, nxt);   // the next tile's scattered loads are in flight while this one is written
-      mbar_wait(a0_empty, ((uint32_t)it & 1u) ^ 1u);
+      Idx i3 = load_idx(it + 3);
+      load_data(i2, d2);                      // tile it+2
+      const int sa = it % NA0;
+      mbar_wait(&a0_empty[sa], ((uint32_t)(it / NA0) & 1u) ^ 1u);
+      d0[0] = d0[3] - d0[0];                  // dxyz = xyz[src] - centroid (zero rows stay zero)
+      d0[1] = d0[4] - d0[1];
+      d0[2] = d0[5] - d0[2];
 #pragma unroll
       for (int c = 0; c < 4; ++c)
-        split_store(smem + L.a0h, smem + L.a0l, sw64_off(r, c), make_float4(cur[4 * c], cur[4 * c + 1], cur[4 * c + 2], cur[4 * c + 3]));
+        split_store(smem + (sa ? L.a0h[1] : L.a0h[0]), smem + (sa ? L.a0l[1] : L.a0l[0]), sw64_off(r, c),
+                    make_float4(d0[4 * c], d0[4 * c + 1], d0[4 * c + 2], d0[4 * c + 3]));
       fence_proxy_async();
-      mbar_arrive(a0_full);
+      mbar_arrive(&a0_full[sa]);
 #pragma unroll
-      for (int k = 0; k < F_K0; ++k) cur[k] = nxt[k];
+      for (int k = 0; k < F_K0; ++k) {
+        d0[k] = d1[k];
+        d1[k] = d2[k];
+      }
+      i2 = i3;
     }
   } else if (warp == W_MMA) {
     // ===================== MMA issuer (+ TMA weight loads) =====================
@@ -291,36 +323,45 @@ sa1_fused_kernel(const Sa1FParams p, const __grid_constant__ CUtensorMap tW0h, c
       tc_fence_after();
       const uint32_t id64 = idesc_tf32(F_C), id128 = idesc_tf32(F_C3);
       auto mma0 = [&](int j) {
-        const int b = j & 1;
-        mbar_wait(a0_full, (uint32_t)j & 1u);
+        const int b = j & 1, sa = j % NA0;
+        mbar_wait(&a0_full[sa], (uint32_t)(j / NA0) & 1u);
         mbar_wait(&acc0_empty[b], (((uint32_t)j >> 1) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t d = tmem_base + ACC0 + (uint32_t)b * F_C;
         uint32_t acc = 0;
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
-          const uint64_t ah = make_desc64(sbase + L.a0h + ks * 32), al = make_desc64(sbase + L.a0l + ks * 32);
+          const uint64_t ah = make_desc64(sbase + (sa ? L.a0h[1] : L.a0h[0]) + ks * 32), al = make_desc64(sbase + (sa ? L.a0l[1] : L.a0l[0]) + ks * 32);
           const uint64_t bh = make_desc64(sbase + L.w0h + ks * 32), bl = make_desc64(sbase + L.w0l + ks * 32);
           umma_tf32(d, al, bh, id64, acc);
           umma_tf32(d, ah, bl, id64, 1u);
           umma_tf32(d, ah, bh, id64, 1u);
           acc = 1u;
         }
-        umma_commit(a0_empty);
+        umma_commit(&a0_empty[sa]);
         umma_commit(&acc0_full[b]);
       };
-      auto mma_k64 = [&](uint32_t d, uint32_t wh, uint32_t wl, int nrows_w, uint32_t idesc) {
+      // D[rows x channels] = act . W^T, or (transposed = true) D[channels x rows] = W . act^T: the accumulator then has one
+      // CHANNEL per TMEM lane and the tile's 128 rows along its columns, which is the layout conv2's consumer wants (a thread
+      // walks the rows of its channel straight out of tcgen05.ld registers: statistics + per-group extremes, no transpose)
+      auto mma_k64 = [&](uint32_t d, uint32_t wh, uint32_t wl, int nrows_w, uint32_t idesc, bool transposed) {
         uint32_t acc = 0;
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
-            const uint32_t aoff = (uint32_t)(kb * F_BM * 128 + ks * 32), boff = (uint32_t)(kb * nrows_w * 128 + ks * 32);
-            const uint64_t ah = make_desc(sbase + L.abh + aoff), al = make_desc(sbase + L.abl + aoff);
-            const uint64_t bh = make_desc(sbase + wh + boff), bl = make_desc(sbase + wl + boff);
-            umma_tf32(d, al, bh, idesc, acc);
-            umma_tf32(d, ah, bl, idesc, 1u);
-            umma_tf32(d, ah, bh, idesc, 1u);
+            const uint32_t xoff = (uint32_t)(kb * F_BM * 128 + ks * 32), woff = (uint32_t)(kb * nrows_w * 128 + ks * 32);
+            const uint64_t xh = make_desc(sbase + L.abh + xoff), xl = make_desc(sbase + L.abl + xoff);
+            const uint64_t wdh = make_desc(sbase + wh + woff), wdl = make_desc(sbase + wl + woff);
+            if (transposed) {
+              umma_tf32(d, wdl, xh, idesc, acc);
+              umma_tf32(d, wdh, xl, idesc, 1u);
+              umma_tf32(d, wdh, xh, idesc, 1u);
+            } else {
+              umma_tf32(d, xl, wdh, idesc, acc);
+              umma_tf32(d, xh, wdl, idesc, 1u);
+              umma_tf32(d, xh, wdh, idesc, 1u);
+            }
             acc = 1u;
           }
         }
@@ -333,7 +374,7 @@ sa1_fused_kernel(const Sa1FParams p, const __grid_constant__ CUtensorMap tW0h, c
           mbar_wait(ab1_full, (uint32_t)it & 1u);
           mbar_wait(&acc1_empty[b], (((uint32_t)it >> 1) & 1u) ^ 1u);
           tc_fence_after();
-          mma_k64(tmem_base + ACC1 + (uint32_t)b * F_C, L.w1h, L.w1l, F_C, id64);
+          mma_k64(tmem_base + ACC1 + (uint32_t)b * F_C, L.w1h, L.w1l, F_C, id64, false);
           umma_commit(&acc1_full[b]);
           if (PHASE == 2) umma_commit(ab_free);
         }
@@ -342,7 +383,7 @@ sa1_fused_kernel(const Sa1FParams p, const __grid_constant__ CUtensorMap tW0h, c
           mbar_wait(ab2_full, (uint32_t)it & 1u);
           mbar_wait(&acc2_empty[b], (((uint32_t)it >> 1) & 1u) ^ 1u);
           tc_fence_after();
-          mma_k64(tmem_base + ACC2 + (uint32_t)b * F_C3, L.w2h, L.w2l, F_C3, id128);
+          mma_k64(tmem_base + ACC2 + (uint32_t)b * F_BM, L.w2h, L.w2l, F_C3, id128, true);
           umma_commit(&acc2_full[b]);
           umma_commit(ab_free);
         }
@@ -364,8 +405,9 @@ sa1_fused_kernel(const Sa1FParams p, const __grid_constant__ CUtensorMap tW0h, c
       tc_fence_after();
       float r[F_C];
       const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + ACC0 + (uint32_t)b * F_C;
-      tmem_ld32(ta, r);
-      tmem_ld32(ta + 32, r + 32);
+      tmem_ld32_async(ta, r);
+      tmem_ld32_async(ta + 32, r + 32);
+      tmem_wait_ld();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc0_empty[b]);
@@ -404,8 +446,9 @@ sa1_fused_kernel(const Sa1FParams p, const __grid_constant__ CUtensorMap tW0h, c
         tc_fence_after();
         float r[F_C];
         const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + ACC1 + (uint32_t)b * F_C;
-        tmem_ld32(ta, r);
-        tmem_ld32(ta + 32, r + 32);
+        tmem_ld32_async(ta, r);
+        tmem_ld32_async(ta + 32, r + 32);
+        tmem_wait_ld();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc1_empty[b]);
@@ -430,24 +473,23 @@ sa1_fused_kernel(const Sa1FParams p, const __grid_constant__ CUtensorMap tW0h, c
       }
     }
   } else {
-    // ===================== E2: conv2 accumulator -> statistics + per-segment extremes =====================
+    // ===================== E2: conv2 accumulator (channel-major) -> statistics + per-group extremes =====================
     if (PHASE >= 3) {
-      const int q = warp & 3;             // TMEM lane quarter = 32-row group of the tile this warp may read
-      const int c = tid - W_E2 * 32;      // column owned in the row loop
+      const int q = warp & 3;             // TMEM lane quarter
+      const int c = q * 32 + lane;        // channel = TMEM lane
       const float* cs = reinterpret_cast<const float*>(smem + L.consts);
-      const bool neg = cs[256 + c] < 0.f;
-      int32_t* mseg = reinterpret_cast<int32_t*>(smem + L.meta);
-      float* mw = reinterpret_cast<float*>(smem + L.meta + 512);
-      unsigned char* st = smem + L.stage;
+      const float sgn = cs[256 + c];      // +1: the pooled value is bn(max y); -1: bn(min y)
+      int32_t* mseg = reinterpret_cast<int32_t*>(smem + L.meta + (warp - W_E2) * 1024);   // this warp's copy
+      float* mw = reinterpret_cast<float*>(smem + L.meta + (warp - W_E2) * 1024 + 512);
+      unsigned char* st = smem + L.stage + (warp - W_E2) * 8192;                           // keep: [64 rows x 128 B] of this warp's 32 channels
       const int cta_row0 = tile0 * F_BM;
       float S0 = 0.f, S1 = 0.f;
       int cur = -1, barg = 0;
       float best = 0.f;
       bool first_flush = true;
       auto flush = [&]() {
-        if (cur < 0) return;
-        const float v = neg ? -best : best;
-        if (first_flush && p.seg_off[cur] < cta_row0) {   // this segment began in the previous CTA's range: partial result
+        const float v = best * sgn;
+        if (first_flush && p.seg_off[cur] < cta_row0) {   // this group began in the previous CTA's range: partial result
           p.part_ext[(long long)blockIdx.x * F_C3 + c] = v;
           p.part_arg[(long long)blockIdx.x * F_C3 + c] = barg;
           if (c == 0) p.seg_part[cur] = (int)blockIdx.x;
@@ -460,70 +502,113 @@ sa1_fused_kernel(const Sa1FParams p, const __grid_constant__ CUtensorMap tW0h, c
       for (int it = 0; it < my_tiles; ++it) {
         const int b = it & 1;
         const int trow0 = (tile0 + it) * F_BM;
-        named_bar(1, 128);   // every E2 thread is done with the previous tile's meta / staging
-        {
-          const int grow = trow0 + c;
-          mseg[c] = grow < M ? p.row_seg[grow] : -1;
-          mw[c] = grow < M ? p.row_w[grow] : 0.f;
+        const int nr = M - trow0;   // live rows of this tile (>= 1)
+        __syncwarp();
+        uint32_t msk[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int grow = trow0 + k * 32 + lane;
+          mseg[k * 32 + lane] = grow < M ? p.row_seg[grow] : -1;
+          mw[k * 32 + lane] = grow < M ? p.row_w[grow] : 0.f;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {   // bit rr of msk[k]: row 32k+rr starts a run (a new ball group, or the tile)
+          const int rr = k * 32 + lane;
+          msk[k] = __ballot_sync(0xffffffffu, rr == 0 || mseg[rr] != mseg[rr - 1]);
         }
         mbar_wait(&acc2_full[b], ((uint32_t)it >> 1) & 1u);
         tc_fence_after();
-        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + ACC2 + (uint32_t)b * F_C3;
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-          if ((q >> 1) == half) {   // this warp's 32 rows belong to this 64-row half: TMEM -> swizzled staging
-            const int lr = (q & 1) * 32 + lane;
-#pragma unroll 1
-            for (int cb = 0; cb < 4; ++cb) {
-              float r[32];
-              tmem_ld32(ta + cb * 32, r);
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + ACC2 + (uint32_t)b * F_BM;
+        float va[32], vb[32];
+        float t0 = 0.f, t1 = 0.f;
+        auto chunk = [&](const float (&v)[32], int k) {   // rows 32k .. 32k+31 of this thread's channel, in registers
+          const int base = k * 32;
+          int nrk = nr - base;          // live rows of this chunk
+          nrk = nrk > 32 ? 32 : nrk;
+          const uint32_t m = msk[k];
 #pragma unroll
-              for (int j = 0; j < 8; ++j)
-                *reinterpret_cast<float4*>(st + cb * 8192 + lr * 128 + ((j ^ (lr & 7)) << 4)) = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-            }
-            if (p.keep) fence_proxy_async();
+          for (int rr = 0; rr < 32; ++rr) {   // unweighted sums of the live rows
+            const float x = rr < nrk ? v[rr] : 0.f;
+            t0 += x;
+            t1 = fmaf(x, x, t1);
           }
-          named_bar(2, 128);
-          if (p.keep && c == 0) {
+          // Run by run (a run = consecutive rows of one ball group inside this chunk; ~1.6 per chunk): the group bookkeeping is
+          // one warp-uniform branch per run, the extreme over the run's rows a predicated sweep of the 32 registers — compact code
+          // (a per-row branch unrolled 32 x 4 times overflowed the instruction cache: 27 us per tile)
+          int r0 = 0;
+          while (r0 < nrk) {
+            const uint32_t mm = r0 < 31 ? (m >> (r0 + 1)) : 0u;
+            int e = mm ? r0 + __ffs((int)mm) : 32;
+            e = e < nrk ? e : nrk;
+            float w1 = 0.f;
+            if ((m >> r0) & 1u) {          // a run that starts here (otherwise it continues from the previous chunk)
+              const int sg = mseg[base + r0];
+              if (sg != cur) {
+                if (cur >= 0) flush();
+                cur = sg;
+                best = -3.4e38f;
+                barg = trow0 + base + r0;
+              }
+              w1 = mw[base + r0] - 1.f;   // the first row of a group carries its duplicate multiplicity
+            }
+            int bi = -1;
+            float f = 0.f;
 #pragma unroll
-            for (int cb = 0; cb < 4; ++cb) tma_store_2d(&tY, smem_u32(st + cb * 8192), cb * 32, trow0 + half * 64);
-            tma_commit();
+            for (int rr = 0; rr < 32; ++rr) {
+              const bool in = rr >= r0 && rr < e;
+              const float key = v[rr] * sgn;
+              const bool better = in && key > best;
+              best = better ? key : best;
+              bi = better ? rr : bi;
+              f = rr == r0 ? v[rr] : f;
+            }
+            t0 = fmaf(w1, f, t0);
+            t1 = fmaf(w1 * f, f, t1);
+            if (bi >= 0) barg = trow0 + base + bi;
+            r0 = e;
           }
-          float t0 = 0.f, t1 = 0.f;
-          const unsigned char* colp = st + (c >> 5) * 8192 + (c & 3) * 4;
-          const int chunk = (c & 31) >> 2;
-          int nr = M - (trow0 + half * 64);
-          nr = nr > 64 ? 64 : nr;
-#pragma unroll 4
-          for (int rr = 0; rr < nr; ++rr) {
-            const int tr = half * 64 + rr;
-            const float v = *reinterpret_cast<const float*>(colp + rr * 128 + ((chunk ^ (rr & 7)) << 4));
-            const int sg = mseg[tr];
-            const float w = mw[tr];
-            t0 = fmaf(w, v, t0);
-            t1 = fmaf(w * v, v, t1);
-            const float key = neg ? -v : v;
-            if (sg != cur) {   // warp-uniform: all columns walk the same rows
-              flush();
-              cur = sg;
-              best = key;
-              barg = trow0 + tr;
-            } else if (key > best) {
-              best = key;
-              barg = trow0 + tr;
+          if (p.keep) {   // this warp's [rows x 32 channels] block of the Y2 tile, swizzled for the TMA store
+            const int h = k >> 1;
+            if ((k & 1) == 0) {
+              if (lane == 0) tma_wait_read0();
+              __syncwarp();
+            }
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) {
+              const int lr = (k & 1) * 32 + rr;
+              *reinterpret_cast<float*>(st + lr * 128 + (((lane >> 2) ^ (lr & 7)) << 4) + (lane & 3) * 4) = v[rr];
+            }
+            if (k & 1) {
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&tY, smem_u32(st), q * 32, trow0 + h * 64);
+                tma_commit();
+              }
             }
           }
-          S0 += t0;
-          S1 += t1;
-          if (p.keep && c == 0) tma_wait_read0();
-          named_bar(3, 128);   // the staging tile is free for the other half / the next tile
-        }
+        };
+        tmem_ld32_async(ta, va);
+        tmem_wait_ld();
+        tmem_ld32_async(ta + 32, vb);
+        chunk(va, 0);
+        tmem_wait_ld();
+        tmem_ld32_async(ta + 64, va);
+        chunk(vb, 1);
+        tmem_wait_ld();
+        tmem_ld32_async(ta + 96, vb);
+        chunk(va, 2);
+        tmem_wait_ld();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc2_empty[b]);
+        chunk(vb, 3);
+        S0 += t0;
+        S1 += t1;
       }
-      flush();
-      if (p.keep && c == 0) tma_wait_all0();
+      if (cur >= 0) flush();   // the CTA's last group (complete, or the head of one that continues in the next CTA's range)
+      if (p.keep && lane == 0) tma_wait_all0();
       p.stats[(long long)blockIdx.x * 2 * F_C3 + c] = S0;
       p.stats[(long long)blockIdx.x * 2 * F_C3 + F_C3 + c] = S1;
     }

@@ -359,14 +359,68 @@ class EncoderFlat:
         self.sa1f_ok = (L0.K <= 16 and (self.layers["sa0.0"].N, self.layers["sa0.1"].N, self.layers["sa0.2"].N) == (64, 64, 128)
                         and self.layers["sa0.1"].K == 64 and self.layers["sa0.2"].K == 64)
         self.sa1f_w = _f(device, int(lib.gaddpg_sa1f_wsplit_floats())) if self.sa1f_ok else None
+        if self.sa1f_ok:   # split jobs (rot = -1) of the same batched launch: [W0 hi | W0 lo | W1 hi | W1 lo | W2 hi | W2 lo]
+            w, off, L = self.sa1f_w.data_ptr(), 0, self.layers
+            for key, kp in (("sa0.0", 16), ("sa0.1", 64), ("sa0.2", 64)):
+                Lk = L[key]
+                jobs.append([Lk.W.data_ptr(), Lk.N, Lk.K, -1, w + 4 * off, kp, w + 4 * (off + Lk.N * kp), kp])
+                off += 2 * Lk.N * kp
+            self.jobs = torch.tensor(jobs, dtype=torch.int64, device=device)
         self.refresh_derived()
 
     def refresh_derived(self):
-        st = current_stream()
-        lib.gaddpg_wprep_batched(dp(self.jobs), self.jobs.shape[0], st)
-        if self.sa1f_ok:
-            L = self.layers
-            lib.gaddpg_sa1f_wprep(dp(L["sa0.0"].W), L["sa0.0"].K, L["sa0.0"].K, dp(L["sa0.1"].W), dp(L["sa0.2"].W), dp(self.sa1f_w), st)
+        lib.gaddpg_wprep_batched(dp(self.jobs), self.jobs.shape[0], current_stream())
+
+
+_refresh_cache = {}
+
+
+def refresh_many(flats):
+    """Derived weight layouts of several networks in ONE launch (their job tables concatenated once)."""
+    key = tuple(id(f) for f in flats)
+    j = _refresh_cache.get(key)
+    if j is None:
+        j = _refresh_cache[key] = torch.cat([f.jobs for f in flats]).contiguous()
+    lib.gaddpg_wprep_batched(dp(j), j.shape[0], current_stream())
+
+
+OPT_CHUNK = 4096
+_OPT_DTYPE = np.dtype([("p", "<u8"), ("g", "<u8"), ("m", "<u8"), ("v", "<u8"), ("target", "<u8"), ("tau_vec", "<u8"), ("dyn", "<u8"),
+                       ("clip", "<u8"), ("absmax_p", "<u8"), ("absmax_g", "<u8"), ("n", "<i8"), ("chunk0", "<i8"), ("eps", "<f4"),
+                       ("weight_decay", "<f4"), ("tau", "<f4"), ("kind", "<i4"), ("write_back", "<i4"), ("pad", "<i4")])
+assert _OPT_DTYPE.itemsize == 120
+
+
+class OptJobs:
+    """Device job table of gaddpg_optim_multi: element ranges of the parameter arenas with what one optimiser phase does to
+    them (Adam [+ Polyak target] [+ abs-max], Polyak only, statistics only) — the whole phase is one launch."""
+
+    def __init__(self, device):
+        self.rows, self.device, self.chunks, self.table = [], device, 0, None
+
+    def _add(self, kind, n, **kw):
+        if n <= 0:
+            return
+        r = np.zeros((), dtype=_OPT_DTYPE)
+        r["kind"], r["n"], r["chunk0"] = kind, n, self.chunks
+        for k, v in kw.items():
+            r[k] = v
+        self.rows.append(r)
+        self.chunks += (n + OPT_CHUNK - 1) // OPT_CHUNK
+
+    def adam(self, arena, off, n, dyn_ptr, eps, wd, clip=0, write_back=0, target=None, tau=0.0, absmax_p=0, absmax_g=0):
+        q = lambda t: 0 if t is None else t.data_ptr() + 4 * off  # noqa: E731
+        self._add(0, n, p=q(arena.p), g=q(arena.g), m=q(arena.m), v=q(arena.v), target=q(target), dyn=dyn_ptr, clip=clip, eps=eps,
+                  weight_decay=wd, tau=tau, write_back=write_back, absmax_p=absmax_p, absmax_g=absmax_g)
+
+    def polyak(self, source, target, off, n, tau=0.0, tau_vec=None, grads=None, absmax_p=0, absmax_g=0):
+        q = lambda t: 0 if t is None else t.data_ptr() + 4 * off  # noqa: E731
+        self._add(1, n, p=q(source), target=q(target), tau=tau, tau_vec=q(tau_vec), g=q(grads), absmax_p=absmax_p, absmax_g=absmax_g)
+
+    def launch(self):
+        if self.table is None:
+            self.table = torch.from_numpy(np.stack(self.rows).view(np.uint8).reshape(len(self.rows), -1).copy()).to(self.device)
+        lib.gaddpg_optim_multi(dp(self.table), len(self.rows), self.chunks, current_stream())
 
 
 # ------------------------------------------------------------------------------------------------

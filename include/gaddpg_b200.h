@@ -289,6 +289,17 @@ GADDPG_API int gaddpg_clip_coef(const float* g, long long n, float max_norm, flo
 GADDPG_API int gaddpg_wprep(const float* W, int N, int K, int rot, float* Wp, int ldp, float* WT, int ldt, void* stream);
 /* all derived layouts of a network in one launch: jobs_dev[j] = {W, N, K, rot, Wp, ldp, WT, ldt} as 8 x int64 (device) */
 GADDPG_API int gaddpg_wprep_batched(const long long* jobs_dev, int njobs, void* stream);
+/* One launch for a whole optimiser phase (replaces the per-network torch.optim.Adam.step / soft_update / module_max_* calls of
+ * /root/reference/core/agent.py:192-209,242-259 and ddpg.py:141-143): jobs_dev = njobs records of 120 bytes
+ *   { float *p, *g, *m, *v, *target; const float *tau_vec, *dyn, *clip; float *absmax_p, *absmax_g; long long n, chunk0;
+ *     float eps, weight_decay, tau; int kind, write_back, pad; }
+ * kind 0: Adam with L2 weight decay on [p, p+n) (dyn = {lr/(1-beta1^t), sqrt(1-beta2^t)} on the device, clip = optional device
+ * scalar multiplied into the gradient, write_back = store the clipped gradient), then target = target*(1-tau) + p*tau if target;
+ * kind 1: that Polyak update only (per-element tau_vec if given); kind 2: statistics only.  absmax_p / absmax_g (optional):
+ * device floats that receive max |p| (after the update) / max |g| through an order-independent atomic max of the bit patterns
+ * (they must hold a non-negative value, normally 0, on entry).  chunk0 = first 4096-element chunk of the job in the launch's
+ * chunk space (running sum of ceil(n / 4096)); total_chunks = that sum over all jobs.  n and every pointer 16-byte aligned. */
+GADDPG_API int gaddpg_optim_multi(const void* jobs_dev, int njobs, int total_chunks, void* stream);
 /* stand-alone EPI_DMASK: D = dX*[Yprev*psc+psh > 0] plus its BN-backward sums (for gradients arriving from autograd) */
 GADDPG_API int gaddpg_dmask_stats(const float* dX, int ldx, const float* Yprev, int C, int M, const float* psc, const float* psh,
                                   const float* pmean, const float* prstd, float* D, float* stats, void* stream);

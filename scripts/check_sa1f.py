@@ -38,7 +38,7 @@ for keep in (True, False):
         if keep:
             line += "  Y%d %.2e" % (l, rel(s1.Y[l][:M], s0.Y[l][:M]))
         print(line, flush=True)
-    print("   pooled out %.2e   arg mismatch %.4f%%   feat %.2e" % (rel(s1.out, s0.out), 100 * float((s1.arg != s0.arg).float().mean()), rel(f1[:, :512], f0[:, :512])), flush=True)
+    print("   pooled out %.2e   arg mismatch %.4f%%   feat %.2e" % (rel(s1.out, s0.out), 100 * float(((s1.arg != s0.arg) & (s0.out > 0)).float().mean()), rel(f1[:, :512], f0[:, :512])), flush=True)
 # timing
 for fused in (False, True):
     for keep in (True, False):
@@ -56,3 +56,30 @@ for fused in (False, True):
             fn(ws, ef, geom, cloud, 6, CH, bc, Cbb, ctx, True, None, keep)
         e1.record(); torch.cuda.synchronize()
         print("SA1 forward fused=%d keep=%d: %.1f us per pass" % (fused, keep, 100 * e0.elapsed_time(e1)), flush=True)
+# ---- per-phase timing of the fused chain (stale BN constants are fine for timing)
+ws = engine.Workspace(dev); geom = engine.Geometry(B, N, dev).build(cloud, 6)
+ctx = engine.EncoderCtx(B, (geom.lv[0].cap, geom.lv[1].cap), engine.WIDTHS, dev)
+l1 = geom.lv[0]; s = ctx.sa[0]; L = ef.layers; b = ws.sa1f(l1.S, l1.cap)
+Cbb = 0 if bc is None else bc.shape[1]
+engine._sa1_fused_forward(ws, ef, geom, cloud, 6, CH, bc, Cbb, ctx, True, None, True)
+def phase(k, keep):
+    lib.gaddpg_sa1_fused_fwd(k, dp(cloud), cloud.shape[1] * cloud.shape[2], cloud.shape[2], 6, CH, dp(bc), Cbb, dp(l1.new_xyz), 32, dp(l1.seg_off),
+                             dp(l1.row_seg), dp(l1.row_src), dp(l1.row_w), l1.cap, l1.M_dev, dp(ef.sa1f_w), dp(s.bn[0].scale), dp(s.bn[0].shift),
+                             dp(s.bn[1].scale), dp(s.bn[1].shift), dp(L["sa0.2"].gamma), dp(ws.stats), dp(s.Y[k - 1]) if keep else None,
+                             dp(b.ext), dp(b.arg), dp(b.part_ext), dp(b.part_arg), dp(b.seg_part), current_stream())
+def fin():
+    lib.gaddpg_sa1_pool_finalize(dp(b.ext), dp(b.arg), dp(b.part_ext), dp(b.part_arg), dp(b.seg_part), dp(L["sa0.2"].gamma),
+                                 dp(s.bn[2].scale), dp(s.bn[2].shift), l1.S, dp(s.out), dp(s.arg), current_stream())
+def bnf():
+    engine.bn_fwd(ws, 128, B * 32 * 64, L["sa0.2"], s.bn[2], True, None)
+def tm(fn, n=10):
+    for _ in range(2): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n): fn()
+    e1.record(); torch.cuda.synchronize()
+    return 1e3 * e0.elapsed_time(e1) / n
+for keep in (False, True):
+    print("keep=%d: phase1 %.1f us  phase2 %.1f us  phase3 %.1f us" % (keep, tm(lambda: phase(1, keep)), tm(lambda: phase(2, keep)), tm(lambda: phase(3, keep))), flush=True)
+print("pool finalize %.1f us   bn_finalize(128) %.1f us" % (tm(fin), tm(bnf)), flush=True)
