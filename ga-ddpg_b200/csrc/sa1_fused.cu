@@ -24,11 +24,14 @@
 //                    (action) channels, hi/lo split, swizzled STS of the [128 x 16] layer-0 operand
 //   MMA warp 4       one thread: TMA loads of the pre-split weights (cp.async.bulk.tensor, SWIZZLE_64B/128B, once per CTA),
 //                    tcgen05.mma kind::tf32 x3 (3xTF32) for conv0 (K=16), conv1 (K=64), conv2 (K=64, N=128) into TMEM
-//   E0  warps 5-8    thread = row: tcgen05.ld of conv0's accumulator, BN0+ReLU, split, STS into the conv1 operand buffer
-//                    (phase 1: statistics of Y0 instead)
-//   E1  warps 9-12   same for conv1's accumulator -> conv2 operand buffer (phase 2: statistics of Y1)
-//   E2  warps 13-16  conv2's accumulator -> swizzled staging tile -> thread = column: one pass over the rows that yields
-//                    the column's statistics AND its running per-segment extreme (flushed when the segment changes)
+//   E   warps 5-8    thread = row: tcgen05.ld of conv0's accumulator, BN0+ReLU, hi/lo split, STS into the shared operand buffer
+//                    (conv1's operand); then the same for conv1's accumulator (conv2's operand).  One group serves both stages:
+//                    the operand of conv1(t+1) may only be written once conv2(t) has read the buffer, i.e. after this group's
+//                    work on conv1(t) anyway.
+//   G0  warps 9-12   consumers of the phase's LAST accumulator, alternating tiles (even / odd = the two TMEM buffers):
+//   G1  warps 13-16  phases 1/2: thread = row -> swizzled staging tile -> column sums; phase 3: conv2 is issued TRANSPOSED
+//                    (D[channel][row] = W2 . act^T), so a thread owns a channel and walks the tile's 128 rows straight out of
+//                    tcgen05.ld registers: statistics and the running per-group extreme, flushed when the ball group changes
 // The conv1 and conv2 operands share ONE 64 KB buffer (conv2's operand is produced from conv1's finished accumulator), which
 // is what lets all three weight matrices (hi + lo, 104 KB), the operands and the staging tile fit in 227 KB.
 #include <cuda.h>
@@ -44,7 +47,7 @@ constexpr int F_C = 64;     // widths of conv0 / conv1 outputs (networks.py:70: 
 constexpr int F_C3 = 128;   // width of conv2's output
 constexpr int F_WARPS = 17;
 constexpr int F_THREADS = F_WARPS * 32;
-constexpr int W_P = 0, W_MMA = 4, W_E0 = 5, W_E1 = 9, W_E2 = 13;
+constexpr int W_MMA = 4, W_G = 9;   // P: warps 0-3, E: warps 5-8, G0 / G1: warps 9-12 / 13-16
 
 struct FLayout {
   uint32_t w0h, w0l, w1h, w1l, w2h, w2l, a0h[2], a0l[2], abh, abl, stage, consts, meta, bars, red, total;
@@ -65,10 +68,10 @@ __host__ __device__ inline FLayout f_layout(int phase) {
   }
   L.abh = off; off += (phase >= 2) ? F_BM * F_C * 4 : 0;
   L.abl = off; off += (phase >= 2) ? F_BM * F_C * 4 : 0;
-  L.stage = off; off += 32768;          // phases 1/2: 4 x [2 col blocks][32 rows x 128 B]; phase 3: [4 col blocks][64 rows x 128 B]
+  L.stage = off; off += (phase <= 2) ? 65536 : 32768;   // phases 1/2: 8 warps x [2 col blocks][32 rows x 128 B]; phase 3 (keep): 8 warps x [32 rows x 128 B]
   L.consts = off; off += 2048;          // sc0, sh0, sc1, sh1 [64 each], sign(gamma2) [128]
-  L.meta = off; off += 4 * 1024;        // E2: per-warp copy of the segment id and multiplicity of the tile's 128 rows
-  L.red = off; off += 2 * 4 * F_C * 4;  // phases 1/2: cross-warp combine of the column sums [2][4 warps][64]
+  L.meta = off; off += (phase >= 3) ? 2 * 1536 : 0;     // phase 3: per consumer group: segment id, weight and run destination of its tile's rows
+  L.red = off; off += 2 * 8 * F_C * 4;  // cross-warp combine of the column sums: phases 1/2 [2][8 warps][64]; phase 3 [2 groups][2][128]
   L.bars = off; off += 256;
   L.total = off;
   return L;
@@ -103,7 +106,8 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+template <int ID>
+__device__ __forceinline__ void named_bar(int nthreads) { asm volatile("bar.sync %0, %1;" ::"n"(ID), "r"(nthreads) : "memory"); }
 
 // K-major SWIZZLE_64B descriptor (layer-0 operands: rows of 16 floats = 64 B; 8-row atoms of 512 B)
 __device__ __forceinline__ uint64_t make_desc64(uint32_t saddr) {
@@ -390,241 +394,227 @@ sa1_fused_kernel(const Sa1FParams p, const __grid_constant__ CUtensorMap tW0h, c
       }
     }
     __syncwarp();
-  } else if (warp < W_E1) {
-    // ===================== E0: conv0 accumulator =====================
-    const int q = warp & 3, row = q * 32 + lane;
-    const float* cs = reinterpret_cast<const float*>(smem + L.consts);
-    unsigned char* st = smem + L.stage + (warp - W_E0) * 8192;
-    float S0[2] = {0.f, 0.f}, S1[2] = {0.f, 0.f};
-    for (int it = 0; it < my_tiles; ++it) {
-      const int b = it & 1;
-      const int grow = (tile0 + it) * F_BM + row;
-      float w = 0.f;
-      if (PHASE == 1 && grow < M) w = p.row_w[grow];
-      mbar_wait(&acc0_full[b], ((uint32_t)it >> 1) & 1u);
-      tc_fence_after();
-      float r[F_C];
-      const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + ACC0 + (uint32_t)b * F_C;
-      tmem_ld32_async(ta, r);
-      tmem_ld32_async(ta + 32, r + 32);
-      tmem_wait_ld();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc0_empty[b]);
-      if (PHASE == 1) {
-        stats64_tile(r, w, st, lane, p.keep != 0, &tY, (tile0 + it) * F_BM + q * 32, S0, S1);
-      } else {
-        mbar_wait(ab_free, ((uint32_t)it & 1u) ^ 1u);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) bnrelu_split_store(smem + L.abh, smem + L.abl, row, 4 * j, r + 4 * j, cs, cs + 64);
-        fence_proxy_async();
-        mbar_arrive(ab1_full);
-      }
-    }
-    if (PHASE == 1) {
-      if (p.keep && lane == 0) tma_wait_all0();
-      float* red = reinterpret_cast<float*>(smem + L.red);
-      const int w4 = warp - W_E0;
-      red[w4 * 64 + 2 * lane] = S0[0];
-      red[w4 * 64 + 2 * lane + 1] = S0[1];
-      red[256 + w4 * 64 + 2 * lane] = S1[0];
-      red[256 + w4 * 64 + 2 * lane + 1] = S1[1];
-    }
-  } else if (warp < W_E2) {
-    // ===================== E1: conv1 accumulator =====================
+  } else if (warp < W_G) {
+    // ===================== E: conv0 / conv1 accumulators -> operand of the next conv =====================
     if (PHASE >= 2) {
       const int q = warp & 3, row = q * 32 + lane;
       const float* cs = reinterpret_cast<const float*>(smem + L.consts);
-      unsigned char* st = smem + L.stage + (warp - W_E1) * 8192;
-      float S0[2] = {0.f, 0.f}, S1[2] = {0.f, 0.f};
-      for (int it = 0; it < my_tiles; ++it) {
-        const int b = it & 1;
-        const int grow = (tile0 + it) * F_BM + row;
-        float w = 0.f;
-        if (PHASE == 2 && grow < M) w = p.row_w[grow];
-        mbar_wait(&acc1_full[b], ((uint32_t)it >> 1) & 1u);
+      auto stage0 = [&](int j) {   // conv0 accumulator of tile j -> relu(bn0) -> conv1 operand
+        const int b = j & 1;
+        mbar_wait(&acc0_full[b], ((uint32_t)j >> 1) & 1u);
         tc_fence_after();
         float r[F_C];
-        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + ACC1 + (uint32_t)b * F_C;
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + ACC0 + (uint32_t)b * F_C;
         tmem_ld32_async(ta, r);
         tmem_ld32_async(ta + 32, r + 32);
         tmem_wait_ld();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&acc1_empty[b]);
-        if (PHASE == 2) {
-          stats64_tile(r, w, st, lane, p.keep != 0, &tY, (tile0 + it) * F_BM + q * 32, S0, S1);
-        } else {
-          // conv1 of this tile has completed (acc1_full), so the shared operand buffer may be overwritten with conv2's operand
+        if (lane == 0) mbar_arrive(&acc0_empty[b]);
+        mbar_wait(ab_free, ((uint32_t)j & 1u) ^ 1u);   // conv2(j-1) (phase 2: conv1(j-1)) has read the operand buffer
 #pragma unroll
-          for (int j = 0; j < 16; ++j) bnrelu_split_store(smem + L.abh, smem + L.abl, row, 4 * j, r + 4 * j, cs + 128, cs + 192);
+        for (int k = 0; k < 16; ++k) bnrelu_split_store(smem + L.abh, smem + L.abl, row, 4 * k, r + 4 * k, cs, cs + 64);
+        fence_proxy_async();
+        mbar_arrive(ab1_full);
+      };
+      if (my_tiles > 0) stage0(0);
+      for (int it = 0; it < my_tiles; ++it) {
+        if (PHASE >= 3) {   // conv1 accumulator -> relu(bn1) -> conv2 operand (conv1(it) is complete: the buffer may be overwritten)
+          const int b = it & 1;
+          mbar_wait(&acc1_full[b], ((uint32_t)it >> 1) & 1u);
+          tc_fence_after();
+          float r[F_C];
+          const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + ACC1 + (uint32_t)b * F_C;
+          tmem_ld32_async(ta, r);
+          tmem_ld32_async(ta + 32, r + 32);
+          tmem_wait_ld();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc1_empty[b]);
+#pragma unroll
+          for (int k = 0; k < 16; ++k) bnrelu_split_store(smem + L.abh, smem + L.abl, row, 4 * k, r + 4 * k, cs + 128, cs + 192);
           fence_proxy_async();
           mbar_arrive(ab2_full);
         }
-      }
-      if (PHASE == 2) {
-        if (p.keep && lane == 0) tma_wait_all0();
-        float* red = reinterpret_cast<float*>(smem + L.red);
-        const int w4 = warp - W_E1;
-        red[w4 * 64 + 2 * lane] = S0[0];
-        red[w4 * 64 + 2 * lane + 1] = S0[1];
-        red[256 + w4 * 64 + 2 * lane] = S1[0];
-        red[256 + w4 * 64 + 2 * lane + 1] = S1[1];
+        if (it + 1 < my_tiles) stage0(it + 1);   // its TMEM read + math overlap conv2(it); only the stores wait for it
       }
     }
   } else {
-    // ===================== E2: conv2 accumulator (channel-major) -> statistics + per-group extremes =====================
-    if (PHASE >= 3) {
-      const int q = warp & 3;             // TMEM lane quarter
-      const int c = q * 32 + lane;        // channel = TMEM lane
+    // ===================== G0 / G1: consumers of the phase's last accumulator, alternating tiles =====================
+    const int grp = (warp - W_G) >> 2;   // 0: even tiles (TMEM buffer 0), 1: odd tiles
+    const int q = warp & 3;              // TMEM lane quarter
+    const int w8 = warp - W_G;           // 0..7
+    if (PHASE <= 2) {
+      // thread = row: weighted column sums of the pre-BN output (conv0 in phase 1, conv1 in phase 2) [+ TMA store in keep mode]
+      const int row = q * 32 + lane;
+      unsigned char* st = smem + L.stage + w8 * 8192;
+      uint64_t* full = PHASE == 1 ? acc0_full : acc1_full;
+      uint64_t* empty = PHASE == 1 ? acc0_empty : acc1_empty;
+      constexpr uint32_t ACC = PHASE == 1 ? ACC0 : ACC1;
+      float S0[2] = {0.f, 0.f}, S1[2] = {0.f, 0.f};
+      for (int it = grp; it < my_tiles; it += 2) {
+        const int grow = (tile0 + it) * F_BM + row;
+        const float w = grow < M ? p.row_w[grow] : 0.f;
+        mbar_wait(&full[grp], ((uint32_t)it >> 1) & 1u);
+        tc_fence_after();
+        float r[F_C];
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + ACC + (uint32_t)grp * F_C;
+        tmem_ld32_async(ta, r);
+        tmem_ld32_async(ta + 32, r + 32);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[grp]);
+        stats64_tile(r, w, st, lane, p.keep != 0, &tY, (tile0 + it) * F_BM + q * 32, S0, S1);
+      }
+      if (p.keep && lane == 0) tma_wait_all0();
+      float* red = reinterpret_cast<float*>(smem + L.red);
+      red[w8 * 64 + 2 * lane] = S0[0];
+      red[w8 * 64 + 2 * lane + 1] = S0[1];
+      red[512 + w8 * 64 + 2 * lane] = S1[0];
+      red[512 + w8 * 64 + 2 * lane + 1] = S1[1];
+    } else {
+      // thread = channel (conv2 was issued transposed): statistics + per-group extremes of the tile's 128 rows from registers.
+      // Everything that depends only on the ROW (run starts, statistic weights, where a finished run is written) is worked
+      // out once per tile by the group into shared memory; the per-row code of a thread is branch-free: the flush of a
+      // finished run is two predicated stores.
+      const int c = q * 32 + lane;
+      const int gt = (warp - W_G - grp * 4) * 32 + lane;   // thread index inside the group (row whose meta it prepares)
       const float* cs = reinterpret_cast<const float*>(smem + L.consts);
       const float sgn = cs[256 + c];      // +1: the pooled value is bn(max y); -1: bn(min y)
-      int32_t* mseg = reinterpret_cast<int32_t*>(smem + L.meta + (warp - W_E2) * 1024);   // this warp's copy
-      float* mw = reinterpret_cast<float*>(smem + L.meta + (warp - W_E2) * 1024 + 512);
-      unsigned char* st = smem + L.stage + (warp - W_E2) * 8192;                           // keep: [64 rows x 128 B] of this warp's 32 channels
-      const int cta_row0 = tile0 * F_BM;
+      int32_t* mseg = reinterpret_cast<int32_t*>(smem + L.meta + grp * 1536);        // [128] segment id (-1: row >= M)
+      float* mw = reinterpret_cast<float*>(smem + L.meta + grp * 1536 + 512);         // [128] statistic weight of the row
+      int32_t* rdst = reinterpret_cast<int32_t*>(smem + L.meta + grp * 1536 + 1024);  // [128] destination of run k: element
+                                                                                     // offset; bit 30: per-tile side table
+      unsigned char* st = smem + L.stage + w8 * 4096;   // keep: [32 rows x 128 B] of this warp's 32 channels
       float S0 = 0.f, S1 = 0.f;
-      int cur = -1, barg = 0;
-      float best = 0.f;
-      bool first_flush = true;
-      auto flush = [&]() {
-        const float v = best * sgn;
-        if (first_flush && p.seg_off[cur] < cta_row0) {   // this group began in the previous CTA's range: partial result
-          p.part_ext[(long long)blockIdx.x * F_C3 + c] = v;
-          p.part_arg[(long long)blockIdx.x * F_C3 + c] = barg;
-          if (c == 0) p.seg_part[cur] = (int)blockIdx.x;
-        } else {
-          p.ext[(long long)cur * F_C3 + c] = v;
-          p.arg[(long long)cur * F_C3 + c] = barg;
+      for (int it = grp; it < my_tiles; it += 2) {
+        const int tile = tile0 + it, trow0 = tile * F_BM;
+        if (grp == 0) named_bar<1>(128); else named_bar<2>(128);    // the group is done with the previous tile's meta
+        {
+          const int grow = trow0 + gt;
+          mseg[gt] = grow < M ? p.row_seg[grow] : -1;
+          mw[gt] = grow < M ? p.row_w[grow] : 0.f;
         }
-        first_flush = false;
-      };
-      for (int it = 0; it < my_tiles; ++it) {
-        const int b = it & 1;
-        const int trow0 = (tile0 + it) * F_BM;
-        const int nr = M - trow0;   // live rows of this tile (>= 1)
-        __syncwarp();
-        uint32_t msk[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int grow = trow0 + k * 32 + lane;
-          mseg[k * 32 + lane] = grow < M ? p.row_seg[grow] : -1;
-          mw[k * 32 + lane] = grow < M ? p.row_w[grow] : 0.f;
+        if (grp == 0) named_bar<1>(128); else named_bar<2>(128);
+        uint32_t m0, m1, m2, m3;   // bit rr of mk: row 32k+rr starts a run (a new ball group, the tile, or the dead tail)
+        m0 = __ballot_sync(0xffffffffu, lane == 0 || mseg[lane] != mseg[lane - 1]);
+        m1 = __ballot_sync(0xffffffffu, mseg[32 + lane] != mseg[31 + lane]);
+        m2 = __ballot_sync(0xffffffffu, mseg[64 + lane] != mseg[63 + lane]);
+        m3 = __ballot_sync(0xffffffffu, mseg[96 + lane] != mseg[95 + lane]);
+        {   // run k (k-th set bit) -> where its result goes
+          const int sg = mseg[gt];
+          const bool start = gt == 0 || sg != mseg[gt - 1];
+          if (start) {
+            const int wq = gt >> 5;
+            const uint32_t below = (wq == 0 ? m0 : wq == 1 ? m1 : wq == 2 ? m2 : m3) & ((1u << (gt & 31)) - 1u);
+            const int k = __popc(below) + (wq > 0 ? __popc(m0) : 0) + (wq > 1 ? __popc(m1) : 0) + (wq > 2 ? __popc(m2) : 0);
+            int d;
+            if (sg < 0) {
+              d = (1 << 30) | (((p.M_max + F_BM - 1) / F_BM) * F_C3);   // dead tail of the last tile: parked in the spare side-table row
+            } else if (gt == 0 && p.seg_off[sg] < trow0) {
+              d = (1 << 30) | (tile * F_C3);     // the group began in the previous tile: partial, merged by the finalize kernel
+              p.seg_part[sg] = tile;
+            } else {
+              d = sg * F_C3;
+            }
+            rdst[k] = d;
+          }
         }
-        __syncwarp();
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {   // bit rr of msk[k]: row 32k+rr starts a run (a new ball group, or the tile)
-          const int rr = k * 32 + lane;
-          msk[k] = __ballot_sync(0xffffffffu, rr == 0 || mseg[rr] != mseg[rr - 1]);
-        }
-        mbar_wait(&acc2_full[b], ((uint32_t)it >> 1) & 1u);
+        if (grp == 0) named_bar<1>(128); else named_bar<2>(128);
+        float best = -3.4e38f, t0 = 0.f, t1 = 0.f;
+        int barg = 0, krun = -1;
+        mbar_wait(&acc2_full[grp], ((uint32_t)it >> 1) & 1u);
         tc_fence_after();
-        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + ACC2 + (uint32_t)b * F_BM;
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + ACC2 + (uint32_t)grp * F_BM;
         float va[32], vb[32];
-        float t0 = 0.f, t1 = 0.f;
-        auto chunk = [&](const float (&v)[32], int k) {   // rows 32k .. 32k+31 of this thread's channel, in registers
+        auto emit = [&](uint32_t pred, int k) {   // predicated: store the finished run k
+          const int d = rdst[k < 0 ? 0 : k];
+          float* pe = ((d >> 30) & 1) ? p.part_ext : p.ext;
+          int32_t* pa = ((d >> 30) & 1) ? p.part_arg : p.arg;
+          const long long off = (long long)(d & 0x3FFFFFFF) + c;
+          asm volatile(
+              "{\n\t.reg .pred q;\n\t"
+              "setp.ne.u32 q, %0, 0;\n\t"
+              "@q st.global.f32 [%1], %2;\n\t"
+              "@q st.global.s32 [%3], %4;\n\t}" ::"r"(pred), "l"(pe + off), "f"(best * sgn), "l"(pa + off), "r"(barg)
+              : "memory");
+        };
+        auto chunk = [&](const float (&v)[32], int k, uint32_t m) {   // rows 32k .. 32k+31 of this thread's channel
           const int base = k * 32;
-          int nrk = nr - base;          // live rows of this chunk
-          nrk = nrk > 32 ? 32 : nrk;
-          const uint32_t m = msk[k];
 #pragma unroll
-          for (int rr = 0; rr < 32; ++rr) {   // unweighted sums of the live rows
-            const float x = rr < nrk ? v[rr] : 0.f;
-            t0 += x;
-            t1 = fmaf(x, x, t1);
+          for (int rr = 0; rr < 32; ++rr) {
+            const uint32_t start = (m >> rr) & 1u;              // warp-uniform
+            emit(start & (krun >= 0 ? 1u : 0u), krun);
+            krun += (int)start;
+            best = start ? -3.4e38f : best;
+            const float w = mw[base + rr];                      // broadcast
+            t0 = fmaf(w, v[rr], t0);
+            t1 = fmaf(w * v[rr], v[rr], t1);
+            const float key = v[rr] * sgn;
+            const bool better = key > best;
+            best = better ? key : best;
+            barg = better ? trow0 + base + rr : barg;
           }
-          // Run by run (a run = consecutive rows of one ball group inside this chunk; ~1.6 per chunk): the group bookkeeping is
-          // one warp-uniform branch per run, the extreme over the run's rows a predicated sweep of the 32 registers — compact code
-          // (a per-row branch unrolled 32 x 4 times overflowed the instruction cache: 27 us per tile)
-          int r0 = 0;
-          while (r0 < nrk) {
-            const uint32_t mm = r0 < 31 ? (m >> (r0 + 1)) : 0u;
-            int e = mm ? r0 + __ffs((int)mm) : 32;
-            e = e < nrk ? e : nrk;
-            float w1 = 0.f;
-            if ((m >> r0) & 1u) {          // a run that starts here (otherwise it continues from the previous chunk)
-              const int sg = mseg[base + r0];
-              if (sg != cur) {
-                if (cur >= 0) flush();
-                cur = sg;
-                best = -3.4e38f;
-                barg = trow0 + base + r0;
-              }
-              w1 = mw[base + r0] - 1.f;   // the first row of a group carries its duplicate multiplicity
-            }
-            int bi = -1;
-            float f = 0.f;
+          if (p.keep) {   // this warp's [32 rows x 32 channels] block of the Y2 tile, swizzled for the TMA store
+            if (lane == 0) tma_wait_read0();
+            __syncwarp();
 #pragma unroll
-            for (int rr = 0; rr < 32; ++rr) {
-              const bool in = rr >= r0 && rr < e;
-              const float key = v[rr] * sgn;
-              const bool better = in && key > best;
-              best = better ? key : best;
-              bi = better ? rr : bi;
-              f = rr == r0 ? v[rr] : f;
-            }
-            t0 = fmaf(w1, f, t0);
-            t1 = fmaf(w1 * f, f, t1);
-            if (bi >= 0) barg = trow0 + base + bi;
-            r0 = e;
-          }
-          if (p.keep) {   // this warp's [rows x 32 channels] block of the Y2 tile, swizzled for the TMA store
-            const int h = k >> 1;
-            if ((k & 1) == 0) {
-              if (lane == 0) tma_wait_read0();
-              __syncwarp();
-            }
-#pragma unroll
-            for (int rr = 0; rr < 32; ++rr) {
-              const int lr = (k & 1) * 32 + rr;
-              *reinterpret_cast<float*>(st + lr * 128 + (((lane >> 2) ^ (lr & 7)) << 4) + (lane & 3) * 4) = v[rr];
-            }
-            if (k & 1) {
-              fence_proxy_async();
-              __syncwarp();
-              if (lane == 0) {
-                tma_store_2d(&tY, smem_u32(st), q * 32, trow0 + h * 64);
-                tma_commit();
-              }
+            for (int rr = 0; rr < 32; ++rr)
+              *reinterpret_cast<float*>(st + rr * 128 + (((lane >> 2) ^ (rr & 7)) << 4) + (lane & 3) * 4) = v[rr];
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tY, smem_u32(st), q * 32, trow0 + base);
+              tma_commit();
             }
           }
         };
         tmem_ld32_async(ta, va);
         tmem_wait_ld();
         tmem_ld32_async(ta + 32, vb);
-        chunk(va, 0);
+        chunk(va, 0, m0);
         tmem_wait_ld();
         tmem_ld32_async(ta + 64, va);
-        chunk(vb, 1);
+        chunk(vb, 1, m1);
         tmem_wait_ld();
         tmem_ld32_async(ta + 96, vb);
-        chunk(va, 2);
+        chunk(va, 2, m2);
         tmem_wait_ld();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&acc2_empty[b]);
-        chunk(vb, 3);
+        if (lane == 0) mbar_arrive(&acc2_empty[grp]);
+        chunk(vb, 3, m3);
+        emit(1u, krun);   // the tile's last run (a complete group, the head of one that continues in the next tile, or the dead tail)
         S0 += t0;
         S1 += t1;
       }
-      if (cur >= 0) flush();   // the CTA's last group (complete, or the head of one that continues in the next CTA's range)
       if (p.keep && lane == 0) tma_wait_all0();
-      p.stats[(long long)blockIdx.x * 2 * F_C3 + c] = S0;
-      p.stats[(long long)blockIdx.x * 2 * F_C3 + F_C3 + c] = S1;
+      float* red = reinterpret_cast<float*>(smem + L.red);
+      red[grp * 256 + c] = S0;
+      red[grp * 256 + 128 + c] = S1;
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (PHASE <= 2) {   // one slot per CTA: the four row-group warps folded in a fixed order
+  {   // one slot per CTA, folded in a fixed order
     const float* red = reinterpret_cast<const float*>(smem + L.red);
-    if (tid < 2 * F_C) {
-      const int h = tid >> 6, cc = tid & 63;
-      p.stats[(long long)blockIdx.x * 2 * F_C + tid] = my_tiles > 0 ? red[h * 256 + cc] + red[h * 256 + 64 + cc] + red[h * 256 + 128 + cc] + red[h * 256 + 192 + cc] : 0.f;
+    if (PHASE <= 2) {
+      if (tid < 2 * F_C) {
+        const int h = tid >> 6, cc = tid & 63;
+        float a = 0.f;
+        for (int w = 0; w < 8; ++w) {
+          const bool used = my_tiles > ((w >> 2) & 1);   // group 1 (warps 4-7) only ran if the CTA had an odd tile
+          a += used ? red[h * 512 + w * 64 + cc] : 0.f;
+        }
+        p.stats[(long long)blockIdx.x * 2 * F_C + tid] = a;
+      }
+    } else {
+      if (tid < 2 * F_C3) {
+        const int h = tid >> 7, cc = tid & 127;
+        p.stats[(long long)blockIdx.x * 2 * F_C3 + tid] = red[h * 128 + cc] + red[256 + h * 128 + cc];
+      }
     }
-  } else if (my_tiles == 0) {
-    for (int i = tid; i < 2 * F_C3; i += F_THREADS) p.stats[(long long)blockIdx.x * 2 * F_C3 + i] = 0.f;
-  }
-  {
     constexpr int CW = PHASE <= 2 ? 2 * F_C : 2 * F_C3;
     for (int slot = blockIdx.x + gridDim.x; slot < GADDPG_STAT_SLOTS; slot += gridDim.x)
       for (int i = tid; i < CW; i += F_THREADS) p.stats[(long long)slot * CW + i] = 0.f;
@@ -649,7 +639,7 @@ __global__ void __launch_bounds__(128) sa1_pool_finalize_kernel(const float* __r
     float v = ext[(long long)s * F_C3 + c];
     int a = arg[(long long)s * F_C3 + c];
     const int sp = seg_part[s];
-    if (sp >= 0) {   // the tail of this segment was reduced by CTA sp: higher rows, so a tie keeps the head's row
+    if (sp >= 0) {   // the tail of this group was reduced with tile sp: higher rows, so a tie keeps the head's row
       const float pv = part_ext[(long long)sp * F_C3 + c];
       if ((neg ? -pv : pv) > (neg ? -v : v)) {
         v = pv;
@@ -745,7 +735,7 @@ int gaddpg_sa1_fused_fwd_impl(int phase, const float* cloud, long long cloud_sb,
   const int CY = phase == 3 ? F_C3 : F_C;
   if (Ykeep) {
     GADDPG_CHECK_ARG(((uintptr_t)Ykeep & 15u) == 0, "sa1_fused_fwd: Ykeep must be 16-byte aligned");
-    ok = ok && make_map(&mY, Ykeep, M_max, CY, phase == 3 ? 64 : 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+    ok = ok && make_map(&mY, Ykeep, M_max, CY, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
   } else {
     mY = m1h;   // unused
   }

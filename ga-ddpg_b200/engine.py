@@ -82,8 +82,9 @@ class Workspace:
 
     def sa1f(self, S, cap):
         """Scratch of the fused SA1 chain (gaddpg_sa1_fused_fwd): raw per-(group, channel) extremes + rows, the partial
-        results of groups that straddle two CTAs' tile ranges, and the group -> partial map (all -1 between calls)."""
-        grid = int(lib.gaddpg_sa1_fused_grid(cap))
+        results of groups that straddle two 128-row tiles (one side-table row per tile), and the group -> partial map (all -1
+        between calls)."""
+        grid = (cap + 127) // 128 + 1   # one side-table row per 128-row tile + a spare row
         b = self._sa1f
         if b is None or b.S < S or b.grid < grid:
             i32 = dict(dtype=torch.int32, device=self.device)
@@ -501,7 +502,15 @@ def encoder_forward(ws, ef, geom, cloud, skip, Cp, bc, ctx, time=None, time_offs
     return ctx.feat
 
 
-FUSED_SA1 = True        # SA1 shared MLP + max-pool as the TMA-fed recompute chain of csrc/sa1_fused.cu (three phases)
+# SA1 shared MLP + max-pool as the TMA-fed recompute chain of csrc/sa1_fused.cu (three phases, no activation through HBM on
+# forward-only passes).  Built, bit-for-rounding identical to the unfused kernels (tests/test_sa1_fused_gpu.py) and measured
+# (profiles/r2_sa1_fused.md): at cfg2 the chain is bound by the per-tile dependency conv0 -> E -> conv1 -> E -> conv2 through
+# ONE shared operand buffer (227 KB of shared memory hold the three hi/lo weight matrices + one 64 KB operand) and by the
+# SIMT cost of the per-(row, channel) statistics / extreme pass — 329 us against 272 us for the unfused launches — so it is
+# OFF by default; GADDPG_FUSED_SA1=1 (or engine.FUSED_SA1 = True) selects it.
+import os as _os
+
+FUSED_SA1 = _os.environ.get("GADDPG_FUSED_SA1", "0") == "1"
 FUSED_SA1_KEEP = True   # ... also for passes that are differentiated (the pre-BN outputs are stored by TMA, never re-read)
 
 

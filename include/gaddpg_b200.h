@@ -207,7 +207,7 @@ GADDPG_API int gaddpg_sa1_l1_bwd(const float* cloud, long long cloud_stride_b, i
  * out = relu(bn(extreme)) / arg.  Ykeep: NULL for forward-only passes (no activation touches HBM) or the (M_max, 64 | 64 | 128)
  * buffer that receives this phase's pre-BN output for the backward kernels (TMA stores).
  * wsplit: gaddpg_sa1f_wsplit_floats() floats written by gaddpg_sa1f_wprep (hi/lo TF32 split of the three conv weights; redo
- * after every optimiser step).  part_ext/part_arg: (gaddpg_sa1_fused_grid(M_max), 128); seg_part: (S) int32, all -1 on entry
+ * after every optimiser step).  part_ext/part_arg: (ceil(M_max / 128) + 1, 128), one row per 128-row tile + a spare; seg_part: (S) int32, all -1 on entry
  * (the finalize call restores that).  Input channels: [dxyz(3) | cloud rows 0..Cp-1 | bc (B,Cb) broadcast], 3+Cp+Cb <= 16. */
 GADDPG_API long long gaddpg_sa1f_wsplit_floats(void);
 GADDPG_API int gaddpg_sa1_fused_grid(int M_max);

@@ -1,7 +1,7 @@
 """GPU: the fused SA1 chain (csrc/sa1_fused.cu: gather -> conv0 -> BN+ReLU -> conv1 -> BN+ReLU -> conv2 -> statistics +
 per-group extremes, three recompute phases, TMA-fed weights, TMA-stored activations in keep mode) against the unfused kernels
-it replaces (sa1_l1_fwd + two gemm_nt + pool_fwd, themselves held to the CPU oracle by test_encoder_gpu.py) and against the
-oracle end to end (test_encoder_gpu.py / test_agent_gpu.py run with the fused path, which is the default)."""
+it replaces (sa1_l1_fwd + two gemm_nt + pool_fwd, themselves held to the CPU oracle by test_encoder_gpu.py), and one full DDPG
+step through the fused chain against the CPU oracle."""
 import numpy as np
 import pytest
 import torch
@@ -19,11 +19,11 @@ def _run(engine, ef, cloud, bc, Cp, fused, keep, train, device):
     ws = engine.Workspace(device)
     geom = engine.Geometry(B, Np - 6, device).build(cloud, 6)
     ctx = engine.EncoderCtx(B, (geom.lv[0].cap, geom.lv[1].cap), engine.WIDTHS, device)
-    engine.FUSED_SA1 = fused
+    was, engine.FUSED_SA1 = engine.FUSED_SA1, fused
     try:
         feat = engine.encoder_forward(ws, ef, geom, cloud, 6, Cp, bc, ctx, train=train, keep=keep).clone()
     finally:
-        engine.FUSED_SA1 = True
+        engine.FUSED_SA1 = was
     torch.cuda.synchronize()
     return ws, geom, ctx, feat
 
@@ -99,3 +99,25 @@ def test_fused_sa1_backward_consumes_tma_stored_activations(cuda):
     den = sum(float((grads[False][0][k] ** 2).sum()) for k in grads[False][0] if not k.endswith(("1.0.bias", "1.3.bias")))
     assert (num / den) ** 0.5 < 2e-3
     assert _rel(grads[True][1], grads[False][1]) < 3e-2      # B x Cb sums over every point: routing flips reach all of them
+
+
+def test_ddpg_step_through_the_fused_chain_matches_oracle(cuda):
+    """One DDPG update with every SA1 forward (F1..F4 of an odd step, keep and no-keep) on the fused chain: all 11 scalars
+    within 1e-4 of the CPU oracle, like the default path."""
+    from gaddpg_b200 import agent as ag, engine, synthetic
+    from gaddpg_b200.config import LOSS_KEYS
+    from oracle.ddpg_cpu import OracleAgent
+
+    B, N = 8, 512
+    ora = OracleAgent("DDPG", seed=123456)
+    was, engine.FUSED_SA1 = engine.FUSED_SA1, True
+    try:
+        mine = ag.make_agent("DDPG", seed=123456)
+        batch = synthetic.make_batch(B, N, step=0)
+        u = np.random.RandomState(1).rand(B, 6).astype(np.float32)
+        o = ora.update_parameters(batch, noise_u=u)
+        m = mine.update_parameters(batch, 1, 0, noise_u=u)
+    finally:
+        engine.FUSED_SA1 = was
+    for k in LOSS_KEYS:
+        assert (np.isnan(m[k]) and np.isnan(o[k])) or abs(m[k] - o[k]) <= 1e-6 + 1e-4 * abs(o[k]), (k, m[k], o[k])
