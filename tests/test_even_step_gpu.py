@@ -142,8 +142,14 @@ def test_even_step_small_with_f64_referee(cuda, over):
             null = [k for k in keys if k.endswith(("1.0.bias", "1.3.bias"))]     # Linear biases in front of BatchNorm1d
             live = [k for k in keys if k not in null]
             A = lambda d, ks: [d[net][k].detach().cpu().double().numpy() for k in ks]  # noqa: E731
-            rep = referee_elems("step %d %s parameters (lr units)" % (step, net), A(sm, live), A(so, live), A(sr, live), k=5.0, big=0.25,
-                                floors=(1e-4, 1e-3), frac_slack=0.002, scales=[lr_of[net]] * len(live))
+            # the float64 referee covers what is stepped from gradients of IDENTICAL weights: everything on odd steps; on even
+            # steps the critic and the value encoder only (the policy side is stepped with the actor-critic gradient, which is
+            # evaluated on the post-Adam critic: _chaotic_ok)
+            ref_keys = [k for k in live if not even or net == "critic" or "value_encoder" in k]
+            rep = None
+            if ref_keys:
+                rep = referee_elems("step %d %s parameters (lr units)" % (step, net), A(sm, ref_keys), A(so, ref_keys), A(sr, ref_keys), k=5.0,
+                                    big=0.25, floors=(1e-4, 1e-3), frac_slack=0.002, scales=[lr_of[net]] * len(ref_keys))
             worst = max(float(np.abs(a - b).max()) for a, b in zip(A(sm, live), A(so, live)))
             assert worst <= 2.0 * lr_of[net] * 1.01, (step, net, worst)                       # the mechanistic bound: one lr per side
             for k_ in null:   # exactly-zero true gradient: pure rounding noise through Adam on both sides — only the 2 lr bound
@@ -155,7 +161,9 @@ def test_even_step_small_with_f64_referee(cuda, over):
         for k in so["state_feat"]:
             if "running" in k:
                 a, b = sm["state_feat"][k].detach().cpu().double(), so["state_feat"][k].double()
-                assert float((a - b).abs().max()) <= 1e-6 + 1e-4 * float(b.abs().max()), (step, k)
+                # odd steps: two passes from identical weights; even steps: the third value-encoder pass (F5) runs on the post-Adam
+                # weights (see _chaotic_ok), which shows at the 1e-4 level in its batch statistics
+                assert float((a - b).abs().max()) <= 1e-6 + (5e-4 if even else 1e-4) * float(b.abs().max()), (step, k)
         if even:
             rep = {}
             _actor_half_checks("small step %d" % step, mine, m, pre, batch, step_no, over, box, True, rep)
