@@ -183,6 +183,9 @@ def main():
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--reduce-mode", default="split", choices=["split", "single"],
+                    help="N>1: 'split' all-reduces everything but SA1's gradients asynchronously behind the SA1 backward (2 ranges per "
+                         "phase, one hidden); 'single' is one blocking all-reduce per optimiser phase")
     ap.add_argument("--no-extra", action="store_true", help="skip the e2e_f64 and dense-worst-case legs")
     ap.add_argument("--no-replay", action="store_true", help="skip the device-resident replay leg (SURVEY.md §8 row f1)")
     ap.add_argument("--aux", action="store_true", help="BASELINE config 3: both auxiliary losses on (use with --batch 512); "
@@ -215,6 +218,7 @@ def main():
     torch.manual_seed(1000 + rank)
     agent = ag.make_agent("DDPG", seed=123456, device=dev, world=world, **AGENT_KW)
     agent.use_graph = not args.no_graph
+    agent.split_reduce = args.reduce_mode == "split"
     nb = 4
     host = make_batches(args.batch, args.points, nb)
     devb = [{k: v.to(dev) for k, v in b.items()} for b in host]
@@ -265,7 +269,11 @@ def main():
     out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=n_gpus, steps=K, warmup=W, ms_per_step=ms_dev / K, higher_is_better=True,
                scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", config=workload(args),
                e2e=dict(value=e2e, unit=UNIT, ms_per_step=ms_e2e / K, h2d_bytes_per_step=agent.h2d_bytes(), d2h_bytes_per_step=64),
-               gpu_launches=int(launches_per_2 * K / 2), clocks=clk.result(), graph=bool(agent.use_graph))
+               gpu_launches=int(launches_per_2 * K / 2), clocks=clk.result(), graph=bool(agent.use_graph),
+               collectives=(dict(mode=args.reduce_mode, calls_per_step=4 if args.reduce_mode == "split" else 2,
+                                 note="one contiguous gradient range per optimiser phase (value encoder + critic | policy encoder + "
+                                      "policy); 'split' reduces all but the SA1 block asynchronously behind the SA1 backward")
+                            if world else None))
 
     if not args.no_extra:
         # ---- e2e_f64: the dict the reference's BaseMemory.sample returns (replay_memory.py:166-176,376): float64 ndarray
