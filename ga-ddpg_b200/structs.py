@@ -37,12 +37,37 @@ class TNProblem(ctypes.Structure):
     _fields_ = [("P", Operand), ("Q", Operand), ("M_max", _I), ("M_dev", _P), ("N", _I), ("K", _I)]
 
 
+_LL = ctypes.c_longlong
+_D = ctypes.c_double
+
+
+class SALayer(ctypes.Structure):
+    """gaddpg_sa_layer (include/gaddpg_b200.h): one conv + BatchNorm of a set-abstraction level."""
+    _fields_ = [("W", _P), ("WT", _P), ("N", _I), ("K", _I), ("Kp", _I),
+                ("gamma", _P), ("beta", _P), ("running_mean", _P), ("running_var", _P), ("num_batches_tracked", _P),
+                ("scale", _P), ("shift", _P), ("mean", _P), ("rstd", _P), ("Y", _P),
+                ("D", _P), ("bw_g", _P), ("bw_m1", _P), ("bw_m2", _P), ("dW", _P), ("dgamma", _P), ("dbeta", _P)]
+
+
+class SALevel(ctypes.Structure):
+    """gaddpg_sa_level: what gaddpg_sa_forward / gaddpg_sa_backward take."""
+    _fields_ = [("layer", SALayer * 3), ("B", _I), ("S", _I), ("M_max", _I), ("M_dev", _P), ("count", _D),
+                ("seg_off", _P), ("row_seg", _P), ("row_src", _P), ("row_w", _P), ("fixed_len", _I),
+                ("G", _P), ("ldg", _I), ("rot", _I),
+                ("cloud", _P), ("cloud_stride_b", _LL), ("cloud_stride_c", _I), ("skip", _I), ("Cp", _I), ("bc", _P), ("Cb", _I),
+                ("ctr", _P), ("npoint", _I), ("out", _P), ("arg", _P)]
+
+
 def check_sizes():
     a, b, c = _I(), _I(), _I()
     lib.gaddpg_struct_sizes(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
     got = (ctypes.sizeof(Operand), ctypes.sizeof(NTProblem), ctypes.sizeof(TNProblem))
     if got != (a.value, b.value, c.value):
         raise RuntimeError("ctypes struct mirror out of sync with include/gaddpg_b200.h: %r vs %r" % (got, (a.value, b.value, c.value)))
+    lib.gaddpg_sa_struct_sizes(ctypes.byref(a), ctypes.byref(b))
+    got = (ctypes.sizeof(SALayer), ctypes.sizeof(SALevel))
+    if got != (a.value, b.value):
+        raise RuntimeError("ctypes mirror of gaddpg_sa_layer / gaddpg_sa_level out of sync: %r vs %r" % (got, (a.value, b.value)))
 
 
 def dp(t):

@@ -251,6 +251,55 @@ GADDPG_API int gaddpg_pool_keys_finalize(unsigned long long* keys, int S, int C,
 GADDPG_API int gaddpg_feat_finish(const float* Y, int C, const float* scale, const float* shift, const float* time,
                                   float time_offset, int B, float* feat, int ld, void* stream);
 
+/* ---- per-level composites (sa_forward_train / sa_forward_eval / sa_backward, adam_fused_step) -----------
+ * One set-abstraction level = upstream PointnetSAModule.forward (shared MLP of three [Conv2d 1x1, BatchNorm2d, ReLU] over the
+ * grouped points, then F.max_pool2d over each ball group; /root/reference/core/networks.py:66-81) and its backward, as ONE call
+ * each: fixed launch sequences over the kernels above, written in C++ (csrc/composite.cu) so that a non-Python host does not
+ * have to re-implement the sequencing of ga-ddpg_b200/engine.py.  Everything is caller-owned device memory.
+ *
+ * gaddpg_sa_layer: one conv + BatchNorm.  W: forward operand (N, Kp) row-major, Kp = K padded to a multiple of 4 (the first
+ * level reads the raw (N, K) parameter instead: Kp = K there); WT: (Kp, N) transposed copy for dX (layers 1, 2; layer 0 of a
+ * generic level when dG is wanted) — gaddpg_wprep_batched writes both layouts.  Y: (M_max, N) pre-BatchNorm output kept for the
+ * backward.  scale/shift/mean/rstd: (N) BatchNorm constants of the pass (outputs of the forward).  D, bw_*: backward scratch
+ * ((M_max, N) and (N) x 3); dW: (N, K) gradient, dgamma/dbeta: (N).
+ * gaddpg_sa_level: generic level: G (M_max, ldg) input rows [feats | rel. xyz | 0-pad] from gaddpg_gather_rows, rot = column
+ * rotation of conv0's weight relative to G (3 when G is [feats | xyz]).  First level: cloud != NULL (see gaddpg_sa1_l1_fwd for
+ * cloud / bc / ctr), layer widths 64, 64, 128.  Row tables from gaddpg_row_table (NULL + fixed_len for GroupAll: SA3).
+ * count = B * npoint * nsample (rows of the dense grouped tensor the BatchNorm statistics are taken over). */
+typedef struct gaddpg_sa_layer {
+  const float* W; const float* WT; int N, K, Kp;
+  const float* gamma; const float* beta; float* running_mean; float* running_var; long long* num_batches_tracked;
+  float* scale; float* shift; float* mean; float* rstd;
+  float* Y;
+  float* D; float* bw_g; float* bw_m1; float* bw_m2;
+  float* dW; float* dgamma; float* dbeta;
+} gaddpg_sa_layer;
+
+typedef struct gaddpg_sa_level {
+  gaddpg_sa_layer layer[3];
+  int B, S, M_max; const int* M_dev; double count;
+  const int32_t* seg_off; const int32_t* row_seg; const int32_t* row_src; const float* row_w; int fixed_len;
+  const float* G; int ldg; int rot;
+  const float* cloud; long long cloud_stride_b; int cloud_stride_c, skip, Cp; const float* bc; int Cb; const float* ctr; int npoint;
+  float* out; int32_t* arg;
+} gaddpg_sa_level;
+
+GADDPG_API int gaddpg_sa_struct_sizes(int* sa_layer, int* sa_level);   /* sizeof() of the two structs above, for binding self-checks */
+GADDPG_API long long gaddpg_sa_level_workspace_bytes(int B, int M_max);
+/* training != 0: batch statistics + PyTorch's running-statistic update (momentum 0.1, unbiased variance); 0: eval mode */
+GADDPG_API int gaddpg_sa_forward(const gaddpg_sa_level* level, int training, void* ws, long long ws_bytes, void* stream);
+/* dOut (S, ld_dout): gradient w.r.t. the pooled output.  want_dw: parameter gradients (accumulate: += instead of =); dG
+ * (M_max, lddg): gradient w.r.t. the input rows of a generic level (may be NULL); dbc (B, Cb): gradient w.r.t. the broadcast
+ * channels of the first level (may be NULL). */
+GADDPG_API int gaddpg_sa_backward(const gaddpg_sa_level* level, const float* dOut, int ld_dout, int want_dw, int accumulate, float* dG,
+                                  int lddg, float* dbc, void* ws, long long ws_bytes, void* stream);
+/* §8(b) adam_fused_step: flat-arena Adam with L2 weight decay, bias correction from `step`, optional gradient-clip coefficient
+ * (device scalar), 1/world gradient scale and Polyak target update in the same pass (replaces torch.optim.Adam.step +
+ * clip_grad_norm_'s scaling + soft_update, utils.py:750-754,969-970; ddpg.py:141-143). */
+GADDPG_API int gaddpg_adam_fused_step(float* p, float* g, float* m, float* v, long long n, double lr, double beta1, double beta2,
+                                      double eps, double weight_decay, long long step, double grad_scale, const float* clip_coef,
+                                      int write_back_grad, float* polyak_target, double tau, void* stream);
+
 /* ---- heads, TD3 target, losses (networks.py:339-371; ddpg.py:61-88,119-130,170-177; agent.py:127-139; loss.py:17-31) -- */
 GADDPG_API int gaddpg_heads_init(const float* act_scale, const float* act_bias, const float* cp_rotz); /* HOST pointers */
 GADDPG_API int gaddpg_policy_head_fwd(const float* raw, int ldr, int B, float* pi, void* stream);
