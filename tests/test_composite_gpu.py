@@ -112,8 +112,8 @@ def test_sa_level_composites_equal_the_engine_path(cuda, lvl):
             L = ef.layers["sa%d.%d" % (lvl, l)]
             assert torch.equal(keep[l]["dW"], L.dW) and torch.equal(keep[l]["dgamma"], L.dgamma) and torch.equal(keep[l]["dbeta"], L.dbeta), l
         # ---- eval mode: running statistics instead of batch statistics
+        engine.encoder_forward(ws, ef, geom, cloud, 6, 4, bc, ctx, train=False)   # (refills the gathered input rows d.G points at)
         lib.gaddpg_sa_forward(ctypes.byref(d), 0, wsb.data_ptr(), nbytes, current_stream())
-        engine.encoder_forward(ws, ef, geom, cloud, 6, 4, bc, ctx, train=False)
         torch.cuda.synchronize()
         assert torch.equal(out, ctx.sa[lvl].out)
     finally:
