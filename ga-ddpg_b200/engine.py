@@ -494,7 +494,8 @@ def encoder_forward(ws, ef, geom, cloud, skip, Cp, bc, ctx, time=None, time_offs
     s = ctx.sa[0]
     W0 = L["sa0.0"]
     assert W0.K == 3 + Cp + Cb, (W0.K, Cp, Cb)
-    if FUSED_SA1 and ef.sa1f_ok and (FUSED_SA1_KEEP or not keep) and lib.gaddpg_get_tensor_core() >= 3:
+    fused = FUSED_SA1 or (FUSED_SA1_EVAL and not train and not keep)
+    if fused and ef.sa1f_ok and (FUSED_SA1_KEEP or not keep) and lib.gaddpg_get_tensor_core() >= 3:
         _sa1_fused_forward(ws, ef, geom, cloud, skip, Cp, bc, Cb, ctx, train, bn_stage, keep)
     else:
         _sa1_unfused_forward(ws, ef, geom, cloud, skip, Cp, bc, Cb, ctx, train, bn_stage, keep)
@@ -512,6 +513,10 @@ import os as _os
 
 FUSED_SA1 = _os.environ.get("GADDPG_FUSED_SA1", "0") == "1"
 FUSED_SA1_KEEP = True   # ... also for passes that are differentiated (the pre-BN outputs are stored by TMA, never re-read)
+# Eval-mode passes (select_action / select_action_batch / extract_feature: running statistics, so ONE phase instead of three)
+# do use the chain by default: same latency as the unfused launches (scripts/bench_select_action.py: 228 vs 226 us of graph
+# time per action at 4096 points) with two launches fewer and no activation written.
+FUSED_SA1_EVAL = _os.environ.get("GADDPG_FUSED_SA1_EVAL", "1") == "1"
 
 
 def _sa1_fused_forward(ws, ef, geom, cloud, skip, Cp, bc, Cb, ctx, train, bn_stage, keep):
