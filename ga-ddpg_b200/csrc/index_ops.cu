@@ -115,36 +115,27 @@ __global__ void __launch_bounds__(T) fps_ballquery_kernel(XyzView xyz, int N, in
     s_ctr[1] = sy[0];
     s_ctr[2] = sz[0];
   }
-  // The packed key (float bits of the min-distance << 32 | ~rank) is compared as a DOUBLE: the distances are non-negative
-  // finite floats (<= 1e10), so the high word is a finite positive double exponent/mantissa pattern and IEEE ordering of
-  // positive doubles equals the ordering of their bit patterns — one DMNMX per candidate and three instructions per shuffle
-  // step instead of a two-word integer compare/select chain.  Key 0 (= +0.0) stays "no candidate".  The tie-break ranks are
-  // loop invariants and live in registers; invalid points (|p|^2 <= 1e-3, or beyond N) carry a sticky zero key.
-  unsigned lowk[P];
-#pragma unroll
-  for (int i = 0; i < P; ++i) lowk[i] = 0xFFFFFFFFu - fps_rank(tid + T * i, bs, log2bs, per);
   float ox = sx[0], oy = sy[0], oz = sz[0];
   for (int j = 1; j < m; ++j) {
-    double best = 0.0;
+    unsigned long long best = 0ull;
 #pragma unroll
     for (int i = 0; i < P; ++i) {
-      const float d = sqdist3(px[i], py[i], pz[i], ox, oy, oz);
-      const float t = fminf(d, pt[i]);
-      pt[i] = t;
-      const bool ok = (valid >> i) & 1u;
-      const double key = __hiloint2double(ok ? (int)__float_as_uint(t) : 0, ok ? (int)lowk[i] : 0);
-      best = fmax(best, key);
+      if (valid & (1u << i)) {
+        float d = sqdist3(px[i], py[i], pz[i], ox, oy, oz);
+        float t = fminf(d, pt[i]);
+        pt[i] = t;
+        unsigned low = 0xFFFFFFFFu - fps_rank(tid + T * i, bs, log2bs, per);
+        unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) | low;
+        best = key > best ? key : best;
+      }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
-    double* slot = reinterpret_cast<double*>(s_slot) + (j & 1) * NW;
+    best = warp_max_u64(best);
+    unsigned long long* slot = s_slot + (j & 1) * NW;
     if (lane == 0) slot[warp] = best;
     __syncthreads();
-    double v = slot[lane & (NW - 1)];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-    const unsigned vlo = (unsigned)__double2loint(v), vhi = (unsigned)__double2hiint(v);
-    old = (vlo | vhi) ? fps_unrank(0xFFFFFFFFu - vlo, bs, log2bs, per) : 0;
+    unsigned long long v = slot[lane & (NW - 1)];
+    v = warp_max_u64(v);
+    old = v ? fps_unrank(0xFFFFFFFFu - (unsigned)(v & 0xFFFFFFFFull), bs, log2bs, per) : 0;
     ox = sx[old];
     oy = sy[old];
     oz = sz[old];

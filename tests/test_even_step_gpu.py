@@ -89,7 +89,8 @@ def _actor_half_checks(name, mine, m, pre, batch, step_no, over, box, with_f64, 
         keys = [k for k, _ in mod.named_parameters() if h32[which].get(k) is not None and not k.endswith(("1.0.bias", "1.3.bias"))]
         pm = dict(mod.named_parameters())
         report["grad_" + which] = referee_elems("%s:actor-loss gradients of the %s" % (name, which), [pm[k].grad.detach().cpu().numpy() for k in keys],
-                                                [h32[which][k].numpy() for k in keys], [h64[which][k].numpy() for k in keys])
+                                                [h32[which][k].numpy() for k in keys], [h64[which][k].numpy() for k in keys],
+                                                floors=(1e-4, 1e-3) if small else (2e-7, 1e-6))
 
 
 @pytest.mark.parametrize("over", [dict(), dict(policy_aux=False, critic_aux=False, extra_latent=3)])
