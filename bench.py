@@ -228,14 +228,24 @@ def main():
             world.barrier()
         torch.cuda.synchronize()
 
-    def run(batches, n, timed):
+    def run(batches, n, timed, pipelined=False):
+        """``pipelined``: the double-buffered feed loop of feed.FeedLoop (step i+1 is enqueued before step i's scalars are read;
+        every step's 11 scalars are still read back inside the timed region) — removes the ~70 us per step the GPU otherwise
+        idles between two synchronous update_parameters calls."""
         sync_all()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        pending = None
         for i in range(n):
             b = batches[i % nb]
-            agent.update_parameters(b, agent.update_step, 0, noise_u=b["noise_u"])
+            h = agent.update_parameters(b, agent.update_step, 0, noise_u=b["noise_u"], defer=pipelined)
             agent.step_scheduler(agent.update_step)
+            if pipelined:
+                if pending is not None:
+                    pending.result()
+                pending = h
+        if pending is not None:
+            pending.result()
         e1.record()
         sync_all()
         ms = e0.elapsed_time(e1)
@@ -256,10 +266,13 @@ def main():
     # ---- value: inputs resident in HBM
     clk = ClockSampler(local)
     clk.start()
-    ms_dev = run(devb, K, True)
+    ms_dev_sync = run(devb, K, True)
+    ms_dev = run(devb, K, True, pipelined=True)
     # ---- e2e: pinned host buffers through the public API (H2D of the batch + D2H of the scalars inside the timed region)
     run(host, 2, False)
-    ms_e2e = run(host, K, True)
+    ms_e2e_sync = run(host, K, True)
+    run(host, 2, False, pipelined=True)
+    ms_e2e = run(host, K, True, pipelined=True)
     clk.stop_flag = True
     clk.join(timeout=2)
     n_gpus = world.size if world else 1
@@ -270,6 +283,12 @@ def main():
                scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", config=workload(args),
                e2e=dict(value=e2e, unit=UNIT, ms_per_step=ms_e2e / K, h2d_bytes_per_step=agent.h2d_bytes(), d2h_bytes_per_step=64),
                gpu_launches=int(launches_per_2 * K / 2), clocks=clk.result(), graph=bool(agent.use_graph),
+               feed=dict(value="pipelined (feed.FeedLoop order: step i+1 enqueued before step i's scalars are read back; all reads inside "
+                               "the timed region)", value_synchronous=n_gpus * K / (ms_dev_sync / 1e3), ms_per_step_synchronous=ms_dev_sync / K,
+                         e2e="pipelined through the same public API (update_parameters(batch, defer=True) = feed.FeedLoop): the pinned-host -> "
+                             "device copy of minibatch i+1 runs on a copy stream while step i computes; every step copies its own inputs "
+                             "and reads its own 64 bytes of scalars inside the timed region",
+                         e2e_synchronous=n_gpus * K / (ms_e2e_sync / 1e3), e2e_ms_per_step_synchronous=ms_e2e_sync / K),
                collectives=(dict(mode=args.reduce_mode, calls_per_step=4 if args.reduce_mode == "split" else 2,
                                  note="one contiguous gradient range per optimiser phase (value encoder + critic | policy encoder + "
                                       "policy); 'split' reduces all but the SA1 block asynchronously behind the SA1 backward")
@@ -289,12 +308,39 @@ def main():
             host64.append(b)
         run(host64, 2, False)
         k64 = max(4, K // 2)
-        ms64 = run(host64, k64, True)
+        ms64 = run(host64, k64, True)          # synchronous: the host float64 -> float32 conversion sits on the critical path
         out["e2e_f64"] = dict(value=n_gpus * k64 / (ms64 / 1e3), unit=UNIT, ms_per_step=ms64 / k64, steps=k64,
                               host_bytes_converted_per_step=2 * host64[0]["point_state_batch"].nbytes,
                               h2d_bytes_per_step=agent.h2d_bytes(), d2h_bytes_per_step=64,
                               note="update_parameters(dict of float64 ndarrays, exactly what BaseMemory.sample returns); the reference "
                                    "pays the same conversion in torch.cuda.FloatTensor(v) (agent.py:221-222)")
+        # the same float64 dicts through feed.FeedLoop: a worker thread converts / pins minibatch i+1 while step i runs
+        from gaddpg_b200.feed import FeedLoop
+
+        class _Cycle:
+            def __init__(self, batches):
+                self.b, self.i = batches, 0
+
+            def sample(self, B):
+                self.i += 1
+                return self.b[(self.i - 1) % len(self.b)]
+
+        loop = FeedLoop(agent, _Cycle(host64), args.batch)
+        loop.train_iter(4)
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        loop.train_iter(k64)
+        e1.record()
+        sync_all()
+        msp = e0.elapsed_time(e1)
+        if world:
+            t = torch.tensor([msp], device=dev)
+            world.all_reduce_max(t)
+            msp = float(t)
+        out["e2e_f64"].update(pipelined_value=n_gpus * k64 / (msp / 1e3), pipelined_ms_per_step=msp / k64,
+                              pipelined_note="feed.FeedLoop(agent, memory).train_iter: prefetch thread (float64 -> pinned float32) + copy "
+                                             "stream + deferred result read-back; same minibatches, same results")
         del host64
         # ---- dense worst case: clouds that defeat duplicate folding (every SA1 ball holds >= 64 distinct points, all 32 SA2
         # centroids lie within one radius): M1 = B*32*64, M2 = B*32*32 live rows — the upper bound of the data-dependent cost
@@ -374,7 +420,7 @@ def replay_leg(agent, devb, args, run, nb, n_gpus=1, gather_bench=True):
             return d
 
     run(Feed(), 4, False)
-    ms = run(Feed(), args.steps, True)
+    ms = run(Feed(), args.steps, True, pipelined=True)
     if not gather_bench:
         return dict(value=n_gpus * args.steps / (ms / 1e3), unit=UNIT, ms_per_step=ms / args.steps, store_transitions=cap,
                     note="every rank feeds update_parameters from its own ReplayMemoryB200 store in HBM (max over ranks, aggregate)")

@@ -230,6 +230,7 @@ class AgentB200:
         self._slot = 0
         self._pending = [None] * RING
         self._optjobs = {}
+        self._h2d_stream = None
         self._pending_reduce = []
         self.step_start_events = self.step_end_events = None    # feed.FeedLoop installs lists here to measure the GPU idle gap between steps
         self.split_reduce = True         # sharded runs: all-reduce everything but SA1's gradients behind the SA1 backward
@@ -276,6 +277,7 @@ class AgentB200:
         self._cloud_shape = (B, C, Np)
         self._cloud_host = [None] * RING        # pinned cloud staging: allocated on first use (host-fed batches only)
         self._next_cloud_host = [None] * RING
+        self._cloud_dev = [None] * RING         # device staging of the prefetching (pipelined) host path
         self.v = NS(**{n: self.vec[o: o + B * w].view(B, w) if w > 1 else self.vec[o: o + B] for n, (o, w) in self._vec_off.items()})
         self.vh = [NS(**{n: vh[o: o + B * w].view(B, w) if w > 1 else vh[o: o + B] for n, (o, w) in self._vec_off.items()})
                    for vh in self.vec_host]
@@ -306,13 +308,15 @@ class AgentB200:
 
     # ---- data staging (agent.py:211-240 prepare_data) ------------------------------------------------------
     @_on_device
-    def prepare_data(self, batch, noise_u=None, after_clouds=None):
+    def prepare_data(self, batch, noise_u=None, after_clouds=None, prefetch=False):
         """Stage one replay minibatch (the dict BaseMemory.sample returns, replay_memory.py:166-176) into the device
         input buffers.  Host batches go through pinned buffers (float64 clouds are converted on the host like
         torch.cuda.FloatTensor(ndarray) does in the reference); a lazy ``ReplayBatch`` of the device-resident replay is
         gathered straight into the buffers by one CUDA launch pair.  ``after_clouds`` is called as soon as the cloud
         transfers are issued (the agents launch the xyz-only geometry kernels there, so the GPU is busy while the host
-        stages the small per-sample fields)."""
+        stages the small per-sample fields).  ``prefetch`` (pipelined callers: update_parameters(defer=True) / feed.FeedLoop):
+        host clouds travel on a dedicated copy stream into per-slot device staging buffers — the DMA of minibatch i+1 runs while
+        step i computes — and reach the kernels' input buffers by a device-to-device copy once both are done."""
         from .replay_memory import ReplayBatch
 
         lazy = isinstance(batch, ReplayBatch) and not batch.materialised
@@ -345,8 +349,26 @@ class AgentB200:
                 ring[slot].copy_(torch.as_tensor(src))   # float64 ndarray of the reference's replay buffer: convert on host
                 dst.copy_(ring[slot], non_blocking=True)
 
-        put_cloud(self.cloud, self._cloud_host, cloud)
-        if self.has_critic:
+        host_src = not (torch.is_tensor(cloud) and cloud.is_cuda)
+        if prefetch and host_src:
+            if self._h2d_stream is None:
+                self._h2d_stream = torch.cuda.Stream(device=self.device)
+                self._h2d_ev = [torch.cuda.Event() for _ in range(RING)]
+            if self._cloud_dev[slot] is None:
+                self._cloud_dev[slot] = [torch.zeros(self._cloud_shape, dtype=torch.float32, device=self.device) for _ in range(2)]
+            stage = self._cloud_dev[slot]
+            with torch.cuda.stream(self._h2d_stream):
+                put_cloud(stage[0], self._cloud_host, cloud)
+                if self.has_critic:
+                    put_cloud(stage[1], self._next_cloud_host, batch["next_point_state_batch"])
+                self._h2d_ev[slot].record(self._h2d_stream)
+            torch.cuda.current_stream().wait_event(self._h2d_ev[slot])
+            self.cloud.copy_(stage[0], non_blocking=True)
+            if self.has_critic:
+                self.next_cloud.copy_(stage[1], non_blocking=True)
+        else:
+            put_cloud(self.cloud, self._cloud_host, cloud)
+        if self.has_critic and not (prefetch and host_src):
             nxt = batch["next_point_state_batch"]
             # only the target chain (side stream) reads it: its H2D copy overlaps the state chain.  A device-resident
             # batch was produced on the current stream, so its D2D copy stays there
@@ -946,7 +968,7 @@ class DDPGB200(AgentB200):
         ``defer=True``: return a ``PendingResult`` instead of waiting for the step's scalars."""
         self._begin_step()
         if not staged:
-            self.prepare_data(batch_data, noise_u, after_clouds=self._geometry)
+            self.prepare_data(batch_data, noise_u, after_clouds=self._geometry, prefetch=defer)
         else:
             self._geometry()
         even = (self.update_step % self.policy_update_gap) == 0
@@ -1002,7 +1024,7 @@ class BCB200(AgentB200):
         """bc.py:40-56."""
         self._begin_step()
         if not staged:
-            self.prepare_data(batch_data, after_clouds=self._geometry)
+            self.prepare_data(batch_data, after_clouds=self._geometry, prefetch=defer)
         else:
             self._geometry()
         self._set_dyn(("policy",) + (("enc",) if self.train_feature else ()))
