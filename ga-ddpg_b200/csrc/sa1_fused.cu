@@ -34,9 +34,8 @@
 //                    tcgen05.ld registers: statistics and the running per-group extreme, flushed when the ball group changes
 // The conv1 and conv2 operands share ONE 64 KB buffer (conv2's operand is produced from conv1's finished accumulator), which
 // is what lets all three weight matrices (hi + lo, 104 KB), the operands and the staging tile fit in 227 KB.
-#include <cuda.h>
-
 #include "tc_common.cuh"
+#include "tma.cuh"
 #include "impl.h"
 
 namespace {
@@ -89,23 +88,6 @@ struct Sa1FParams {
   int keep;
 };
 
-// ---- PTX: TMA + transaction barriers ------------------------------------------------------------------
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst_smem),
-               "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src_smem, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tm)),
-               "r"(src_smem), "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 template <int ID>
 __device__ __forceinline__ void named_bar(int nthreads) { asm volatile("bar.sync %0, %1;" ::"n"(ID), "r"(nthreads) : "memory"); }
 
@@ -678,31 +660,6 @@ __global__ void sa1f_wprep_kernel(const float* __restrict__ W0, int ld0, int K1,
   }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)p;
-  }
-  return fn;
-}
-// row-major [rows][cols] float32 matrix, box = [box_rows][box_cols] with box_cols * 4 == swizzle span
-bool make_map(CUtensorMap* tm, const float* base, int rows, int cols, int box_rows, int box_cols, CUtensorMapSwizzle sw) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) return false;
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
-  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
-  cuuint32_t es[2] = {1, 1};
-  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
-            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 }  // namespace
 
 int gaddpg_sa1f_wprep_impl(const float* W0, int ld0, int K1, const float* W1, const float* W2, float* wsplit, void* stream) {
@@ -729,13 +686,13 @@ int gaddpg_sa1_fused_fwd_impl(int phase, const float* cloud, long long cloud_sb,
   const int n0 = F_C * F_K0, n1 = F_C * F_C, n2 = F_C3 * F_C;
   const float *w0h = wsplit, *w0l = wsplit + n0, *w1h = wsplit + 2 * n0, *w1l = w1h + n1, *w2h = w1h + 2 * n1, *w2l = w2h + n2;
   CUtensorMap m0h, m0l, m1h, m1l, m2h, m2l, mY;
-  bool ok = make_map(&m0h, w0h, F_C, F_K0, F_C, F_K0, CU_TENSOR_MAP_SWIZZLE_64B) && make_map(&m0l, w0l, F_C, F_K0, F_C, F_K0, CU_TENSOR_MAP_SWIZZLE_64B) &&
-            make_map(&m1h, w1h, F_C, F_C, F_C, 32, CU_TENSOR_MAP_SWIZZLE_128B) && make_map(&m1l, w1l, F_C, F_C, F_C, 32, CU_TENSOR_MAP_SWIZZLE_128B) &&
-            make_map(&m2h, w2h, F_C3, F_C, F_C3, 32, CU_TENSOR_MAP_SWIZZLE_128B) && make_map(&m2l, w2l, F_C3, F_C, F_C3, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+  bool ok = make_map(&m0h, w0h, F_C, F_K0, F_K0, F_C, F_K0, CU_TENSOR_MAP_SWIZZLE_64B) && make_map(&m0l, w0l, F_C, F_K0, F_K0, F_C, F_K0, CU_TENSOR_MAP_SWIZZLE_64B) &&
+            make_map(&m1h, w1h, F_C, F_C, F_C, F_C, 32, CU_TENSOR_MAP_SWIZZLE_128B) && make_map(&m1l, w1l, F_C, F_C, F_C, F_C, 32, CU_TENSOR_MAP_SWIZZLE_128B) &&
+            make_map(&m2h, w2h, F_C3, F_C, F_C, F_C3, 32, CU_TENSOR_MAP_SWIZZLE_128B) && make_map(&m2l, w2l, F_C3, F_C, F_C, F_C3, 32, CU_TENSOR_MAP_SWIZZLE_128B);
   const int CY = phase == 3 ? F_C3 : F_C;
   if (Ykeep) {
     GADDPG_CHECK_ARG(((uintptr_t)Ykeep & 15u) == 0, "sa1_fused_fwd: Ykeep must be 16-byte aligned");
-    ok = ok && make_map(&mY, Ykeep, M_max, CY, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+    ok = ok && make_map(&mY, Ykeep, M_max, CY, CY, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
   } else {
     mY = m1h;   // unused
   }

@@ -17,8 +17,10 @@
 //   warps 9-12 epilogue  : tcgen05.ld 32x32b -> registers -> smem re-layout -> 16-byte global stores (four full 128-byte
 //                          row segments per instruction), mask reads and per-column BatchNorm statistics (fixed order,
 //                          one slot per CTA); shared with tc_gemm_kc.cu (tc_common.cuh: epi_block32)
-// No TMA here by design: every A element passes through a per-element prologue before it may reach the tensor
-// core, so the producer warps ARE the copy engine; W is 16-64 KB and loaded once per CTA.
+// TMA: the A operand passes through a per-element prologue (BN+ReLU / BN-backward) before it may reach the tensor core, so the
+// producer warps are its copy engine; the WEIGHTS arrive by cp.async.bulk.tensor loads when the caller provides their
+// pre-split hi / lo images (gaddpg_nt_problem.Bw_hi / Bw_lo: the SA1 forward layers), and full output blocks of the plain
+// store epilogue leave by cp.async.bulk.tensor stores (epi_store_tma32).
 #ifdef TC_PROFILE
 __device__ unsigned long long g_tc_prof[148 * 16];
 #define TCP_ADD(slot, v) atomicAdd(&g_tc_prof[blockIdx.x * 16 + (slot)], (unsigned long long)(v))
@@ -28,7 +30,11 @@ __device__ unsigned long long g_tc_prof[148 * 16];
 #define TCP_T() 0ll
 #endif
 
+#include <stdlib.h>
+#include <string.h>
+
 #include "tc_common.cuh"
+#include "tma.cuh"
 #include "impl.h"
 
 namespace {
@@ -60,7 +66,7 @@ __host__ __device__ inline TcSmemLayout tc_layout(int N, int K) {
     L.a_hi[s] = off; off += (uint32_t)TC_BM * TC_KS * 4;
     L.a_lo[s] = off; off += (uint32_t)TC_BM * TC_KS * 4;
   }
-  L.stage_buf = off; off += 4 * 32 * EPI_LD * 4;   // per-epilogue-warp transpose buffers
+  L.stage_buf = off; off += 4 * 5120;              // per-epilogue-warp transpose buffers (1024-byte aligned: TMA store boxes)
   L.cc = off; off += 5 * 128 * 4;                // per-column prologue constants c0..c4 [5][K <= 128]
   L.bars = off; off += 256;                     // mbarriers + tmem address + stats scratch header
   off += 2 * 4 * 256 * 4;                       // cross-warp stats combine: [2][4 warps][N<=256]
@@ -103,9 +109,44 @@ struct ColConsts {
   }
 };
 
+// One full 32-row x 32-column block of a plain store epilogue through the TMA.  Staging tile = [32 rows x 128 B] with the
+// SWIZZLE_128B pattern (16-byte chunk j of row r at chunk j ^ (r & 7)): conflict-free for the row-wise STS.128 of the TMEM
+// layout (lane = row) and for the LDS.128 of the statistics layout (lane -> rows 4i + (lane >> 3), columns 4 (lane & 7) ..).
+__device__ __forceinline__ void epi_store_tma32(uint32_t taddr, unsigned char* stage, int lane, int row_base, int col0, const CUtensorMap* tmC,
+                                                const float (&wr)[8], bool do_stats, float (&s0)[4], float (&s1)[4]) {
+  float r[32];
+  tmem_ld32(taddr, r);
+  if (lane == 0) tma_wait_read0();   // the previous block's store has read the staging tile
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(stage + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+  fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_2d(tmC, smem_u32(stage), col0, row_base);
+    tma_commit();
+  }
+  if (do_stats) {
+    const int rsub = lane >> 3, ch = lane & 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = 4 * i + rsub;
+      const float4 x = *reinterpret_cast<const float4*>(stage + row * 128 + ((ch ^ (row & 7)) << 4));
+      const float w = wr[i];
+      s0[0] = fmaf(w, x.x, s0[0]); s1[0] = fmaf(w * x.x, x.x, s1[0]);
+      s0[1] = fmaf(w, x.y, s0[1]); s1[1] = fmaf(w * x.y, x.y, s1[1]);
+      s0[2] = fmaf(w, x.z, s0[2]); s1[2] = fmaf(w * x.z, x.z, s1[2]);
+      s0[3] = fmaf(w, x.w, s0[3]); s1[3] = fmaf(w * x.w, x.w, s1[3]);
+    }
+  }
+}
+
 // NCB = 32-column accumulator blocks the epilogue keeps statistics for: 4 (N <= 128, the SA1 layers) or 8 (N <= 256)
 template <int K, int AMODE, int EMODE, int NCB>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProblem p) {
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProblem p, const __grid_constant__ CUtensorMap tmC,
+                                                                   const int tma_store, const __grid_constant__ CUtensorMap tmWh,
+                                                                   const __grid_constant__ CUtensorMap tmWl, const int tma_w) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // SWIZZLE_128B operands need 1024-byte aligned bases (the host adds 1024 bytes of slack)
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -134,7 +175,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], 4);
     }
-    mbar_init(w_full, TC_PT);
+    mbar_init(w_full, tma_w ? 1 : TC_PT);   // weights: one TMA transaction barrier, or one arrival per producer thread
     fence_barrier_init();
   }
   if (warp == TC_PW) tmem_alloc(tmem_slot, tmem_cols);
@@ -161,13 +202,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
     constexpr bool BWD = (AMODE == OP_BNBWD || AMODE == OP_BNBWD_POOL);
     constexpr int U = BWD ? TC_U_BWD : TC_U_FWD;  // row-iterations per pipeline unit (two register sets in flight)
     static_assert(K % TC_KS == 0 && ITERS % U == 0, "K must be 64 or 128");
-    for (int idx = tid; idx < N * KQ4; idx += TC_PT) {
-      int n = idx / KQ4, k = (idx % KQ4) << 2;
-      float4 v = ldg4(p.Bw + (long long)n * p.ldb + k);
-      split_store(smem + L.w_hi, smem + L.w_lo, sw128_off(n, k, N), v);
+    if (!tma_w) {   // no pre-split image of this weight matrix: split it here (once per CTA)
+      for (int idx = tid; idx < N * KQ4; idx += TC_PT) {
+        int n = idx / KQ4, k = (idx % KQ4) << 2;
+        float4 v = ldg4(p.Bw + (long long)n * p.ldb + k);
+        split_store(smem + L.w_hi, smem + L.w_lo, sw128_off(n, k, N), v);
+      }
+      fence_proxy_async();
+      mbar_arrive(w_full);
     }
-    fence_proxy_async();
-    mbar_arrive(w_full);
     const int kc = (tid % SQ4) << 2, rsub = tid / SQ4;  // column inside the 64-wide stage, first row served
     const float* cct = reinterpret_cast<const float*>(smem + L.cc);
     // Software pipeline over "units" of U row-iterations: the global loads of unit u+1 are issued into a second
@@ -279,6 +322,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
       // N>>3 at bit 17, M>>4 at bit 24
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       const uint32_t sbase = smem_u32(smem);
+      if (tma_w) {   // pre-split hi / lo weight images (refreshed once per optimiser step) arrive by TMA: one [N x 32] box per
+                     // 32-column K block lands directly in the K-major SWIZZLE_128B operand layout
+        mbar_expect_tx(w_full, (uint32_t)(2 * N * K * 4));
+        for (int kb = 0; kb < K / 32; ++kb) {
+          tma_load_2d(sbase + L.w_hi + kb * N * 128, &tmWh, kb * 32, 0, w_full);
+          tma_load_2d(sbase + L.w_lo + kb * N * 128, &tmWl, kb * 32, 0, w_full);
+        }
+      }
       mbar_wait(w_full, 0);
       tc_fence_after();
       int it = 0, g = 0;
@@ -326,7 +377,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
   } else {
     // ===================== epilogue =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    float* stage = reinterpret_cast<float*>(smem + L.stage_buf) + (warp - TC_PW - 1) * 32 * EPI_LD;
+    float* stage = reinterpret_cast<float*>(smem + L.stage_buf + (warp - TC_PW - 1) * 5120);
     const bool do_stats = (p.stats != nullptr);
     const int rsub = lane >> 3;
     float s0[NCB][4], s1[NCB][4];
@@ -357,16 +408,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
       }
       tc_fence_after();
       const long long te0 = TCP_T();
+      // full 32 x 32 blocks of a plain store epilogue leave through the TMA: tcgen05.ld -> swizzled staging tile -> ONE
+      // cp.async.bulk.tensor store per block (the 8 x STG.128 per lane of the generic path were the measured limiter of the
+      // forward kernels: profiles/r1_tc_roles.md); statistics are read back from the same staging tile
+      const bool tma_blk = (EMODE == EPI_STORE) && tma_store && (row_base + 32 <= M) && !p.relu && p.bias == nullptr && p.pool_keys == nullptr;
 #pragma unroll
       for (int cb = 0; cb < NCB; ++cb) {
-        if (cb * 32 < N)
-          epi_block32<EMODE>(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * N + cb * 32), stage, lane, row_base, cb * 32,
-                             M, N, wr, do_stats, s0[cb], s1[cb]);
+        if (cb * 32 < N) {
+          const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * N + cb * 32);
+          if (EMODE == EPI_STORE && tma_blk && cb * 32 + 32 <= N)
+            epi_store_tma32(ta, reinterpret_cast<unsigned char*>(stage), lane, row_base, cb * 32, &tmC, wr, do_stats, s0[cb], s1[cb]);
+          else
+            epi_block32<EMODE>(p, ta, stage, lane, row_base, cb * 32, M, N, wr, do_stats, s0[cb], s1[cb]);
+        }
       }
       if (warp == TC_PW + 1 && lane == 0) { TCP_ADD(6, TCP_T() - te0); TCP_ADD(7, 1); }
       tc_fence_before();
       if (lane == 0) mbar_arrive(&acc_empty[b]);
     }
+    if (EMODE == EPI_STORE && tma_store && lane == 0) tma_wait_all0();
     if (do_stats) {
 #pragma unroll
       for (int cb = 0; cb < NCB; ++cb) {
@@ -431,11 +491,25 @@ int gaddpg_tc_gemm_nt_impl(const NTProblem* p, int amode, int emode, void* strea
   int tiles = ceil_div(p->M_max, TC_BM);
   int grid = tiles < gaddpg_sm_count() ? tiles : gaddpg_sm_count();
   cudaStream_t st = (cudaStream_t)stream;
+  // C tiles of the plain store epilogue leave through cp.async.bulk.tensor stores (GADDPG_TMA_STORE=0: the STG path, for A/B)
+  static const bool tma_env = []() { const char* e = getenv("GADDPG_TMA_STORE"); return !(e && e[0] == '0'); }();
+  CUtensorMap tmC;
+  memset(&tmC, 0, sizeof(tmC));
+  int tma_store = 0;
+  if (tma_env && emode == EPI_STORE && !p->no_store && p->C && (p->N % 32) == 0 && (p->ldc % 4) == 0 && ((uintptr_t)p->C & 15u) == 0)
+    tma_store = make_map(&tmC, p->C, p->M_max, p->N, p->ldc, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B) ? 1 : 0;
+  CUtensorMap tmWh, tmWl;
+  memset(&tmWh, 0, sizeof(tmWh));
+  memset(&tmWl, 0, sizeof(tmWl));
+  int tma_w = 0;
+  if (tma_env && p->Bw_hi && p->Bw_lo && p->N <= 256)
+    tma_w = (make_map(&tmWh, p->Bw_hi, p->N, p->K, p->K, p->N, 32, CU_TENSOR_MAP_SWIZZLE_128B) &&
+             make_map(&tmWl, p->Bw_lo, p->N, p->K, p->K, p->N, 32, CU_TENSOR_MAP_SWIZZLE_128B)) ? 1 : 0;
 #define TC_LAUNCH(KK, A, E, NCB_)                                                                              \
   {                                                                                                            \
     auto kern = tc_gemm_nt_kernel<KK, A, E, NCB_>;                                                             \
     GADDPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
-    kern<<<grid, TC_THREADS, smem, st>>>(*p);                                                          \
+    kern<<<grid, TC_THREADS, smem, st>>>(*p, tmC, tma_store, tmWh, tmWl, tma_w);                       \
     GADDPG_CHECK_LAUNCH("tc_gemm_nt_kernel");                                                                  \
     return GADDPG_OK;                                                                                          \
   }

@@ -169,7 +169,7 @@ def nt(problems, amode, emode):
 
 
 def nt_problem(A, Bw, ldb, C, ldc, M_max, M_dev, N, K, bias=None, relu=0, stats=None, srw=None, Yprev=None, ldyp=0,
-               pbn=None, pool_keys=None, pool_seg=None, pool_gamma=None, no_store=0):
+               pbn=None, pool_keys=None, pool_seg=None, pool_gamma=None, no_store=0, w_split=None):
     p = NTProblem(A=A, Bw=dp(Bw) if torch.is_tensor(Bw) else Bw, ldb=ldb, bias=dp(bias), C=dp(C) if torch.is_tensor(C) else C,
                   ldc=ldc, M_max=M_max, M_dev=M_dev, N=N, K=K, relu=relu, stats=dp(stats), srw=dp(srw),
                   Yprev=dp(Yprev) if torch.is_tensor(Yprev) else Yprev, ldyp=ldyp)
@@ -177,6 +177,8 @@ def nt_problem(A, Bw, ldb, C, ldc, M_max, M_dev, N, K, bias=None, relu=0, stats=
         p.psc, p.psh, p.pmean, p.prstd = dp(pbn.scale), dp(pbn.shift), dp(pbn.mean), dp(pbn.rstd)
     if pool_keys is not None:
         p.pool_keys, p.pool_seg, p.pool_gamma, p.no_store = dp(pool_keys), dp(pool_seg), dp(pool_gamma), no_store
+    if w_split is not None:
+        p.Bw_hi, p.Bw_lo = w_split
     return p
 
 
@@ -365,6 +367,7 @@ class EncoderFlat:
             for key, kp in (("sa0.0", 16), ("sa0.1", 64), ("sa0.2", 64)):
                 Lk = L[key]
                 jobs.append([Lk.W.data_ptr(), Lk.N, Lk.K, -1, w + 4 * off, kp, w + 4 * (off + Lk.N * kp), kp])
+                Lk.W_hi, Lk.W_lo = w + 4 * off, w + 4 * (off + Lk.N * kp)   # TMA sources of the forward row-GEMMs (K = Kp = 64)
                 off += 2 * Lk.N * kp
             self.jobs = torch.tensor(jobs, dtype=torch.int64, device=device)
         self.refresh_derived()
@@ -626,7 +629,8 @@ def _mlp_tail_forward(ws, layers, s, first, M_max, M_dev, rw, count, train, bn_s
             g.p[0] = prob
             fused = lib.gaddpg_gemm_nt_path(ctypes.byref(g), 1, OP_BNRELU, EPI_STORE) in (1, 2)
         if not fused:
-            prob = nt_problem(A, Lp.Wf, Lp.Kp, s.Y[l], Lp.N, M_max, M_dev, Lp.N, Lp.Kp, **kw)
+            ws_ = (Lp.W_hi, Lp.W_lo) if (getattr(Lp, "W_hi", None) and Lp.Wf is Lp.W) else None   # SA1: TMA-fetched weight images
+            prob = nt_problem(A, Lp.Wf, Lp.Kp, s.Y[l], Lp.N, M_max, M_dev, Lp.N, Lp.Kp, w_split=ws_, **kw)
         nt([prob], OP_BNRELU, EPI_STORE)
         bn_fwd(ws, Lp.N, count, Lp, s.bn[l], train, bn_stage)
         if pool is not None and j == len(layers) - 1:

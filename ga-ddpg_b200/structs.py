@@ -26,7 +26,7 @@ class NTProblem(ctypes.Structure):
                 ("M_max", _I), ("M_dev", _P), ("N", _I), ("K", _I), ("relu", _I),
                 ("stats", _P), ("srw", _P), ("Yprev", _P), ("ldyp", _I),
                 ("psc", _P), ("psh", _P), ("pmean", _P), ("prstd", _P),
-                ("pool_keys", _P), ("pool_seg", _P), ("pool_gamma", _P), ("no_store", _I)]
+                ("pool_keys", _P), ("pool_seg", _P), ("pool_gamma", _P), ("no_store", _I), ("Bw_hi", _P), ("Bw_lo", _P)]
 
 
 class NTGroup(ctypes.Structure):

@@ -136,6 +136,10 @@ typedef struct gaddpg_nt_problem {
    * keys into out / arg once the batch statistics are known and re-zeroes them.
    * pool_seg (M): segment of every row.  no_store: do not write C at all (passes that never run backward). */
   unsigned long long* pool_keys; const int32_t* pool_seg; const float* pool_gamma; int no_store;
+  /* optional: dense (N, K) images of Bw split for 3xTF32 (hi = x & 0xFFFFE000, lo = x - hi; gaddpg_wprep_batched split jobs).
+   * When both are given the tcgen05 whole-K kernel fetches the weights with TMA (cp.async.bulk.tensor) instead of
+   * splitting Bw in every CTA. */
+  const float* Bw_hi; const float* Bw_lo;
 } gaddpg_nt_problem;
 
 typedef struct gaddpg_nt_group { gaddpg_nt_problem p[GADDPG_MAX_GROUP]; } gaddpg_nt_group;
