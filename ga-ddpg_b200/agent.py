@@ -889,12 +889,16 @@ class DDPGB200(AgentB200):
                                    1 if self.critic_aux else 0, B, 1.0, dp(self.cc1.dqa), self.out.data_ptr() + 4 * O_CRITIC, s)
         if part == "all":
             with engine.side_dw(dw):
-                engine.critic_backward(ws, self.cf, f1, self.cc1, B, self.cf.nb, self.ctx_v1, self.sc, accumulate=0)     # B1
-                engine.encoder_backward(ws, self.ef_v, self.ctx_v1, self.sc, want_dw=True, want_dbc=False, accumulate=0)
+                et = engine.entry_tail(ws, self.ef_v, self.ctx_v1, self.sc, want_dw=True, accumulate=0)
+                engine.critic_backward(ws, self.cf, f1, self.cc1, B, self.cf.nb, self.ctx_v1, self.sc, accumulate=0, enc_tail=et)  # B1
+                engine.encoder_backward(ws, self.ef_v, self.ctx_v1, self.sc, want_dw=True, want_dbc=False, accumulate=0,
+                                        entry_done=et is not None)
         elif part == "a":
             with engine.side_dw(dw):
-                engine.critic_backward(ws, self.cf, f1, self.cc1, B, self.cf.nb, self.ctx_v1, self.sc, accumulate=0)
-                engine.encoder_backward(ws, self.ef_v, self.ctx_v1, self.sc, want_dw=True, want_dbc=False, accumulate=0, part="upper")
+                et = engine.entry_tail(ws, self.ef_v, self.ctx_v1, self.sc, want_dw=True, accumulate=0)
+                engine.critic_backward(ws, self.cf, f1, self.cc1, B, self.cf.nb, self.ctx_v1, self.sc, accumulate=0, enc_tail=et)
+                engine.encoder_backward(ws, self.ef_v, self.ctx_v1, self.sc, want_dw=True, want_dbc=False, accumulate=0, part="upper",
+                                        entry_done=et is not None)
         else:
             with engine.side_dw(dw):
                 engine.encoder_backward(ws, self.ef_v, self.ctx_v1, self.sc, want_dw=True, want_dbc=False, accumulate=0, part="sa1")
@@ -942,8 +946,9 @@ class DDPGB200(AgentB200):
             lib.gaddpg_actor_critic_loss(dp(qa5), QA_LD, QA_Q2, dp(v.ret), dp(v.expert_flag), float(mix), B, 1.0, QA_LD,
                                          dp(self.cc5.dqa), self.out.data_ptr() + 4 * O_AC, s)
             with engine.side_dw(dw):
-                engine.critic_backward(ws, self.cf, f5, self.cc5, B, 2, self.ctx_v5, self.sc, accumulate=1)
-                dpi = engine.encoder_backward(ws, self.ef_v, self.ctx_v5, self.sc, want_dw=False, want_dbc=True)
+                et = engine.entry_tail(ws, self.ef_v, self.ctx_v5, self.sc, want_dw=False, accumulate=0)
+                engine.critic_backward(ws, self.cf, f5, self.cc5, B, 2, self.ctx_v5, self.sc, accumulate=1, enc_tail=et)
+                dpi = engine.encoder_backward(ws, self.ef_v, self.ctx_v5, self.sc, want_dw=False, want_dbc=True, entry_done=et is not None)
             self.dpi_ac.zero_()
             self.dpi_ac[:, : self.Cb_value].copy_(dpi)
         ranges, n_grad = self.pf.adam_ranges(self.policy_aux)
@@ -951,9 +956,10 @@ class DDPGB200(AgentB200):
                               1 if self.policy_aux else 0, float(1.0 - mix), dp(self.dpi_ac) if even else None, B, 1.0,
                               dp(self.pc.draw), self.pf.NHp, self.out.data_ptr() + 4 * O_BC, s)
         with engine.side_dw(dw):
-            engine.policy_backward(ws, self.pf, f4, self.pc, B, n_grad, self.ctx_p, self.sc, accumulate=0)          # B2
+            et = engine.entry_tail(ws, self.ef_p, self.ctx_p, self.sc, want_dw=True, accumulate=0)
+            engine.policy_backward(ws, self.pf, f4, self.pc, B, n_grad, self.ctx_p, self.sc, accumulate=0, enc_tail=et)   # B2
             engine.encoder_backward(ws, self.ef_p, self.ctx_p, self.sc, want_dw=True, want_dbc=False, accumulate=0,
-                                    part="upper" if part == "a" else "all")
+                                    part="upper" if part == "a" else "all", entry_done=et is not None)
 
     # -- phase 3: actor step, targets, statistics --------------------------------------------------------------
     def _phase3(self, hard):
@@ -1012,8 +1018,10 @@ class BCB200(AgentB200):
                               1 if self.policy_aux else 0, 1.0, None, B, 1.0, dp(self.pc.draw), self.pf.NHp,
                               self.out.data_ptr() + 4 * O_BC, s)
         with engine.side_dw(self.side_dw if self.overlap else None):
-            engine.policy_backward(ws, self.pf, f, self.pc, B, n_grad, self.ctx_p, self.sc, accumulate=0)
-            engine.encoder_backward(ws, self.ef_p, self.ctx_p, self.sc, want_dw=True, want_dbc=False, accumulate=0)
+            et = engine.entry_tail(ws, self.ef_p, self.ctx_p, self.sc, want_dw=True, accumulate=0)
+            engine.policy_backward(ws, self.pf, f, self.pc, B, n_grad, self.ctx_p, self.sc, accumulate=0, enc_tail=et)
+            engine.encoder_backward(ws, self.ef_p, self.ctx_p, self.sc, want_dw=True, want_dbc=False, accumulate=0,
+                                    entry_done=et is not None)
 
     def _phase_opt(self):
         self._opt_jobs("bc").launch()

@@ -6,7 +6,7 @@
 #include "common.cuh"
 #include "impl.h"
 
-#define GADDPG_ABI_VERSION 3
+#define GADDPG_ABI_VERSION 4
 
 static thread_local char g_err[512] = "";
 long long g_gaddpg_launches = 0;
@@ -115,9 +115,9 @@ int gaddpg_bn_running_update(float* running, const float* staged, long long n, f
 int gaddpg_sa1_l1_fwd(const float* cloud, long long cloud_stride_b, int cloud_stride_c, int skip, int Cp, const float* bc, int Cb,
                       int B, const float* ctr, int npoint, const int32_t* seg_off, const int32_t* row_seg, const int32_t* row_src,
                       const float* row_w, int M_max, const int* M_dev, const float* W, int ldw, float* bcbias_ws, float* Y,
-                      float* stats, void* stream) {
+                      float* stats, const gaddpg_bn_tail* tail, void* stream) {
   return gaddpg_sa1_l1_fwd_impl(cloud, cloud_stride_b, cloud_stride_c, skip, Cp, bc, Cb, B, ctr, npoint, seg_off, row_seg, row_src,
-                                row_w, M_max, M_dev, W, ldw, bcbias_ws, Y, stats, stream);
+                                row_w, M_max, M_dev, W, ldw, bcbias_ws, Y, stats, tail, stream);
 }
 int gaddpg_sa1_l1_bwd(const float* cloud, long long cloud_stride_b, int cloud_stride_c, int skip, int Cp, const float* bc, int Cb,
                       int B, const float* ctr, int npoint, const int32_t* seg_off, const int32_t* row_seg, const int32_t* row_src,
@@ -162,13 +162,13 @@ int gaddpg_pool_fwd(const float* Y, int C, const float* scale, const float* shif
 }
 int gaddpg_pool_bwd(const float* dOut, int ld_dout, const float* out, const int32_t* arg, const float* Y, int C,
                     const int32_t* row_seg, int fixed_len, int M_max, const int* M_dev, const float* mean, const float* rstd,
-                    float* D, float* stats, void* stream) {
-  return gaddpg_pool_bwd_impl(dOut, ld_dout, out, arg, Y, C, row_seg, fixed_len, M_max, M_dev, mean, rstd, D, stats, stream);
+                    float* D, float* stats, const gaddpg_bn_tail* tail, void* stream) {
+  return gaddpg_pool_bwd_impl(dOut, ld_dout, out, arg, Y, C, row_seg, fixed_len, M_max, M_dev, mean, rstd, D, stats, tail, stream);
 }
 int gaddpg_pool_bwd_sparse(const float* dOut, int ldo, const float* out, const int32_t* arg, const float* Y, int C, int S,
                            const float* mean, const float* rstd, float* E, uint32_t* mask, int M_max, float* stats,
-                                void* stream) {
-  return gaddpg_pool_bwd_sparse_impl(dOut, ldo, out, arg, Y, C, S, mean, rstd, E, mask, M_max, stats, stream);
+                           const gaddpg_bn_tail* tail, void* stream) {
+  return gaddpg_pool_bwd_sparse_impl(dOut, ldo, out, arg, Y, C, S, mean, rstd, E, mask, M_max, stats, tail, stream);
 }
 int gaddpg_pool_keys_finalize(unsigned long long* keys, int S, int C, const float* gamma, const float* scale, const float* shift, float* out,
                               int32_t* arg, void* stream) {
@@ -226,8 +226,8 @@ int gaddpg_wprep_batched(const long long* jobs_dev, int njobs, void* stream) {
   return gaddpg_wprep_batched_impl(jobs_dev, njobs, stream);
 }
 int gaddpg_dmask_stats(const float* dX, int ldx, const float* Yprev, int C, int M, const float* psc, const float* psh,
-                       const float* pmean, const float* prstd, float* D, float* stats, void* stream) {
-  return gaddpg_dmask_stats_impl(dX, ldx, Yprev, C, M, psc, psh, pmean, prstd, D, stats, stream);
+                       const float* pmean, const float* prstd, float* D, float* stats, const gaddpg_bn_tail* tail, void* stream) {
+  return gaddpg_dmask_stats_impl(dX, ldx, Yprev, C, M, psc, psh, pmean, prstd, D, stats, tail, stream);
 }
 int gaddpg_polyak(float* target, const float* source, long long n, double tau, void* stream) {
   return gaddpg_polyak_impl(target, source, n, tau, stream);

@@ -18,10 +18,11 @@ namespace {
 
 constexpr float kEps = 1e-5f, kMomentum = 0.1f;   // torch.nn.BatchNorm2d defaults, as instantiated by upstream build_shared_mlp
 
-size_t stats_floats() { return (size_t)GADDPG_STAT_SLOTS * 2 * 1024; }
+size_t stats_floats() { return (size_t)GADDPG_STAT_SLOTS * 2 * 1024 + 4; }   // + the ticket word of the BatchNorm tails (16 bytes)
 
 struct Ws {
   float* stats;
+  unsigned int* counter;   // ticket of the fused BatchNorm tails (zeroed at the start of every composite call)
   float* tn;
   size_t tn_bytes;
   float* sa1;
@@ -39,6 +40,7 @@ bool carve(void* ws, long long ws_bytes, int B, int M_max, Ws* out) {
   if (!ws || ws_bytes < (long long)need || ((uintptr_t)ws & 15u)) return false;
   char* p = (char*)ws;
   out->stats = (float*)p;
+  out->counter = (unsigned int*)(out->stats + (size_t)GADDPG_STAT_SLOTS * 2 * 1024);
   p += stats_floats() * sizeof(float);
   out->tn = (float*)p;
   out->tn_bytes = gaddpg_gemm_tn_workspace_bytes_impl();
@@ -77,19 +79,53 @@ Operand bnbwd(const float* d, int ldd, const float* y, int ldy, const gaddpg_sa_
   return o;
 }
 
-int finalize_fwd(const Ws& w, const gaddpg_sa_layer& L, double count, int training, void* st) {
+// eval mode: scale / shift from the running statistics (training passes finalize in the tail of the producing kernel)
+int finalize_eval(const Ws& w, const gaddpg_sa_layer& L, double count, void* st) {
   return gaddpg_bn_finalize_fwd_impl(w.stats, L.N, count, L.gamma, L.beta, kEps, kMomentum, L.running_mean, L.running_var,
-                                     L.num_batches_tracked, training, L.scale, L.shift, L.mean, L.rstd, st);
+                                     L.num_batches_tracked, 0, L.scale, L.shift, L.mean, L.rstd, st);
 }
-int finalize_bwd(const Ws& w, const gaddpg_sa_layer& L, double count, int want_grads, int accumulate, void* st) {
-  return gaddpg_bn_finalize_bwd_impl(w.stats, L.N, count, L.gamma, L.rstd, L.bw_g, L.bw_m1, L.bw_m2, want_grads ? L.dgamma : nullptr,
-                                     want_grads ? L.dbeta : nullptr, accumulate, st);
+// BatchNorm finalize descriptors handed to the kernel that produces the statistics (gaddpg_bn_tail)
+gaddpg_bn_tail tail_fwd(const Ws& w, const gaddpg_sa_layer& L, double count, int training) {
+  gaddpg_bn_tail t = {};
+  if (!training) return t;
+  t.kind = 1;
+  t.count = count;
+  t.a = L.gamma;
+  t.b = L.beta;
+  t.eps = kEps;
+  t.momentum = kMomentum;
+  t.running_mean = L.running_mean;
+  t.running_var = L.running_var;
+  t.num_batches_tracked = L.num_batches_tracked;
+  t.o0 = L.scale;
+  t.o1 = L.shift;
+  t.o2 = L.mean;
+  t.o3 = L.rstd;
+  t.counter = w.counter;
+  return t;
+}
+gaddpg_bn_tail tail_bwd(const Ws& w, const gaddpg_sa_layer& L, double count, int want_grads, int accumulate) {
+  gaddpg_bn_tail t = {};
+  t.kind = 2;
+  t.accumulate = accumulate;
+  t.count = count;
+  t.a = L.gamma;
+  t.b = L.rstd;
+  t.o0 = L.bw_g;
+  t.o1 = L.bw_m1;
+  t.o2 = L.bw_m2;
+  t.dgamma = want_grads ? L.dgamma : nullptr;
+  t.dbeta = want_grads ? L.dbeta : nullptr;
+  t.counter = w.counter;
+  return t;
 }
 
 int nt1(const Operand& A, const float* Bw, int ldb, float* C, int ldc, int M_max, const int* M_dev, int N, int K, float* stats,
-        const float* srw, const float* Yprev, int ldyp, const gaddpg_sa_layer* pbn, int amode, int emode, void* st) {
+        const float* srw, const float* Yprev, int ldyp, const gaddpg_sa_layer* pbn, int amode, int emode, void* st,
+        const gaddpg_bn_tail* tail = nullptr) {
   NTGroup g = {};
   NTProblem& p = g.p[0];
+  if (tail && stats) p.tail = *tail;
   p.A = A;
   p.Bw = Bw;
   p.ldb = ldb;
@@ -154,22 +190,25 @@ int gaddpg_sa_forward(const gaddpg_sa_level* d, int training, void* ws, long lon
   if (d->M_max == 0) return GADDPG_OK;
   const gaddpg_sa_layer* L = d->layer;
   float* stats = training ? w.stats : nullptr;
+  GADDPG_CUDA(cudaMemsetAsync(w.counter, 0, 16, (cudaStream_t)stream));
+  gaddpg_bn_tail t0 = tail_fwd(w, L[0], d->count, training);
   if (d->cloud) {   // first level: conv0 straight from the cloud (grouped input never built)
     GADDPG_CHECK_ARG(L[0].N == 64 && d->row_seg && d->row_src && d->row_w && d->seg_off && d->ctr, "sa_forward: first-level arguments");
     float* bcbias = w.sa1 + (w.sa1_bytes / sizeof(float) - (size_t)d->B * 64);
     TRY(gaddpg_sa1_l1_fwd_impl(d->cloud, d->cloud_stride_b, d->cloud_stride_c, d->skip, d->Cp, d->bc, d->Cb, d->B, d->ctr, d->npoint,
                                d->seg_off, d->row_seg, d->row_src, d->row_w, d->M_max, d->M_dev, L[0].W, L[0].Kp, bcbias, L[0].Y, stats,
-                               stream));
+                               &t0, stream));
   } else {
     GADDPG_CHECK_ARG(d->G && d->ldg >= L[0].Kp, "sa_forward: input rows");
     TRY(nt1(plain(d->G, d->ldg), L[0].W, L[0].Kp, L[0].Y, L[0].N, d->M_max, d->M_dev, L[0].N, L[0].Kp, stats, d->row_w, nullptr, 0, nullptr,
-            OP_PLAIN, EPI_STORE, stream));
+            OP_PLAIN, EPI_STORE, stream, &t0));
   }
-  TRY(finalize_fwd(w, L[0], d->count, training, stream));
+  if (!training) TRY(finalize_eval(w, L[0], d->count, stream));
   for (int l = 1; l < 3; ++l) {
+    const gaddpg_bn_tail tl = tail_fwd(w, L[l], d->count, training);
     TRY(nt1(bnrelu(L[l - 1].Y, L[l - 1].N, L[l - 1]), L[l].W, L[l].Kp, L[l].Y, L[l].N, d->M_max, d->M_dev, L[l].N, L[l].Kp, stats, d->row_w,
-            nullptr, 0, nullptr, OP_BNRELU, EPI_STORE, stream));
-    TRY(finalize_fwd(w, L[l], d->count, training, stream));
+            nullptr, 0, nullptr, OP_BNRELU, EPI_STORE, stream, &tl));
+    if (!training) TRY(finalize_eval(w, L[l], d->count, stream));
   }
   return gaddpg_pool_fwd_impl(L[2].Y, L[2].N, L[2].scale, L[2].shift, d->seg_off, d->fixed_len, d->S, d->out, d->arg, stream);
 }
@@ -186,10 +225,12 @@ int gaddpg_sa_backward(const gaddpg_sa_level* d, const float* dOut, int ld_dout,
   for (int l = 0; l < 3; ++l)
     GADDPG_CHECK_ARG(L[l].D && L[l].bw_g && L[l].bw_m1 && L[l].bw_m2 && (!want_dw || (L[l].dW && L[l].dgamma && L[l].dbeta)) && (l == 0 || L[l].WT),
                      "sa_backward: layer %d lacks backward buffers", l);
+  GADDPG_CUDA(cudaMemsetAsync(w.counter, 0, 16, (cudaStream_t)stream));
+  const gaddpg_bn_tail t2 = tail_bwd(w, L[2], d->count, want_dw, accumulate);
   TRY(gaddpg_pool_bwd_impl(dOut, ld_dout, d->out, d->arg, L[2].Y, L[2].N, d->row_seg, d->fixed_len, d->M_max, d->M_dev, L[2].mean,
-                           L[2].rstd, L[2].D, w.stats, stream));
+                           L[2].rstd, L[2].D, w.stats, &t2, stream));
   for (int l = 2; l >= 1; --l) {
-    TRY(finalize_bwd(w, L[l], d->count, want_dw, accumulate, stream));
+    const gaddpg_bn_tail tp = tail_bwd(w, L[l - 1], d->count, want_dw, accumulate);   // statistics of the DMASK epilogue below
     const Operand dy = bnbwd(L[l].D, L[l].N, L[l].Y, L[l].N, L[l], d->row_w);
     if (want_dw) {
       TNProblem t = {};
@@ -202,9 +243,8 @@ int gaddpg_sa_backward(const gaddpg_sa_level* d, const float* dOut, int ld_dout,
       TRY(gaddpg_gemm_tn_impl(&t, OP_BNBWD, OP_BNRELU, L[l].dW, L[l].K, L[l].N, L[l].K, 0, nullptr, accumulate, w.tn, w.tn_bytes, stream));
     }
     TRY(nt1(dy, L[l].WT, L[l].N, L[l - 1].D, L[l].Kp, d->M_max, d->M_dev, L[l].Kp, L[l].N, w.stats, nullptr, L[l - 1].Y, L[l].Kp, &L[l - 1],
-            OP_BNBWD, EPI_DMASK, stream));
+            OP_BNBWD, EPI_DMASK, stream, &tp));
   }
-  TRY(finalize_bwd(w, L[0], d->count, want_dw, accumulate, stream));
   if (d->cloud) {
     return gaddpg_sa1_l1_bwd_impl(d->cloud, d->cloud_stride_b, d->cloud_stride_c, d->skip, d->Cp, d->bc, d->Cb, d->B, d->ctr, d->npoint,
                                   d->seg_off, d->row_seg, d->row_src, d->row_w, d->M_max, d->M_dev, L[0].D, L[0].Y, L[0].bw_g, L[0].bw_m1,

@@ -15,6 +15,7 @@
 #include <stdlib.h>
 
 #include "impl.h"
+#include "bn_tail.cuh"
 
 namespace {
 
@@ -538,6 +539,32 @@ int gaddpg_gemm_nt_impl(const NTGroup* g, int nprob, int amode, int emode, void*
       GADDPG_CHECK_ARG(!p.psc || p.psh, "gemm_nt[%d]: psc without psh", i);
     }
   }
+  // BatchNorm finalize tails (gaddpg_bn_tail): fused into the tcgen05 / mma.sync kernels of single-problem launches; every other
+  // path runs the separate finalize kernel behind the product, so the call means the same everywhere
+  bool any_tail = false;
+  for (int i = 0; i < nprob; ++i) {
+    const NTProblem& p = g->p[i];
+    if (p.tail.kind == 0) continue;
+    GADDPG_CHECK_ARG(p.stats && (p.tail.kind == 1 || p.tail.kind == 2) && p.tail.a && p.tail.b && p.tail.o0 && p.tail.o1 &&
+                         (p.tail.kind == 1 || p.tail.o2) && p.tail.count >= 1.0,
+                     "gemm_nt[%d]: incomplete BatchNorm tail", i);
+    any_tail = true;
+  }
+  if (any_tail) {
+    const bool fused_path = nprob == 1 && bnt_fusable(g->p[0].tail, g->p[0].N) &&
+                            ((gaddpg_get_tensor_core_impl() >= 1 && gaddpg_get_tensor_core_impl() <= 3 && gaddpg_tc_gemm_supported(g->p[0], amode, emode)) ||
+                             (gaddpg_get_tensor_core_impl() >= 2 && gaddpg_tc_nt_kc_supported(g->p[0], amode, emode)) ||
+                             (gaddpg_skinny_enabled() && gaddpg_skinny_supported(*g, nprob, amode, emode) && !g->p[0].pool_keys &&
+                              !g->p[0].no_store && amode != OP_BNBWD_POOL));
+    if (!fused_path) {
+      NTGroup plain = *g;
+      for (int i = 0; i < nprob; ++i) plain.p[i].tail.kind = 0;
+      int rc = gaddpg_gemm_nt_impl(&plain, nprob, amode, emode, stream);
+      for (int i = 0; i < nprob && rc == GADDPG_OK; ++i)
+        if (g->p[i].tail.kind) rc = gaddpg_bn_tail_separate(g->p[i].tail, g->p[i].stats, g->p[i].N, stream);
+      return rc;
+    }
+  }
   if (nprob == 1 && gaddpg_get_tensor_core_impl() >= 1 && gaddpg_get_tensor_core_impl() <= 3 &&
       gaddpg_tc_gemm_supported(g->p[0], amode, emode))
     return gaddpg_tc_gemm_nt_impl(&g->p[0], amode, emode, stream);  // tcgen05 3xTF32 path for the wide SA layers
@@ -664,6 +691,16 @@ int gaddpg_bn_finalize_fwd_impl(const float* stats, int C, double count, const f
                                                                             running_mean, running_var, nbt, training,
                                                                             scale, shift, mean_out, rstd_out);
   GADDPG_CHECK_LAUNCH("bn_finalize_fwd_kernel");
+  return GADDPG_OK;
+}
+
+// a BatchNorm tail as its own launch (producers without a fused tail)
+int gaddpg_bn_tail_separate(const BNTail& t, const float* stats, int C, void* stream) {
+  if (t.kind == 1)
+    return gaddpg_bn_finalize_fwd_impl(stats, C, t.count, t.a, t.b, t.eps, t.momentum, t.running_mean, t.running_var,
+                                       t.num_batches_tracked, 1, t.o0, t.o1, t.o2, t.o3, stream);
+  if (t.kind == 2)
+    return gaddpg_bn_finalize_bwd_impl(stats, C, t.count, t.a, t.b, t.o0, t.o1, t.o2, t.dgamma, t.dbeta, t.accumulate, stream);
   return GADDPG_OK;
 }
 

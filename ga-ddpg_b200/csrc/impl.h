@@ -39,7 +39,7 @@ int gaddpg_bn_running_update_impl(float* running, const float* staged, long long
 int gaddpg_sa1_l1_fwd_impl(const float* cloud, long long cloud_sb, int cloud_sc, int skip, int Cp, const float* bc, int Cb,
                            int B, const float* ctr, int npoint, const int32_t* seg_off, const int32_t* row_seg,
                            const int32_t* row_src, const float* row_w, int M_max, const int* M_dev, const float* W, int ldw,
-                           float* bcbias_ws, float* Y, float* stats, void* stream);
+                           float* bcbias_ws, float* Y, float* stats, const gaddpg_bn_tail* tail, void* stream);
 int gaddpg_sa1_l1_bwd_impl(const float* cloud, long long cloud_sb, int cloud_sc, int skip, int Cp, const float* bc, int Cb,
                            int B, const float* ctr, int npoint, const int32_t* seg_off, const int32_t* row_seg,
                            const int32_t* row_src, const float* row_w, int M_max, const int* M_dev, const float* D,
@@ -55,10 +55,10 @@ int gaddpg_pool_fwd_impl(const float* Y, int C, const float* scale, const float*
                          int S, float* out, int32_t* arg, void* stream);
 int gaddpg_pool_bwd_impl(const float* dOut, int ldo, const float* out, const int32_t* arg, const float* Y, int C,
                          const int32_t* row_seg, int fixed_len, int M_max, const int* M_dev, const float* mean,
-                         const float* rstd, float* D, float* stats, void* stream);
+                         const float* rstd, float* D, float* stats, const gaddpg_bn_tail* tail, void* stream);
 int gaddpg_pool_bwd_sparse_impl(const float* dOut, int ldo, const float* out, const int32_t* arg, const float* Y, int C, int S,
                                 const float* mean, const float* rstd, float* E, uint32_t* mask, int M_max, float* stats,
-                                void* stream);
+                                const gaddpg_bn_tail* tail, void* stream);
 int gaddpg_pool_keys_finalize_impl(unsigned long long* keys, int S, int C, const float* gamma, const float* scale, const float* shift, float* out,
                                    int32_t* arg, void* stream);
 int gaddpg_feat_finish_impl(const float* Y, int C, const float* scale, const float* shift, const float* time,
@@ -99,7 +99,7 @@ int gaddpg_adam_step_impl(float* p, float* g, float* m, float* v, long long n, d
 int gaddpg_optim_multi_impl(const void* jobs_dev, int njobs, int total_chunks, void* stream);
 int gaddpg_wprep_batched_impl(const long long* jobs_dev, int njobs, void* stream);
 int gaddpg_dmask_stats_impl(const float* dX, int ldx, const float* Yprev, int C, int M, const float* psc, const float* psh,
-                            const float* pmean, const float* prstd, float* D, float* stats, void* stream);
+                            const float* pmean, const float* prstd, float* D, float* stats, const gaddpg_bn_tail* tail, void* stream);
 int gaddpg_polyak_impl(float* target, const float* source, long long n, double tau, void* stream);
 int gaddpg_polyak_vec_impl(float* target, const float* source, const float* tau_vec, long long n, void* stream);
 int gaddpg_absmax_impl(const float* x, long long n, float* out, float* ws, void* stream);

@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "gemm_rows.cuh"
 #include "impl.h"
+#include "bn_tail.cuh"
 
 namespace {
 
@@ -63,7 +64,7 @@ __global__ void __launch_bounds__(256, 2) sa1_l1_fwd_kernel(const float* __restr
                                                             const float* __restrict__ row_w, int B, int jmax,
                                                             const float* __restrict__ W, int ldw,
                                                             const float* __restrict__ bcbias, float* __restrict__ Y,
-                                                            float* __restrict__ stats) {
+                                                            float* __restrict__ stats, const BNTail tail) {
   __shared__ __align__(16) float sIn[8 * 32 * SA1_LDI];
   __shared__ float sRw[8 * 32];
   __shared__ float red[8 * 2 * SA1_CO];
@@ -127,8 +128,13 @@ __global__ void __launch_bounds__(256, 2) sa1_l1_fwd_kernel(const float* __restr
     float v = 0.f;
     if (tid < 2 * SA1_CO)
       for (int y = 0; y < 8; ++y) v += red[y * 2 * SA1_CO + tid];
-    for (int slot = blockIdx.x; slot < GADDPG_STAT_SLOTS; slot += gridDim.x)
-      if (tid < 2 * SA1_CO) stats[(long long)slot * 2 * SA1_CO + tid] = (slot == (int)blockIdx.x) ? v : 0.f;
+    if (tail.kind != 0) {   // BatchNorm finalize by the last CTA (the staging tile is free)
+      if (tid < 2 * SA1_CO) stats[(long long)blockIdx.x * 2 * SA1_CO + tid] = v;
+      bnt_run<16>(tail, stats, SA1_CO, (int)gridDim.x, gridDim.x, reinterpret_cast<double*>(sIn), (int)(sizeof(sIn) / sizeof(double)));
+    } else {
+      for (int slot = blockIdx.x; slot < GADDPG_STAT_SLOTS; slot += gridDim.x)
+        if (tid < 2 * SA1_CO) stats[(long long)slot * 2 * SA1_CO + tid] = (slot == (int)blockIdx.x) ? v : 0.f;
+    }
   }
 }
 
@@ -578,8 +584,8 @@ __global__ void __launch_bounds__(256) dmask_stats_kernel(const float* __restric
                                                           int C, int M, const float* __restrict__ psc,
                                                           const float* __restrict__ psh, const float* __restrict__ pmean,
                                                           const float* __restrict__ prstd, float* __restrict__ D,
-                                                          float* __restrict__ stats) {
-  __shared__ float red[512];
+                                                          float* __restrict__ stats, const BNTail tail) {
+  __shared__ __align__(16) float red[4096];   // [512] partial sums; 16 KB so that it also serves the BatchNorm tail
   const int tid = threadIdx.x, cl = tid & 63, rl = tid >> 6;
   const int c = blockIdx.x * 64 + cl;
   float a0 = 0.f, a1 = 0.f;
@@ -600,6 +606,10 @@ __global__ void __launch_bounds__(256) dmask_stats_kernel(const float* __restric
     stats[c] = red[cl] + red[64 + cl] + red[128 + cl] + red[192 + cl];
     stats[C + c] = red[256 + cl] + red[320 + cl] + red[384 + cl] + red[448 + cl];
   }
+  if (tail.kind != 0) {   // one live slot: the last CTA finalizes all channels
+    bnt_run(tail, stats, C, 1, gridDim.x, reinterpret_cast<double*>(red), 2048);
+    return;
+  }
   // remaining slots are zero
   for (long long e = (long long)blockIdx.x * 256 + tid; e < (long long)(GADDPG_STAT_SLOTS - 1) * 2 * C; e += (long long)gridDim.x * 256)
     stats[2 * C + e] = 0.f;
@@ -608,11 +618,14 @@ __global__ void __launch_bounds__(256) dmask_stats_kernel(const float* __restric
 }  // namespace
 
 int gaddpg_dmask_stats_impl(const float* dX, int ldx, const float* Yprev, int C, int M, const float* psc, const float* psh,
-                            const float* pmean, const float* prstd, float* D, float* stats, void* stream) {
+                            const float* pmean, const float* prstd, float* D, float* stats, const BNTail* tail, void* stream) {
   GADDPG_CHECK_ARG(dX && Yprev && psc && psh && pmean && prstd && D && stats && C >= 1 && ldx >= C, "dmask_stats: bad argument");
-  dmask_stats_kernel<<<ceil_div(C, 64), 256, 0, (cudaStream_t)stream>>>(dX, ldx, Yprev, C, M, psc, psh, pmean, prstd, D, stats);
+  BNTail t = tail_or_none(tail);
+  const bool fused = bnt_fusable(t, C);
+  if (!fused) t.kind = 0;
+  dmask_stats_kernel<<<ceil_div(C, 64), 256, 0, (cudaStream_t)stream>>>(dX, ldx, Yprev, C, M, psc, psh, pmean, prstd, D, stats, t);
   GADDPG_CHECK_LAUNCH("dmask_stats_kernel");
-  return GADDPG_OK;
+  return (tail && tail->kind && !fused) ? gaddpg_bn_tail_separate(*tail, stats, C, stream) : GADDPG_OK;
 }
 
 static int sa1_jmax(int M_max, int B) { return ceil_div(ceil_div(M_max, B > 0 ? B : 1), SA1_ITEM); }
@@ -620,8 +633,9 @@ static int sa1_jmax(int M_max, int B) { return ceil_div(ceil_div(M_max, B > 0 ? 
 int gaddpg_sa1_l1_fwd_impl(const float* cloud, long long cloud_sb, int cloud_sc, int skip, int Cp, const float* bc, int Cb,
                            int B, const float* ctr, int npoint, const int32_t* seg_off, const int32_t* row_seg,
                            const int32_t* row_src, const float* row_w, int M_max, const int* M_dev, const float* W, int ldw,
-                           float* bcbias_ws, float* Y, float* stats, void* stream) {
+                           float* bcbias_ws, float* Y, float* stats, const BNTail* tail, void* stream) {
   GADDPG_CHECK_ARG(cloud && ctr && seg_off && row_seg && row_src && row_w && W && Y, "sa1_l1_fwd: null pointer");
+  GADDPG_CHECK_ARG(!(tail && tail->kind) || stats, "sa1_l1_fwd: a BatchNorm tail needs the statistics buffer");
   GADDPG_CHECK_ARG(Cp >= 3 && 3 + Cp <= SA1_KMAX && Cb >= 0 && ldw >= 3 + Cp + Cb, "sa1_l1_fwd: bad channels Cp=%d Cb=%d", Cp, Cb);
   GADDPG_CHECK_ARG(Cb == 0 || (bc && bcbias_ws), "sa1_l1_fwd: broadcast channels need bc and workspace");
   (void)M_dev;  // the live row count is seg_off[B*npoint]
@@ -634,10 +648,13 @@ int gaddpg_sa1_l1_fwd_impl(const float* cloud, long long cloud_sb, int cloud_sc,
   const int jmax = sa1_jmax(M_max, B);
   int grid = B * jmax;
   grid = grid < GADDPG_STAT_SLOTS ? grid : GADDPG_STAT_SLOTS;
+  BNTail t = tail_or_none(tail);
+  const bool fused = bnt_fusable(t, SA1_CO);
+  if (!fused) t.kind = 0;
   sa1_l1_fwd_kernel<<<grid, 256, 0, st>>>(cloud, cloud_sb, cloud_sc, skip, Cp, ctr, npoint, seg_off, row_seg, row_src, row_w, B, jmax,
-                                          W, ldw, Cb > 0 ? bcbias_ws : nullptr, Y, stats);
+                                          W, ldw, Cb > 0 ? bcbias_ws : nullptr, Y, stats, t);
   GADDPG_CHECK_LAUNCH("sa1_l1_fwd_kernel");
-  return GADDPG_OK;
+  return (tail && tail->kind && !fused) ? gaddpg_bn_tail_separate(*tail, stats, SA1_CO, stream) : GADDPG_OK;
 }
 
 int gaddpg_sa1_l1_bwd_impl(const float* cloud, long long cloud_sb, int cloud_sc, int skip, int Cp, const float* bc, int Cb,
@@ -718,7 +735,7 @@ int gaddpg_pool_fwd_impl(const float* Y, int C, const float* scale, const float*
 
 int gaddpg_pool_bwd_impl(const float* dOut, int ldo, const float* out, const int32_t* arg, const float* Y, int C,
                          const int32_t* row_seg, int fixed_len, int M_max, const int* M_dev, const float* mean,
-                         const float* rstd, float* D, float* stats, void* stream) {
+                         const float* rstd, float* D, float* stats, const BNTail* tail, void* stream) {
   GADDPG_CHECK_ARG(dOut && out && arg && Y && mean && rstd && D && stats, "pool_bwd: null pointer");
   GADDPG_CHECK_ARG((C % 64) == 0 && C <= 1024 && ldo >= C && (row_seg || fixed_len >= 1), "pool_bwd: bad shape C=%d", C);
   if (M_max == 0) return GADDPG_OK;
@@ -730,12 +747,14 @@ int gaddpg_pool_bwd_impl(const float* dOut, int ldo, const float* out, const int
   pool_bwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(dOut, ldo, out, arg, Y, C, row_seg, fixed_len, M_max, M_dev, mean, rstd,
                                                             D, stats);
   GADDPG_CHECK_LAUNCH("pool_bwd_kernel");
-  return GADDPG_OK;
+  // the tail runs as its own launch here: this kernel fills up to 296 full-width slots (C up to 1024), which one CTA cannot sum
+  // faster than the C/32-CTA finalize kernel does, and the tail's registers would cost this streaming kernel its occupancy
+  return (tail && tail->kind) ? gaddpg_bn_tail_separate(*tail, stats, C, stream) : GADDPG_OK;
 }
 
 int gaddpg_pool_bwd_sparse_impl(const float* dOut, int ldo, const float* out, const int32_t* arg, const float* Y, int C, int S,
                                 const float* mean, const float* rstd, float* E, uint32_t* mask, int M_max, float* stats,
-                                void* stream) {
+                                const BNTail* tail, void* stream) {
   GADDPG_CHECK_ARG(dOut && out && arg && Y && mean && rstd && E && mask && stats && M_max >= 1, "pool_bwd_sparse: bad argument");
   GADDPG_CUDA(cudaMemsetAsync(mask, 0, (size_t)M_max * (C / 32) * sizeof(uint32_t), (cudaStream_t)stream));
   GADDPG_CHECK_ARG((C == 64 || C == 128 || C == 256) && ldo >= C && S >= 1, "pool_bwd_sparse: bad shape C=%d S=%d", C, S);
@@ -744,7 +763,7 @@ int gaddpg_pool_bwd_sparse_impl(const float* dOut, int ldo, const float* out, co
   grid = grid < GADDPG_STAT_SLOTS ? grid : GADDPG_STAT_SLOTS;
   pool_bwd_sparse_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dOut, ldo, out, arg, Y, C, S, mean, rstd, E, mask, stats);
   GADDPG_CHECK_LAUNCH("pool_bwd_sparse_kernel");
-  return GADDPG_OK;
+  return (tail && tail->kind) ? gaddpg_bn_tail_separate(*tail, stats, C, stream) : GADDPG_OK;   // as in pool_bwd
 }
 
 int gaddpg_pool_keys_finalize_impl(unsigned long long* keys, int S, int C, const float* gamma, const float* scale,

@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "gemm_rows.cuh"
 #include "impl.h"
+#include "bn_tail.cuh"
 
 namespace {
 
@@ -91,6 +92,7 @@ __global__ void __launch_bounds__(256) skinny_nt_kernel(const NTGroup grp) {
   constexpr int SK_BN = BN, SK_B_FLOATS = BN * SK_LD;
   constexpr int NWN = BN / 8, NWM = 8 / NWN, MFW = 2 / NWM;
   constexpr int STAGE_FLOATS = SK_A_FLOATS * (AMODE == OP_BNBWD ? 2 : 1) + SK_B_FLOATS;
+  static_assert(SK_STAGES * STAGE_FLOATS / 2 >= BNT_SCRATCH_DOUBLES, "the cp.async ring must hold the BatchNorm tail's scratch");
 
   const NTProblem& p = grp.p[blockIdx.y];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
@@ -260,9 +262,29 @@ __global__ void __launch_bounds__(256) skinny_nt_kernel(const NTGroup grp) {
   }
   if (do_stats) {
     __syncthreads();
-    for (int slot = blockIdx.x; slot < GADDPG_STAT_SLOTS; slot += gridDim.x) {
-      const bool mine = (slot == (int)blockIdx.x);
-      for (int c = tid; c < 2 * N; c += 256) p.stats[(long long)slot * 2 * N + c] = mine ? s_acc[c] : 0.f;
+    if (p.tail.kind != 0) {
+      // BatchNorm finalize by the last CTA.  One tile per CTA (the usual case: a few hundred rows): the slot is the ROW tile and
+      // a CTA writes its own BN columns only, so the tail sums tiles_m slots instead of one per CTA.
+      const int ntile = tiles_m * tiles_n;
+      const bool compact = ntile <= (int)gridDim.x;
+      if (compact) {
+        if ((int)blockIdx.x < ntile) {
+          const int tm = blockIdx.x / tiles_n, col0 = (blockIdx.x % tiles_n) * SK_BN;
+          if (tid < 2 * SK_BN) {
+            const int c = col0 + (tid % SK_BN);
+            if (c < N) p.stats[(long long)tm * 2 * N + (tid < SK_BN ? 0 : N) + c] = s_acc[(tid < SK_BN ? 0 : N) + c];
+          }
+        }
+      } else {
+        for (int c = tid; c < 2 * N; c += 256) p.stats[(long long)blockIdx.x * 2 * N + c] = s_acc[c];
+      }
+      // scratch: the cp.async ring (every copy has landed and been consumed)
+      bnt_run(p.tail, p.stats, N, compact ? tiles_m : (int)gridDim.x, gridDim.x, reinterpret_cast<double*>(sk_smem), SK_STAGES * STAGE_FLOATS / 2);
+    } else {
+      for (int slot = blockIdx.x; slot < GADDPG_STAT_SLOTS; slot += gridDim.x) {
+        const bool mine = (slot == (int)blockIdx.x);
+        for (int c = tid; c < 2 * N; c += 256) p.stats[(long long)slot * 2 * N + c] = mine ? s_acc[c] : 0.f;
+      }
     }
   }
 }

@@ -36,6 +36,7 @@ __device__ unsigned long long g_tc_prof[148 * 16];
 #include "tc_common.cuh"
 #include "tma.cuh"
 #include "impl.h"
+#include "bn_tail.cuh"
 
 namespace {
 
@@ -456,13 +457,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
       p.stats[(long long)blockIdx.x * 2 * N + c] = a0;
       p.stats[(long long)blockIdx.x * 2 * N + N + c] = a1;
     }
-    for (int slot = blockIdx.x + gridDim.x; slot < GADDPG_STAT_SLOTS; slot += gridDim.x)
-      for (int c = tid; c < 2 * N; c += TC_THREADS) p.stats[(long long)slot * 2 * N + c] = 0.f;
+    if (p.tail.kind == 0)   // (a fused tail reads the gridDim.x live slots only)
+      for (int slot = blockIdx.x + gridDim.x; slot < GADDPG_STAT_SLOTS; slot += gridDim.x)
+        for (int c = tid; c < 2 * N; c += TC_THREADS) p.stats[(long long)slot * 2 * N + c] = 0.f;
   }
   if (warp == TC_PW) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
+  // BatchNorm finalize by the last CTA (the operand stages are free: every MMA and store of this CTA has completed)
+  if (p.stats && p.tail.kind != 0) bnt_run<13>(p.tail, p.stats, N, ntiles < (int)gridDim.x ? ntiles : (int)gridDim.x, gridDim.x, reinterpret_cast<double*>(smem), 8192);
 }
 
 }  // namespace

@@ -19,6 +19,7 @@
 // (dW tile) stays in TMEM for the whole kernel and is written once as a per-split partial.
 #include "tc_common.cuh"
 #include "impl.h"
+#include "bn_tail.cuh"
 
 namespace {
 
@@ -334,16 +335,20 @@ __global__ void __launch_bounds__(KC_NT_THREADS, 1) tc_nt_kc_kernel(const NTProb
         p.stats[(long long)blockIdx.x * 2 * N + N + n0 + c] = a1;
       }
     }
-    for (int slot = blockIdx.x + gridDim.x; slot < GADDPG_STAT_SLOTS; slot += gridDim.x)
-      for (int c = tid; c < 2 * BN; c += KC_NT_THREADS) {
-        const int cc = (c < BN) ? c : c - BN;
-        if (n0 + cc < N) p.stats[(long long)slot * 2 * N + (c < BN ? 0 : N) + n0 + cc] = 0.f;
-      }
+    if (p.tail.kind == 0)   // (a fused tail reads the gridDim.x live slots only)
+      for (int slot = blockIdx.x + gridDim.x; slot < GADDPG_STAT_SLOTS; slot += gridDim.x)
+        for (int c = tid; c < 2 * BN; c += KC_NT_THREADS) {
+          const int cc = (c < BN) ? c : c - BN;
+          if (n0 + cc < N) p.stats[(long long)slot * 2 * N + (c < BN ? 0 : N) + n0 + cc] = 0.f;
+        }
   }
   if (warp == KC_PW) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
+  // BatchNorm finalize by the last CTA of the (m-tile, n-tile) grid: slot = blockIdx.x, the n-tiles own disjoint columns
+  if (p.stats && p.tail.kind != 0)
+    bnt_run<13>(p.tail, p.stats, N, ntiles < (int)gridDim.x ? ntiles : (int)gridDim.x, gridDim.x * gridDim.y, reinterpret_cast<double*>(smem), 8192);
 }
 
 // =====================================================================================================

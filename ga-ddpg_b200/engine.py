@@ -16,6 +16,7 @@ Data layout in HBM (all fp32, row-major):
   parameters       one arena per network: [params | grads | Adam m | Adam v] (nets.Arena)
 """
 import ctypes
+import os as _os
 from types import SimpleNamespace as NS
 
 import numpy as np
@@ -23,7 +24,7 @@ import torch
 
 from . import nets
 from .capi import current_stream, lib
-from .structs import (EPI_DMASK, EPI_STORE, OP_BNBWD, OP_BNBWD_POOL, OP_BNRELU, OP_PLAIN, STAT_SLOTS, NTGroup, NTProblem, Operand,
+from .structs import (EPI_DMASK, EPI_STORE, OP_BNBWD, OP_BNBWD_POOL, OP_BNRELU, OP_PLAIN, STAT_SLOTS, BNTail, NTGroup, NTProblem, Operand,
                       TNProblem, check_sizes, dp, op_bnbwd, op_bnbwd_pool, op_bnrelu, op_plain)
 
 BN_EPS, BN_MOMENTUM = 1e-5, 0.1
@@ -63,7 +64,9 @@ class Workspace:
     def __init__(self, device):
         _init_once(device)
         self.device = device
-        self.stats = _f(device, STAT_SLOTS * 2 * 1024)
+        self.stats = _f(device, STAT_SLOTS * 2 * 1024 + 4)
+        # ticket word of the BatchNorm tails (gaddpg_bn_tail.counter): zero between launches, one per statistics buffer
+        self.counter = self.stats.data_ptr() + 4 * STAT_SLOTS * 2 * 1024
         self.tn_bytes = int(lib.gaddpg_gemm_tn_workspace_bytes())
         self.tn = _f(device, self.tn_bytes // 4)
         self.red = _f(device, 2048)
@@ -169,7 +172,7 @@ def nt(problems, amode, emode):
 
 
 def nt_problem(A, Bw, ldb, C, ldc, M_max, M_dev, N, K, bias=None, relu=0, stats=None, srw=None, Yprev=None, ldyp=0,
-               pbn=None, pool_keys=None, pool_seg=None, pool_gamma=None, no_store=0, w_split=None):
+               pbn=None, pool_keys=None, pool_seg=None, pool_gamma=None, no_store=0, w_split=None, tail=None):
     p = NTProblem(A=A, Bw=dp(Bw) if torch.is_tensor(Bw) else Bw, ldb=ldb, bias=dp(bias), C=dp(C) if torch.is_tensor(C) else C,
                   ldc=ldc, M_max=M_max, M_dev=M_dev, N=N, K=K, relu=relu, stats=dp(stats), srw=dp(srw),
                   Yprev=dp(Yprev) if torch.is_tensor(Yprev) else Yprev, ldyp=ldyp)
@@ -179,6 +182,8 @@ def nt_problem(A, Bw, ldb, C, ldc, M_max, M_dev, N, K, bias=None, relu=0, stats=
         p.pool_keys, p.pool_seg, p.pool_gamma, p.no_store = dp(pool_keys), dp(pool_seg), dp(pool_gamma), no_store
     if w_split is not None:
         p.Bw_hi, p.Bw_lo = w_split
+    if tail is not None:
+        p.tail = tail
     return p
 
 
@@ -218,6 +223,48 @@ class side_dw:
         if self.side is not None:
             self.side.join()
         SIDE = self.prev
+
+
+# BatchNorm finalize as the tail of the kernel that produced the statistics (gaddpg_bn_tail; csrc/bn_tail.cuh): built, parity-green
+# (tests/test_bn_tail_gpu.py) and measured at cfg2 (profiles/r2_bn_tail.md): 252 instead of 322 launches per step, but the step
+# is 2.4 % SLOWER (211.4 vs 216.7 steps/s, A/B in one session): what a finalize costs on the dependency chain is its two
+# dependent L2 round trips (slots, then constants / running statistics) plus the ticket, not its launch — and one CTA does
+# them no faster than the C/32-CTA kernel.  OFF by default; GADDPG_BN_TAIL=1 selects it.
+FUSED_BN_TAIL = _os.environ.get("GADDPG_BN_TAIL", "0") == "1"
+
+
+def fwd_tail(ws, C, count, bnp, st, train, stage=None):
+    """gaddpg_bn_tail of a training-mode forward BatchNorm: the kernel that writes the statistics of this layer into ws.stats also
+    finalizes them (scale / shift / mean / rstd into ``st``, running statistics into the layer or the pass's BNStage).  None in
+    eval mode (no batch statistics: call bn_fwd) or with FUSED_BN_TAIL off (then bn_fwd_after runs the separate kernel)."""
+    if not train or not FUSED_BN_TAIL:
+        return None
+    t = BNTail(kind=1, count=float(count), a=dp(bnp.gamma), b=dp(bnp.beta), eps=BN_EPS, o0=dp(st.scale), o1=dp(st.shift),
+               o2=dp(st.mean), o3=dp(st.rstd), counter=ws.counter)
+    if stage is not None:   # deferred running-stat update: stage the batch statistics (momentum 1 = verbatim)
+        t.momentum, t.running_mean, t.running_var = 1.0, dp(stage.rm[bnp.key]), dp(stage.rv[bnp.key])
+    else:
+        t.momentum, t.running_mean, t.running_var, t.num_batches_tracked = BN_MOMENTUM, dp(bnp.rm), dp(bnp.rv), dp(bnp.nbt)
+    return t
+
+
+def bn_fwd_after(tail, ws, C, count, bnp, st, train, stage=None):
+    """The separate finalize launch, unless the producer carried ``tail``."""
+    if tail is None:
+        bn_fwd(ws, C, count, bnp, st, train, stage)
+
+
+def bwd_tail(ws, C, count, bnp, st, bb, want_grads, accumulate=0):
+    """gaddpg_bn_tail of a BatchNorm backward: m1 / m2 / g into ``bb``, dgamma / dbeta into the gradient arena."""
+    if not FUSED_BN_TAIL:
+        return None
+    return BNTail(kind=2, accumulate=accumulate, count=float(count), a=dp(bnp.gamma), b=dp(st.rstd), o0=dp(bb.g), o1=dp(bb.m1),
+                  o2=dp(bb.m2), dgamma=dp(bnp.dgamma) if want_grads else None, dbeta=dp(bnp.dbeta) if want_grads else None,
+                  counter=ws.counter)
+
+
+def _tp(tail):
+    return None if tail is None else ctypes.byref(tail)
 
 
 def bn_fwd(ws, C, count, bnp, st, train, stage=None):
@@ -512,8 +559,6 @@ def encoder_forward(ws, ef, geom, cloud, skip, Cp, bc, ctx, time=None, time_offs
 # ONE shared operand buffer (227 KB of shared memory hold the three hi/lo weight matrices + one 64 KB operand) and by the
 # SIMT cost of the per-(row, channel) statistics / extreme pass — 329 us against 272 us for the unfused launches — so it is
 # OFF by default; GADDPG_FUSED_SA1=1 (or engine.FUSED_SA1 = True) selects it.
-import os as _os
-
 FUSED_SA1 = _os.environ.get("GADDPG_FUSED_SA1", "0") == "1"
 FUSED_SA1_KEEP = True   # ... also for passes that are differentiated (the pre-BN outputs are stored by TMA, never re-read)
 # Eval-mode passes (select_action / select_action_batch / extract_feature: running statistics, so ONE phase instead of three)
@@ -559,10 +604,11 @@ def _sa1_unfused_forward(ws, ef, geom, cloud, skip, Cp, bc, Cb, ctx, train, bn_s
     l1 = geom.lv[0]
     s, L = ctx.sa[0], ef.layers
     W0 = L["sa0.0"]
+    t0 = fwd_tail(ws, 64, B * geom.npoint * l1.ns, W0, s.bn[0], train, bn_stage)
     lib.gaddpg_sa1_l1_fwd(dp(cloud), C * Np, Np, skip, Cp, dp(bc), Cb, B, dp(l1.new_xyz), geom.npoint, dp(l1.seg_off),
                           dp(l1.row_seg), dp(l1.row_src), dp(l1.row_w), l1.cap, l1.M_dev, dp(W0.W), W0.K, dp(ctx.bcbias),
-                          dp(s.Y[0]), dp(ws.stats) if train else None, st)
-    bn_fwd(ws, 64, B * geom.npoint * l1.ns, W0, s.bn[0], train, bn_stage)
+                          dp(s.Y[0]), dp(ws.stats) if train else None, _tp(t0), st)
+    bn_fwd_after(t0, ws, 64, B * geom.npoint * l1.ns, W0, s.bn[0], train, bn_stage)
     _mlp_tail_forward(ws, [L["sa0.1"], L["sa0.2"]], s, 1, l1.cap, l1.M_dev, l1.row_w, B * geom.npoint * l1.ns, train, bn_stage,
                       pool=NS(lv=l1, keep=keep))
 
@@ -592,21 +638,24 @@ def _encoder_forward_upper(ws, ef, geom, ctx, time, time_offset, train, bn_stage
     # ---- FC head: Linear + BN1d + ReLU twice
     f = ctx.fc
     F0, F1 = L["fc0"], L["fc1"]
+    t0 = fwd_tail(ws, 1024, B, F0, f.bn[0], train, bn_stage)
     nt([nt_problem(op_plain(s3.out), F0.Wf, F0.Kp, f.Y[0], 1024, B, None, 1024, 512, bias=F0.bias,
-                   stats=ws.stats if train else None)], OP_PLAIN, EPI_STORE)
-    bn_fwd(ws, 1024, B, F0, f.bn[0], train, bn_stage)
+                   stats=ws.stats if train else None, tail=t0)], OP_PLAIN, EPI_STORE)
+    bn_fwd_after(t0, ws, 1024, B, F0, f.bn[0], train, bn_stage)
+    t1 = fwd_tail(ws, 512, B, F1, f.bn[1], train, bn_stage)
     nt([nt_problem(op_bnrelu(f.Y[0], f.bn[0]), F1.Wf, F1.Kp, f.Y[1], 512, B, None, 512, 1024, bias=F1.bias,
-                   stats=ws.stats if train else None)], OP_BNRELU, EPI_STORE)
-    bn_fwd(ws, 512, B, F1, f.bn[1], train, bn_stage)
+                   stats=ws.stats if train else None, tail=t1)], OP_BNRELU, EPI_STORE)
+    bn_fwd_after(t1, ws, 512, B, F1, f.bn[1], train, bn_stage)
     lib.gaddpg_feat_finish(dp(f.Y[1]), 512, dp(f.bn[1].scale), dp(f.bn[1].shift), dp(time), float(time_offset), B, dp(ctx.feat),
                            516, st)
     return ctx.feat
 
 
 def _mlp_first_forward(ws, Lp, s, M_max, M_dev, rw, count, train, bn_stage=None):
+    t0 = fwd_tail(ws, Lp.N, count, Lp, s.bn[0], train, bn_stage)
     nt([nt_problem(op_plain(s.G), Lp.Wf, Lp.Kp, s.Y[0], Lp.N, M_max, M_dev, Lp.N, Lp.Kp, stats=ws.stats if train else None,
-                   srw=rw)], OP_PLAIN, EPI_STORE)
-    bn_fwd(ws, Lp.N, count, Lp, s.bn[0], train, bn_stage)
+                   srw=rw, tail=t0)], OP_PLAIN, EPI_STORE)
+    bn_fwd_after(t0, ws, Lp.N, count, Lp, s.bn[0], train, bn_stage)
 
 
 FUSED_POOL = False  # max-pool of SA1 / SA2 inside the epilogue of their last layer: correct and bit-identical, but measured slower
@@ -618,7 +667,8 @@ def _mlp_tail_forward(ws, layers, s, first, M_max, M_dev, rw, count, train, bn_s
     turned into s.out / s.arg by gaddpg_pool_keys_finalize once the batch statistics exist)."""
     for j, Lp in enumerate(layers):
         l = first + j
-        kw = dict(stats=ws.stats if train else None, srw=rw)
+        tl = fwd_tail(ws, Lp.N, count, Lp, s.bn[l], train, bn_stage)
+        kw = dict(stats=ws.stats if train else None, srw=rw, tail=tl)
         A = op_bnrelu(s.Y[l - 1], s.bn[l - 1])
         fused = False
         if pool is not None and j == len(layers) - 1 and FUSED_POOL:
@@ -632,7 +682,7 @@ def _mlp_tail_forward(ws, layers, s, first, M_max, M_dev, rw, count, train, bn_s
             ws_ = (Lp.W_hi, Lp.W_lo) if (getattr(Lp, "W_hi", None) and Lp.Wf is Lp.W) else None   # SA1: TMA-fetched weight images
             prob = nt_problem(A, Lp.Wf, Lp.Kp, s.Y[l], Lp.N, M_max, M_dev, Lp.N, Lp.Kp, w_split=ws_, **kw)
         nt([prob], OP_BNRELU, EPI_STORE)
-        bn_fwd(ws, Lp.N, count, Lp, s.bn[l], train, bn_stage)
+        bn_fwd_after(tl, ws, Lp.N, count, Lp, s.bn[l], train, bn_stage)
         if pool is not None and j == len(layers) - 1:
             lv, st = pool.lv, current_stream()
             if fused:
@@ -643,7 +693,14 @@ def _mlp_tail_forward(ws, layers, s, first, M_max, M_dev, rw, count, train, bn_s
                                     dp(s.arg), st)
 
 
-def encoder_backward(ws, ef, ctx, sc, want_dw=True, want_dbc=False, accumulate=0, dfeat=None, part="all"):
+def entry_tail(ws, ef, ctx, sc, want_dw=True, accumulate=0):
+    """BatchNorm-backward tail of the encoder's last FC BatchNorm, for the kernel that writes its (sum D, sum D*xhat) statistics:
+    the EPI_DMASK epilogue at the end of policy_backward / critic_backward.  Pass it there as ``enc_tail`` and call
+    encoder_backward(..., entry_done=(tail is not None)) with the same want_dw / accumulate."""
+    return bwd_tail(ws, 512, ctx.B, ef.layers["fc1"], ctx.fc.bn[1], sc.bbfc[1], want_dw, accumulate)
+
+
+def encoder_backward(ws, ef, ctx, sc, want_dw=True, want_dbc=False, accumulate=0, dfeat=None, part="all", entry_done=False):
     """Backward of ``encoder_forward``.  Entry: either ``dfeat`` (B, >=512) is given (gradient w.r.t. ctx.feat;
     masked here), or the caller already produced sc.Dfc[1] and its BN sums in ws.stats through an EPI_DMASK
     epilogue (the fused path).  Writes parameter gradients into the arena (``want_dw``) and, for the broadcast
@@ -660,18 +717,23 @@ def encoder_backward(ws, ef, ctx, sc, want_dw=True, want_dbc=False, accumulate=0
     f = ctx.fc
     F0, F1 = L["fc0"], L["fc1"]
     if dfeat is not None:
+        te = bwd_tail(ws, 512, B, F1, f.bn[1], sc.bbfc[1], want_dw, accumulate)
         lib.gaddpg_dmask_stats(dp(dfeat), dfeat.shape[1], dp(f.Y[1]), 512, B, dp(f.bn[1].scale), dp(f.bn[1].shift),
-                               dp(f.bn[1].mean), dp(f.bn[1].rstd), dp(sc.Dfc[1]), dp(ws.stats), st)
+                               dp(f.bn[1].mean), dp(f.bn[1].rstd), dp(sc.Dfc[1]), dp(ws.stats), _tp(te), st)
+        entry_done = te is not None
     s3 = ctx.sa[2]
-    # ---- FC head
-    bn_bwd(ws, 512, B, F1, f.bn[1], sc.bbfc[1], want_dw, accumulate)
+    # ---- FC head (entry_done: the kernel that produced sc.Dfc[1] also finalized this BatchNorm's backward sums)
+    if not entry_done:
+        bn_bwd(ws, 512, B, F1, f.bn[1], sc.bbfc[1], want_dw, accumulate)
     dy1 = op_bnbwd(sc.Dfc[1], f.Y[1], f.bn[1], sc.bbfc[1])
     if want_dw:
         tn(ws, dy1, op_bnrelu(f.Y[0], f.bn[0]), OP_BNBWD, OP_BNRELU, B, None, 512, 1024, F1.dW, 1024, 512, 1024,
            dbias=F1.dbias, accumulate=accumulate)
+    t0 = bwd_tail(ws, 1024, B, F0, f.bn[0], sc.bbfc[0], want_dw, accumulate)
     nt([nt_problem(dy1, F1.WT, 512, sc.Dfc[0], 1024, B, None, 1024, 512, stats=ws.stats, Yprev=f.Y[0], ldyp=1024,
-                   pbn=f.bn[0])], OP_BNBWD, EPI_DMASK)
-    bn_bwd(ws, 1024, B, F0, f.bn[0], sc.bbfc[0], want_dw, accumulate)
+                   pbn=f.bn[0], tail=t0)], OP_BNBWD, EPI_DMASK)
+    if t0 is None:
+        bn_bwd(ws, 1024, B, F0, f.bn[0], sc.bbfc[0], want_dw, accumulate)
     dy0 = op_bnbwd(sc.Dfc[0], f.Y[0], f.bn[0], sc.bbfc[0])
     if want_dw:
         tn(ws, dy0, op_plain(s3.out), OP_BNBWD, OP_PLAIN, B, None, 1024, 512, F0.dW, 512, 1024, 512, dbias=F0.dbias,
@@ -725,15 +787,18 @@ def _sa_backward(ws, layers, s, sc, lvl, dOut, ld_dout, row_seg, fixed_len, M_ma
     # is never written; its consumers (dX and dW of layer 2) rebuild it from the (S, C) tables (GADDPG_OP_BNBWD_POOL)
     sparse = (SPARSE_POOL and lvl == 0 and row_seg is not None and C3 == 128 and layers[2].Kp == 64
               and lib.gaddpg_get_tensor_core() >= 3)
+    # every kernel that writes BatchNorm-backward statistics finalizes them in its tail (bwd_tail); tl = tail of layer l's sums
+    tl = bwd_tail(ws, C3, count, layers[2], s.bn[2], bb[2], want_dw, accumulate)
     if sparse:
         lib.gaddpg_pool_bwd_sparse(dp(dOut), ld_dout, dp(s.out), dp(s.arg), dp(s.Y[2]), C3, s.out.shape[0], dp(s.bn[2].mean),
-                                   dp(s.bn[2].rstd), dp(sc.E), dp(sc.mask), M_max, dp(ws.stats), st)
+                                   dp(s.bn[2].rstd), dp(sc.E), dp(sc.mask), M_max, dp(ws.stats), _tp(tl), st)
     else:
         lib.gaddpg_pool_bwd(dp(dOut), ld_dout, dp(s.out), dp(s.arg), dp(s.Y[2]), C3, dp(row_seg), fixed_len, M_max, M_dev,
-                            dp(s.bn[2].mean), dp(s.bn[2].rstd), dp(D[2]), dp(ws.stats), st)
+                            dp(s.bn[2].mean), dp(s.bn[2].rstd), dp(D[2]), dp(ws.stats), _tp(tl), st)
     for l in (2, 1):
         Lp = layers[l]
-        bn_bwd(ws, Lp.N, count, Lp, s.bn[l], bb[l], want_dw, accumulate)
+        if tl is None:
+            bn_bwd(ws, Lp.N, count, Lp, s.bn[l], bb[l], want_dw, accumulate)
         if sparse and l == 2:
             dy, dmode = op_bnbwd_pool(sc.E, sc.mask, row_seg, s.Y[l], s.bn[l], bb[l], rw=rw), OP_BNBWD_POOL
         else:
@@ -741,10 +806,12 @@ def _sa_backward(ws, layers, s, sc, lvl, dOut, ld_dout, row_seg, fixed_len, M_ma
         if want_dw:
             tn(ws, dy, op_bnrelu(s.Y[l - 1], s.bn[l - 1]), dmode, OP_BNRELU, M_max, M_dev, Lp.N, Lp.Kp, Lp.dW, Lp.K, Lp.N,
                Lp.K, accumulate=accumulate)
+        tl = bwd_tail(ws, layers[l - 1].N, count, layers[l - 1], s.bn[l - 1], bb[l - 1], want_dw, accumulate)
         nt([nt_problem(dy, Lp.WT, Lp.N, D[l - 1], Lp.Kp, M_max, M_dev, Lp.Kp, Lp.N, stats=ws.stats, Yprev=s.Y[l - 1],
-                       ldyp=Lp.Kp, pbn=s.bn[l - 1])], dmode, EPI_DMASK)
+                       ldyp=Lp.Kp, pbn=s.bn[l - 1], tail=tl)], dmode, EPI_DMASK)
     L0 = layers[0]
-    bn_bwd(ws, L0.N, count, L0, s.bn[0], bb[0], want_dw, accumulate)
+    if tl is None:
+        bn_bwd(ws, L0.N, count, L0, s.bn[0], bb[0], want_dw, accumulate)
     if generic_l0:
         dy = op_bnbwd(D[0], s.Y[0], s.bn[0], bb[0], rw=rw)
         if want_dw:
@@ -826,9 +893,10 @@ def policy_forward(pf, feat, pc, B):
     return pc.raw
 
 
-def policy_backward(ws, pf, feat, pc, B, n_grad, enc_ctx, sc, accumulate=0):
+def policy_backward(ws, pf, feat, pc, B, n_grad, enc_ctx, sc, accumulate=0, enc_tail=None):
     """pc.draw (B, NHp): gradient w.r.t. the raw head output (columns >= n_grad are zero).  Ends in the encoder's
-    FC head through the fused mask epilogue: sc.Dfc[1] + BN sums in ws.stats (entry state of encoder_backward)."""
+    FC head through the fused mask epilogue: sc.Dfc[1] + BN sums in ws.stats (entry state of encoder_backward);
+    ``enc_tail`` (entry_tail()): that kernel also finalizes the sums."""
     tn(ws, op_plain(pc.draw), op_plain(pc.H2), OP_PLAIN, OP_PLAIN, B, None, pf.NHp, H, pf.dWh, H, n_grad, H, dbias=pf.dbh,
        accumulate=accumulate)
     nt([nt_problem(op_plain(pc.draw), pf.WhT, pf.NHp, pc.dZ2, H, B, None, H, pf.NHp, Yprev=pc.H2, ldyp=H)], OP_PLAIN, EPI_DMASK)
@@ -838,7 +906,7 @@ def policy_backward(ws, pf, feat, pc, B, n_grad, enc_ctx, sc, accumulate=0):
        dbias=pf.db1, accumulate=accumulate)
     f = enc_ctx.fc
     nt([nt_problem(op_plain(pc.dZ1), pf.W1T, H, sc.Dfc[1], 512, B, None, 512, H, stats=ws.stats, Yprev=f.Y[1], ldyp=512,
-                   pbn=f.bn[1])], OP_PLAIN, EPI_DMASK)
+                   pbn=f.bn[1], tail=enc_tail)], OP_PLAIN, EPI_DMASK)
 
 
 class CriticFlat:
@@ -938,7 +1006,7 @@ def critic_forward(cf, feat, cc, B, nb=None):
     return cc.qa
 
 
-def critic_backward(ws, cf, feat, cc, B, nb, enc_ctx, sc, accumulate=0):
+def critic_backward(ws, cf, feat, cc, B, nb, enc_ctx, sc, accumulate=0, enc_tail=None):
     """cc.dqa (B,16): gradient w.r.t. [q1 | q2 | aux_raw]; ``nb`` = branches that carry gradient (2 in the actor
     step, where the aux branch is not part of the loss).  Ends like policy_backward in sc.Dfc[1] + ws.stats."""
     n = cf.nb * H
@@ -956,4 +1024,4 @@ def critic_backward(ws, cf, feat, cc, B, nb, enc_ctx, sc, accumulate=0):
        cf.Kin, dbias=cf.db1, accumulate=accumulate)
     f = enc_ctx.fc
     nt([nt_problem(op_plain(cc.dZ1, n), cf.W1T, n, sc.Dfc[1], 512, B, None, 512, nb * H, stats=ws.stats, Yprev=f.Y[1], ldyp=512,
-                   pbn=f.bn[1])], OP_PLAIN, EPI_DMASK)
+                   pbn=f.bn[1], tail=enc_tail)], OP_PLAIN, EPI_DMASK)

@@ -21,12 +21,21 @@ class Operand(ctypes.Structure):
                 ("c0", _P), ("c1", _P), ("c2", _P), ("c3", _P), ("c4", _P), ("pmask", _P), ("pseg", _P)]
 
 
+class BNTail(ctypes.Structure):
+    """gaddpg_bn_tail: BatchNorm finalize run by the last CTA of the kernel that produced the statistics."""
+    _fields_ = [("kind", _I), ("accumulate", _I), ("count", ctypes.c_double), ("a", _P), ("b", _P),
+                ("eps", ctypes.c_float), ("momentum", ctypes.c_float), ("running_mean", _P), ("running_var", _P),
+                ("num_batches_tracked", _P), ("o0", _P), ("o1", _P), ("o2", _P), ("o3", _P), ("dgamma", _P), ("dbeta", _P),
+                ("counter", _P)]
+
+
 class NTProblem(ctypes.Structure):
     _fields_ = [("A", Operand), ("Bw", _P), ("ldb", _I), ("bias", _P), ("C", _P), ("ldc", _I),
                 ("M_max", _I), ("M_dev", _P), ("N", _I), ("K", _I), ("relu", _I),
                 ("stats", _P), ("srw", _P), ("Yprev", _P), ("ldyp", _I),
                 ("psc", _P), ("psh", _P), ("pmean", _P), ("prstd", _P),
-                ("pool_keys", _P), ("pool_seg", _P), ("pool_gamma", _P), ("no_store", _I), ("Bw_hi", _P), ("Bw_lo", _P)]
+                ("pool_keys", _P), ("pool_seg", _P), ("pool_gamma", _P), ("no_store", _I), ("Bw_hi", _P), ("Bw_lo", _P),
+                ("tail", BNTail)]
 
 
 class NTGroup(ctypes.Structure):

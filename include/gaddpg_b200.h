@@ -116,6 +116,31 @@ typedef struct gaddpg_operand {
   const uint32_t* pmask; const int32_t* pseg;
 } gaddpg_operand;
 
+/* BatchNorm finalize as the TAIL of the kernel that produced the statistics (kind != 0): the CTA that finishes last (one
+ * atomic ticket per CTA on *counter) sums the statistic slots in the fixed slot order and writes what
+ * gaddpg_bn_finalize_fwd (kind 1) / gaddpg_bn_finalize_bwd (kind 2) would have written — same arithmetic, one launch fewer per
+ * BatchNorm layer and pass.  Replaces the batch-statistics half of torch.nn.BatchNorm2d / BatchNorm1d (training mode) behind
+ * upstream build_shared_mlp and /root/reference/core/networks.py:84-91.
+ *   kind 1: a = gamma, b = beta, o0..o3 = scale, shift, mean, rstd (o2 / o3 may be NULL); running_mean / running_var / nbt as in
+ *           gaddpg_bn_finalize_fwd (momentum == 1: staging mode);
+ *   kind 2: a = gamma, b = rstd (forward pass), o0..o2 = g, m1, m2; dgamma / dbeta (may be NULL) (+)= per `accumulate`.
+ * counter: one zero-initialised device word per statistics buffer (stream-ordered reuse); the kernel leaves it zero.
+ * Kernels without a fused tail run the separate finalize kernel after the producer, so the call has the same effect on
+ * every path. */
+typedef struct gaddpg_bn_tail {
+  int kind; int accumulate;
+  double count;
+  const float* a; const float* b;
+  float eps, momentum;
+  float* running_mean; float* running_var; long long* num_batches_tracked;
+  float* o0; float* o1; float* o2; float* o3;
+  float* dgamma; float* dbeta;
+  unsigned int* counter;
+} gaddpg_bn_tail;
+
+/* The other statistics producers (gaddpg_sa1_l1_fwd, gaddpg_pool_bwd, gaddpg_pool_bwd_sparse, gaddpg_dmask_stats) take the same
+ * descriptor as a trailing `const gaddpg_bn_tail* tail` argument (a HOST pointer, read during the call; NULL = no tail). */
+
 typedef struct gaddpg_nt_problem {
   gaddpg_operand A;
   const float* Bw; int ldb;
@@ -140,6 +165,8 @@ typedef struct gaddpg_nt_problem {
    * When both are given the tcgen05 whole-K kernel fetches the weights with TMA (cp.async.bulk.tensor) instead of
    * splitting Bw in every CTA. */
   const float* Bw_hi; const float* Bw_lo;
+  /* optional BatchNorm finalize of `stats` as the tail of this launch (see gaddpg_bn_tail; kind 0 = none) */
+  gaddpg_bn_tail tail;
 } gaddpg_nt_problem;
 
 typedef struct gaddpg_nt_group { gaddpg_nt_problem p[GADDPG_MAX_GROUP]; } gaddpg_nt_group;
@@ -193,7 +220,7 @@ GADDPG_API int gaddpg_bn_running_update(float* running, const float* staged, lon
 GADDPG_API int gaddpg_sa1_l1_fwd(const float* cloud, long long cloud_stride_b, int cloud_stride_c, int skip, int Cp, const float* bc,
                                  int Cb, int B, const float* ctr, int npoint, const int32_t* seg_off, const int32_t* row_seg,
                                  const int32_t* row_src, const float* row_w, int M_max, const int* M_dev, const float* W, int ldw,
-                                 float* bcbias_ws, float* Y, float* stats, void* stream);
+                                 float* bcbias_ws, float* Y, float* stats, const gaddpg_bn_tail* tail, void* stream);
 /* backward of the same layer: dW (may be NULL), dbc (B,Cb) (may be NULL); dY1 is never materialised.
  * ws: (GADDPG_STAT_SLOTS*64*16 + B*64*(1 + ceil(M_max/B/256))) floats */
 GADDPG_API int gaddpg_sa1_l1_bwd(const float* cloud, long long cloud_stride_b, int cloud_stride_c, int skip, int Cp, const float* bc,
@@ -237,7 +264,7 @@ GADDPG_API int gaddpg_pool_fwd(const float* Y, int C, const float* scale, const 
                                int S, float* out, int32_t* arg, void* stream);
 GADDPG_API int gaddpg_pool_bwd(const float* dOut, int ld_dout, const float* out, const int32_t* arg, const float* Y, int C,
                                const int32_t* row_seg, int fixed_len, int M_max, const int* M_dev, const float* mean,
-                               const float* rstd, float* D, float* stats, void* stream);
+                               const float* rstd, float* D, float* stats, const gaddpg_bn_tail* tail, void* stream);
 /* Sparse form of the max-pool backward for levels whose layer-3 operand is consumed as GADDPG_OP_BNBWD_POOL:
  * E[s][c] = out[s][c] > 0 ? dOut[s][c] : 0, the arg-max bit mask (M_max, C/32) (zeroed here, then one bit per (s, c)) and
  * the BatchNorm-backward sums (sum D, sum D*xhat) of the implied dense D, gathered from the S*C arg-max elements of Y only
@@ -245,7 +272,7 @@ GADDPG_API int gaddpg_pool_bwd(const float* dOut, int ld_dout, const float* out,
  * Replaces the autograd backward of F.max_pool2d(kernel=[1,nsample]) + ReLU in upstream _PointnetSAModuleBase.forward. */
 GADDPG_API int gaddpg_pool_bwd_sparse(const float* dOut, int ldo, const float* out, const int32_t* arg, const float* Y, int C,
                                       int S, const float* mean, const float* rstd, float* E, uint32_t* mask, int M_max,
-                                      float* stats, void* stream);
+                                      float* stats, const gaddpg_bn_tail* tail, void* stream);
 /* Second half of the fused max-pool (see gaddpg_nt_problem.pool_keys): out[s][c] = relu(v*scale[c]+shift[c]) with
  * v = the extreme value held by keys[s][c] (max for gamma[c] >= 0, min otherwise), arg[s][c] = the row attaining it;
  * every key is reset to 0 (= empty) for the next pass.  keys must be zero-initialised once by the caller. */
@@ -355,7 +382,8 @@ GADDPG_API int gaddpg_wprep_batched(const long long* jobs_dev, int njobs, void* 
 GADDPG_API int gaddpg_optim_multi(const void* jobs_dev, int njobs, int total_chunks, void* stream);
 /* stand-alone EPI_DMASK: D = dX*[Yprev*psc+psh > 0] plus its BN-backward sums (for gradients arriving from autograd) */
 GADDPG_API int gaddpg_dmask_stats(const float* dX, int ldx, const float* Yprev, int C, int M, const float* psc, const float* psh,
-                                  const float* pmean, const float* prstd, float* D, float* stats, void* stream);
+                                  const float* pmean, const float* prstd, float* D, float* stats, const gaddpg_bn_tail* tail,
+                                  void* stream);
 GADDPG_API int gaddpg_f64_to_f32(const double* src, float* dst, long long n, void* stream);
 
 /* ---- device-resident replay buffer -------------------------------------------------------

@@ -132,10 +132,10 @@ if "pool" in which or which == "nt,tn":
     lib.gaddpg_pool_fwd(dp(Y2), C, dp(b2.scale), dp(b2.shift), dp(seg_off), 0, S, dp(outp), dp(arg), 0)
     dOut = torch.randn(S, C + 4, device=dev)
     Dd = torch.zeros(Mmax, C, device=dev); E = torch.zeros(S, C, device=dev); mask = torch.full((Mmax, C // 32), -1, dtype=torch.int32, device=dev)
-    lib.gaddpg_pool_bwd(dp(dOut), C + 4, dp(outp), dp(arg), dp(Y2), C, dp(row_seg), 0, Mmax, Mdev.data_ptr(), dp(b2.mean), dp(b2.rstd), dp(Dd), dp(ws.stats), 0)
+    lib.gaddpg_pool_bwd(dp(dOut), C + 4, dp(outp), dp(arg), dp(Y2), C, dp(row_seg), 0, Mmax, Mdev.data_ptr(), dp(b2.mean), dp(b2.rstd), dp(Dd), dp(ws.stats), None, 0)
     torch.cuda.synchronize()
     st_dense = ws.stats[: STAT_SLOTS * 2 * C].view(STAT_SLOTS, 2, C).double().sum(0).clone()
-    lib.gaddpg_pool_bwd_sparse(dp(dOut), C + 4, dp(outp), dp(arg), dp(Y2), C, S, dp(b2.mean), dp(b2.rstd), dp(E), dp(mask), Mmax, dp(ws.stats), 0)
+    lib.gaddpg_pool_bwd_sparse(dp(dOut), C + 4, dp(outp), dp(arg), dp(Y2), C, S, dp(b2.mean), dp(b2.rstd), dp(E), dp(mask), Mmax, dp(ws.stats), None, 0)
     torch.cuda.synchronize()
     st_sparse = ws.stats[: STAT_SLOTS * 2 * C].view(STAT_SLOTS, 2, C).double().sum(0).clone()
     Dre = torch.zeros(Mmax, C, device=dev)

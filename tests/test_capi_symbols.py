@@ -19,7 +19,7 @@ def test_every_declared_symbol_is_exported():
     lib = capi.lib.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert capi.lib.gaddpg_version() == 3
+    assert capi.lib.gaddpg_version() == 4
     assert b"sm_100a" in capi.lib.gaddpg_build_info()
 
 
