@@ -356,21 +356,70 @@ __global__ void __launch_bounds__(KC_NT_THREADS, 1) tc_nt_kc_kernel(const NTProb
 // =====================================================================================================
 constexpr int TN_R = 32;  // rows (reduction index) per stage = 4 MMA K-steps of 8
 
-template <int BKT>
+// cp.async helpers of the TN producers (LDGSTS: global -> shared without a register stop; src-size 0 zero-fills)
+__device__ __forceinline__ void tn_cp16(unsigned char* dst, const void* src, bool valid) {
+  const int n = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(n) : "memory");
+}
+// 16-byte copy of which only the first `bytes` (0..16) are read; the rest of the destination is zero-filled
+__device__ __forceinline__ void tn_cp16n(unsigned char* dst, const void* src, int bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tn_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tn_cp_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// Shared memory: NSTAGE operand stages in the UMMA layout (hi / lo of P and Q) + a RAW ring of D units.  A unit is half a
+// chunk (16 rows): the raw rows of P (X, and Y / row weights / arg-max bits for the BatchNorm-backward forms) and Q exactly as
+// they lie in global memory, landed by cp.async — so the bytes in flight per SM are bounded by shared memory (D units), not by
+// the producers' registers.  Every thread copies, and later transforms, only its own 16-byte pieces: no barrier between the
+// copy and the transform, just cp.async.wait_group.
+// 16 producer warps (the cp.async staging leaves them at <= 96 registers): four per scheduler instead of two — their streams are
+// chains of LDS -> FMA -> STS with little ILP, so the transform rate scales with the warps in flight.
+constexpr int TN_PW = 16;
+constexpr int TN_THREADS = (TN_PW + 1 + 4) * 32;
+
+template <int BKT, int PMODE, bool P64>
 struct TnLayout {
-  static constexpr int NSTAGE = (BKT == 128) ? 3 : 4;
+  static_assert(!(P64 && BKT != 64), "the 64-channel P mapping is built for BKT = 64");
+  static constexpr bool PBWD = (PMODE == OP_BNBWD || PMODE == OP_BNBWD_POOL);
+  static constexpr bool POOL = (PMODE == OP_BNBWD_POOL);
+  static constexpr int NSTAGE = 2;
   static constexpr uint32_t P_BYTES = 4 * TN_R * 128;            // 128 channels = 4 blocks of [32 rows x 128 B]
   static constexpr uint32_t Q_BYTES = (BKT / 32) * TN_R * 128;
   static constexpr uint32_t STAGE_BYTES = 2 * P_BYTES + 2 * Q_BYTES;
-  static constexpr uint32_t OFF_BARS = NSTAGE * STAGE_BYTES;
+  static constexpr int NT = TN_PW * 32;                          // producer threads (512)
+  // unit = what one producer pass covers: P64: a whole chunk (32 rows x 16 float4 of P, 32 x 16 of Q); otherwise half a chunk of P
+  // (16 rows x 32 float4) plus, for BKT = 64, the whole chunk of Q (32 rows x 16 float4) in the first half only, for BKT = 128
+  // the same 16 rows of Q (16 x 32 float4).  One float4 of P (and of Y) and at most one of Q per thread and unit.
+  static constexpr int HPC = P64 ? 1 : 2;                        // units per chunk
+  static constexpr int UROWS = TN_R / HPC;                       // P rows per unit
+  static constexpr int QEVERY = (!P64 && BKT == 64) ? 2 : 1;     // Q is issued in units with h % QEVERY == 0 ...
+  static constexpr int QROWS = NT / (BKT / 4);                   // ... and covers this many rows (32 or 16)
+  static constexpr uint32_t RAW_PX = NT * 16, RAW_PY = PBWD ? RAW_PX : 0, RAW_Q = NT * 16;
+  // row weights / arg-max bit masks of a unit's rows: copied once per WARP (4-byte cp.async serialise 32-fold in the shared
+  // memory pipe: measured), 16 bytes per lane, read back by every lane after a __syncwarp
+  static constexpr uint32_t RAW_W = PBWD ? TN_PW * UROWS * 4 : 0, RAW_M = POOL ? TN_PW * UROWS * 16 : 0;
+  static constexpr uint32_t OFF_PY = RAW_PX, OFF_Q = OFF_PY + RAW_PY, OFF_W = OFF_Q + RAW_Q, OFF_M = OFF_W + RAW_W;
+  static constexpr uint32_t UNIT_BYTES = OFF_M + RAW_M;
+  static constexpr uint32_t OFF_RAW = NSTAGE * STAGE_BYTES;
+  static constexpr uint32_t TAIL_BYTES = 256 + NT * 16;          // barriers + bias combine
+  static constexpr int D_FIT = (int)((227u * 1024u - 1024u - OFF_RAW - TAIL_BYTES) / UNIT_BYTES);
+  static constexpr int D = D_FIT > 8 ? 8 : D_FIT;                // units in flight
+  static constexpr uint32_t OFF_BARS = OFF_RAW + D * UNIT_BYTES;
   static constexpr uint32_t OFF_BIAS = OFF_BARS + 256;
-  static constexpr uint32_t TOTAL = OFF_BIAS + KC_PW * 128 * 4;
+  static constexpr uint32_t TOTAL = OFF_BIAS + NT * 16;
+  static_assert(D >= 3, "raw ring too shallow");
 };
 
-template <int BKT, int PMODE, int QMODE>
-__global__ void __launch_bounds__(KC_NT_THREADS, 1) tc_tn_kernel(const TNProblem p, float* __restrict__ partial,
+// P64: the P operand has <= 64 channels (dW of a 64-wide layer): its producers cover 32 rows x 16 float4 per pass instead of
+// 16 rows x 32 float4 with half of the threads idle; P blocks 2, 3 of every stage stay zero (zeroed once).
+template <int BKT, int PMODE, int QMODE, bool P64>
+__global__ void __launch_bounds__(TN_THREADS, 1) tc_tn_kernel(const TNProblem p, float* __restrict__ partial,
                                                                float* __restrict__ partial_bias, int splits, int tiles_k) {
-  using L = TnLayout<BKT>;
+  using L = TnLayout<BKT, PMODE, P64>;
   constexpr int NSTAGE = L::NSTAGE;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -394,27 +443,34 @@ __global__ void __launch_bounds__(KC_NT_THREADS, 1) tc_tn_kernel(const TNProblem
 
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
-      mbar_init(&full[s], KC_PW * 32);
+      mbar_init(&full[s], TN_PW * 32);
       mbar_init(&empty[s], 1);
     }
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
-  if (warp == KC_PW) tmem_alloc(tmem_slot, tmem_cols);
+  if (warp == TN_PW) tmem_alloc(tmem_slot, tmem_cols);
+  if (P64) {  // P blocks 2, 3 (channels 64..127) of every stage: zero, never written again
+    for (int i = tid; i < NSTAGE * 2 * (int)(L::P_BYTES / 2) / 16; i += TN_THREADS) {
+      const int s = i / (2 * (int)(L::P_BYTES / 2) / 16), r = i % (2 * (int)(L::P_BYTES / 2) / 16);
+      const int hl = r / ((int)(L::P_BYTES / 2) / 16), o = r % ((int)(L::P_BYTES / 2) / 16);
+      *reinterpret_cast<float4*>(smem + (uint32_t)s * L::STAGE_BYTES + hl * L::P_BYTES + L::P_BYTES / 2 + o * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    fence_proxy_async();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < KC_PW) {
+  if (warp < TN_PW) {
     // ===================== producers =====================
-    constexpr bool PBWD = (PMODE == OP_BNBWD || PMODE == OP_BNBWD_POOL);
-    constexpr int HPC = PBWD ? 2 : 1;  // pipeline units per chunk
-    constexpr int PROWS = KC_PW;                      // rows the producer threads cover per P iteration (32 float4 per row)
-    constexpr int PU = (TN_R / PROWS) / HPC;          // P row-iterations per unit
-    constexpr int QROWS = (KC_PW * 32) / (BKT / 4);   // rows the producer threads cover per Q iteration (8 or 16)
-    constexpr int QU = (TN_R / QROWS) / HPC;          // Q row-iterations per unit
-    const int pq = tid & 31, pr = tid >> 5;           // P: float4 column, first row
+    constexpr bool PBWD = L::PBWD, POOL = L::POOL;
+    constexpr int HPC = L::HPC, D = L::D, QEVERY = L::QEVERY, QROWS = L::QROWS, PU = 1;
+    constexpr int PQ4 = P64 ? 16 : 32;                // float4 per P row
+    constexpr int PROWS = L::NT / PQ4;                // rows the producer threads cover per P pass (32 or 16)
+    static_assert(PROWS == L::UROWS && QROWS * HPC == TN_R * QEVERY, "producer mapping");
+    const int pq = tid % PQ4, pr = tid / PQ4;         // P: float4 column, first row
     const int qq = tid % (BKT / 4), qr = tid / (BKT / 4);
     const int pcol = n0 + (pq << 2), qcol = k0 + (qq << 2);
     const bool pok = pcol < N, qok = qcol < K;
@@ -424,14 +480,12 @@ __global__ void __launch_bounds__(KC_NT_THREADS, 1) tc_tn_kernel(const TNProblem
     qc.load(p.Q, qcol, qok);
     const uint32_t poff_blk = (uint32_t)(pq >> 3) * (TN_R * 128), qoff_blk = (uint32_t)(qq >> 3) * (TN_R * 128);
     float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
-    struct Regs {
-      float4 x[PU], y[PU];
-      float w[PU];
-      uint32_t m[PU];
-      float4 q[QU];
-    };
     const int total_units = my_chunks * HPC;
-    int segn[PU];  // BNBWD_POOL: segments of the rows of the NEXT unit to be issued
+    unsigned char* raw = smem + L::OFF_RAW;
+    const uint32_t my16 = (uint32_t)tid * 16;
+    constexpr int UROWS = L::UROWS;
+    const int mwords = POOL ? (p.P.ldx >> 5) : 0;     // arg-max mask words per row (<= 4)
+    int segn[PU];  // BNBWD_POOL: segment of the row of the NEXT unit to be issued (dependent load, one unit ahead)
     auto prefetch_seg = [&](int u) {
       const int ci = u / HPC, h = u % HPC;
       const int rowc = (split + ci * splits) * TN_R;
@@ -441,70 +495,81 @@ __global__ void __launch_bounds__(KC_NT_THREADS, 1) tc_tn_kernel(const TNProblem
         segn[k] = (u < total_units && row < M && pok) ? p.P.pseg[row] : 0;
       }
     };
-    auto issue = [&](Regs& R, int u) {
+    auto issue = [&](int u) {
       const int ci = u / HPC, h = u % HPC;
       const int rowc = (split + ci * splits) * TN_R;
+      unsigned char* slot = raw + (uint32_t)(u % D) * L::UNIT_BYTES;
 #pragma unroll
       for (int k = 0; k < PU; ++k) {
         const int row = rowc + pr + PROWS * (h * PU + k);
-        R.x[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        R.y[k] = R.x[k];
-        R.w[k] = 1.f;
-        if (row < M && pok) {
-          if (PMODE != OP_BNBWD_POOL) R.x[k] = ldg4(p.P.X + (long long)row * p.P.ldx + pcol);
-          if (PBWD) {
-            R.y[k] = ldg4(p.P.Y + (long long)row * p.P.ldy + pcol);
-            if (p.P.rw) R.w[k] = p.P.rw[row];
-          }
+        const bool ok = row < M && pok;
+        const long long r = ok ? row : 0;
+        const int c = pok ? pcol : 0;
+        if (!POOL) {
+          tn_cp16(slot + k * L::NT * 16 + my16, p.P.X + r * p.P.ldx + c, ok);
+        } else {  // max-pool gradient rebuilt from E (S x C, L2 resident) + the arg-max bit mask (see tc_gemm.cu)
+          tn_cp16(slot + k * L::NT * 16 + my16, p.P.X + (long long)segn[k] * p.P.ldx + c, ok);
+        }
+        if (PBWD) tn_cp16(slot + L::OFF_PY + k * L::NT * 16 + my16, p.P.Y + r * p.P.ldy + c, ok);
+      }
+      {  // per-warp copies of the unit's row weights (16 rows x 4 B) and arg-max masks (16 rows x mwords x 4 B)
+        const int R0 = rowc + UROWS * h;
+        if (PBWD && p.P.rw && lane < UROWS / 4) {
+          int nb = (M - (R0 + 4 * lane)) * 4;
+          nb = nb < 0 ? 0 : (nb > 16 ? 16 : nb);
+          tn_cp16n(slot + L::OFF_W + warp * (UROWS * 4) + lane * 16, p.P.rw + (nb > 0 ? R0 + 4 * lane : 0), nb);
+        }
+        if (POOL && lane < (UROWS * mwords) / 4) {
+          int nb = (M - R0) * mwords * 4 - 16 * lane;
+          nb = nb < 0 ? 0 : (nb > 16 ? 16 : nb);
+          tn_cp16n(slot + L::OFF_M + warp * (UROWS * 16) + lane * 16, p.P.pmask + (nb > 0 ? (long long)R0 * mwords + 4 * lane : 0), nb);
         }
       }
-      if (PMODE == OP_BNBWD_POOL) {  // max-pool gradient rebuilt from E + the arg-max bit mask (see tc_gemm.cu)
-#pragma unroll
-        for (int k = 0; k < PU; ++k) {
-          const int row = rowc + pr + PROWS * (h * PU + k);
-          R.m[k] = 0u;
-          if (row < M && pok) {
-            R.x[k] = ldg4(p.P.X + (long long)segn[k] * p.P.ldx + pcol);
-            R.m[k] = p.P.pmask[(long long)row * (p.P.ldx >> 5) + (pcol >> 5)];
-          }
-        }
-        prefetch_seg(u + 1);
-      }
-#pragma unroll
-      for (int k = 0; k < QU; ++k) {
-        const int row = rowc + qr + QROWS * (h * QU + k);
-        R.q[k] = (row < M && qok) ? ldg4(p.Q.X + (long long)row * p.Q.ldx + qcol) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (POOL) prefetch_seg(u + 1);
+      if (h % QEVERY == 0) {
+        const int row = rowc + qr + QROWS * (h / QEVERY);
+        const bool ok = row < M && qok;
+        tn_cp16(slot + L::OFF_Q + my16, p.Q.X + (long long)(ok ? row : 0) * p.Q.ldx + (qok ? qcol : 0), ok);
       }
     };
-    auto process = [&](const Regs& R, int u) {
+    auto process = [&](int u) {
       const int ci = u / HPC, h = u % HPC;
       const int s = ci % NSTAGE;
       const int rowc = (split + ci * splits) * TN_R;
+      const unsigned char* slot = raw + (uint32_t)(u % D) * L::UNIT_BYTES;
       if (h == 0) mbar_wait(&empty[s], ((uint32_t)(ci / NSTAGE) & 1u) ^ 1u);
       unsigned char* st = smem + (uint32_t)s * L::STAGE_BYTES;
+      if (PBWD) __syncwarp();   // the warp's shared row-weight / mask copies are visible to all of its lanes
 #pragma unroll
       for (int k = 0; k < PU; ++k) {
         const int r = pr + PROWS * (h * PU + k);
-        float4 x = R.x[k];
-        if (PMODE == OP_BNBWD_POOL) {
-          const uint32_t bits = R.m[k] >> (pcol & 31);
+        float4 x = *reinterpret_cast<const float4*>(slot + k * L::NT * 16 + my16);
+        float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+        float w = 1.f;
+        if (PBWD) {
+          y = *reinterpret_cast<const float4*>(slot + L::OFF_PY + k * L::NT * 16 + my16);
+          if (p.P.rw) w = *reinterpret_cast<const float*>(slot + L::OFF_W + warp * (UROWS * 4) + (r - UROWS * h) * 4);
+        }
+        if (POOL) {
+          const uint32_t bits =
+              *reinterpret_cast<const uint32_t*>(slot + L::OFF_M + warp * (UROWS * 16) + ((r - UROWS * h) * mwords + (pcol >> 5)) * 4) >> (pcol & 31);
           x.x = (bits & 1u) ? x.x : 0.f;
           x.y = (bits & 2u) ? x.y : 0.f;
           x.z = (bits & 4u) ? x.z : 0.f;
           x.w = (bits & 8u) ? x.w : 0.f;
         }
-        float4 v = (rowc + r < M && pok) ? pc.apply(x, R.y[k], R.w[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 v = (rowc + r < M && pok) ? pc.apply(x, y, w) : make_float4(0.f, 0.f, 0.f, 0.f);
         bsum.x += v.x;
         bsum.y += v.y;
         bsum.z += v.z;
         bsum.w += v.w;
         split_store(st, st + L::P_BYTES, poff_blk + blk_off_mn(r, pq & 7), v);
       }
-#pragma unroll
-      for (int k = 0; k < QU; ++k) {
-        const int r = qr + QROWS * (h * QU + k);
+      if (h % QEVERY == 0) {
+        const int r = qr + QROWS * (h / QEVERY);
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 v = (rowc + r < M && qok) ? qc.apply(R.q[k], z, 1.f) : z;
+        const float4 qv = *reinterpret_cast<const float4*>(slot + L::OFF_Q + my16);
+        float4 v = (rowc + r < M && qok) ? qc.apply(qv, z, 1.f) : z;
         split_store(st + 2 * L::P_BYTES, st + 2 * L::P_BYTES + L::Q_BYTES, qoff_blk + blk_off_mn(r, qq & 7), v);
       }
       if (h == HPC - 1) {
@@ -512,18 +577,21 @@ __global__ void __launch_bounds__(KC_NT_THREADS, 1) tc_tn_kernel(const TNProblem
         mbar_arrive(&full[s]);
       }
     };
-    Regs RA, RB;
-    if (PMODE == OP_BNBWD_POOL) prefetch_seg(0);
-    if (total_units > 0) issue(RA, 0);
-#pragma unroll 1
-    for (int u = 0; u < total_units; u += 2) {
-      if (u + 1 < total_units) issue(RB, u + 1);
-      process(RA, u);
-      if (u + 2 < total_units) issue(RA, u + 2);
-      if (u + 1 < total_units) process(RB, u + 1);
+    if (POOL) prefetch_seg(0);
+#pragma unroll
+    for (int u = 0; u < D - 1; ++u) {   // fill the ring: D - 1 units in flight before the first transform
+      if (u < total_units) issue(u);
+      tn_cp_commit();
     }
-    if (want_bias) *reinterpret_cast<float4*>(bias_comb + pr * 128 + (pq << 2)) = bsum;
-  } else if (warp == KC_PW) {
+#pragma unroll 1
+    for (int u = 0; u < total_units; ++u) {
+      if (u + D - 1 < total_units) issue(u + D - 1);
+      tn_cp_commit();                   // (possibly empty) group: exactly one per iteration keeps the wait count static
+      tn_cp_wait<D - 1>();              // this thread's copies of unit u have landed
+      process(u);
+    }
+    if (want_bias) *reinterpret_cast<float4*>(bias_comb + pr * (PQ4 * 4) + (pq << 2)) = bsum;   // [PROWS row groups][channels]
+  } else if (warp == TN_PW) {
     // ===================== MMA issuer =====================
     if (lane == 0 && my_chunks > 0) {
       // both operands MN-major (bits 15, 16): the reduction index (rows) is the MMA K dimension
@@ -579,11 +647,14 @@ __global__ void __launch_bounds__(KC_NT_THREADS, 1) tc_tn_kernel(const TNProblem
   }
   tc_fence_before();
   __syncthreads();
-  if (want_bias && tid < 128 && n0 + tid < N)
-    partial_bias[(long long)split * N + n0 + tid] =
-        ((bias_comb[tid] + bias_comb[128 + tid]) + (bias_comb[256 + tid] + bias_comb[384 + tid])) +
-        ((bias_comb[512 + tid] + bias_comb[640 + tid]) + (bias_comb[768 + tid] + bias_comb[896 + tid]));
-  if (warp == KC_PW) {
+  if (want_bias && tid < (P64 ? 64 : 128) && n0 + tid < N) {   // row groups folded in group order (deterministic)
+    constexpr int NG = TN_PW * 32 / (P64 ? 16 : 32), W = P64 ? 64 : 128;
+    float b = 0.f;
+#pragma unroll 8
+    for (int g = 0; g < NG; ++g) b += bias_comb[g * W + tid];
+    partial_bias[(long long)split * N + n0 + tid] = b;
+  }
+  if (warp == TN_PW) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
@@ -659,11 +730,13 @@ int gaddpg_tc_tn_impl(const TNProblem* p, int pmode, int qmode, float* ws, size_
   dim3 grid(tiles, splits);
   cudaStream_t st = (cudaStream_t)stream;
 #define TN_LAUNCH(BK_, PM, QM)                                                                                 \
+  if (p->N <= 64 && BK_ == 64) TN_LAUNCH_(64, PM, QM, true) else TN_LAUNCH_(BK_, PM, QM, false)
+#define TN_LAUNCH_(BK_, PM, QM, P64_)                                                                          \
   {                                                                                                            \
-    auto kern = tc_tn_kernel<BK_, PM, QM>;                                                                     \
-    const size_t smem = TnLayout<BK_>::TOTAL + 1024;                                                           \
+    auto kern = tc_tn_kernel<BK_, PM, QM, P64_>;                                                               \
+    const size_t smem = TnLayout<BK_, PM, P64_>::TOTAL + 1024;                                                 \
     GADDPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
-    kern<<<grid, KC_NT_THREADS, smem, st>>>(*p, ws, ws_bias, splits, tiles_k);                                    \
+    kern<<<grid, TN_THREADS, smem, st>>>(*p, ws, ws_bias, splits, tiles_k);                                    \
     GADDPG_CHECK_LAUNCH("tc_tn_kernel");                                                                       \
     return GADDPG_OK;                                                                                          \
   }
@@ -678,6 +751,7 @@ int gaddpg_tc_tn_impl(const TNProblem* p, int pmode, int qmode, float* ws, size_
   TN_CASE(OP_BNBWD_POOL, OP_BNRELU)
 #undef TN_CASE
 #undef TN_LAUNCH
+#undef TN_LAUNCH_
   gaddpg_set_error("tc_tn: unsupported mode pair (%d,%d)", pmode, qmode);
   return GADDPG_ERR_UNSUPPORTED;
 }
