@@ -195,6 +195,10 @@ class AgentB200:
         # stream-level overlap inside a step (identical arithmetic, see _phase1): a second encoder chain and the
         # weight-gradient products run on side streams; ``overlap = False`` issues everything on one stream
         self.overlap = True
+        # F4 (policy encoder on the state cloud) beside the critic backward instead of beside the target chain (see _phase1_critic);
+        # GADDPG_F4_LATE=0/1 for A/B
+        # measured at cfg2 (A/B/A/B in one session): 218.3 / 219.0 steps/s late vs 222.1 / 222.4 early -> off
+        self.f4_late = os.environ.get("GADDPG_F4_LATE", "0") == "1"
         # geometry is launched before the small-field staging for device-resident batches (+1 % steps/s: the GPU no longer
         # idles behind ~100 us of host work); for host batches that ordering measured 0.17 ms SLOWER per step (5.59 vs
         # 5.42 ms, A/B in one process), so they keep transfers -> staging -> geometry
@@ -237,6 +241,10 @@ class AgentB200:
         self._shape = None
         self._graphs = {}
         self.use_graph = True
+        self._in_outer = False
+        # phases 1-3 of an update (and, in a sharded run with one all-reduce per phase, the two NCCL calls between them) as ONE
+        # CUDA graph per (step parity, target-copy step, schedule index) instead of five; GADDPG_WHOLE_GRAPH=0/1 for A/B
+        self.whole_graph = os.environ.get("GADDPG_WHOLE_GRAPH", "1") == "1"
         self._built = True
         self.policy.sample = self.policy_sample   # reference call style: agent.policy.sample(feat) (networks.py:353-371)
 
@@ -538,10 +546,20 @@ class AgentB200:
             e.record()
             self.step_start_events.append(e)
 
-    def _run(self, key, fn):
-        """Run ``fn`` eagerly the first time for a key, then capture and replay it as a CUDA graph."""
-        if not self.use_graph:
+    def _run(self, key, fn, outer=False):
+        """Run ``fn`` eagerly the first time for a key, then capture and replay it as a CUDA graph.  ``outer``: ``fn`` is a
+        whole sequence whose pieces call ``_run`` themselves — they run inline, so the sequence becomes ONE graph."""
+        if not self.use_graph or self._in_outer:
             return fn()
+        if outer:
+            inner = fn
+
+            def fn():
+                self._in_outer = True
+                try:
+                    inner()
+                finally:
+                    self._in_outer = False
         g = self._graphs.get(key)
         if g is None:
             fn()  # eager warm-up doubles as this call's execution
@@ -860,9 +878,14 @@ class DDPGB200(AgentB200):
         self.out.zero_()
         f1 = engine.encoder_forward(ws, self.ef_v, self.geom_s, self.cloud, self.skip, self.Cp_value, self._bc(v.action, 0), self.ctx_v1,
                                     time=v.time, time_offset=0.0, train=True, bn_stage=self.bnst[1])              # F1
+        if not (self.overlap and self.f4_late):
+            self._f4(ws)
+        engine.critic_forward(self.cf, f1, self.cc1, B)
+
+    def _f4(self, ws):
+        v = self.v
         engine.encoder_forward(ws, self.ef_p, self.geom_s, self.cloud, self.skip, self.Cp_policy, None, self.ctx_p,
                                time=v.time, time_offset=0.0, train=True, bn_stage=self.bnst[4])                   # F4
-        engine.critic_forward(self.cf, f1, self.cc1, B)
 
     def _phase1_target(self, ws):
         B, v, s = self.B, self.v, current_stream()
@@ -882,8 +905,16 @@ class DDPGB200(AgentB200):
         B, ws, v, s = self.B, self.ws, self.v, current_stream()
         qa, f1 = self.cc1.qa, self.ctx_v1.feat
         dw = self.side_dw if self.overlap else None
+        late = self.overlap and self.f4_late
         if part != "b":
-            for k in (1, 3, 2, 4):
+            if late:
+                # F4 (policy encoder on the state cloud; consumed in phase 2) beside the critic backward: the upper half of
+                # B1 is a chain of small launches that leaves most SMs idle, while phase 1 already has two chains in flight
+                side = self.side_enc
+                side.fork()
+                with torch.cuda.stream(side.stream):
+                    self._f4(side.ws)
+            for k in ((1, 3) if late else (1, 3, 2, 4)):
                 self.bnst[k].apply()
             lib.gaddpg_critic_loss(dp(qa), QA_LD, QA_Q2, QA_AUX, dp(self.y), dp(v.perturb_flag), dp(v.ret), dp(v.goal),
                                    1 if self.critic_aux else 0, B, 1.0, dp(self.cc1.dqa), self.out.data_ptr() + 4 * O_CRITIC, s)
@@ -902,6 +933,10 @@ class DDPGB200(AgentB200):
         else:
             with engine.side_dw(dw):
                 engine.encoder_backward(ws, self.ef_v, self.ctx_v1, self.sc, want_dw=True, want_dbc=False, accumulate=0, part="sa1")
+        if late and part != "b":
+            self.side_enc.join()
+            for k in (2, 4):   # policy encoder's running statistics in the reference's order (F2, F4)
+                self.bnst[k].apply()
 
     def _phase1(self, sig):
         if self.overlap:
@@ -981,6 +1016,14 @@ class DDPGB200(AgentB200):
         hard = (self.update_step % self.target_update_interval) == 0
         sig = (self._mix_idx(),)
         self._set_dyn(("critic", "venc", "policy") + (("enc",) if self.train_feature else ()))
+        if self.whole_graph and not (self._sharded() and self.split_reduce):
+            self._run(("step", even, hard) + sig, lambda: self._step_body(even, hard, sig), outer=True)
+        else:
+            self._step_body(even, hard, sig)
+        self.update_step += 1
+        return self._finish(defer)
+
+    def _step_body(self, even, hard, sig):
         self._phase1(sig)
         self._reduce_late(self.gpool_c, self.ef_v)
         if self._sharded() and self.split_reduce:
@@ -991,8 +1034,6 @@ class DDPGB200(AgentB200):
             self._run(("p2", even) + sig, lambda: self._phase2(even))
         self._reduce_late(self.gpool_a, self.ef_p)
         self._run(("p3", hard) + sig, lambda: self._phase3(hard))
-        self.update_step += 1
-        return self._finish(defer)
 
 
 class BCB200(AgentB200):

@@ -31,6 +31,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   } while (!ok);
 }
+// the same wait for a role that has nothing to do for a long time (the TN epilogue waits for the whole row loop): back off between
+// polls so that the spinning warps do not take issue slots from the producers that share their schedulers
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned ns) {
+  uint32_t ok = 0;
+  const uint32_t addr = smem_u32(bar);
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) break;
+    __nanosleep(ns);
+  }
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

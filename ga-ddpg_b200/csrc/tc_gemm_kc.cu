@@ -626,7 +626,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) tc_tn_kernel(const TNProblem p,
     const int n = n0 + q * 32 + lane;
     float* out = partial + ((long long)split * N + n) * K + k0;
     if (my_chunks > 0) {
-      mbar_wait(acc_full, 0);
+      mbar_wait_sleep(acc_full, 0, 500);
       tc_fence_after();
     }
 #pragma unroll
