@@ -183,7 +183,7 @@ def main():
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--reduce-mode", default="split", choices=["split", "single"],
+    ap.add_argument("--reduce-mode", default="single", choices=["split", "single"],
                     help="N>1: 'split' all-reduces everything but SA1's gradients asynchronously behind the SA1 backward (2 ranges per "
                          "phase, one hidden); 'single' is one blocking all-reduce per optimiser phase")
     ap.add_argument("--no-extra", action="store_true", help="skip the e2e_f64 and dense-worst-case legs")
