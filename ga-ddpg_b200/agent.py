@@ -19,6 +19,7 @@ Step structure (ddpg.py:146-185; F = encoder forward, B = backward):
   phase 3   Adam(policy), Adam(policy encoder), Polyak targets, statistics
 Each phase is captured once per step parity into a CUDA graph and replayed.
 """
+import contextlib
 import math
 import os
 from types import SimpleNamespace as NS
@@ -235,6 +236,10 @@ class AgentB200:
         self._pending = [None] * RING
         self._optjobs = {}
         self._h2d_stream = None
+        self._prep_pending = False
+        # pipelined callers (defer=True) that pass dicts of DEVICE tensors: True = those tensors are complete when they are handed
+        # over (e.g. pre-generated batches), so their staging copies + geometry may run on the prep streams beside the running step
+        self.static_device_batches = False
         self._pending_reduce = []
         self.step_start_events = self.step_end_events = None    # feed.FeedLoop installs lists here to measure the GPU idle gap between steps
         # sharded runs: False = ONE all-reduce per optimiser phase over its contiguous gradient range (NCCL: captured inside the
@@ -274,8 +279,11 @@ class AgentB200:
         N = Np - skip
         self._shape = (B, C, Np)
         self.B, self.skip, self.N = B, skip, N
-        self.cloud = torch.zeros(B, C, Np, dtype=torch.float32, device=dev)
-        self.next_cloud = torch.zeros(B, C, Np, dtype=torch.float32, device=dev)
+        # The step's INPUTS (clouds, small fields, geometry) exist once per staging slot: a pipelined caller prepares step i+1 —
+        # transfers / gather AND the xyz-only geometry kernels — on the prep streams while step i still computes from the
+        # other slot (prepare_data(prefetch=True)).  ``self.cloud`` etc. are properties of the current slot.
+        self._cloud_s = [torch.zeros(B, C, Np, dtype=torch.float32, device=dev) for _ in range(RING)]
+        self._next_cloud_s = [torch.zeros(B, C, Np, dtype=torch.float32, device=dev) for _ in range(RING)]
         seg = lambda n: (n + 3) // 4 * 4  # noqa: E731
         names = [("action", 6), ("expert_action", 6), ("goal", 7), ("noise_u", 6), ("reward", 1), ("ret", 1), ("done", 1),
                  ("time", 1), ("expert_flag", 1), ("perturb_flag", 1)]
@@ -283,17 +291,17 @@ class AgentB200:
         for n, w in names:
             self._vec_off[n] = (total, w)
             total += seg(B * w)
-        self.vec = torch.zeros(total, dtype=torch.float32, device=dev)
+        self._vec_s = [torch.zeros(total, dtype=torch.float32, device=dev) for _ in range(RING)]
         self.vec_host = [torch.zeros(total, dtype=torch.float32).pin_memory() for _ in range(RING)]
         self._cloud_shape = (B, C, Np)
         self._cloud_host = [None] * RING        # pinned cloud staging: allocated on first use (host-fed batches only)
         self._next_cloud_host = [None] * RING
-        self._cloud_dev = [None] * RING         # device staging of the prefetching (pipelined) host path
-        self.v = NS(**{n: self.vec[o: o + B * w].view(B, w) if w > 1 else self.vec[o: o + B] for n, (o, w) in self._vec_off.items()})
+        self._v_s = [NS(**{n: vec[o: o + B * w].view(B, w) if w > 1 else vec[o: o + B] for n, (o, w) in self._vec_off.items()})
+                     for vec in self._vec_s]
         self.vh = [NS(**{n: vh[o: o + B * w].view(B, w) if w > 1 else vh[o: o + B] for n, (o, w) in self._vec_off.items()})
                    for vh in self.vec_host]
-        self.geom_s = engine.Geometry(B, N, dev)
-        self.geom_n = engine.Geometry(B, N, dev)
+        self._geom_s_s = [engine.Geometry(B, N, dev) for _ in range(RING)]
+        self._geom_n_s = [engine.Geometry(B, N, dev) for _ in range(RING)]
         caps = (self.geom_s.lv[0].cap, self.geom_s.lv[1].cap)
         mk = lambda: engine.EncoderCtx(B, caps, engine.WIDTHS, dev)  # noqa: E731
         self.ctx_p = mk()                      # F4 (policy encoder, state) — kept for B2
@@ -308,6 +316,30 @@ class AgentB200:
         self.dpi_ac = torch.zeros(B, 6, dtype=torch.float32, device=dev)
         self._bc_buf = [torch.zeros(B, max(self.Cb_value, 1), dtype=torch.float32, device=dev) for _ in range(3)]
         self._graphs = {}
+
+    # inputs of the current staging slot
+    cloud = property(lambda self: self._cloud_s[self._slot])
+    next_cloud = property(lambda self: self._next_cloud_s[self._slot])
+    vec = property(lambda self: self._vec_s[self._slot])
+    v = property(lambda self: self._v_s[self._slot])
+    geom_s = property(lambda self: self._geom_s_s[self._slot])
+    geom_n = property(lambda self: self._geom_n_s[self._slot])
+
+    def _prep_streams(self):
+        """Two streams that carry the input staging + geometry of the NEXT step of a pipelined caller (state side / next-state
+        side), and one event per slot and side that the compute stream waits for before the step's first phase."""
+        if self._h2d_stream is None:
+            self._h2d_stream = (torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device))
+            self._h2d_ev = [(torch.cuda.Event(), torch.cuda.Event()) for _ in range(RING)]
+        return self._h2d_stream
+
+    def _wait_prep(self):
+        """Compute stream <- the prep streams of this slot (no-op for a synchronous prepare_data)."""
+        if self._prep_pending:
+            cur = torch.cuda.current_stream()
+            for e in self._h2d_ev[self._slot]:
+                cur.wait_event(e)
+            self._prep_pending = False
 
     def _bc(self, action, slot):
         """The value encoder sees critic_input_dim - cloud_channels action channels (6 with the reference spec; the
@@ -336,13 +368,21 @@ class AgentB200:
             B, (C, Np) = len(batch.batch_idx), mem.row
             if self._shape != (B, C, Np):
                 self._alloc(B, C, Np)
-            mem.gather_into(batch.batch_idx, self.cloud, self.next_cloud if self.has_critic else None, self.vec, self._vec_off)
-            mem._lazy.pop(id(batch), None)   # consumed: a later write to the buffer need not snapshot it
-            if after_clouds is not None:
-                after_clouds()
-            if self.has_critic:
-                self.v.noise_u.copy_(torch.rand(B, 6, device=self.device) if noise_u is None
-                                     else torch.as_tensor(noise_u, dtype=torch.float32).view(B, 6), non_blocking=True)
+            pre = prefetch and after_clouds is not None
+            with (torch.cuda.stream(self._prep_streams()[0]) if pre else contextlib.nullcontext()):
+                mem.gather_into(batch.batch_idx, self.cloud, self.next_cloud if self.has_critic else None, self.vec, self._vec_off)
+                mem._lazy.pop(id(batch), None)   # consumed: a later write to the buffer need not snapshot it
+                if pre:     # gather + geometry of both clouds behind the running step; the compute stream joins in _wait_prep
+                    self._geometry(prep=True)
+                elif after_clouds is not None:
+                    after_clouds()
+                if self.has_critic:
+                    self.v.noise_u.copy_(torch.rand(B, 6, device=self.device) if noise_u is None
+                                         else torch.as_tensor(noise_u, dtype=torch.float32).view(B, 6), non_blocking=True)
+                if pre:
+                    for e in self._h2d_ev[self._slot]:
+                        e.record()
+                    self._prep_pending = True
             return
         cloud = batch["point_state_batch"]
         B, C, Np = cloud.shape
@@ -360,26 +400,36 @@ class AgentB200:
                 ring[slot].copy_(torch.as_tensor(src))   # float64 ndarray of the reference's replay buffer: convert on host
                 dst.copy_(ring[slot], non_blocking=True)
 
-        host_src = not (torch.is_tensor(cloud) and cloud.is_cuda)
-        if prefetch and host_src:
-            if self._h2d_stream is None:
-                self._h2d_stream = torch.cuda.Stream(device=self.device)
-                self._h2d_ev = [torch.cuda.Event() for _ in range(RING)]
-            if self._cloud_dev[slot] is None:
-                self._cloud_dev[slot] = [torch.zeros(self._cloud_shape, dtype=torch.float32, device=self.device) for _ in range(2)]
-            stage = self._cloud_dev[slot]
-            with torch.cuda.stream(self._h2d_stream):
-                put_cloud(stage[0], self._cloud_host, cloud)
-                if self.has_critic:
-                    put_cloud(stage[1], self._next_cloud_host, batch["next_point_state_batch"])
-                self._h2d_ev[slot].record(self._h2d_stream)
-            torch.cuda.current_stream().wait_event(self._h2d_ev[slot])
-            self.cloud.copy_(stage[0], non_blocking=True)
+        # device-resident sources take the prep streams only when the caller vouches that nothing is still writing them
+        # (static_device_batches): the prep streams do not wait for the compute stream — that is their point
+        dev_src = torch.is_tensor(cloud) and cloud.is_cuda
+        pre = prefetch and after_clouds is not None and (not dev_src or self.static_device_batches)
+        if pre:
+            # pipelined caller: this slot's buffers are free (the step that used them has finished, _begin_step), the running
+            # step reads the OTHER slot -> transfers, small fields and both geometries go to the two prep streams now
+            p_state, p_next = self._prep_streams()
+            ev = self._h2d_ev[slot]
             if self.has_critic:
-                self.next_cloud.copy_(stage[1], non_blocking=True)
-        else:
-            put_cloud(self.cloud, self._cloud_host, cloud)
-        if self.has_critic and not (prefetch and host_src):
+                with torch.cuda.stream(p_next):
+                    put_cloud(self.next_cloud, self._next_cloud_host, batch["next_point_state_batch"])
+                    self._run(("gn",), lambda: self.geom_n.build(self.next_cloud, self.skip))
+                    ev[1].record()
+            else:
+                ev[1].record(p_next)
+            self._prep_pending = True
+        with (torch.cuda.stream(self._prep_streams()[0]) if pre else contextlib.nullcontext()):
+            self._prepare_state_side(batch, cloud, noise_u, after_clouds, put_cloud, slot, pre)
+            if pre:
+                self._h2d_ev[slot][0].record()
+
+    def _prepare_state_side(self, batch, cloud, noise_u, after_clouds, put_cloud, slot, pre):
+        """State cloud, (synchronous callers: next-state cloud,) geometry, the small per-sample fields."""
+        B = cloud.shape[0]
+        put_cloud(self.cloud, self._cloud_host, cloud)
+        if pre:
+            self._run(("gs",), lambda: self.geom_s.build(self.cloud, self.skip))
+            after_clouds = None
+        if self.has_critic and not pre:
             nxt = batch["next_point_state_batch"]
             # only the target chain (side stream) reads it: its H2D copy overlaps the state chain.  A device-resident
             # batch was produced on the current stream, so its D2D copy stays there
@@ -412,11 +462,12 @@ class AgentB200:
             after_clouds()
 
     # ---- geometry (FPS, ball query, row tables) of the minibatch's clouds: needs xyz only ------------------------
-    def _geometry(self):
+    def _geometry(self, prep=False):
         """Launched right after the cloud transfers are issued.  State cloud on the main stream, next-state cloud on the
-        target chain's stream (which already carries its H2D copy, or is forked off the main stream for device batches)."""
+        target chain's stream (which already carries its H2D copy, or is forked off the main stream for device batches).
+        ``prep``: both on the current (prep) stream — they run behind the previous step, off its critical path."""
         if self.has_critic:
-            if self.overlap:
+            if self.overlap and not prep:
                 side = self.side_enc
                 side.fork()
                 with torch.cuda.stream(side.stream):
@@ -554,6 +605,7 @@ class AgentB200:
         whole sequence whose pieces call ``_run`` themselves — they run inline, so the sequence becomes ONE graph."""
         if not self.use_graph or self._in_outer:
             return fn()
+        key = key + (self._slot,)   # the step's inputs (clouds, fields, geometry) are per staging slot: one capture per slot
         if outer:
             inner = fn
 
@@ -1015,6 +1067,7 @@ class DDPGB200(AgentB200):
             self.prepare_data(batch_data, noise_u, after_clouds=self._geometry, prefetch=defer)
         else:
             self._geometry()
+        self._wait_prep()
         even = (self.update_step % self.policy_update_gap) == 0
         hard = (self.update_step % self.target_update_interval) == 0
         sig = (self._mix_idx(),)
@@ -1079,6 +1132,7 @@ class BCB200(AgentB200):
             self.prepare_data(batch_data, after_clouds=self._geometry, prefetch=defer)
         else:
             self._geometry()
+        self._wait_prep()
         self._set_dyn(("policy",) + (("enc",) if self.train_feature else ()))
         self._run(("bc",), self._phase)
         self._reduce_late(self.gpool_a, self.ef_p)   # BC is one short backward: a single blocking call
