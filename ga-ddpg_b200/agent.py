@@ -200,6 +200,8 @@ class AgentB200:
         # GADDPG_F4_LATE=0/1 for A/B
         # measured at cfg2 (A/B/A/B in one session): 218.3 / 219.0 steps/s late vs 222.1 / 222.4 early -> off
         self.f4_late = os.environ.get("GADDPG_F4_LATE", "0") == "1"
+        # F4 as a THIRD concurrent chain on the (idle in phase 1) weight-gradient stream: 226.1 / 225.7 vs 229.6 / 229.6 steps/s -> off
+        self.f4_par = os.environ.get("GADDPG_F4_PAR", "0") == "1"
         # geometry is launched before the small-field staging for device-resident batches (+1 % steps/s: the GPU no longer
         # idles behind ~100 us of host work); for host batches that ordering measured 0.17 ms SLOWER per step (5.59 vs
         # 5.42 ms, A/B in one process), so they keep transfers -> staging -> geometry
@@ -931,9 +933,14 @@ class DDPGB200(AgentB200):
     def _phase1_state(self):
         B, ws, v = self.B, self.ws, self.v
         self.out.zero_()
+        if self.overlap and self.f4_par and not self.f4_late:
+            # F4 as a third concurrent chain (the weight-gradient stream and its scratch are idle during phase 1)
+            self.side_dw.run(lambda w: self._f4(w))
         f1 = engine.encoder_forward(ws, self.ef_v, self.geom_s, self.cloud, self.skip, self.Cp_value, self._bc(v.action, 0), self.ctx_v1,
                                     time=v.time, time_offset=0.0, train=True, bn_stage=self.bnst[1])              # F1
-        if not (self.overlap and self.f4_late):
+        if self.overlap and self.f4_par and not self.f4_late:
+            self.side_dw.join()
+        elif not (self.overlap and self.f4_late):
             self._f4(ws)
         engine.critic_forward(self.cf, f1, self.cc1, B)
 
