@@ -384,7 +384,14 @@ def main():
     if rank == 0:
         print(json.dumps(out))
     if world:
-        world.close()
+        # The captured whole-step graphs hold NCCL kernels; destroying the process group while they exist blocked the 8-rank run
+        # at exit (the JSON line was out, the workers never returned).  Drop the graphs, drain the device, and leave without the
+        # collective teardown: every rank has passed the barrier above, nothing is in flight.
+        agent._graphs.clear()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def replay_leg(agent, devb, args, run, nb, n_gpus=1, gather_bench=True):
