@@ -69,6 +69,42 @@ def test_host_memory_prefetch_thread_matches_synchronous_loop(cuda):
     _same(out[True], out[False])
 
 
+def test_prep_streams_for_static_device_batches_change_nothing(cuda):
+    """Per-slot input buffers + prep streams (agent.static_device_batches: dicts of finished DEVICE tensors, bench.py's `value`
+    leg): the staging copies and the FPS / ball-query / row-table kernels of minibatch i+1 run beside step i, and every returned
+    scalar — twelve steps over three distinct minibatches, both step parities — equals the synchronous loop's bit for bit."""
+    from gaddpg_b200 import agent as ag, synthetic
+
+    B, N = 32, 1024
+    batches = []
+    for i in range(3):
+        b = synthetic.make_batch(B, N, step=20 + i)
+        t = {k: torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32)).to(cuda) for k, v in b.items()
+             if k not in ("grasp_sample_batch", "batch_idx")}
+        t["noise_u"] = torch.from_numpy(np.random.RandomState(i).rand(B, 6).astype(np.float32)).to(cuda)
+        batches.append(t)
+    torch.cuda.synchronize()
+    out = {}
+    for mode in ("sync", "pipe"):
+        agent = ag.make_agent("DDPG", seed=123456)
+        agent.static_device_batches = True
+        res, pending = [], None
+        for i in range(12):
+            b = batches[i % 3]
+            h = agent.update_parameters(b, agent.update_step, 0, noise_u=b["noise_u"], defer=(mode == "pipe"))
+            agent.step_scheduler(agent.update_step)
+            if mode == "sync":
+                res.append(h)
+                continue
+            if pending is not None:
+                res.append(pending.result())
+            pending = h
+        if pending is not None:
+            res.append(pending.result())
+        out[mode] = res
+    _same(out["pipe"], out["sync"])
+
+
 def test_batched_select_action_and_extract_feature(cuda):
     """test_realworld_ros_final.py:1257-1261: a batch of view-point clouds through extract_feature + policy.sample.  Row b
     of the batched call equals the single-cloud ``select_action`` of cloud b, and both match the oracle within 1e-4."""
