@@ -127,6 +127,8 @@ __device__ __forceinline__ void split_store(unsigned char* hi_base, unsigned cha
 }
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+// pull a line towards L2 ahead of the register-staged load that will need it (no functional effect)
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <int MODE>
 __device__ __forceinline__ float4 load_operand4(const Operand& d, int row, int col, int M, int W) {

@@ -52,6 +52,11 @@ constexpr int TC_THREADS = (TC_PW + 1 + 4) * 32;
 #ifndef TC_U_BWD
 #define TC_U_BWD 4
 #endif
+#ifndef TC_PFD
+#define TC_PFD 1   // producer units prefetched into L2 ahead of their register-staged loads (0: off).  Measured (graph-timed,
+                   // M = 423 k): dX 64->64 85.9 -> 75.3 us, dX 128->64 142.9 -> 122.7 us, fwd 64->128 78.6 -> 72.5 us (1, 2 and 3
+                   // units ahead within 2 %); fwd 64->64 47.4 -> 48.2 us: store-bound, left without prefetch
+#endif
 
 constexpr int TC_KS = 64;  // K width of one shared-memory A stage (a K = 128 tile is two stages: its second half loads
                            // while the tensor core works on the first)
@@ -214,6 +219,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
     }
     const int kc = (tid % SQ4) << 2, rsub = tid / SQ4;  // column inside the 64-wide stage, first row served
     const float* cct = reinterpret_cast<const float*>(smem + L.cc);
+    const bool pf_on = BWD || N > 64;   // (uniform) the 64 -> 64 forward layer is bound by its stores, not by its loads
     // Software pipeline over "units" of U row-iterations: the global loads of unit u+1 are issued into a second
     // register set before unit u is transformed and stored, so HBM latency overlaps the prologue math and the
     // shared-memory stores (and runs ahead across stage and tile boundaries, independent of the smem-stage barriers).
@@ -269,6 +275,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
           }
         }
         prefetch_seg(u + 1);
+      }
+      if (TC_PFD > 0 && pf_on && u + TC_PFD < total_units) {
+        // L2 prefetch of the unit TC_PFD ahead: the producers wait on these loads (long-scoreboard stalls dominate their issue
+        // slots, ncu); with the line already in L2 the register-staged load of that unit returns in a fraction of the time.  A
+        // unit is U*16 consecutive rows x 64 columns (two 128-byte lines per row and operand): one line per producer thread.
+        const int up = u + TC_PFD;
+        const int it2 = up / UPT, v2 = up % UPT;
+        constexpr int LPO = U * 32;                               // lines per operand and unit
+        const int li = tid % LPO, op = tid / LPO;                 // op 0: X, op 1: Y (BatchNorm-backward forms)
+        const int row = ((int)blockIdx.x + it2 * (int)gridDim.x) * TC_BM + (v2 % UPS) * U * RPI + (li >> 1);
+        const int col = (v2 / UPS) * TC_KS + (li & 1) * 32;
+        if (row < M) {
+          if (op == 0 && AMODE != OP_BNBWD_POOL) prefetch_l2(p.A.X + (long long)row * p.A.ldx + col);
+          if (op == 1 && BWD) prefetch_l2(p.A.Y + (long long)row * p.A.ldy + col);
+        }
       }
     };
     auto process = [&](const Regs& R, int u) {
@@ -401,6 +422,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const NTProbl
           const int row = row_base + 4 * i + rsub;
           wr[i] = (row < M) ? p.srw[row] : 0.f;
         }
+      }
+      if (EMODE == EPI_DMASK && TC_PFD > 0) {
+        // mask source of this CTA's NEXT tile towards L2 while the accumulator of this one is still being produced (the
+        // epilogue's Yprev loads were its longest exposed latency: profiles/r1_tc_roles.md)
+        const int rown = (t + (int)gridDim.x) * TC_BM + q * 32 + lane;
+        if (rown < M)
+          for (int c = 0; c < N; c += 32) prefetch_l2(p.Yprev + (long long)rown * p.ldyp + c);
       }
       {
         const long long t0 = TCP_T();
