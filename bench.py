@@ -488,7 +488,7 @@ def profile(agent, devb, args):
             agent.update_parameters(b, agent.update_step, 0, noise_u=b["noise_u"])
     torch.cuda.synchronize()
     mres = {}
-    for g in (agent.geom_s, agent.geom_n):
+    for g in list(agent._geom_s_s) + list(agent._geom_n_s):   # every staging slot: the two profiled steps use two of them
         for l in g.lv:
             mres[l.M_dev] = int(l.seg_off[-1])
     tab = prof.table(mres)
