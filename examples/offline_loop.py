@@ -27,6 +27,9 @@ def main():
     ap.add_argument("--points", type=int, default=1024, help="uniform_num_pts of the replay clouds (reference default 1024)")
     ap.add_argument("--episodes", type=int, default=40)
     ap.add_argument("--out", default="/tmp/gaddpg_b200_demo")
+    ap.add_argument("--synchronous", action="store_true",
+                    help="the reference's strictly sequential order (sample, update, read the scalars) instead of the double-buffered "
+                         "feed loop (feed.FeedLoop: step i+1 is staged and its geometry built while step i computes)")
     args = ap.parse_args()
 
     from gaddpg_b200 import agent as ag, synthetic
@@ -42,12 +45,21 @@ def main():
 
     losses = {k: [] for k in LOSS_KEYS}
     t0 = time.time()
-    for i in range(args.updates):
-        batch_data = memory.sample(batch_size=args.batch)                   # train_test_offline.py:120
-        loss = agent.update_parameters(batch_data, agent.update_step, i)    # :123
-        agent.step_scheduler(agent.update_step)                             # :129
-        for k, v in loss.items():
-            losses[k].append(v)
+    if args.synchronous:
+        for i in range(args.updates):
+            batch_data = memory.sample(batch_size=args.batch)                   # train_test_offline.py:120
+            loss = agent.update_parameters(batch_data, agent.update_step, i)    # :123
+            agent.step_scheduler(agent.update_step)                             # :129
+            for k, v in loss.items():
+                losses[k].append(v)
+    else:
+        # the same three calls per update, issued by feed.FeedLoop one step ahead of the device (trainer.py:202-293 overlaps the next
+        # minibatch with the current update through ray; here it is done in-process) — identical losses, bit for bit
+        from gaddpg_b200.feed import FeedLoop
+
+        for loss in FeedLoop(agent, memory, args.batch).train_iter(args.updates):
+            for k, v in loss.items():
+                losses[k].append(v)
     dt = time.time() - t0
     print("%d updates of %d samples in %.2f s (%.1f updates/s, first calls include CUDA-graph capture)" % (args.updates, args.batch, dt, args.updates / dt))
     for k, v in losses.items():
