@@ -30,6 +30,32 @@ def test_struct_mirrors_match_header():
     assert ctypes.sizeof(structs.NTGroup) == 4 * ctypes.sizeof(structs.NTProblem)
 
 
+def _header_fields(name):
+    """Member names of ``typedef struct <name> { ... } <name>;`` in declaration order."""
+    hdr = open(os.path.join(ROOT, "include", "gaddpg_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), hdr, flags=re.S).group(1)
+    out = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        first, *rest = decl.split(",")
+        out.append(re.search(r"(\w+)(\[\w+\])?$", first.strip()).group(1))
+        out += [re.search(r"(\w+)$", r.strip()).group(1) for r in rest]
+    return out
+
+
+def test_struct_mirror_field_order_matches_header():
+    """sizeof() equality (above) does not catch two swapped members of the same size: compare the member names, in order, of every
+    descriptor struct the Python side fills (Operand, BatchNorm tail, NT / TN problems, the per-level composites)."""
+    from gaddpg_b200 import structs
+
+    for cname, cls in (("gaddpg_operand", structs.Operand), ("gaddpg_bn_tail", structs.BNTail), ("gaddpg_nt_problem", structs.NTProblem),
+                       ("gaddpg_tn_problem", structs.TNProblem), ("gaddpg_sa_layer", structs.SALayer), ("gaddpg_sa_level", structs.SALevel)):
+        assert _header_fields(cname) == [f[0] for f in cls._fields_], cname
+
+
 def test_opt_n_threads_rule_matches_oracle():
     from gaddpg_b200 import capi
     from oracle.pointnet2_ops_cpu import pointnet2_utils as U
