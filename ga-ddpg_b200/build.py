@@ -63,7 +63,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    subprocess.run([NVCC, "-shared", "-o", LIB] + objs + ["-Xcompiler", "-fvisibility=hidden", "-lcudart_static", "-lpthread", "-ldl", "-lrt"], check=True)
+    # the link step gets the same -gencode: without it nvcc adds an (empty) device-link stub for its default architecture
+    subprocess.run([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs +
+                   ["-Xcompiler", "-fvisibility=hidden", "-lcudart_static", "-lpthread", "-ldl", "-lrt"], check=True)
     open(stamp_file, "w").write(stamp)
     return LIB
 
