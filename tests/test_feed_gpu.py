@@ -69,7 +69,8 @@ def test_host_memory_prefetch_thread_matches_synchronous_loop(cuda):
     _same(out[True], out[False])
 
 
-def test_prep_streams_for_static_device_batches_change_nothing(cuda):
+@pytest.mark.parametrize("policy", ["DDPG", "BC"])
+def test_prep_streams_for_static_device_batches_change_nothing(cuda, policy):
     """Per-slot input buffers + prep streams (agent.static_device_batches: dicts of finished DEVICE tensors, bench.py's `value`
     leg): the staging copies and the FPS / ball-query / row-table kernels of minibatch i+1 run beside step i, and every returned
     scalar — twelve steps over three distinct minibatches, both step parities — equals the synchronous loop's bit for bit."""
@@ -86,7 +87,7 @@ def test_prep_streams_for_static_device_batches_change_nothing(cuda):
     torch.cuda.synchronize()
     out = {}
     for mode in ("sync", "pipe"):
-        agent = ag.make_agent("DDPG", seed=123456)
+        agent = ag.make_agent(policy, seed=123456)
         agent.static_device_batches = True
         res, pending = [], None
         for i in range(12):
